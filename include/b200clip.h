@@ -1,0 +1,174 @@
+/*
+ * b200clip — C ABI of the B200-native (sm_100a) CLIP hot path.
+ *
+ * The reference (lmb-freiburg/understanding-clip-ood @ /root/reference) is pure Python: it has no
+ * FFI/plugin interface of its own.  Its drop-in boundary is a set of Python call signatures
+ * (SURVEY.md §8b); every entry point below states which reference call site(s) it replaces.  The
+ * Python host side (understanding_clip_ood_b200/) binds these with ctypes, passing
+ * `tensor.data_ptr()` and `torch.cuda.current_stream().cuda_stream`.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller unless the
+ *    name ends in `_host`; the library never allocates memory that outlives a call;
+ *  - `stream` is a `cudaStream_t` passed as `void*`; all work is enqueued on it, nothing
+ *    synchronises, so every call is CUDA-graph capturable;
+ *  - return value: 0 = ok, <0 = invalid argument, >0 = CUDA error code (`cudaError_t`);
+ *    `b200clip_last_error()` returns a thread-local message for the last non-zero return;
+ *  - `dtype`: activation/weight storage type of the call (B200CLIP_F32 / BF16 / F16).  In the 16-bit
+ *    modes LayerNorm affine parameters, embedding tables and positional tables stay fp32, exactly
+ *    like `convert_weights_to_lp` leaves them (deps/open_clip/src/open_clip/model.py:396-423).
+ *  - matrices are row-major with explicit leading dimensions in elements.
+ */
+#ifndef B200CLIP_H_
+#define B200CLIP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CLIP_F32 0
+#define B200CLIP_BF16 1
+#define B200CLIP_F16 2
+
+/* GEMM epilogues (fused into the accumulator read-out) */
+#define B200CLIP_EPI_BIAS 0      /* C = A W^T + b                     (MHA in-proj, functional.py _in_projection_packed) */
+#define B200CLIP_EPI_GELU 1      /* C = gelu_erf(A W^T + b)           (mlp.c_fc + nn.GELU, transformer.py:231-235)       */
+#define B200CLIP_EPI_QUICKGELU 2 /* C = x*sigmoid(1.702x)             (QuickGELU, transformer.py:33-36)                  */
+#define B200CLIP_EPI_RESIDUAL 3  /* C = R + (A W^T + b)               (out_proj / c_proj + residual, transformer.py:262-263) */
+#define B200CLIP_EPI_PATCH 4     /* patch-embedding: row remap + positional add (transformer.py:602-609)                 */
+
+int b200clip_version(void);
+const char* b200clip_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+uint64_t b200clip_launch_count(void);
+
+/* C[M,N] = epilogue(A[M,K] @ W[N,K]^T + bias[N]).  W is an nn.Linear weight ([out,in], K contiguous).
+ * 16-bit dtypes run on tcgen05 tensor cores (TMA-fed, TMEM accumulators); F32 runs an FFMA kernel with
+ * fp32 accumulation (the 1e-4 parity mode).  `bias`, `residual` may be NULL when the epilogue does not
+ * use them.  EPI_PATCH: row m of the product is written to row (m / g_in) * g_out + m % g_in + 1 of C
+ * after adding pos[(m % g_in) + 1, :] (fp32 table, ld = N); g_in = patches per image, g_out = g_in + 1.
+ * Replaces: F.linear / nn.Linear / `@` call sites of transformer.py:224-235,249-263,638 and model.py:282. */
+int b200clip_gemm(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
+                  const void* residual, int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue,
+                  const float* pos, int g_in, int g_out, void* stream);
+
+/* y[r,:] = LayerNorm(x[row_index(r),:]) * gamma + beta, fp32 statistics, eps as given (1e-5).
+ * `row_stride_rows` > 0 selects every row_stride_rows-th row starting at row_offset (CLS pooling:
+ * stride L, offset 0); `row_idx` (int32, may be NULL) adds a per-output-row offset (EOT pooling).
+ * Replaces LayerNorm / LayerNormFp32 (transformer.py:15-30) at ln_pre, ln_1, ln_2, ln_post, ln_final. */
+int b200clip_layernorm(int dtype, const void* x, int64_t ldx, const float* gamma, const float* beta, void* y,
+                       int64_t ldy, int rows, int width, float eps, int row_stride_rows, const int32_t* row_idx,
+                       void* stream);
+
+/* Multi-head softmax attention over a packed qkv buffer: qkv[M, 3W] with q|k|v column blocks, row
+ * b*L + l, head h = columns [64h, 64h+64) of each block; out[M, W].  scale = 1/sqrt(64) is applied to
+ * the scores; `causal` != 0 adds the strict upper-triangular -inf mask of the text tower.
+ * Replaces nn.MultiheadAttention's SDPA core (transformer.py:224,249-251; torch functional.py
+ * multi_head_attention_forward) and build_causal_mask (transformer.py:751-757). */
+int b200clip_attention(int dtype, const void* qkv, void* out, int batch, int seq_len, int heads, int causal,
+                       void* stream);
+
+/* Patch im2col: image [B,3,H,H] NCHW -> patches [B*g*g, kpad] with K order (channel, ky, kx) zero-padded to
+ * kpad, and the class-token rows x[b*(g*g+1), :] = class_emb + pos[0] written into `x` (ld = width).
+ * Replaces the unfold part of conv1 + class-token cat (transformer.py:602-609). */
+int b200clip_patchify(int dtype, const void* image, void* patches, int batch, int image_size, int patch,
+                      int kpad, const float* class_emb, const float* pos, void* x, int width, void* stream);
+
+/* x[t*L + l, :] = token_embedding[text[t, l], :] + positional_embedding[l, :]  (model.py:272-274);
+ * also writes eot[t] = argmax_l text[t, l] (int32) for text_global_pool (transformer.py:654).
+ * `text` is int64 [T, ctx]; only the first L <= ctx positions are embedded (causal truncation). */
+int b200clip_text_embed(int dtype, const int64_t* text, int ctx, const float* tok_emb, const float* pos_emb,
+                        void* x, int32_t* eot, int T, int L, int width, void* stream);
+
+/* y = x / max(||x||_2, eps) per row (F.normalize, model.py:267,284; xclip/zero_shot.py:34,50). */
+int b200clip_normalize(int dtype, const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int dim, float eps,
+                       void* stream);
+
+/* Zero-shot similarity stage: img_feat[B,D] (un-normalised when `normalize_img` != 0) against unit-norm
+ * prompt_feat[C,D]; writes logits[B,C] (fp32, may be NULL), topk_idx[B,k] (int64, descending, ties to the
+ * lower class index like torch.argmax/topk) and topk_val[B,k] (fp32, may be NULL).  k <= 8.
+ * Replaces xclip/zero_shot.py:42-60,103-109 (_compute_img_feat's normalize, _compute_logits, argmax) and
+ * training/zero_shot.py:11-14 (topk). */
+int b200clip_zeroshot(int dtype, const void* img_feat, const void* prompt_feat, float* logits, int64_t* topk_idx,
+                      float* topk_val, int B, int C, int D, int k, int normalize_img, float logit_scale,
+                      void* stream);
+
+/* prompt_feat[c,:] = normalize(mean_t normalize(txt_feat[c*T + t, :])) (xclip/zero_shot.py:231-234). */
+int b200clip_class_mean(int dtype, const void* txt_feat, void* prompt_feat, int classes, int templates, int D,
+                        void* stream);
+
+/* ClipLoss local-loss forward+backward on gathered features (loss.py:102-131).  fp32 features.
+ *   loss      = (CE(s*img_loc@all_txt^T, lab) + CE(s*txt_loc@all_img^T, lab)) / 2, lab_i = i + n*rank
+ *   d_img_loc, d_txt_loc [n,D]: gradient through the local operands,
+ *   d_all_img, d_all_txt [N,D]: gradient through the gathered operands (reduce-scattered by the caller,
+ *   as torch.distributed.nn.all_gather's backward does), d_scale: gradient of the logit scale.
+ * Gradients are for `loss` with upstream gradient `grad_out` (device scalar, may be NULL = 1).
+ * Any gradient pointer may be NULL (forward only when all are NULL).  workspace >= 2*n*N floats. */
+int b200clip_cliploss(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt,
+                      const float* logit_scale, int rank, int n, int N, int D, float* loss, const float* grad_out,
+                      float* d_img_loc, float* d_txt_loc, float* d_all_img, float* d_all_txt, float* d_scale,
+                      float* workspace, void* stream);
+
+/* ----- whole-tower drivers: one call per encode_image / encode_text ------------------------------ */
+
+typedef struct b200clip_tower_cfg {
+    int32_t dtype;       /* B200CLIP_* */
+    int32_t width;       /* W */
+    int32_t layers;
+    int32_t heads;       /* W / 64 */
+    int32_t mlp_width;   /* 4W */
+    int32_t embed_dim;   /* D */
+    int32_t seq_len;     /* L: image tokens incl. CLS, or text context length */
+    int32_t quick_gelu;  /* 0 = erf GELU, 1 = QuickGELU */
+    int32_t image_size;  /* vision only */
+    int32_t patch_size;  /* vision only */
+    int32_t patch_kpad;  /* vision only: 3*P*P rounded up to a multiple of 64 */
+    int32_t vocab_size;  /* text only */
+} b200clip_tower_cfg;
+
+/* per-layer weights, all device pointers.  16-bit modes: matrices/biases in `dtype`, LN params fp32. */
+typedef struct b200clip_block_weights {
+    const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    const void *in_proj_w, *in_proj_b;   /* [3W,W], [3W] */
+    const void *out_proj_w, *out_proj_b; /* [W,W],  [W]  */
+    const void *fc_w, *fc_b;             /* [4W,W], [4W] */
+    const void *proj_w, *proj_b;         /* [W,4W], [W]  */
+} b200clip_block_weights;
+
+typedef struct b200clip_vit_weights {
+    const void* conv1_w;      /* [W, patch_kpad] (K zero-padded), dtype */
+    const float* class_emb;   /* [W] fp32 */
+    const float* pos_emb;     /* [L, W] fp32 */
+    const float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
+    const void* proj_t;       /* [D, W]: visual.proj transposed, dtype */
+    const b200clip_block_weights* blocks_host; /* HOST array of `layers` entries */
+} b200clip_vit_weights;
+
+typedef struct b200clip_text_weights {
+    const float* tok_emb;     /* [vocab, W] fp32 */
+    const float* pos_emb;     /* [ctx, W] fp32 */
+    const float *ln_final_g, *ln_final_b;
+    const void* proj_t;       /* [D, W]: text_projection transposed, dtype */
+    const b200clip_block_weights* blocks_host;
+} b200clip_text_weights;
+
+/* bytes of scratch a forward of `batch` items needs (seq_len from cfg; text may pass a truncated L) */
+int64_t b200clip_workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len);
+
+/* VisionTransformer.forward (transformer.py:601-643): image [B,3,S,S] dtype -> out [B,D] dtype
+ * (L2-normalised when `normalize` != 0, CLIP.encode_image model.py:265-267). */
+int b200clip_vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out,
+                         int batch, int normalize, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* CLIP.encode_text (model.py:269-284): text int64 [T, ctx] -> out [T,D].  `seq_len` <= ctx is the number of
+ * leading positions actually run (ctx = reference behaviour; max(eot)+1 is exact by causality). */
+int b200clip_text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text,
+                          void* out, int batch, int seq_len, int normalize, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CLIP_H_ */

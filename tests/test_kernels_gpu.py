@@ -1,0 +1,301 @@
+"""Per-kernel numerics on the B200: every C-ABI kernel entry point against a plain PyTorch fp32 restatement
+of the same op (these are floating-point kernels; tolerances are written next to each assert).
+Tower-level parity against the oracle / the reference's golden vectors lives in test_parity_gpu.py."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from understanding_clip_ood_b200 import _lib as L  # noqa: E402
+from understanding_clip_ood_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def _gen(seed=0):
+    return torch.Generator(device=DEV).manual_seed(seed)
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------ GEMM (tcgen05) ------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K,epi,bn", [
+    (128, 128, 64, L.EPI_BIAS, 128),
+    (128, 256, 64, L.EPI_BIAS, 256),
+    (6400, 2304, 768, L.EPI_BIAS, 0),        # ViT-B/32 QKV, 128 images
+    (6400, 3072, 768, L.EPI_GELU, 0),        # c_fc + GELU
+    (6400, 3072, 768, L.EPI_QUICKGELU, 0),   # c_fc + QuickGELU
+    (6400, 768, 3072, L.EPI_RESIDUAL, 0),    # c_proj + residual
+    (3200, 768, 768, L.EPI_RESIDUAL, 128),   # out_proj + residual
+    (6622, 1536, 512, L.EPI_BIAS, 0),        # text tower QKV, 86 prompts (ragged M)
+    (77, 512, 512, L.EPI_BIAS, 0),           # single ragged tile
+    (1000, 264, 72, L.EPI_BIAS, 128),        # ragged M, N and K tails
+    (64, 512, 768, L.EPI_BIAS, 0),           # pooled projection
+])
+def test_gemm_tc(dtype, M, N, K, epi, bn):
+    g = _gen(1)
+    a = (torch.randn(M, K, device=DEV, generator=g) * 0.5).to(dtype)
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.05).to(dtype)
+    bias = (torch.randn(N, device=DEV, generator=g) * 0.1).to(dtype)
+    res = torch.randn(M, N, device=DEV, generator=g).to(dtype) if epi == L.EPI_RESIDUAL else None
+    out = ops.gemm(a, w, bias, epilogue=epi, residual=res, block_n=bn)
+    lin = (a.float() @ w.float().t() + bias.float()).to(dtype).float()   # the reference rounds the linear output
+    if epi == L.EPI_GELU:
+        ref = F.gelu(lin)
+    elif epi == L.EPI_QUICKGELU:
+        ref = lin * torch.sigmoid(1.702 * lin)
+    elif epi == L.EPI_RESIDUAL:
+        ref = lin + res.float()
+    else:
+        ref = lin
+    ref = ref.to(dtype).float()
+    # one ulp of the 16-bit output type on top of fp32-accumulation-order noise
+    ulp = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    tol = 2 * ulp * ref.abs().max().item() + 1e-3
+    assert (out.float() - ref).abs().max().item() <= tol
+    assert _rel(out, ref) < 3e-3
+
+
+def test_gemm_tc_inplace_residual_and_nobias():
+    g = _gen(2)
+    M, N, K = 640, 768, 768
+    a = (torch.randn(M, K, device=DEV, generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.05).bfloat16()
+    x = torch.randn(M, N, device=DEV, generator=g).bfloat16()
+    ref = ((a.float() @ w.float().t()).bfloat16().float() + x.float()).bfloat16()
+    out = ops.gemm(a, w, None, epilogue=L.EPI_RESIDUAL, residual=x, out=x)
+    assert out.data_ptr() == x.data_ptr()
+    assert _rel(out, ref) < 3e-3
+
+
+def test_gemm_bad_args_raise():
+    a = torch.zeros(8, 12, device=DEV, dtype=torch.bfloat16)   # K % 8 != 0
+    w = torch.zeros(16, 12, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(L.B200ClipError):
+        ops.gemm(a, w)
+    with pytest.raises(L.B200ClipError):
+        ops.gemm(torch.zeros(8, 16), torch.zeros(16, 16))      # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------ GEMM (fp32 parity path) ----------
+@pytest.mark.parametrize("M,N,K,epi", [
+    (3200, 2304, 768, L.EPI_BIAS), (3200, 3072, 768, L.EPI_GELU), (3200, 768, 3072, L.EPI_RESIDUAL),
+    (130, 516, 100, L.EPI_QUICKGELU), (64, 512, 768, L.EPI_BIAS),
+])
+def test_gemm_f32(M, N, K, epi):
+    g = _gen(3)
+    a = torch.randn(M, K, device=DEV, generator=g) * 0.5
+    w = torch.randn(N, K, device=DEV, generator=g) * 0.05
+    bias = torch.randn(N, device=DEV, generator=g) * 0.1
+    res = torch.randn(M, N, device=DEV, generator=g) if epi == L.EPI_RESIDUAL else None
+    out = ops.gemm(a, w, bias, epilogue=epi, residual=res)
+    lin = (a.double() @ w.double().t() + bias.double())
+    if epi == L.EPI_GELU:
+        ref = F.gelu(lin)
+    elif epi == L.EPI_QUICKGELU:
+        ref = lin * torch.sigmoid(1.702 * lin)
+    elif epi == L.EPI_RESIDUAL:
+        ref = lin + res.double()
+    else:
+        ref = lin
+    assert _rel(out, ref) < 2e-6   # fp32 FMA accumulation vs fp64
+
+
+# ------------------------------------------------------------------ patch embedding ------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("S,P,W", [(224, 32, 768), (224, 16, 768), (224, 14, 1024)])
+def test_patch_embed(dtype, S, P, W):
+    g = _gen(4)
+    B = 5
+    grid = S // P
+    Lq = grid * grid + 1
+    kreal = 3 * P * P
+    kpad = (kreal + 63) // 64 * 64
+    img = torch.randn(B, 3, S, S, device=DEV, generator=g).to(dtype)
+    conv_w = (torch.randn(W, 3, P, P, device=DEV, generator=g) * 0.02).to(dtype)
+    cls = torch.randn(W, device=DEV, generator=g) * 0.05
+    pos = torch.randn(Lq, W, device=DEV, generator=g) * 0.05
+    wpad = torch.zeros(W, kpad, device=DEV, dtype=dtype)
+    wpad[:, :kreal] = conv_w.reshape(W, kreal)
+    x = torch.empty(B * Lq, W, device=DEV, dtype=dtype)
+    patches = ops.patchify(img, P, kpad, cls, pos, x)
+    ref_p = img.view(B, 3, grid, P, grid, P).permute(0, 2, 4, 1, 3, 5).reshape(B * grid * grid, kreal)
+    assert torch.equal(patches[:, :kreal], ref_p)
+    assert patches[:, kreal:].abs().sum().item() == 0
+    ops.gemm(patches, wpad, None, epilogue=L.EPI_PATCH, out=x, pos=pos, g_in=grid * grid, g_out=Lq)
+    conv = F.conv2d(img.float(), conv_w.float(), stride=P).to(dtype).float()   # [B,W,g,g]
+    tok = conv.reshape(B, W, -1).permute(0, 2, 1)
+    full = torch.cat([cls.to(dtype).float().expand(B, 1, W), tok], dim=1) + pos.to(dtype).float()
+    ref = full.to(dtype).reshape(B * Lq, W)
+    tol = 3e-3 if dtype == torch.bfloat16 else 2e-6
+    assert _rel(x, ref) < tol
+
+
+# ------------------------------------------------------------------ LayerNorm / normalise ------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("rows,width", [(6400, 768), (77 * 3, 512), (1000, 1024), (5, 64)])
+def test_layernorm(dtype, rows, width):
+    g = _gen(5)
+    x = (torch.randn(rows, width, device=DEV, generator=g) * 2 + 0.3).to(dtype)
+    gamma = torch.randn(width, device=DEV, generator=g)
+    beta = torch.randn(width, device=DEV, generator=g)
+    out = ops.layernorm(x, gamma, beta)
+    ref = F.layer_norm(x.float(), (width,), gamma, beta, 1e-5).to(dtype)
+    tol = {torch.bfloat16: 2 ** -8, torch.float16: 2 ** -11, torch.float32: 1e-6}[dtype]
+    assert (out.float() - ref.float()).abs().max().item() <= tol * ref.float().abs().max().item() + 1e-6
+    # in place
+    y = x.clone()
+    ops.layernorm(y, gamma, beta, out=y)
+    assert torch.equal(y, out)
+
+
+def test_layernorm_pooling_gather():
+    g = _gen(6)
+    B, Lq, W = 7, 50, 768
+    x = torch.randn(B * Lq, W, device=DEV, generator=g).bfloat16()
+    gamma = torch.randn(W, device=DEV, generator=g)
+    beta = torch.randn(W, device=DEV, generator=g)
+    out = ops.layernorm(x, gamma, beta, rows=B, row_stride_rows=Lq)
+    ref = F.layer_norm(x.view(B, Lq, W)[:, 0].float(), (W,), gamma, beta, 1e-5).bfloat16()
+    assert _rel(out, ref) < 3e-3
+    idx = torch.randint(0, Lq, (B,), device=DEV, generator=g, dtype=torch.int32)
+    out = ops.layernorm(x, gamma, beta, rows=B, row_stride_rows=Lq, row_idx=idx)
+    ref = F.layer_norm(x.view(B, Lq, W)[torch.arange(B, device=DEV), idx.long()].float(), (W,), gamma, beta, 1e-5).bfloat16()
+    assert _rel(out, ref) < 3e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_normalize(dtype):
+    g = _gen(7)
+    x = (torch.randn(333, 512, device=DEV, generator=g) * 3).to(dtype)
+    x[5] = 0  # eps clamp path
+    out = ops.normalize(x)
+    ref = F.normalize(x.float(), dim=-1).to(dtype)
+    assert (out.float() - ref.float()).abs().max().item() <= (2 ** -7 if dtype == torch.bfloat16 else 1e-6)
+    assert out[5].abs().sum().item() == 0
+
+
+# ------------------------------------------------------------------ attention ------------------------
+def _attn_ref(qkv, B, Lq, H, causal):
+    W = H * 64
+    q, k, v = qkv.float().view(B, Lq, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / 8.0
+    if causal:
+        s = s + torch.full((Lq, Lq), float("-inf"), device=qkv.device).triu_(1)
+    o = torch.softmax(s, dim=-1) @ v
+    return o.permute(0, 2, 1, 3).reshape(B * Lq, W)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("B,Lq,H,causal", [(3, 50, 12, False), (2, 77, 8, True), (2, 197, 12, False), (1, 257, 16, False),
+                                           (4, 16, 8, True), (2, 64, 2, True), (2, 130, 2, True)])
+def test_attention(dtype, B, Lq, H, causal):
+    g = _gen(8)
+    qkv = (torch.randn(B * Lq, 3 * H * 64, device=DEV, generator=g) * 1.5).to(dtype)
+    out = ops.attention(qkv, B, Lq, H, causal)
+    ref = _attn_ref(qkv, B, Lq, H, causal)
+    tol = {torch.bfloat16: 1e-2, torch.float16: 2e-3, torch.float32: 2e-6}[dtype]
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < tol
+
+
+# ------------------------------------------------------------------ text embedding -------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_text_embed(dtype):
+    g = _gen(9)
+    T, ctx, W, V = 9, 77, 512, 49408
+    text = torch.zeros(T, ctx, dtype=torch.int64, device=DEV)
+    eot_ref = []
+    for t in range(T):
+        n = 3 + t
+        text[t, 0] = 49406
+        text[t, 1:n] = torch.randint(1, 40000, (n - 1,), device=DEV, generator=g)
+        text[t, n] = 49407
+        eot_ref.append(n)
+    tok = torch.randn(V, W, device=DEV, generator=g) * 0.02
+    pos = torch.randn(ctx, W, device=DEV, generator=g) * 0.01
+    for Lq in (ctx, 16):
+        x, eot = ops.text_embed(text, tok, pos, dtype, seq_len=Lq)
+        ref = (tok[text[:, :Lq]].to(dtype) + pos[:Lq].to(dtype)).reshape(T * Lq, W)
+        assert torch.equal(x, ref)
+        assert eot.tolist() == eot_ref
+
+
+# ------------------------------------------------------------------ zero-shot stage ------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,C,D,k", [(64, 345, 512, 5), (1024, 345, 512, 1), (13, 1000, 768, 5), (3, 7, 64, 7)])
+def test_zeroshot(dtype, B, C, D, k):
+    g = _gen(10)
+    img = (torch.randn(B, D, device=DEV, generator=g) * 4).to(dtype)
+    prm = F.normalize(torch.randn(C, D, device=DEV, generator=g), dim=-1).to(dtype)
+    logits, idx, val = ops.zeroshot(img, prm, k)
+    n = F.normalize(img.float(), dim=-1).to(dtype).float()
+    ref = (n.double() @ prm.double().t()).float()
+    if dtype == torch.float32:
+        assert (logits - ref).abs().max().item() < 2e-6
+    else:
+        assert (logits - ref).abs().max().item() < 2 ** -8
+    # the indices must be exactly the top-k of the logits this kernel wrote (ties -> lower index)
+    order = torch.sort(logits, dim=1, descending=True, stable=True).indices[:, :k]
+    assert torch.equal(idx, order)
+    assert torch.equal(val, torch.gather(logits, 1, idx))
+    assert torch.equal(idx[:, 0], logits.argmax(dim=1))
+
+
+def test_zeroshot_tie_break_and_prenormalized():
+    D, C = 64, 40
+    prm = torch.zeros(C, D, device=DEV)
+    prm[:, 0] = 1.0                      # every class has the same logit
+    img = torch.zeros(4, D, device=DEV)
+    img[:, 0] = 2.0
+    logits, idx, _ = ops.zeroshot(img, prm, 5)
+    assert idx.tolist() == [[0, 1, 2, 3, 4]] * 4
+    assert torch.allclose(logits, torch.ones_like(logits))
+    logits2, _, _ = ops.zeroshot(img, prm, 1, normalize_img=False)
+    assert torch.allclose(logits2, 2 * torch.ones_like(logits2))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_class_mean(dtype):
+    g = _gen(11)
+    Cn, T, D = 11, 86, 512
+    txt = (torch.randn(Cn * T, D, device=DEV, generator=g) * 3).to(dtype)
+    out = ops.class_mean(txt, Cn, T)
+    e = F.normalize(txt.float().view(Cn, T, D), dim=-1).to(dtype).float()
+    m = e.mean(dim=1).to(dtype).float()
+    ref = F.normalize(m, dim=-1).to(dtype)
+    assert _rel(out, ref) < (1e-2 if dtype == torch.bfloat16 else 1e-6)
+
+
+# ------------------------------------------------------------------ ClipLoss -------------------------
+@pytest.mark.parametrize("n,world,rank,D", [(256, 1, 0, 512), (128, 4, 2, 512), (256, 8, 7, 512), (12, 2, 1, 64)])
+def test_cliploss_fwd_bwd(n, world, rank, D):
+    g = _gen(12)
+    N = n * world
+    all_img = F.normalize(torch.randn(N, D, device=DEV, generator=g), dim=-1)
+    all_txt = F.normalize(torch.randn(N, D, device=DEV, generator=g) + 0.5 * all_img, dim=-1)
+    img_loc = all_img[rank * n:(rank + 1) * n].clone()
+    txt_loc = all_txt[rank * n:(rank + 1) * n].clone()
+    scale = torch.tensor(1 / 0.07, device=DEV)
+
+    # torch restatement of loss.py:102-131 with separate leaves for local and gathered operands
+    il, tl, ai, at, s = [t.clone().double().requires_grad_(True) for t in (img_loc, txt_loc, all_img, all_txt, scale)]
+    labels = torch.arange(n, device=DEV) + n * rank
+    ref_loss = (F.cross_entropy(s * il @ at.t(), labels) + F.cross_entropy(s * tl @ ai.t(), labels)) / 2
+    ref_loss.backward()
+
+    loss, grads = ops.cliploss_fwd_bwd(img_loc, txt_loc, all_img, all_txt, scale, rank)
+    assert abs(loss.item() - ref_loss.item()) / abs(ref_loss.item()) < 1e-5   # north_star: loss within 1e-3 relative
+    for got, want in zip(grads, (il.grad, tl.grad, ai.grad, at.grad, s.grad)):
+        assert _rel(got, want) < 1e-4
+    loss2, none = ops.cliploss_fwd_bwd(img_loc, txt_loc, all_img, all_txt, scale, rank, want_grad=False)
+    assert none is None and abs(loss2.item() - loss.item()) < 1e-6
+    g_out = torch.tensor(0.25, device=DEV)
+    _, grads3 = ops.cliploss_fwd_bwd(img_loc, txt_loc, all_img, all_txt, scale, rank, grad_out=g_out)
+    assert _rel(grads3[0], 0.25 * il.grad) < 1e-4

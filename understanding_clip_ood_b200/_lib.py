@@ -1,0 +1,126 @@
+"""ctypes binding of libb200clip.so (include/b200clip.h).
+
+There is NO fallback: if the shared library is missing or a call fails, this module raises.  The product
+path never routes around the CUDA extension (no PyTorch-op / CPU substitute).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libb200clip.so"
+
+F32, BF16, F16 = 0, 1, 2
+EPI_BIAS, EPI_GELU, EPI_QUICKGELU, EPI_RESIDUAL, EPI_PATCH = 0, 1, 2, 3, 4
+
+_DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+
+
+class B200ClipError(RuntimeError):
+    pass
+
+
+class TowerCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "dtype", "width", "layers", "heads", "mlp_width", "embed_dim", "seq_len", "quick_gelu",
+        "image_size", "patch_size", "patch_kpad", "vocab_size")]
+
+
+class BlockWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b",
+        "fc_w", "fc_b", "proj_w", "proj_b")]
+
+
+class VitWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "conv1_w", "class_emb", "pos_emb", "ln_pre_g", "ln_pre_b", "ln_post_g", "ln_post_b", "proj_t",
+        "blocks_host")]
+
+
+class TextWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "tok_emb", "pos_emb", "ln_final_g", "ln_final_b", "proj_t", "blocks_host")]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); must list every symbol include/b200clip.h declares (tests check this)
+SIGNATURES = {
+    "b200clip_version": (C.c_int, []),
+    "b200clip_last_error": (C.c_char_p, []),
+    "b200clip_launch_count": (C.c_uint64, []),
+    "b200clip_gemm": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "b200clip_layernorm": (C.c_int, [_I, _P, _L, _P, _P, _P, _L, _I, _I, _F, _I, _P, _P]),
+    "b200clip_attention": (C.c_int, [_I, _P, _P, _I, _I, _I, _I, _P]),
+    "b200clip_patchify": (C.c_int, [_I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "b200clip_text_embed": (C.c_int, [_I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200clip_normalize": (C.c_int, [_I, _P, _L, _P, _L, _I, _I, _F, _P]),
+    "b200clip_zeroshot": (C.c_int, [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
+    "b200clip_class_mean": (C.c_int, [_I, _P, _P, _I, _I, _I, _P]),
+    "b200clip_cliploss": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200clip_workspace_bytes": (C.c_int64, [C.POINTER(TowerCfg), _I, _I]),
+    "b200clip_vit_forward": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(VitWeights), _P, _P, _I, _I, _P, _L, _P]),
+    "b200clip_text_forward": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(TextWeights), _P, _P, _I, _I, _I, _P, _L, _P]),
+}
+# not part of the public header: test hook that forces the GEMM N-tile
+_EXTRA = {
+    "b200clip_gemm_tile": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libb200clip.so; raises B200ClipError (never falls back) when it is absent or incomplete."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise B200ClipError(
+            f"{LIB_PATH} is missing: build it with `python -m understanding_clip_ood_b200.build` "
+            "(there is no CPU / PyTorch fallback for this path)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in {**SIGNATURES, **_EXTRA}.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise B200ClipError(f"{LIB_PATH} does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().b200clip_last_error().decode(errors="replace")
+        raise B200ClipError(f"{what} failed (rc={rc}): {msg}")
+
+
+def dtype_code(t: torch.dtype) -> int:
+    try:
+        return _DTYPE_CODE[t]
+    except KeyError:
+        raise B200ClipError(f"unsupported dtype {t}") from None
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise B200ClipError("b200clip kernels need CUDA tensors (no CPU fallback exists for this path)")
+
+
+def launch_count() -> int:
+    return int(load().b200clip_launch_count())

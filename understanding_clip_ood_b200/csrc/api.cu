@@ -1,0 +1,160 @@
+// extern "C" surface of libb200clip.so (declared in include/b200clip.h) + error / bookkeeping helpers.
+#include "../../include/b200clip.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace b200clip {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_last_error("CUDA error %d (%s) at %s", static_cast<int>(e), cudaGetErrorString(e), what);
+    return static_cast<int>(e) > 0 ? static_cast<int>(e) : 1;
+}
+
+void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+int num_sms() {
+    // per-device cache: one process drives one GPU, but stay correct if the current device changes
+    static int cached_dev = -1;
+    static int cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached = v;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+int gemm_any(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
+             int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in, int g_out,
+             cudaStream_t stream) {
+    if (dtype == B200CLIP_F32)
+        return gemm_f32(static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, static_cast<const float*>(bias),
+                        static_cast<const float*>(residual), ldr, static_cast<float*>(C), ldc, M, N, K, epilogue, pos, g_in, g_out,
+                        stream);
+    if (dtype == B200CLIP_BF16 || dtype == B200CLIP_F16)
+        return gemm_tc(dtype == B200CLIP_BF16, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, pos, g_in, g_out, 0,
+                       stream);
+    set_last_error("gemm: unknown dtype %d", dtype);
+    return -1;
+}
+
+int64_t workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len);
+int vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out, int batch,
+                int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s);
+int text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
+                 int seq_len, int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s);
+
+}  // namespace b200clip
+
+using namespace b200clip;
+
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+int b200clip_version(void) { return 100; }  // 0.1.0
+
+const char* b200clip_last_error(void) { return g_err; }
+
+uint64_t b200clip_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int b200clip_gemm(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
+                  int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in, int g_out,
+                  void* stream) {
+    B2C_CHECK_ARG(A != nullptr && W != nullptr && C != nullptr, "gemm: null pointer");
+    B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 4, "gemm: unknown epilogue %d", epilogue);
+    return gemm_any(dtype, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, pos, g_in, g_out, S(stream));
+}
+
+/* test hook: same as b200clip_gemm for 16-bit dtypes but with a forced N tile (128 or 256) */
+int b200clip_gemm_tile(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
+                       int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in,
+                       int g_out, int block_n, void* stream) {
+    B2C_CHECK_ARG(A != nullptr && W != nullptr && C != nullptr, "gemm: null pointer");
+    B2C_CHECK_ARG(dtype == B200CLIP_BF16 || dtype == B200CLIP_F16, "gemm_tile: 16-bit dtypes only");
+    B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 4, "gemm: unknown epilogue %d", epilogue);
+    return gemm_tc(dtype == B200CLIP_BF16, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, pos, g_in, g_out, block_n,
+                   S(stream));
+}
+
+int b200clip_layernorm(int dtype, const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
+                       int rows, int width, float eps, int row_stride_rows, const int32_t* row_idx, void* stream) {
+    B2C_CHECK_ARG(x && gamma && beta && y, "layernorm: null pointer");
+    return layernorm(dtype, x, ldx, gamma, beta, y, ldy, rows, width, eps, row_stride_rows, row_idx, S(stream));
+}
+
+int b200clip_attention(int dtype, const void* qkv, void* out, int batch, int seq_len, int heads, int causal, void* stream) {
+    B2C_CHECK_ARG(qkv && out, "attention: null pointer");
+    return attention(dtype, qkv, out, batch, seq_len, heads, causal, S(stream));
+}
+
+int b200clip_patchify(int dtype, const void* image, void* patches, int batch, int image_size, int patch, int kpad,
+                      const float* class_emb, const float* pos, void* x, int width, void* stream) {
+    B2C_CHECK_ARG(image && patches, "patchify: null pointer");
+    return patchify(dtype, image, patches, batch, image_size, patch, kpad, class_emb, pos, x, width, S(stream));
+}
+
+int b200clip_text_embed(int dtype, const int64_t* text, int ctx, const float* tok_emb, const float* pos_emb, void* x, int32_t* eot,
+                        int T, int L, int width, void* stream) {
+    B2C_CHECK_ARG(text && tok_emb && pos_emb && x, "text_embed: null pointer");
+    return text_embed(dtype, text, ctx, tok_emb, pos_emb, x, eot, T, L, width, S(stream));
+}
+
+int b200clip_normalize(int dtype, const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int dim, float eps, void* stream) {
+    B2C_CHECK_ARG(x && y, "normalize: null pointer");
+    return normalize_rows(dtype, x, ldx, y, ldy, rows, dim, eps, S(stream));
+}
+
+int b200clip_zeroshot(int dtype, const void* img_feat, const void* prompt_feat, float* logits, int64_t* topk_idx, float* topk_val,
+                      int B, int C, int D, int k, int normalize_img, float logit_scale, void* stream) {
+    B2C_CHECK_ARG(img_feat && prompt_feat, "zeroshot: null pointer");
+    return zeroshot(dtype, img_feat, prompt_feat, logits, topk_idx, topk_val, B, C, D, k, normalize_img, logit_scale, S(stream));
+}
+
+int b200clip_class_mean(int dtype, const void* txt_feat, void* prompt_feat, int classes, int templates, int D, void* stream) {
+    B2C_CHECK_ARG(txt_feat && prompt_feat, "class_mean: null pointer");
+    return class_mean(dtype, txt_feat, prompt_feat, classes, templates, D, S(stream));
+}
+
+int b200clip_cliploss(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt,
+                      const float* logit_scale, int rank, int n, int N, int D, float* loss, const float* grad_out,
+                      float* d_img_loc, float* d_txt_loc, float* d_all_img, float* d_all_txt, float* d_scale, float* workspace,
+                      void* stream) {
+    return cliploss(img_loc, txt_loc, all_img, all_txt, logit_scale, rank, n, N, D, loss, grad_out, d_img_loc, d_txt_loc, d_all_img,
+                    d_all_txt, d_scale, workspace, S(stream));
+}
+
+int64_t b200clip_workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {
+    return workspace_bytes(cfg, batch, seq_len);
+}
+
+int b200clip_vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out, int batch,
+                         int normalize, void* workspace, int64_t workspace_bytes, void* stream) {
+    return vit_forward(cfg, w, image, out, batch, normalize, workspace, workspace_bytes, S(stream));
+}
+
+int b200clip_text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
+                          int seq_len, int normalize, void* workspace, int64_t workspace_bytes, void* stream) {
+    return text_forward(cfg, w, text, out, batch, seq_len, normalize, workspace, workspace_bytes, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+// Internal C++ entry points shared between the kernel translation units and the C ABI (api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200clip {
+
+void count_launch(int n = 1);
+
+int gemm_tc(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
+            int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in, int g_out,
+            int force_block_n, cudaStream_t stream);
+
+int gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* residual, int64_t ldr,
+             float* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in, int g_out,
+             cudaStream_t stream);
+
+// dtype-dispatching GEMM used by the tower drivers
+int gemm_any(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
+             int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in, int g_out,
+             cudaStream_t stream);
+
+int layernorm(int dtype, const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy, int rows,
+              int width, float eps, int row_stride_rows, const int32_t* row_idx, cudaStream_t stream);
+
+int attention(int dtype, const void* qkv, void* out, int batch, int seq_len, int heads, int causal, cudaStream_t stream);
+
+int patchify(int dtype, const void* image, void* patches, int batch, int image_size, int patch, int kpad,
+             const float* class_emb, const float* pos, void* x, int width, cudaStream_t stream);
+
+int text_embed(int dtype, const int64_t* text, int ctx, const float* tok_emb, const float* pos_emb, void* x, int32_t* eot,
+               int T, int L, int width, cudaStream_t stream);
+
+int normalize_rows(int dtype, const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int dim, float eps,
+                   cudaStream_t stream);
+
+int zeroshot(int dtype, const void* img_feat, const void* prompt_feat, float* logits, int64_t* topk_idx, float* topk_val,
+             int B, int C, int D, int k, int normalize_img, float logit_scale, cudaStream_t stream);
+
+int class_mean(int dtype, const void* txt_feat, void* prompt_feat, int classes, int templates, int D, cudaStream_t stream);
+
+int cliploss(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt, const float* logit_scale,
+             int rank, int n, int N, int D, float* loss, const float* grad_out, float* d_img_loc, float* d_txt_loc,
+             float* d_all_img, float* d_all_txt, float* d_scale, float* workspace, cudaStream_t stream);
+
+inline int dtype_size(int dtype) { return dtype == 0 ? 4 : 2; }
+
+}  // namespace b200clip

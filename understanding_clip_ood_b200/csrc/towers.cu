@@ -1,0 +1,170 @@
+// Whole-tower drivers: one C-ABI call per CLIP.encode_image / CLIP.encode_text.
+//
+//   vit_forward  = VisionTransformer.forward (deps/open_clip/src/open_clip/transformer.py:601-643)
+//   text_forward = CLIP.encode_text          (deps/open_clip/src/open_clip/model.py:269-284)
+//   both run the ResidualAttentionBlock stack (transformer.py:253-264, Transformer.forward :350-359)
+//
+// The driver only enqueues kernels on the caller's stream into a caller-provided workspace: no allocation,
+// no synchronisation, so a whole forward is CUDA-graph capturable.  Per layer: LN1 -> QKV GEMM(+bias) ->
+// attention -> out-proj GEMM(+bias+residual, in place on x) -> LN2 -> c_fc GEMM(+bias+GELU) -> c_proj
+// GEMM(+bias+residual, in place) = 7 launches, residual adds / activations / bias all fused in GEMM epilogues.
+// Token layout is batch-major [B*L, W] (the reference's LND transpose, transformer.py:351, is an
+// implementation detail of nn.MultiheadAttention, not a contract).
+#include "../../include/b200clip.h"
+#include "common.cuh"
+#include "internal.h"
+
+namespace b200clip {
+
+int text_embed_v(int dtype, const int64_t* text, int ctx, const float* tok_emb, const float* pos_emb, void* x, int32_t* eot,
+                 int T, int L, int width, int vocab, cudaStream_t stream);
+
+namespace {
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+    char* x;
+    char* h;
+    char* qkv;
+    char* mlp;
+    char* pooled;
+    int32_t* eot;
+    int64_t total;
+};
+
+Workspace carve(const b200clip_tower_cfg& c, int batch, int seq_len, void* base) {
+    const int64_t es = dtype_size(c.dtype);
+    const int64_t rows = static_cast<int64_t>(batch) * seq_len;
+    int64_t mlp_cols = c.mlp_width;
+    if (c.patch_kpad > mlp_cols) mlp_cols = c.patch_kpad;
+    Workspace w;
+    int64_t off = 0;
+    char* b = static_cast<char*>(base);
+    auto take = [&](int64_t bytes) {
+        char* p = b ? b + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    w.x = take(rows * c.width * es);
+    w.h = take(rows * c.width * es);
+    w.qkv = take(rows * 3 * c.width * es);
+    w.mlp = take(rows * mlp_cols * es);
+    w.pooled = take(static_cast<int64_t>(batch) * c.width * es);
+    w.eot = reinterpret_cast<int32_t*>(take(static_cast<int64_t>(batch) * 4));
+    w.total = off;
+    return w;
+}
+
+int check_cfg(const b200clip_tower_cfg* c) {
+    B2C_CHECK_ARG(c != nullptr, "tower: null cfg");
+    B2C_CHECK_ARG(c->dtype >= 0 && c->dtype <= 2, "tower: unknown dtype %d", c->dtype);
+    B2C_CHECK_ARG(c->width > 0 && c->width % 64 == 0 && c->heads * 64 == c->width, "tower: width %d must be heads*64 (heads=%d)",
+                  c->width, c->heads);
+    B2C_CHECK_ARG(c->layers > 0 && c->mlp_width > 0 && c->mlp_width % 8 == 0 && c->embed_dim > 0 && c->embed_dim % 8 == 0,
+                  "tower: bad layers/mlp_width/embed_dim");
+    B2C_CHECK_ARG(c->seq_len > 0, "tower: bad seq_len");
+    return 0;
+}
+
+int run_blocks(const b200clip_tower_cfg& c, const b200clip_block_weights* blocks, const Workspace& ws, int batch, int L,
+               int causal, cudaStream_t s) {
+    const int dt = c.dtype;
+    const int M = batch * L;
+    const int W = c.width;
+    const int act = c.quick_gelu ? B200CLIP_EPI_QUICKGELU : B200CLIP_EPI_GELU;
+    int rc;
+    for (int l = 0; l < c.layers; ++l) {
+        const b200clip_block_weights& bw = blocks[l];
+        if ((rc = layernorm(dt, ws.x, W, bw.ln1_g, bw.ln1_b, ws.h, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
+        if ((rc = gemm_any(dt, ws.h, W, bw.in_proj_w, W, bw.in_proj_b, nullptr, 0, ws.qkv, 3 * W, M, 3 * W, W, B200CLIP_EPI_BIAS,
+                           nullptr, 0, 0, s)) != 0) return rc;
+        if ((rc = attention(dt, ws.qkv, ws.h, batch, L, c.heads, causal, s)) != 0) return rc;
+        if ((rc = gemm_any(dt, ws.h, W, bw.out_proj_w, W, bw.out_proj_b, ws.x, W, ws.x, W, M, W, W, B200CLIP_EPI_RESIDUAL, nullptr, 0,
+                           0, s)) != 0) return rc;
+        if ((rc = layernorm(dt, ws.x, W, bw.ln2_g, bw.ln2_b, ws.h, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
+        if ((rc = gemm_any(dt, ws.h, W, bw.fc_w, W, bw.fc_b, nullptr, 0, ws.mlp, c.mlp_width, M, c.mlp_width, W, act, nullptr, 0, 0,
+                           s)) != 0) return rc;
+        if ((rc = gemm_any(dt, ws.mlp, c.mlp_width, bw.proj_w, c.mlp_width, bw.proj_b, ws.x, W, ws.x, W, M, W, c.mlp_width,
+                           B200CLIP_EPI_RESIDUAL, nullptr, 0, 0, s)) != 0) return rc;
+    }
+    return 0;
+}
+
+}  // namespace
+
+int64_t workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {
+    if (cfg == nullptr || batch <= 0 || seq_len <= 0) return -1;
+    return carve(*cfg, batch, seq_len, nullptr).total;
+}
+
+int vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out, int batch,
+                int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s) {
+    int rc;
+    if ((rc = check_cfg(cfg)) != 0) return rc;
+    const b200clip_tower_cfg& c = *cfg;
+    B2C_CHECK_ARG(w != nullptr && image != nullptr && out != nullptr && workspace != nullptr && w->blocks_host != nullptr,
+                  "vit_forward: null pointer");
+    B2C_CHECK_ARG(batch > 0, "vit_forward: empty batch");
+    B2C_CHECK_ARG(c.patch_size > 0 && c.image_size % c.patch_size == 0, "vit_forward: image %d not divisible by patch %d",
+                  c.image_size, c.patch_size);
+    const int g = c.image_size / c.patch_size;
+    const int L = g * g + 1;
+    B2C_CHECK_ARG(L == c.seq_len, "vit_forward: seq_len %d != (image/patch)^2+1 = %d", c.seq_len, L);
+    B2C_CHECK_ARG(c.patch_kpad >= 3 * c.patch_size * c.patch_size && c.patch_kpad % 8 == 0, "vit_forward: bad patch_kpad %d",
+                  c.patch_kpad);
+    B2C_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 256 == 0, "vit_forward: workspace must be 256-byte aligned");
+    const Workspace ws = carve(c, batch, L, workspace);
+    B2C_CHECK_ARG(ws.total <= workspace_bytes_, "vit_forward: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes_,
+                  (long long)ws.total);
+    const int dt = c.dtype;
+    const int W = c.width;
+    const int M = batch * L;
+
+    // patch embedding: im2col -> GEMM whose epilogue scatters to token rows 1..L-1 and adds the positional embedding
+    if ((rc = patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s)) != 0)
+        return rc;
+    if ((rc = gemm_any(dt, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, batch * g * g, W,
+                       c.patch_kpad, B200CLIP_EPI_PATCH, w->pos_emb, g * g, L, s)) != 0)
+        return rc;
+    if ((rc = layernorm(dt, ws.x, W, w->ln_pre_g, w->ln_pre_b, ws.x, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
+    if ((rc = run_blocks(c, w->blocks_host, ws, batch, L, 0, s)) != 0) return rc;
+    // pool_type 'tok': ln_post on the class token only (LN is per-row, so pooling first is exact), then @ proj
+    if ((rc = layernorm(dt, ws.x, W, w->ln_post_g, w->ln_post_b, ws.pooled, W, batch, W, 1e-5f, L, nullptr, s)) != 0) return rc;
+    if ((rc = gemm_any(dt, ws.pooled, W, w->proj_t, W, nullptr, nullptr, 0, out, c.embed_dim, batch, c.embed_dim, W,
+                       B200CLIP_EPI_BIAS, nullptr, 0, 0, s)) != 0)
+        return rc;
+    if (normalize && (rc = normalize_rows(dt, out, c.embed_dim, out, c.embed_dim, batch, c.embed_dim, 1e-12f, s)) != 0) return rc;
+    return 0;
+}
+
+int text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
+                 int seq_len, int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s) {
+    int rc;
+    if ((rc = check_cfg(cfg)) != 0) return rc;
+    const b200clip_tower_cfg& c = *cfg;
+    B2C_CHECK_ARG(w != nullptr && text != nullptr && out != nullptr && workspace != nullptr && w->blocks_host != nullptr,
+                  "text_forward: null pointer");
+    B2C_CHECK_ARG(batch > 0, "text_forward: empty batch");
+    B2C_CHECK_ARG(seq_len > 0 && seq_len <= c.seq_len, "text_forward: seq_len %d outside (0, %d]", seq_len, c.seq_len);
+    B2C_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 256 == 0, "text_forward: workspace must be 256-byte aligned");
+    const int L = seq_len;
+    const Workspace ws = carve(c, batch, L, workspace);
+    B2C_CHECK_ARG(ws.total <= workspace_bytes_, "text_forward: workspace too small (%lld < %lld bytes)",
+                  (long long)workspace_bytes_, (long long)ws.total);
+    const int dt = c.dtype;
+    const int W = c.width;
+    if ((rc = text_embed_v(dt, text, c.seq_len, w->tok_emb, w->pos_emb, ws.x, ws.eot, batch, L, W,
+                           c.vocab_size > 0 ? c.vocab_size : 0x7fffffff, s)) != 0)
+        return rc;
+    if ((rc = run_blocks(c, w->blocks_host, ws, batch, L, 1, s)) != 0) return rc;
+    // ln_final only on the pooled (EOT) rows: LN is per-row, so this equals pooling after ln_final
+    if ((rc = layernorm(dt, ws.x, W, w->ln_final_g, w->ln_final_b, ws.pooled, W, batch, W, 1e-5f, L, ws.eot, s)) != 0) return rc;
+    if ((rc = gemm_any(dt, ws.pooled, W, w->proj_t, W, nullptr, nullptr, 0, out, c.embed_dim, batch, c.embed_dim, W,
+                       B200CLIP_EPI_BIAS, nullptr, 0, 0, s)) != 0)
+        return rc;
+    if (normalize && (rc = normalize_rows(dt, out, c.embed_dim, out, c.embed_dim, batch, c.embed_dim, 1e-12f, s)) != 0) return rc;
+    return 0;
+}
+
+}  // namespace b200clip

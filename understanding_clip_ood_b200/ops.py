@@ -1,0 +1,170 @@
+"""Tensor-level wrappers over the C ABI (one function per `b200clip_*` kernel entry point).
+
+PyTorch is only used for device memory and streams here; all arithmetic happens in libb200clip.so.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, epilogue: int = L.EPI_BIAS,
+         residual: torch.Tensor | None = None, out: torch.Tensor | None = None, pos: torch.Tensor | None = None,
+         g_in: int = 0, g_out: int = 0, block_n: int = 0) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T + bias).  See include/b200clip.h:b200clip_gemm."""
+    L.require_cuda(a, w, bias, residual, out, pos)
+    a, w = _c(a), _c(w)
+    M, K = a.shape
+    N, K2 = w.shape
+    if K != K2:
+        raise L.B200ClipError(f"gemm: inner dimensions differ ({K} vs {K2})")
+    if w.dtype != a.dtype:
+        raise L.B200ClipError("gemm: a and w must share a dtype")
+    if out is None:
+        rows = M if epilogue != L.EPI_PATCH else (M // g_in) * g_out
+        out = torch.empty((rows, N), dtype=a.dtype, device=a.device)
+    lib = L.load()
+    args = [L.dtype_code(a.dtype), a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), L.ptr(bias), L.ptr(residual),
+            residual.stride(0) if residual is not None else 0, out.data_ptr(), out.stride(0), M, N, K, epilogue,
+            L.ptr(pos), g_in, g_out]
+    if block_n:
+        rc = lib.b200clip_gemm_tile(*args, block_n, L.stream_ptr())
+    else:
+        rc = lib.b200clip_gemm(*args, L.stream_ptr())
+    L.check(rc, "b200clip_gemm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, *, rows: int | None = None,
+              row_stride_rows: int = 1, row_idx: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    L.require_cuda(x, gamma, beta, row_idx, out)
+    x = _c(x)
+    width = x.shape[-1]
+    x2 = x.view(-1, width)
+    if rows is None:
+        rows = x2.shape[0] // row_stride_rows
+    if out is None:
+        out = torch.empty((rows, width), dtype=x.dtype, device=x.device)
+    rc = L.load().b200clip_layernorm(L.dtype_code(x.dtype), x2.data_ptr(), x2.stride(0), gamma.data_ptr(), beta.data_ptr(),
+                                     out.data_ptr(), out.stride(0), rows, width, eps, row_stride_rows, L.ptr(row_idx),
+                                     L.stream_ptr())
+    L.check(rc, "b200clip_layernorm")
+    return out
+
+
+def attention(qkv: torch.Tensor, batch: int, seq_len: int, heads: int, causal: bool = False,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """qkv [batch*seq_len, 3*heads*64] -> out [batch*seq_len, heads*64]."""
+    L.require_cuda(qkv, out)
+    qkv = _c(qkv)
+    W = heads * 64
+    if qkv.shape != (batch * seq_len, 3 * W):
+        raise L.B200ClipError(f"attention: qkv shape {tuple(qkv.shape)} != {(batch * seq_len, 3 * W)}")
+    if out is None:
+        out = torch.empty((batch * seq_len, W), dtype=qkv.dtype, device=qkv.device)
+    rc = L.load().b200clip_attention(L.dtype_code(qkv.dtype), qkv.data_ptr(), out.data_ptr(), batch, seq_len, heads,
+                                     int(causal), L.stream_ptr())
+    L.check(rc, "b200clip_attention")
+    return out
+
+
+def patchify(image: torch.Tensor, patch: int, kpad: int, class_emb: torch.Tensor | None = None,
+             pos: torch.Tensor | None = None, x: torch.Tensor | None = None) -> torch.Tensor:
+    L.require_cuda(image, class_emb, pos, x)
+    image = _c(image)
+    B, Cc, S, S2 = image.shape
+    if Cc != 3 or S != S2:
+        raise L.B200ClipError("patchify: image must be [B,3,S,S]")
+    g = S // patch
+    patches = torch.empty((B * g * g, kpad), dtype=image.dtype, device=image.device)
+    width = x.shape[-1] if x is not None else 0
+    rc = L.load().b200clip_patchify(L.dtype_code(image.dtype), image.data_ptr(), patches.data_ptr(), B, S, patch, kpad,
+                                    L.ptr(class_emb), L.ptr(pos), L.ptr(x), width, L.stream_ptr())
+    L.check(rc, "b200clip_patchify")
+    return patches
+
+
+def text_embed(text: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Tensor, dtype: torch.dtype, seq_len: int | None = None):
+    L.require_cuda(text, tok_emb, pos_emb)
+    text = _c(text)
+    T, ctx = text.shape
+    Lq = ctx if seq_len is None else seq_len
+    width = tok_emb.shape[1]
+    x = torch.empty((T * Lq, width), dtype=dtype, device=text.device)
+    eot = torch.empty((T,), dtype=torch.int32, device=text.device)
+    rc = L.load().b200clip_text_embed(L.dtype_code(dtype), text.data_ptr(), ctx, tok_emb.data_ptr(), pos_emb.data_ptr(),
+                                      x.data_ptr(), eot.data_ptr(), T, Lq, width, L.stream_ptr())
+    L.check(rc, "b200clip_text_embed")
+    return x, eot
+
+
+def normalize(x: torch.Tensor, eps: float = 1e-12, out: torch.Tensor | None = None) -> torch.Tensor:
+    L.require_cuda(x, out)
+    x = _c(x)
+    x2 = x.view(-1, x.shape[-1])
+    if out is None:
+        out = torch.empty_like(x2)
+    rc = L.load().b200clip_normalize(L.dtype_code(x.dtype), x2.data_ptr(), x2.stride(0), out.data_ptr(), out.stride(0),
+                                     x2.shape[0], x2.shape[1], eps, L.stream_ptr())
+    L.check(rc, "b200clip_normalize")
+    return out.view(x.shape)
+
+
+def zeroshot(img_feat: torch.Tensor, prompt_feat: torch.Tensor, k: int = 1, *, normalize_img: bool = True,
+             want_logits: bool = True, logit_scale: float = 1.0):
+    """-> (logits fp32 [B,C] | None, topk_idx int64 [B,k] | None, topk_val fp32 [B,k] | None)."""
+    L.require_cuda(img_feat, prompt_feat)
+    img_feat, prompt_feat = _c(img_feat), _c(prompt_feat)
+    B, D = img_feat.shape
+    Cn, D2 = prompt_feat.shape
+    if D != D2 or img_feat.dtype != prompt_feat.dtype:
+        raise L.B200ClipError("zeroshot: feature dims / dtypes differ")
+    dev = img_feat.device
+    logits = torch.empty((B, Cn), dtype=torch.float32, device=dev) if want_logits else None
+    idx = torch.empty((B, k), dtype=torch.int64, device=dev) if k > 0 else None
+    val = torch.empty((B, k), dtype=torch.float32, device=dev) if k > 0 else None
+    rc = L.load().b200clip_zeroshot(L.dtype_code(img_feat.dtype), img_feat.data_ptr(), prompt_feat.data_ptr(), L.ptr(logits),
+                                    L.ptr(idx), L.ptr(val), B, Cn, D, k, int(normalize_img), logit_scale, L.stream_ptr())
+    L.check(rc, "b200clip_zeroshot")
+    return logits, idx, val
+
+
+def class_mean(txt_feat: torch.Tensor, classes: int, templates: int) -> torch.Tensor:
+    L.require_cuda(txt_feat)
+    txt_feat = _c(txt_feat)
+    D = txt_feat.shape[-1]
+    out = torch.empty((classes, D), dtype=txt_feat.dtype, device=txt_feat.device)
+    rc = L.load().b200clip_class_mean(L.dtype_code(txt_feat.dtype), txt_feat.data_ptr(), out.data_ptr(), classes, templates, D,
+                                      L.stream_ptr())
+    L.check(rc, "b200clip_class_mean")
+    return out
+
+
+def cliploss_fwd_bwd(img_loc: torch.Tensor, txt_loc: torch.Tensor, all_img: torch.Tensor, all_txt: torch.Tensor,
+                     logit_scale: torch.Tensor, rank: int, *, want_grad: bool = True, grad_out: torch.Tensor | None = None):
+    """fp32 features.  -> loss (0-dim), (d_img_loc, d_txt_loc, d_all_img, d_all_txt, d_scale) or None."""
+    L.require_cuda(img_loc, txt_loc, all_img, all_txt, logit_scale, grad_out)
+    for t in (img_loc, txt_loc, all_img, all_txt, logit_scale):
+        if t.dtype != torch.float32:
+            raise L.B200ClipError("cliploss: fp32 tensors required")
+    img_loc, txt_loc, all_img, all_txt = _c(img_loc), _c(txt_loc), _c(all_img), _c(all_txt)
+    n, D = img_loc.shape
+    N = all_img.shape[0]
+    dev = img_loc.device
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    ws = torch.empty((2 * n * N + 4 * n,), dtype=torch.float32, device=dev)
+    grads = None
+    if want_grad:
+        grads = (torch.empty_like(img_loc), torch.empty_like(txt_loc), torch.empty_like(all_img), torch.empty_like(all_txt),
+                 torch.empty((), dtype=torch.float32, device=dev))
+    g = grads if grads is not None else (None,) * 5
+    rc = L.load().b200clip_cliploss(img_loc.data_ptr(), txt_loc.data_ptr(), all_img.data_ptr(), all_txt.data_ptr(),
+                                    logit_scale.data_ptr(), rank, n, N, D, loss.data_ptr(), L.ptr(grad_out), L.ptr(g[0]),
+                                    L.ptr(g[1]), L.ptr(g[2]), L.ptr(g[3]), L.ptr(g[4]), ws.data_ptr(), L.stream_ptr())
+    L.check(rc, "b200clip_cliploss")
+    return loss, grads
