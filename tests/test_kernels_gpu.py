@@ -129,7 +129,7 @@ def test_patch_embed(dtype, S, P, W):
     assert torch.equal(patches[:, :kreal], ref_p)
     assert patches[:, kreal:].abs().sum().item() == 0
     ops.gemm(patches, wpad, None, epilogue=L.EPI_PATCH, out=x, pos=pos, g_in=grid * grid, g_out=Lq)
-    conv = F.conv2d(img.float(), conv_w.float(), stride=P).to(dtype).float()   # [B,W,g,g]
+    conv = F.conv2d(img.double(), conv_w.double(), stride=P).to(dtype).float()   # [B,W,g,g]; fp64: cuDNN fp32 conv may use TF32
     tok = conv.reshape(B, W, -1).permute(0, 2, 1)
     full = torch.cat([cls.to(dtype).float().expand(B, 1, W), tok], dim=1) + pos.to(dtype).float()
     ref = full.to(dtype).reshape(B * Lq, W)
