@@ -82,6 +82,10 @@ int b200clip_patchify(int dtype, const void* image, void* patches, int batch, in
 int b200clip_text_embed(int dtype, const int64_t* text, int ctx, const float* tok_emb, const float* pos_emb,
                         void* x, int32_t* eot, int T, int L, int width, void* stream);
 
+/* eot[t] = argmax_l text[t, l] over the full context (first maximum), int32: the EOT position used by
+ * text_global_pool (transformer.py:654); lets the host pick the exact causal truncation length max(eot)+1. */
+int b200clip_eot_argmax(const int64_t* text, int ctx, int32_t* eot, int T, void* stream);
+
 /* y = x / max(||x||_2, eps) per row (F.normalize, model.py:267,284; xclip/zero_shot.py:34,50). */
 int b200clip_normalize(int dtype, const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int dim, float eps,
                        void* stream);
@@ -105,7 +109,7 @@ int b200clip_class_mean(int dtype, const void* txt_feat, void* prompt_feat, int 
  *   d_all_img, d_all_txt [N,D]: gradient through the gathered operands (reduce-scattered by the caller,
  *   as torch.distributed.nn.all_gather's backward does), d_scale: gradient of the logit scale.
  * Gradients are for `loss` with upstream gradient `grad_out` (device scalar, may be NULL = 1).
- * Any gradient pointer may be NULL (forward only when all are NULL).  workspace >= 2*n*N floats. */
+ * Any gradient pointer may be NULL (forward only when all are NULL).  workspace >= 2*n*N + 4*n floats. */
 int b200clip_cliploss(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt,
                       const float* logit_scale, int rank, int n, int N, int D, float* loss, const float* grad_out,
                       float* d_img_loc, float* d_txt_loc, float* d_all_img, float* d_all_txt, float* d_scale,

@@ -1,0 +1,233 @@
+"""CPU suite, part 2: host-side logic — the C-ABI library loads and exports every symbol of include/b200clip.h (no
+compute calls without a GPU), the drop-in module mirrors the reference's state_dict / signatures / init / tokenizer,
+the product path refuses to run without CUDA, and the multi-rank feature gather works under 2-process gloo."""
+import inspect
+import os
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "b200clip.h"
+
+
+# ------------------------------------------------------------------ C ABI ---------------------------
+def _declared_symbols():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(b200clip_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from understanding_clip_ood_b200 import _lib
+    lib = _lib.load()                                   # raises if the .so is missing: there is no fallback
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/b200clip.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes SIGNATURES out of sync with the header"
+    assert lib.b200clip_version() >= 100
+    assert lib.b200clip_launch_count() == 0 or lib.b200clip_launch_count() > 0   # callable without a device
+
+
+def test_bad_arguments_are_reported_not_crashed():
+    from understanding_clip_ood_b200 import _lib
+    lib = _lib.load()
+    rc = lib.b200clip_gemm(1, None, 0, None, 0, None, None, 0, None, 0, 0, 0, 0, 0, None, 0, 0, None)
+    assert rc < 0 and b"null" in lib.b200clip_last_error()
+    rc = lib.b200clip_zeroshot(0, None, None, None, None, None, 1, 1, 4, 1, 1, 1.0, None)
+    assert rc < 0
+    assert lib.b200clip_workspace_bytes(None, 1, 1) == -1
+
+
+def test_workspace_bytes_formula():
+    from understanding_clip_ood_b200 import _lib
+    lib = _lib.load()
+    import ctypes as C
+    cfg = _lib.TowerCfg(dtype=1, width=768, layers=12, heads=12, mlp_width=3072, embed_dim=512, seq_len=50, quick_gelu=0,
+                        image_size=224, patch_size=32, patch_kpad=3072, vocab_size=0)
+    n = lib.b200clip_workspace_bytes(C.byref(cfg), 128, 50)
+    rows = 128 * 50
+    expect = rows * 768 * 2 * 2 + rows * 2304 * 2 + rows * 3072 * 2 + 128 * 768 * 2 + 128 * 4
+    assert expect <= n <= expect + 6 * 256
+
+
+# ------------------------------------------------------------------ module surface ------------------
+def test_no_cpu_fallback():
+    from understanding_clip_ood_b200 import _lib, open_clip, ops
+    m = open_clip.create_model("ViT-B-32", vision_cfg={"image_size": 64, "layers": 1, "width": 64, "patch_size": 32},
+                               text_cfg={"context_length": 77, "vocab_size": 64, "width": 64, "heads": 1, "layers": 1},
+                               embed_dim=64)
+    with pytest.raises(_lib.B200ClipError):
+        m.encode_image(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(_lib.B200ClipError):
+        m.encode_text(torch.zeros(1, 77, dtype=torch.long))
+    with pytest.raises(_lib.B200ClipError):
+        ops.normalize(torch.zeros(2, 8))
+    with pytest.raises(_lib.B200ClipError):
+        open_clip.ClipLoss()(torch.zeros(4, 8), torch.zeros(4, 8), torch.tensor(1.0))
+
+
+def test_state_dict_layout_vit_b_32():
+    from understanding_clip_ood_b200 import open_clip
+    m = open_clip.create_model("ViT-B-32", precision="bf16")
+    sd = m.state_dict()
+    assert len(sd) == 302
+    assert sum(p.numel() for p in m.parameters()) == 151_277_313
+    assert sd["visual.conv1.weight"].shape == (768, 3, 32, 32)
+    assert sd["visual.transformer.resblocks.11.attn.in_proj_weight"].shape == (2304, 768)
+    assert sd["transformer.resblocks.0.mlp.c_proj.weight"].shape == (512, 2048)
+    assert sd["token_embedding.weight"].shape == (49408, 512) and sd["text_projection"].shape == (512, 512)
+    assert "attn_mask" not in sd                                           # non-persistent buffer (model.py:248)
+    n_lp = sum(v.dtype == torch.bfloat16 for v in sd.values())
+    n_f32 = sum(v.dtype == torch.float32 for v in sd.values())
+    assert (n_lp, n_f32) == (195, 107)                                     # convert_weights_to_lp split (probe)
+    for k in ("visual.ln_pre.weight", "visual.class_embedding", "visual.positional_embedding", "positional_embedding",
+              "token_embedding.weight", "logit_scale", "ln_final.bias"):
+        assert sd[k].dtype == torch.float32
+    assert abs(float(sd["logit_scale"]) - 2.6593) < 1e-3
+    assert m.context_length == 77 and m.vocab_size == 49408 and m.visual.image_size == (224, 224)
+    assert m.visual.preprocess_cfg["mean"][0] == pytest.approx(0.48145466)
+
+
+def test_configs_and_errors():
+    from understanding_clip_ood_b200 import open_clip
+    assert {"ViT-B-32", "ViT-B-16", "ViT-L-14", "ViT-B-32-quickgelu"} <= set(open_clip.list_models())
+    assert open_clip.get_model_config("ViT-L-14")["vision_cfg"]["width"] == 1024
+    with pytest.raises(RuntimeError):
+        open_clip.create_model("RN50")
+    with pytest.raises(RuntimeError):
+        open_clip.create_model("ViT-B-32", precision="amp")
+    with pytest.raises(RuntimeError):
+        open_clip.create_model("ViT-B-32", pretrained="laion2b_s34b_b79k")
+    m = open_clip.create_model("ViT-B-32-quickgelu", vision_cfg={"image_size": 64, "layers": 1, "width": 64, "patch_size": 32},
+                               text_cfg={"context_length": 77, "vocab_size": 64, "width": 64, "heads": 1, "layers": 1},
+                               embed_dim=64, output_dict=True)
+    assert m.quick_gelu and m.visual.quick_gelu and m.output_dict
+    m.set_grad_checkpointing()
+    assert m.transformer.grad_checkpointing and m.visual.transformer.grad_checkpointing
+    m.lock_image_tower()
+    assert not any(p.requires_grad for p in m.visual.parameters())
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    from understanding_clip_ood_b200 import open_clip
+    kw = dict(vision_cfg={"image_size": 64, "layers": 1, "width": 64, "patch_size": 32},
+              text_cfg={"context_length": 77, "vocab_size": 64, "width": 64, "heads": 1, "layers": 1}, embed_dim=64)
+    a = open_clip.create_model("ViT-B-32", **kw)
+    path = tmp_path / "epoch_1.pt"
+    torch.save({"epoch": 1, "name": "x", "state_dict": {"module." + k: v for k, v in a.state_dict().items()}}, path)
+    b = open_clip.create_model("ViT-B-32", pretrained=str(path), **kw)
+    for k, v in a.state_dict().items():
+        assert torch.equal(v, b.state_dict()[k])
+    from understanding_clip_ood_b200.xclip.open_clip import OpenCLIP
+    w, _, _ = OpenCLIP.from_pretrained("ViT-B-32", str(path), precision="fp32", **kw)
+    assert torch.equal(w.clip.state_dict()["visual.proj"], a.state_dict()["visual.proj"])
+    assert float(w.logit_scale) == pytest.approx(1 / 0.07, rel=1e-5)
+
+
+# ------------------------------------------------------------------ pinned against the live reference
+def _ref():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    return ref_loader.load()
+
+
+def test_signatures_match_reference():
+    ref_oc, ref_zs, ref_xo = _ref()
+    from understanding_clip_ood_b200 import open_clip as mine
+    from understanding_clip_ood_b200.xclip import open_clip as my_xo
+    from understanding_clip_ood_b200.xclip import zero_shot as my_zs
+
+    def params(fn):
+        return [(p.name, p.default) for p in inspect.signature(fn).parameters.values() if p.kind != p.VAR_KEYWORD]
+
+    assert params(mine.create_model) == params(ref_oc.create_model)
+    assert params(mine.ClipLoss.__init__) == params(ref_oc.ClipLoss.__init__)
+    assert params(mine.ClipLoss.forward) == params(ref_oc.ClipLoss.forward)
+    assert params(mine.CLIP.encode_image) == params(ref_oc.CLIP.encode_image)
+    assert params(mine.CLIP.encode_text) == params(ref_oc.CLIP.encode_text)
+    assert params(mine.CLIP.forward) == params(ref_oc.CLIP.forward)
+    assert [n for n, _ in params(mine.create_model_and_transforms)] == [n for n, _ in params(ref_oc.create_model_and_transforms)]
+    for cls in ("ZeroShotClassifier", "OpenAIZeroShotClassifier"):
+        assert [n for n, _ in params(getattr(my_zs, cls).__init__)] == [n for n, _ in params(getattr(ref_zs, cls).__init__)]
+        for meth in ("predict", "predict_from_features", "variance_from_features"):
+            assert params(getattr(getattr(my_zs, cls), meth)) == params(getattr(getattr(ref_zs, cls), meth))
+    assert params(my_xo.OpenCLIP.from_pretrained) == params(ref_xo.OpenCLIP.from_pretrained)
+    assert my_zs.OpenAIZeroShotClassifier.templates == ref_zs.OpenAIZeroShotClassifier.templates
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
+def test_seeded_init_equals_reference(precision):
+    ref_oc, _, _ = _ref()
+    from understanding_clip_ood_b200 import open_clip as mine
+    kw = dict(embed_dim=64, vision_cfg={"image_size": 64, "layers": 2, "width": 128, "patch_size": 16},
+              text_cfg={"context_length": 77, "vocab_size": 300, "width": 64, "heads": 1, "layers": 2})
+    torch.manual_seed(123)
+    r = ref_oc.create_model("ViT-B-32", precision=precision, **kw).state_dict()
+    torch.manual_seed(123)
+    m = mine.create_model("ViT-B-32", precision=precision, **kw).state_dict()
+    assert list(r) == list(m)
+    for k in r:
+        assert r[k].dtype == m[k].dtype and torch.equal(r[k], m[k]), k
+
+
+def test_seeded_init_equals_reference_full_vit_b_32():
+    ref_oc, _, _ = _ref()
+    from understanding_clip_ood_b200 import open_clip as mine
+    torch.manual_seed(0)
+    r = ref_oc.create_model("ViT-B-32").state_dict()
+    torch.manual_seed(0)
+    m = mine.create_model("ViT-B-32").state_dict()
+    assert all(torch.equal(r[k], m[k]) for k in r) and list(r) == list(m)
+
+
+def test_tokenizer_equals_reference():
+    ref_oc, ref_zs, _ = _ref()
+    from understanding_clip_ood_b200 import open_clip as mine
+    import json
+    names = json.loads((ROOT / "understanding_clip_ood_b200" / "data" / "domainnet_classes.json").read_text())
+    texts = [t.format(c) for c in names[::9] for t in ref_zs.OpenAIZeroShotClassifier.templates[::5]]
+    texts += ["Hello, World!  it's  42 things &amp; more...", "naïve café ☕ 日本語", "x" * 400, ""]
+    a, b = ref_oc.get_tokenizer("ViT-B-32")(texts), mine.get_tokenizer("ViT-B-32")(texts)
+    assert torch.equal(a, b)
+    tok = mine.get_tokenizer("ViT-B-32")
+    assert tok.decode(tok.encode("a photo of a dog")).strip() == "a photo of a dog"
+
+
+# ------------------------------------------------------------------ multi-rank host logic (gloo, CPU) -
+def _gather_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from understanding_clip_ood_b200.open_clip.loss import gather_features, local_labels
+    n, D = 4, 8
+    g = torch.Generator().manual_seed(100 + rank)
+    img = torch.randn(n, D, generator=g, requires_grad=True)
+    txt = torch.randn(n, D, generator=g, requires_grad=True)
+    all_img, all_txt = gather_features(img, txt, local_loss=True, gather_with_grad=True, rank=rank, world_size=world)
+    # a loss whose gradient w.r.t. the gathered rows depends on the rank: backward must SUM over ranks (reduce-scatter)
+    ((rank + 1) * (all_img.sum() + 2 * all_txt.sum())).backward()
+    ng_img, ng_txt = gather_features(img, txt, local_loss=False, gather_with_grad=False, rank=rank, world_size=world)
+    ret[rank] = {"img": img.detach(), "txt": txt.detach(), "all_img": all_img.detach(), "all_txt": all_txt.detach(),
+                 "d_img": img.grad.clone(), "d_txt": txt.grad.clone(), "ng_requires": (ng_img.requires_grad, ng_txt.requires_grad),
+                 "ng_img": ng_img.detach(), "labels": local_labels(n, rank, world, True)}
+    dist.destroy_process_group()
+
+
+def test_gather_features_two_rank_gloo():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gather_worker, args=(2, 29541, ret), nprocs=2, join=True)
+    r0, r1 = ret[0], ret[1]
+    cat_img, cat_txt = torch.cat([r0["img"], r1["img"]]), torch.cat([r0["txt"], r1["txt"]])
+    for r in (r0, r1):
+        assert torch.equal(r["all_img"], cat_img) and torch.equal(r["all_txt"], cat_txt)     # rank-major order (loss.py:48-50)
+        assert torch.equal(r["ng_img"], cat_img) and r["ng_requires"] == (True, True)        # local slice keeps its grad (:56-59)
+        # d(all.sum)/d(local row) summed over ranks: (1 + 2) for img, 2 * (1 + 2) for txt
+        assert torch.allclose(r["d_img"], torch.full_like(r["d_img"], 3.0))
+        assert torch.allclose(r["d_txt"], torch.full_like(r["d_txt"], 6.0))
+    assert r0["labels"].tolist() == [0, 1, 2, 3] and r1["labels"].tolist() == [4, 5, 6, 7]   # loss.py:92-94

@@ -119,6 +119,11 @@ int b200clip_text_embed(int dtype, const int64_t* text, int ctx, const float* to
     return text_embed(dtype, text, ctx, tok_emb, pos_emb, x, eot, T, L, width, S(stream));
 }
 
+int b200clip_eot_argmax(const int64_t* text, int ctx, int32_t* eot, int T, void* stream) {
+    B2C_CHECK_ARG(text && eot, "eot_argmax: null pointer");
+    return eot_argmax(text, ctx, eot, T, S(stream));
+}
+
 int b200clip_normalize(int dtype, const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int dim, float eps, void* stream) {
     B2C_CHECK_ARG(x && y, "normalize: null pointer");
     return normalize_rows(dtype, x, ldx, y, ldy, rows, dim, eps, S(stream));

@@ -180,6 +180,13 @@ int text_embed_v(int dtype, const int64_t* text, int ctx, const float* tok_emb, 
     return -1;
 }
 
+int eot_argmax(const int64_t* text, int ctx, int32_t* eot, int T, cudaStream_t stream) {
+    B2C_CHECK_ARG(T > 0 && ctx > 0, "eot_argmax: bad shape T=%d ctx=%d", T, ctx);
+    eot_kernel<<<(T + 7) / 8, 256, 0, stream>>>(text, ctx, eot, T, ctx);
+    B2C_LAUNCH_CHECK("eot_kernel");
+    return 0;
+}
+
 int text_embed(int dtype, const int64_t* text, int ctx, const float* tok_emb, const float* pos_emb, void* x, int32_t* eot,
                int T, int L, int width, cudaStream_t stream) {
     return text_embed_v(dtype, text, ctx, tok_emb, pos_emb, x, eot, T, L, width, 0x7fffffff, stream);

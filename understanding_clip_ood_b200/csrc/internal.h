@@ -31,6 +31,8 @@ int patchify(int dtype, const void* image, void* patches, int batch, int image_s
 int text_embed(int dtype, const int64_t* text, int ctx, const float* tok_emb, const float* pos_emb, void* x, int32_t* eot,
                int T, int L, int width, cudaStream_t stream);
 
+int eot_argmax(const int64_t* text, int ctx, int32_t* eot, int T, cudaStream_t stream);
+
 int normalize_rows(int dtype, const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int dim, float eps,
                    cudaStream_t stream);
 

@@ -1,0 +1,162 @@
+"""ClipLoss with the reference's constructor / forward signature (deps/open_clip/src/open_clip/loss.py:66-131),
+computed by the fused forward+backward CUDA path (`b200clip_cliploss`) and, for world_size > 1, ONE NCCL
+all-gather of the concatenated img‖txt features (the reference issues two, loss.py:49-50) whose autograd backward
+is one reduce-scatter — the same semantics as torch.distributed.nn.all_gather.
+
+There is no PyTorch-op fallback for the loss arithmetic: CPU feature tensors raise.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+try:
+    import torch.distributed as dist
+    has_distributed = dist.is_available()
+except ImportError:  # pragma: no cover
+    dist = None
+    has_distributed = False
+
+from .. import _lib as L
+from .. import ops
+
+__all__ = ["ClipLoss", "gather_features", "local_labels"]
+
+
+def local_labels(num_logits: int, rank: int, world_size: int, local_loss: bool, device=None) -> torch.Tensor:
+    """Ground-truth column of each local row (loss.py:89-100): i, offset by n*rank for the local-loss layout."""
+    labels = torch.arange(num_logits, device=device, dtype=torch.long)
+    if world_size > 1 and local_loss:
+        labels = labels + num_logits * rank
+    return labels
+
+
+class _GatherCat(torch.autograd.Function):
+    """all_gather along dim 0 with gradient: forward = all_gather_into_tensor, backward = reduce_scatter(SUM)
+    (torch/distributed/nn/functional.py:_AllGather semantics).  Backends without reduce_scatter (gloo, used by the
+    CPU host-logic tests) fall back to all_reduce + slice, which is the same sum."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, group):
+        world = dist.get_world_size(group)
+        ctx.group, ctx.rank, ctx.n = group, dist.get_rank(group), x.shape[0]
+        x = x.contiguous()
+        out = torch.empty((world * x.shape[0], *x.shape[1:]), dtype=x.dtype, device=x.device)
+        if x.is_cuda:
+            dist.all_gather_into_tensor(out, x, group=group)
+        else:
+            dist.all_gather(list(out.chunk(world, dim=0)), x, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        grad_out = grad_out.contiguous()
+        if grad_out.is_cuda:
+            gx = torch.empty((ctx.n, *grad_out.shape[1:]), dtype=grad_out.dtype, device=grad_out.device)
+            dist.reduce_scatter_tensor(gx, grad_out, op=dist.ReduceOp.SUM, group=ctx.group)
+        else:
+            total = grad_out.clone()
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=ctx.group)
+            gx = total[ctx.rank * ctx.n:(ctx.rank + 1) * ctx.n].clone()
+        return gx, None
+
+
+def gather_features(image_features, text_features, local_loss=False, gather_with_grad=False, rank=0, world_size=1,
+                    use_horovod=False, group=None):
+    """Same contract as loss.py:19-63 (rank-major concatenation along dim 0), one fused collective for both
+    modalities.  Horovod is not supported."""
+    assert has_distributed, "torch.distributed did not import correctly, please use a PyTorch version with support."
+    if use_horovod:
+        raise NotImplementedError("horovod is not supported; use torch.distributed (NCCL)")
+    D = image_features.shape[1]
+    both = torch.cat([image_features, text_features], dim=1)          # [n, 2D]: one message per rank
+    if gather_with_grad:
+        gathered = _GatherCat.apply(both, group)
+    else:
+        with torch.no_grad():
+            gathered = _GatherCat.apply(both.detach(), group)
+        if not local_loss:
+            # ensure grads for the local rank when the gathered features do not carry a gradient (loss.py:56-59)
+            n = both.shape[0]
+            gathered = torch.cat([gathered[:rank * n], both, gathered[(rank + 1) * n:]], dim=0)
+    return gathered[:, :D], gathered[:, D:]
+
+
+class _FusedClipLoss(torch.autograd.Function):
+    """loss (+ all five gradients) from one C-ABI call; backward only rescales by the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, img_loc, txt_loc, all_img, all_txt, logit_scale, rank: int):
+        needs = [t.requires_grad for t in (img_loc, txt_loc, all_img, all_txt, logit_scale)]
+        f32 = [t.detach().float().contiguous() for t in (img_loc, txt_loc, all_img, all_txt)]
+        scale = logit_scale.detach().float().reshape(()).contiguous()
+        loss, grads = ops.cliploss_fwd_bwd(*f32, scale, rank, want_grad=any(needs))
+        ctx.dtypes = [t.dtype for t in (img_loc, txt_loc, all_img, all_txt, logit_scale)]
+        ctx.scale_shape = logit_scale.shape
+        ctx.save_for_backward(*(grads if grads is not None else ()))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = ctx.saved_tensors
+        if not grads:
+            return (None,) * 6
+        out = []
+        for i, (gr, dt) in enumerate(zip(grads, ctx.dtypes)):
+            if not ctx.needs_input_grad[i]:
+                out.append(None)
+                continue
+            gi = (gr * g).to(dt)
+            out.append(gi.reshape(ctx.scale_shape) if i == 4 else gi)
+        return (*out, None)
+
+
+class ClipLoss(nn.Module):
+    def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1, use_horovod=False):
+        super().__init__()
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.cache_labels = cache_labels
+        self.rank = rank
+        self.world_size = world_size
+        self.use_horovod = use_horovod
+        # cache state (kept for API compatibility; the fused kernel derives labels from (n, rank) itself)
+        self.prev_num_logits = 0
+        self.labels = {}
+
+    def get_ground_truth(self, device, num_logits) -> torch.Tensor:
+        if self.prev_num_logits != num_logits or device not in self.labels:
+            labels = local_labels(num_logits, self.rank, self.world_size, self.local_loss, device)
+            if self.cache_labels:
+                self.labels[device] = labels
+                self.prev_num_logits = num_logits
+        else:
+            labels = self.labels[device]
+        return labels
+
+    def _operands(self, image_features, text_features):
+        """-> (img_rows, txt_rows, all_img, all_txt, rank_offset): the row / column operands of the two logit blocks."""
+        if self.world_size > 1:
+            all_img, all_txt = gather_features(image_features, text_features, self.local_loss, self.gather_with_grad,
+                                               self.rank, self.world_size, self.use_horovod)
+            if self.local_loss:
+                return image_features, text_features, all_img, all_txt, self.rank
+            return all_img, all_txt, all_img, all_txt, 0
+        return image_features, text_features, image_features, text_features, 0
+
+    def get_logits(self, image_features, text_features, logit_scale):
+        """Materialised logits (API compatibility; the loss itself never goes through this)."""
+        rows_i, rows_t, all_img, all_txt, _ = self._operands(image_features, text_features)
+        s = float(logit_scale)
+        li, _, _ = ops.zeroshot(rows_i.float(), all_txt.float(), 0, normalize_img=False, logit_scale=s)
+        lt, _, _ = ops.zeroshot(rows_t.float(), all_img.float(), 0, normalize_img=False, logit_scale=s)
+        return li, lt
+
+    def forward(self, image_features, text_features, logit_scale, output_dict=False):
+        if not image_features.is_cuda:
+            raise L.B200ClipError("ClipLoss: CUDA feature tensors required — this path has no CPU fallback")
+        if not torch.is_tensor(logit_scale):
+            logit_scale = torch.tensor(float(logit_scale), device=image_features.device)
+        rows_i, rows_t, all_img, all_txt, rank = self._operands(image_features, text_features)
+        total_loss = _FusedClipLoss.apply(rows_i, rows_t, all_img, all_txt, logit_scale, rank)
+        return {"contrastive_loss": total_loss} if output_dict else total_loss

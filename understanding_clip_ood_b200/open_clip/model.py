@@ -1,0 +1,519 @@
+"""Host-side CLIP module: same constructor arguments, attributes, call signatures and `state_dict` keys as the
+reference's `open_clip.model.CLIP` (deps/open_clip/src/open_clip/model.py:220-315) and its `VisionTransformer`
+/ `TextTransformer` (transformer.py:427-643, 661-802), but every forward is ONE call into libb200clip.so
+(`b200clip_vit_forward` / `b200clip_text_forward`).  The nn.Module tree below only holds parameters — it
+contains no PyTorch arithmetic and there is no CPU / eager fallback: calling an encoder with CPU tensors or
+without the built library raises.
+
+Scope notes: inference forward only — outputs carry no autograd graph (tower backward is the
+"next" row §8(f)1); precision modes fp32 / bf16 / fp16 / pure_bf16 / pure_fp16 (the `amp*` modes need autocast
+through eager modules and are rejected by `create_model`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib as L
+
+__all__ = ["CLIP", "VisionTower", "convert_weights_to_lp", "get_cast_dtype", "get_input_dtype"]
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers (names chosen so that state_dict keys equal the reference's)
+# ------------------------------------------------------------------------------------------------
+class _Affine(nn.Module):
+    """LayerNorm parameters (ln_pre / ln_1 / ln_2 / ln_post / ln_final)."""
+
+    def __init__(self, width: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(width))
+        self.bias = nn.Parameter(torch.zeros(width))
+
+
+class _Dense(nn.Module):
+    """nn.Linear-shaped parameters: weight [out, in], bias [out]."""
+
+    def __init__(self, fan_in: int, fan_out: int, bias: bool = True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(fan_out, fan_in))
+        self.bias = nn.Parameter(torch.empty(fan_out)) if bias else None
+
+
+class _PatchConv(nn.Module):
+    """conv1: weight [W, 3, P, P], no bias (transformer.py:461)."""
+
+    def __init__(self, width: int, patch: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(width, 3, patch, patch))
+
+
+class _TokenTable(nn.Module):
+    def __init__(self, vocab: int, width: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(vocab, width))
+
+
+class _PackedMHA(nn.Module):
+    """nn.MultiheadAttention parameter layout: in_proj_weight [3W, W] rows ordered q|k|v, out_proj."""
+
+    def __init__(self, width: int):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * width, width))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * width))
+        self.out_proj = _Dense(width, width)
+
+
+class _MLP(nn.Module):
+    def __init__(self, width: int, hidden: int):
+        super().__init__()
+        self.c_fc = _Dense(width, hidden)
+        self.c_proj = _Dense(hidden, width)
+
+
+class _Block(nn.Module):
+    def __init__(self, width: int, hidden: int):
+        super().__init__()
+        self.ln_1 = _Affine(width)
+        self.attn = _PackedMHA(width)
+        self.ln_2 = _Affine(width)
+        self.mlp = _MLP(width, hidden)
+
+
+class _Stack(nn.Module):
+    """`transformer` sub-module: resblocks.{i}.* keys; mirrors Transformer's public attributes."""
+
+    def __init__(self, width: int, layers: int, heads: int, mlp_ratio: float):
+        super().__init__()
+        self.width, self.layers, self.heads = width, layers, heads
+        self.mlp_width = int(width * mlp_ratio)
+        self.grad_checkpointing = False
+        self.resblocks = nn.ModuleList([_Block(width, self.mlp_width) for _ in range(layers)])
+
+    def get_cast_dtype(self) -> torch.dtype:
+        return self.resblocks[0].mlp.c_fc.weight.dtype
+
+
+# ------------------------------------------------------------------------------------------------
+# random init: same distributions, and the same draw ORDER from the global torch RNG, as constructing the
+# reference modules (nn.Conv2d / nn.MultiheadAttention / nn.Linear / nn.Embedding default resets followed by
+# TextTransformer.init_parameters, transformer.py:724-745), so `torch.manual_seed(s); create_model(...)` yields
+# the reference's weights for the same seed on CPU.
+# ------------------------------------------------------------------------------------------------
+def _uniform_(p: torch.Tensor, bound: float) -> None:
+    with torch.no_grad():
+        p.uniform_(-bound, bound)
+
+
+def _weight_bound(fan_in: int) -> float:
+    """Bound of nn.Linear / nn.Conv2d's default weight reset, kaiming_uniform_(a=sqrt(5)) (~ 1/sqrt(fan_in)); written
+    with torch.nn.init's own operation order so the double-precision bound is bit-identical."""
+    gain = math.sqrt(2.0 / (1 + math.sqrt(5) ** 2))
+    std = gain / math.sqrt(fan_in)
+    return math.sqrt(3.0) * std
+
+
+def _bias_bound(fan_in: int) -> float:
+    return 1 / math.sqrt(fan_in)
+
+
+def _xavier_bound(fan_in: int, fan_out: int) -> float:
+    std = 1.0 * math.sqrt(2.0 / float(fan_in + fan_out))
+    return math.sqrt(3.0) * std
+
+
+def _init_stack(stack: _Stack) -> None:
+    W, Hd = stack.width, stack.mlp_width
+    for blk in stack.resblocks:
+        # nn.MultiheadAttention.__init__: out_proj (Linear reset) is built first, then _reset_parameters()
+        _uniform_(blk.attn.out_proj.weight, _weight_bound(W))
+        _uniform_(blk.attn.out_proj.bias, _bias_bound(W))
+        _uniform_(blk.attn.in_proj_weight, _xavier_bound(W, 3 * W))
+        with torch.no_grad():
+            blk.attn.in_proj_bias.zero_()
+            blk.attn.out_proj.bias.zero_()
+        _uniform_(blk.mlp.c_fc.weight, _weight_bound(W))
+        _uniform_(blk.mlp.c_fc.bias, _bias_bound(W))
+        _uniform_(blk.mlp.c_proj.weight, _weight_bound(Hd))
+        _uniform_(blk.mlp.c_proj.bias, _bias_bound(Hd))
+
+
+# ------------------------------------------------------------------------------------------------
+# C-ABI plumbing shared by both towers
+# ------------------------------------------------------------------------------------------------
+class _Engine:
+    """Builds and caches the ctypes weight structs + workspace for one tower; rebuilt when any parameter changes."""
+
+    def __init__(self):
+        self.sig = None
+        self.keep = []          # tensors whose storage the structs point into
+        self.blocks = None
+        self.weights = None
+        self.cfg = None
+        self.ws = None          # uint8 workspace tensor
+
+    @staticmethod
+    def signature(params) -> tuple:
+        return tuple((p.data_ptr(), p._version, p.dtype) for p in params)
+
+    def workspace(self, nbytes: int, device) -> torch.Tensor:
+        if self.ws is None or self.ws.numel() < nbytes or self.ws.device != device:
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return self.ws
+
+
+def _f32(t: torch.Tensor, keep: list) -> int:
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.detach().to(torch.float32).contiguous()
+    keep.append(t)
+    return t.data_ptr()
+
+
+def _as(t: Optional[torch.Tensor], dtype: torch.dtype, keep: list) -> Optional[int]:
+    if t is None:
+        return None
+    if t.dtype != dtype or not t.is_contiguous():
+        t = t.detach().to(dtype).contiguous()
+    keep.append(t)
+    return t.data_ptr()
+
+
+def _pack_blocks(stack: _Stack, dtype: torch.dtype, keep: list):
+    arr = (L.BlockWeights * stack.layers)()
+    for i, blk in enumerate(stack.resblocks):
+        b = arr[i]
+        b.ln1_g, b.ln1_b = _f32(blk.ln_1.weight, keep), _f32(blk.ln_1.bias, keep)
+        b.ln2_g, b.ln2_b = _f32(blk.ln_2.weight, keep), _f32(blk.ln_2.bias, keep)
+        b.in_proj_w, b.in_proj_b = _as(blk.attn.in_proj_weight, dtype, keep), _as(blk.attn.in_proj_bias, dtype, keep)
+        b.out_proj_w, b.out_proj_b = _as(blk.attn.out_proj.weight, dtype, keep), _as(blk.attn.out_proj.bias, dtype, keep)
+        b.fc_w, b.fc_b = _as(blk.mlp.c_fc.weight, dtype, keep), _as(blk.mlp.c_fc.bias, dtype, keep)
+        b.proj_w, b.proj_b = _as(blk.mlp.c_proj.weight, dtype, keep), _as(blk.mlp.c_proj.bias, dtype, keep)
+    return arr
+
+
+def _check_device(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise L.B200ClipError(f"{what}: CUDA tensors required — this path has no CPU fallback (got {t.device})")
+
+
+# ------------------------------------------------------------------------------------------------
+# vision tower
+# ------------------------------------------------------------------------------------------------
+class VisionTower(nn.Module):
+    """Parameters + driver of the ViT image tower; the `model.visual` object (VisionTransformer in the reference)."""
+
+    def __init__(self, image_size: int, patch_size: int, width: int, layers: int, heads: int, mlp_ratio: float,
+                 output_dim: int, quick_gelu: bool = False):
+        super().__init__()
+        if isinstance(image_size, (tuple, list)):
+            if image_size[0] != image_size[1]:
+                raise ValueError("only square images are supported")
+            image_size = image_size[0]
+        if image_size % patch_size != 0:
+            raise ValueError(f"image_size {image_size} must be divisible by patch_size {patch_size}")
+        if heads * 64 != width:
+            raise ValueError(f"head_width must be 64 (width {width}, heads {heads}): the attention kernel is specialised for it")
+        self.image_size = (image_size, image_size)
+        self.patch_size = (patch_size, patch_size)
+        self.grid_size = (image_size // patch_size, image_size // patch_size)
+        self.output_dim = output_dim
+        self.quick_gelu = bool(quick_gelu)
+        self.pool_type = "tok"
+        self.output_tokens = False
+        scale = width ** -0.5
+        self.conv1 = _PatchConv(width, patch_size)
+        _uniform_(self.conv1.weight, _weight_bound(3 * patch_size * patch_size))
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn(self.grid_size[0] * self.grid_size[1] + 1, width))
+        self.ln_pre = _Affine(width)
+        self.transformer = _Stack(width, layers, heads, mlp_ratio)
+        _init_stack(self.transformer)
+        self.ln_post = _Affine(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self._engine = _Engine()
+
+    # -- reference API surface ---------------------------------------------------------------
+    def set_grad_checkpointing(self, enable: bool = True):
+        self.transformer.grad_checkpointing = enable
+
+    def lock(self, unlocked_groups: int = 0, freeze_bn_stats: bool = False):
+        for p in self.parameters():
+            p.requires_grad = False
+
+    def _compute_dtype(self) -> torch.dtype:
+        return self.transformer.get_cast_dtype()
+
+    def _build(self, device) -> _Engine:
+        params = list(self.parameters())
+        sig = _Engine.signature(params)
+        eng = self._engine
+        if eng.sig == sig:
+            return eng
+        dt = self._compute_dtype()
+        keep: list = []
+        W = self.transformer.width
+        P = self.patch_size[0]
+        kreal = 3 * P * P
+        kpad = kreal if dt == torch.float32 else (kreal + 63) // 64 * 64
+        conv = self.conv1.weight.detach().to(dt).reshape(W, kreal)
+        if kpad != kreal:
+            padded = torch.zeros((W, kpad), dtype=dt, device=device)
+            padded[:, :kreal] = conv
+            conv = padded
+        conv = conv.contiguous()
+        keep.append(conv)
+        proj_t = self.proj.detach().to(dt).t().contiguous()
+        keep.append(proj_t)
+        blocks = _pack_blocks(self.transformer, dt, keep)
+        w = L.VitWeights()
+        w.conv1_w = conv.data_ptr()
+        w.class_emb = _f32(self.class_embedding, keep)
+        w.pos_emb = _f32(self.positional_embedding, keep)
+        w.ln_pre_g, w.ln_pre_b = _f32(self.ln_pre.weight, keep), _f32(self.ln_pre.bias, keep)
+        w.ln_post_g, w.ln_post_b = _f32(self.ln_post.weight, keep), _f32(self.ln_post.bias, keep)
+        w.proj_t = proj_t.data_ptr()
+        w.blocks_host = C.cast(blocks, C.c_void_p)
+        cfg = L.TowerCfg(dtype=L.dtype_code(dt), width=W, layers=self.transformer.layers, heads=self.transformer.heads,
+                         mlp_width=self.transformer.mlp_width, embed_dim=self.output_dim,
+                         seq_len=self.grid_size[0] * self.grid_size[1] + 1, quick_gelu=int(self.quick_gelu),
+                         image_size=self.image_size[0], patch_size=P, patch_kpad=kpad, vocab_size=0)
+        eng.sig, eng.keep, eng.blocks, eng.weights, eng.cfg = sig, keep, blocks, w, cfg
+        return eng
+
+    def forward(self, image: torch.Tensor, normalize: bool = False) -> torch.Tensor:
+        """[B,3,S,S] -> [B,D] (transformer.py:601-643); `normalize` fuses CLIP.encode_image's F.normalize."""
+        _check_device(image, "encode_image")
+        _check_device(self.proj, "encode_image (model weights)")
+        dt = self._compute_dtype()
+        if image.dtype != dt:
+            raise RuntimeError(f"Input type ({image.dtype}) and weight type ({dt}) should be the same "
+                               f"(cast the batch with get_input_dtype(precision), as the reference requires)")
+        if image.ndim != 4 or image.shape[1] != 3 or tuple(image.shape[2:]) != self.image_size:
+            raise RuntimeError(f"expected images of shape [B, 3, {self.image_size[0]}, {self.image_size[1]}], got {tuple(image.shape)}")
+        image = image.contiguous()
+        B = image.shape[0]
+        if B == 0:
+            return torch.empty((0, self.output_dim), dtype=dt, device=image.device)
+        lib = L.load()
+        with torch.cuda.device(image.device):
+            eng = self._build(image.device)
+            nbytes = lib.b200clip_workspace_bytes(C.byref(eng.cfg), B, eng.cfg.seq_len)
+            ws = eng.workspace(nbytes, image.device)
+            out = torch.empty((B, self.output_dim), dtype=dt, device=image.device)
+            rc = lib.b200clip_vit_forward(C.byref(eng.cfg), C.byref(eng.weights), image.data_ptr(), out.data_ptr(), B,
+                                          int(normalize), ws.data_ptr(), ws.numel(), L.stream_ptr())
+        L.check(rc, "b200clip_vit_forward")
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CLIP
+# ------------------------------------------------------------------------------------------------
+class CLIP(nn.Module):
+    """Drop-in for open_clip.model.CLIP (model.py:220-315) on the ViT + text-transformer path."""
+
+    def __init__(self, embed_dim: int, vision_cfg: dict, text_cfg: dict, quick_gelu: bool = False,
+                 init_logit_scale: float = np.log(1 / 0.07), init_logit_bias: Optional[float] = None,
+                 cast_dtype: Optional[torch.dtype] = None, output_dict: bool = False):
+        super().__init__()
+        from .model_configs import TEXT_DEFAULTS, VISION_DEFAULTS
+        v = {**VISION_DEFAULTS, **(vision_cfg if isinstance(vision_cfg, dict) else vars(vision_cfg))}
+        t = {**TEXT_DEFAULTS, **(text_cfg if isinstance(text_cfg, dict) else vars(text_cfg))}
+        if isinstance(v["layers"], (tuple, list)) or v.get("timm_model_name") or t.get("hf_model_name"):
+            raise RuntimeError("only ViT image towers with the native text transformer are on this hot path "
+                               "(ModifiedResNet / timm / HF towers: SURVEY.md §8(f))")
+        for k in ("attentional_pool", "no_ln_pre", "final_ln_after_pool", "output_tokens"):
+            if v.get(k):
+                raise RuntimeError(f"vision_cfg.{k} is not supported on this hot path")
+        if v.get("pool_type", "tok") != "tok" or v.get("pos_embed_type", "learnable") != "learnable":
+            raise RuntimeError("only pool_type='tok' with learnable positional embeddings is supported")
+        if v.get("ls_init_value") is not None or t.get("ls_init_value") is not None:
+            raise RuntimeError("LayerScale (ls_init_value) is not supported on this hot path")
+        for k in ("embed_cls", "no_causal_mask", "proj_bias", "output_tokens"):
+            if t.get(k):
+                raise RuntimeError(f"text_cfg.{k} is not supported on this hot path")
+        if t.get("pool_type", "argmax") != "argmax":
+            raise RuntimeError("only text pool_type='argmax' is supported")
+        self.output_dict = output_dict
+        self.quick_gelu = bool(quick_gelu)
+
+        self.visual = VisionTower(v["image_size"], v["patch_size"], v["width"], v["layers"], v["width"] // v["head_width"],
+                                  v["mlp_ratio"], embed_dim, quick_gelu)
+
+        # text tower; parameters are re-exported on the CLIP module like the reference does (model.py:239-248)
+        Wt = t["width"]
+        if t["heads"] * 64 != Wt:
+            raise RuntimeError(f"text head width must be 64 (width {Wt}, heads {t['heads']})")
+        self.context_length = t["context_length"]
+        self.vocab_size = t["vocab_size"]
+        self.text_pool_type = "argmax"
+        # registration order (= state_dict key order) follows the reference: transformer, token_embedding, ln_final;
+        # the RNG draws below keep the reference's construction order: nn.Embedding reset, then the blocks
+        self.transformer = _Stack(Wt, t["layers"], t["heads"], t["mlp_ratio"])
+        self.token_embedding = _TokenTable(self.vocab_size, Wt)
+        with torch.no_grad():
+            self.token_embedding.weight.normal_()                       # nn.Embedding default reset (consumes RNG)
+        self.positional_embedding = nn.Parameter(torch.empty(self.context_length, Wt))
+        _init_stack(self.transformer)
+        self.ln_final = _Affine(Wt)
+        self.text_projection = nn.Parameter(torch.empty(Wt, embed_dim))
+        self.register_buffer("attn_mask", torch.full((self.context_length, self.context_length), float("-inf")).triu_(1),
+                             persistent=False)
+        self._init_text_parameters()
+
+        self.logit_scale = nn.Parameter(torch.ones([]) * init_logit_scale)
+        self.logit_bias = nn.Parameter(torch.ones([]) * init_logit_bias) if init_logit_bias is not None else None
+
+        # exact causal truncation of encode_text at max(EOT)+1; off = run all `context_length`
+        # positions like the reference.  Costs one small device->host read per call.
+        self.truncate_text_at_eot = False
+        self._text_engine = _Engine()
+
+    def _init_text_parameters(self) -> None:
+        """TextTransformer.init_parameters (transformer.py:724-745)."""
+        st = self.transformer
+        proj_std = (st.width ** -0.5) * ((2 * st.layers) ** -0.5)
+        attn_std = st.width ** -0.5
+        fc_std = (2 * st.width) ** -0.5
+        with torch.no_grad():
+            self.token_embedding.weight.normal_(std=0.02)
+            self.positional_embedding.normal_(std=0.01)
+            for blk in st.resblocks:
+                blk.attn.in_proj_weight.normal_(std=attn_std)
+                blk.attn.out_proj.weight.normal_(std=proj_std)
+                blk.mlp.c_fc.weight.normal_(std=fc_std)
+                blk.mlp.c_proj.weight.normal_(std=proj_std)
+            self.text_projection.normal_(std=st.width ** -0.5)
+
+    # -- reference API surface ---------------------------------------------------------------
+    def lock_image_tower(self, unlocked_groups: int = 0, freeze_bn_stats: bool = False):
+        self.visual.lock(unlocked_groups=unlocked_groups, freeze_bn_stats=freeze_bn_stats)
+
+    def set_grad_checkpointing(self, enable: bool = True):
+        self.visual.set_grad_checkpointing(enable)
+        self.transformer.grad_checkpointing = enable
+
+    def encode_image(self, image: torch.Tensor, normalize: bool = False) -> torch.Tensor:
+        return self.visual(image, normalize=normalize)
+
+    def _build_text(self, device) -> _Engine:
+        params = [self.token_embedding.weight, self.positional_embedding, self.ln_final.weight, self.ln_final.bias,
+                  self.text_projection, *self.transformer.parameters()]
+        sig = _Engine.signature(params)
+        eng = self._text_engine
+        if eng.sig == sig:
+            return eng
+        dt = self.transformer.get_cast_dtype()
+        keep: list = []
+        proj_t = self.text_projection.detach().to(dt).t().contiguous()
+        keep.append(proj_t)
+        blocks = _pack_blocks(self.transformer, dt, keep)
+        w = L.TextWeights()
+        w.tok_emb = _f32(self.token_embedding.weight, keep)
+        w.pos_emb = _f32(self.positional_embedding, keep)
+        w.ln_final_g, w.ln_final_b = _f32(self.ln_final.weight, keep), _f32(self.ln_final.bias, keep)
+        w.proj_t = proj_t.data_ptr()
+        w.blocks_host = C.cast(blocks, C.c_void_p)
+        st = self.transformer
+        cfg = L.TowerCfg(dtype=L.dtype_code(dt), width=st.width, layers=st.layers, heads=st.heads, mlp_width=st.mlp_width,
+                         embed_dim=self.text_projection.shape[1], seq_len=self.context_length, quick_gelu=int(self.quick_gelu),
+                         image_size=0, patch_size=0, patch_kpad=0, vocab_size=self.vocab_size)
+        eng.sig, eng.keep, eng.blocks, eng.weights, eng.cfg = sig, keep, blocks, w, cfg
+        return eng
+
+    def encode_text(self, text: torch.Tensor, normalize: bool = False) -> torch.Tensor:
+        """[T, context_length] int64 -> [T, D] (model.py:269-284)."""
+        _check_device(text, "encode_text")
+        _check_device(self.text_projection, "encode_text (model weights)")
+        if text.ndim != 2 or text.shape[1] != self.context_length:
+            raise RuntimeError(f"expected token ids of shape [T, {self.context_length}], got {tuple(text.shape)}")
+        if text.dtype != torch.int64:
+            text = text.long()
+        text = text.contiguous()
+        T = text.shape[0]
+        dt = self.transformer.get_cast_dtype()
+        D = self.text_projection.shape[1]
+        if T == 0:
+            return torch.empty((0, D), dtype=dt, device=text.device)
+        lib = L.load()
+        with torch.cuda.device(text.device):
+            seq_len = self.context_length
+            if self.truncate_text_at_eot:
+                eot = torch.empty((T,), dtype=torch.int32, device=text.device)
+                L.check(lib.b200clip_eot_argmax(text.data_ptr(), self.context_length, eot.data_ptr(), T, L.stream_ptr()),
+                        "b200clip_eot_argmax")
+                seq_len = int(np.max(eot.cpu().numpy())) + 1
+            eng = self._build_text(text.device)
+            nbytes = lib.b200clip_workspace_bytes(C.byref(eng.cfg), T, seq_len)
+            ws = eng.workspace(nbytes, text.device)
+            out = torch.empty((T, D), dtype=dt, device=text.device)
+            rc = lib.b200clip_text_forward(C.byref(eng.cfg), C.byref(eng.weights), text.data_ptr(), out.data_ptr(), T, seq_len,
+                                           int(normalize), ws.data_ptr(), ws.numel(), L.stream_ptr())
+        L.check(rc, "b200clip_text_forward")
+        return out
+
+    def get_logits(self, image, text):
+        from .. import ops
+        image_features = self.encode_image(image, normalize=True)
+        text_features = self.encode_text(text, normalize=True)
+        scale = float(self.logit_scale.detach().exp())
+        logits, _, _ = ops.zeroshot(image_features, text_features, 0, normalize_img=False, want_logits=True, logit_scale=scale)
+        image_logits = logits.to(image_features.dtype)
+        if self.logit_bias is not None:
+            image_logits = image_logits + self.logit_bias
+        return image_logits, image_logits.T
+
+    def forward(self, image: Optional[torch.Tensor] = None, text: Optional[torch.Tensor] = None):
+        image_features = self.encode_image(image, normalize=True) if image is not None else None
+        text_features = self.encode_text(text, normalize=True) if text is not None else None
+        if self.output_dict:
+            out = {"image_features": image_features, "text_features": text_features, "logit_scale": self.logit_scale.exp()}
+            if self.logit_bias is not None:
+                out["logit_bias"] = self.logit_bias
+            return out
+        if self.logit_bias is not None:
+            return image_features, text_features, self.logit_scale.exp(), self.logit_bias
+        return image_features, text_features, self.logit_scale.exp()
+
+
+# ------------------------------------------------------------------------------------------------
+# precision helpers (model.py:86-101, 396-423)
+# ------------------------------------------------------------------------------------------------
+def get_cast_dtype(precision: str):
+    return {"bf16": torch.bfloat16, "fp16": torch.float16}.get(precision)
+
+
+def get_input_dtype(precision: str):
+    if precision in ("bf16", "pure_bf16"):
+        return torch.bfloat16
+    if precision in ("fp16", "pure_fp16"):
+        return torch.float16
+    return None
+
+
+def convert_weights_to_lp(model: nn.Module, dtype=torch.float16):
+    """Cast the GEMM operands (conv / linear / MHA weights+biases and the two projections) to `dtype`; LayerNorm
+    parameters, embeddings, positional tables and logit_scale stay fp32 — same split as model.py:396-423."""
+
+    def _convert(m):
+        if isinstance(m, (_Dense, _PatchConv)):
+            m.weight.data = m.weight.data.to(dtype)
+            if getattr(m, "bias", None) is not None:
+                m.bias.data = m.bias.data.to(dtype)
+        if isinstance(m, _PackedMHA):
+            m.in_proj_weight.data = m.in_proj_weight.data.to(dtype)
+            m.in_proj_bias.data = m.in_proj_bias.data.to(dtype)
+        if isinstance(m, CLIP):
+            m.text_projection.data = m.text_projection.data.to(dtype)
+        if isinstance(m, VisionTower):
+            m.proj.data = m.proj.data.to(dtype)
+
+    model.apply(_convert)
+
+
+convert_weights_to_fp16 = convert_weights_to_lp  # backwards-compatible alias, as in the reference
