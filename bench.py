@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the CLIP zero-shot hot path (BASELINE.json configs[1]): ViT-B-32 bf16, synthetic 224x224 images,
+345 DomainNet-shaped class prompts, 1024 images per GPU per step.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path through the drop-in API / C ABI)
+    python bench.py --impl reference --steps K --warmup W    # reference arm: the CPU oracle port on the host cores
+
+A step = one pass of the hot path over one batch: image tower -> L2-normalise -> image x class-prompt logits -> top-5.
+The class-prompt features are built once before the timed region (they are per checkpoint, not per batch).
+N > 1 (torchrun, one process per GPU, NCCL): every rank processes its own 1024-image batches (weak scaling, no
+data-path collective); the only collective is the final all-reduce of [top-1 hits, top-5 hits, n].
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+MODEL = "ViT-B-32"
+BATCH = 1024
+CLASSES, TEMPLATES = 345, 86
+TOPK = 5
+METRIC = "zero_shot_images_per_sec"
+UNIT = "images/s"
+# algorithmic FLOPs per image of the ViT-B/32 tower (= docs/model_profile.csv:8) + logits
+FLOPS_PER_IMAGE = 8.818e9 + 2 * 512 * CLASSES
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "hbm_gbs": d["hbm_gbs"],
+                "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def domainnet_tokens() -> torch.Tensor:
+    z = np.load(ROOT / "tests" / "golden" / "domainnet_prompts.npz")
+    tok = torch.zeros((z["tokens"].shape[0], int(z["context_length"])), dtype=torch.long)
+    tok[:, : z["tokens"].shape[1]] = torch.from_numpy(z["tokens"].astype(np.int64))
+    return tok
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (cpu_baseline of our line; the whole `--impl reference` line)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_hot_path(sd, image, prompt_feat):
+    from oracle import clip_oracle as O
+    feat = O.vit_forward(sd, image)
+    logits = O.zero_shot_logits(feat, prompt_feat)
+    return O.topk(logits, TOPK)
+
+
+def cpu_setup(sample_images: int):
+    from understanding_clip_ood_b200 import open_clip
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = open_clip.create_model(MODEL, precision="fp32", device="cpu")     # parameter container only; never called on CPU
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    image = torch.randn(sample_images, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    prompt = torch.nn.functional.normalize(torch.randn(CLASSES, 512, generator=torch.Generator().manual_seed(2)), dim=-1)
+    return sd, image, prompt
+
+
+def run_cpu_baseline(sample_images: int = 16, reps: int = 2) -> dict:
+    sd, image, prompt = cpu_setup(sample_images)
+    cpu_hot_path(sd, image[:2], prompt)                                            # warm-up (thread pool, allocator)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cpu_hot_path(sd, image, prompt)
+    dt = time.perf_counter() - t0
+    return {"value": sample_images * reps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{reps} x {sample_images} images, fp32 oracle port of the same hot path (ViT-B-32 tower + logits + top-5), "
+                      f"{dt:.1f} s of CPU work"}
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 16
+    sd, image, prompt = cpu_setup(sample)
+    for _ in range(max(args.warmup, 1)):
+        cpu_hot_path(sd, image[:4], prompt)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_hot_path(sd, image, prompt)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus, extra={"cpu_sample_images_per_step": sample}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps x {sample} images (bounded sample of the 1024-image batch), fp32 oracle "
+                                       "port of the reference algorithm; /root/reference is pure Python + PyTorch and does not exist on "
+                                       "the GPU box"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus: int, extra: dict | None = None) -> dict:
+    cfg = {"workload": f"{MODEL} zero-shot DomainNet-shaped eval: synthetic 224x224, {CLASSES} class prompts x {TEMPLATES} templates, "
+                       f"batch {BATCH} per GPU, image tower -> normalize -> logits -> top-{TOPK}",
+           "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "classes": CLASSES, "topk": TOPK, "precision": "bf16",
+           "parallelism": f"dp{n_gpus} (independent shards, final accuracy all-reduce only)",
+           "l2_policy": "inputs_larger_than_l2 (308 MB image batch + >300 MB activations per step vs 126 MB L2)",
+           "weights": "random init, torch.manual_seed(0)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def time_gemm_roofline(ops, L, peaks) -> dict:
+    """Dominant kernel timed alone with CUDA events on the launching stream: the c_fc GEMM (+bias+GELU epilogue) of one
+    layer at the benchmark's token count (M = 1024*50).  Operands (78 MB in, 314 MB out) exceed the L2."""
+    M, N, K = BATCH * 50, 3072, 768
+    g = torch.Generator(device="cuda").manual_seed(7)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.04).bfloat16()
+    b = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.gemm(a, w, b, epilogue=L.EPI_GELU, out=out)
+    iters = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        ops.gemm(a, w, b, epilogue=L.EPI_GELU, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * M * N * K
+    achieved = flops / (ms * 1e-3) / 1e12
+    traffic = None
+    tp = ROOT / "profiles" / "roofline_traffic.json"
+    if tp.exists():
+        traffic = json.loads(tp.read_text()).get("gemm_tc_cfc_bytes_per_launch")
+    return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
+            "kernel": f"gemm_tc_kernel<bf16, EPI_GELU> M={M} N={N} K={K} (mlp.c_fc of one layer at batch {BATCH})",
+            "ms_per_launch": ms, "flops_per_launch": flops, "peak_source": f"{peaks['source']} burst bf16 GEMM (MEASURED_PEAKS.json)"}
+
+
+def run_ours(args) -> None:
+    from understanding_clip_ood_b200 import _lib as L
+    from understanding_clip_ood_b200 import open_clip, ops
+    from understanding_clip_ood_b200.xclip import zero_shot as zs
+    from understanding_clip_ood_b200.xclip.open_clip import OpenCLIP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+    peaks = measured_peaks()
+
+    # ---- model + class-prompt features (outside the timed region) -------------------------------------------------
+    torch.manual_seed(0)
+    model = open_clip.create_model(MODEL, precision="bf16", device="cpu").to(dev).eval()
+    model.truncate_text_at_eot = True
+    clip = OpenCLIP(model)
+    tokens = domainnet_tokens()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    classifier = zs.OpenAIZeroShotClassifier.from_tokens(clip, tokens, CLASSES, TEMPLATES)
+    torch.cuda.synchronize()
+    classifier_build_s = time.perf_counter() - t0
+    prompt = classifier.prompt_feat
+
+    # ---- synthetic inputs -----------------------------------------------------------------------------------------
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    image = torch.randn(BATCH, 3, 224, 224, device=dev, generator=g).bfloat16()
+    labels = torch.randint(0, CLASSES, (BATCH,), device=dev, generator=g)
+    hits = torch.zeros(3, dtype=torch.int64, device=dev)
+
+    def step_device():
+        feat = model.encode_image(image, normalize=True)
+        _, idx, _ = ops.zeroshot(feat, prompt, TOPK, normalize_img=False, want_logits=False)
+        return idx
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        idx = step_device()
+        hits[0] += (idx[:, 0] == labels).sum()
+        hits[1] += (idx == labels[:, None]).any(dim=1).sum()
+        hits[2] += BATCH
+    if dist is not None:
+        dist.all_reduce(hits)                                   # the only collective: final accuracy reduction
+    e1.record()
+    barrier()
+    launches = L.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t)
+    value = BATCH * world * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region ---------
+    host_img = [torch.randn(BATCH, 3, 224, 224, generator=torch.Generator().manual_seed(11 + i)).bfloat16().pin_memory() for i in range(2)]
+    host_pred = torch.empty((BATCH,), dtype=torch.int64).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_img = [torch.empty_like(image), torch.empty_like(image)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            dev_img[i % 2].copy_(host_img[i % 2], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def e2e_run(steps):
+        for ev in consumed:
+            ev.record()
+        upload(0)
+        for i in range(steps):
+            if i + 1 < steps:
+                upload(i + 1)                                    # next batch's H2D overlaps this batch's compute
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            pred = classifier.predict(dev_img[i % 2])["pred"]    # the call a user makes (xclip.zero_shot API)
+            consumed[i % 2].record()
+            host_pred.copy_(pred, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_run(3)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(args.steps)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = BATCH * world * args.steps / float(t)
+
+    # ---- ClipLoss step (BASELINE config 4 shape: 256 local rows per rank), reported next to the headline ---------
+    n_loc = 256
+    gl = torch.Generator(device=dev).manual_seed(100 + rank)
+    fi = ops.normalize(torch.randn(n_loc, 512, device=dev, generator=gl)).requires_grad_(True)
+    ft = ops.normalize(torch.randn(n_loc, 512, device=dev, generator=gl)).requires_grad_(True)
+    ls = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
+    loss_fn = open_clip.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+
+    def loss_step():
+        fi.grad = ft.grad = ls.grad = None
+        loss_fn(fi, ft, ls).backward()
+
+    for _ in range(5):
+        loss_step()
+    barrier()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
+    loss_iters = 50
+    for _ in range(loss_iters):
+        loss_step()
+    l1.record()
+    barrier()
+    t = torch.tensor([l0.elapsed_time(l1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cliploss = {"steps_per_s": loss_iters / (float(t) * 1e-3), "local_rows": n_loc, "gathered_rows": n_loc * world, "dim": 512,
+                "what": "ClipLoss(local_loss, gather_with_grad) fwd+bwd incl. feature all-gather / reduce-scatter, fp32"}
+
+    if rank == 0:
+        roof = time_gemm_roofline(ops, L, peaks)
+        cpu = run_cpu_baseline()
+        tower_tflops = FLOPS_PER_IMAGE * value / world / 1e12
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 2, "d2h_bytes_per_step": BATCH * 8,
+                        "what": "ZeroShotClassifier.predict(images) from pinned host bf16 batches, H2D double-buffered on a copy stream, "
+                                "int64 predictions copied back to pinned host memory"},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "per_gpu": {"images_per_s": value / world, "algorithmic_tflops": tower_tflops,
+                            "frac_of_bf16_peak_burst": tower_tflops / peaks["bf16_tflops"],
+                            "frac_of_bf16_peak_sustained": tower_tflops / peaks["bf16_tflops_sustained"] if peaks["bf16_tflops_sustained"] else None},
+                "classifier_build_s": classifier_build_s, "classifier_prompts": int(tokens.shape[0]), "cliploss": cliploss,
+                "accuracy_reduction": {"top1_hits": int(hits[0]), "top5_hits": int(hits[1]), "n": int(hits[2])}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
