@@ -14,6 +14,7 @@
 // Rounding points mirror the reference's bf16/fp16 eager path: the linear output (acc + bias) is
 // rounded to the storage type before the activation / residual add, which round again.
 #include "common.cuh"
+#include "tmap.h"
 
 #include <mutex>
 
@@ -271,43 +272,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // Host side: tensor maps + launch
 // ---------------------------------------------------------------------------------------------
-using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    });
-    return fn;
-}
-
 // 2D row-major [rows, cols] 16-bit matrix, box = [box_rows, 64 cols], 128B swizzle, OOB reads give zeros.
 int make_tmap(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (fn == nullptr) {
-        set_last_error("cuTensorMapEncodeTiled not available from the driver");
-        return -1;
-    }
-    const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {ld * 2};
-    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_last_error("cuTensorMapEncodeTiled failed (CUresult %d) for ptr=%p rows=%llu cols=%llu ld=%llu", (int)r, ptr,
-                       (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
-        return -1;
-    }
-    return 0;
+    return make_tmap_2d(map, is_bf16, ptr, rows, cols, ld, box_rows, kBlockK);
 }
 
 template <typename T, int BLOCK_N, int EPI>
