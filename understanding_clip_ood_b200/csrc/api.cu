@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -43,6 +44,15 @@ int num_sms() {
     return cached;
 }
 
+// B200CLIP_GEMM_SINGLE_CTA=1 routes every 16-bit GEMM to the single-CTA kernel (A/B measurements only)
+static bool force_single_cta_gemm() {
+    static const bool v = [] {
+        const char* e = getenv("B200CLIP_GEMM_SINGLE_CTA");
+        return e != nullptr && e[0] == '1';
+    }();
+    return v;
+}
+
 int gemm_any(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
              int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in, int g_out,
              cudaStream_t stream) {
@@ -50,9 +60,13 @@ int gemm_any(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, 
         return gemm_f32(static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, static_cast<const float*>(bias),
                         static_cast<const float*>(residual), ldr, static_cast<float*>(C), ldc, M, N, K, epilogue, pos, g_in, g_out,
                         stream);
-    if (dtype == B200CLIP_BF16 || dtype == B200CLIP_F16)
+    if (dtype == B200CLIP_BF16 || dtype == B200CLIP_F16) {
+        // the patch-embedding epilogue remaps rows (no TMA-store box), it stays on the single-CTA kernel
+        if (epilogue != B200CLIP_EPI_PATCH && !force_single_cta_gemm())
+            return gemm_pair(dtype == B200CLIP_BF16, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, 0, 0, stream);
         return gemm_tc(dtype == B200CLIP_BF16, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, pos, g_in, g_out, 0,
                        stream);
+    }
     set_last_error("gemm: unknown dtype %d", dtype);
     return -1;
 }
@@ -92,6 +106,9 @@ int b200clip_gemm_tile(int dtype, const void* A, int64_t lda, const void* W, int
     B2C_CHECK_ARG(A != nullptr && W != nullptr && C != nullptr, "gemm: null pointer");
     B2C_CHECK_ARG(dtype == B200CLIP_BF16 || dtype == B200CLIP_F16, "gemm_tile: 16-bit dtypes only");
     B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 4, "gemm: unknown epilogue %d", epilogue);
+    if (block_n >= 1000)  // 1000 + BLOCK_N: CTA-pair kernel (clusters of 2); 2000 + BLOCK_N: clusters of 4 with W multicast
+        return gemm_pair(dtype == B200CLIP_BF16, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, block_n % 1000,
+                         block_n / 1000, S(stream));
     return gemm_tc(dtype == B200CLIP_BF16, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, pos, g_in, g_out, block_n,
                    S(stream));
 }

@@ -106,6 +106,61 @@ __device__ __forceinline__ float erf_fast(float z) {
 __device__ __forceinline__ float gelu_erf_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
 
 // ---------------------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot) and the epilogue GELU built on it.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack_f2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul_f2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// erf-GELU for the 16-bit GEMM epilogue, two elements per call:  x * Phi(x) = x / (1 + 2^(x * q(x^2))), where x*q(x^2) is a
+// degree-9 odd polynomial fitted to -log2(e) * logit(Phi(x)) (tools/fit_gelu.py).  Max |error| vs the exact erf form is
+// 3.9e-6 absolute over all x, i.e. < 0.05 bf16 ulp wherever |gelu(x)| >= 0.01: the value rounded to bf16/fp16 equals the
+// rounded exact value for all but a few per cent of the elements that sit next to a rounding boundary.  6 packed FP32 +
+// 4 MUFU issue slots per pair instead of ~50 for two erff() calls, which made the c_fc GEMM epilogue-bound.
+// The fp32 parity path (gemm_f32.cu) keeps erff.
+__device__ __forceinline__ void gelu_pair_fast(float& x0, float& x1) {
+    constexpr float kL = -1.4426950408889634f;
+    const uint64_t x = pack_f2(x0, x1);
+    const uint64_t s = mul_f2(x, x);
+    uint64_t q = fma_f2(pack_f2(2.28182475e-06f * kL, 2.28182475e-06f * kL), s, pack_f2(-6.19073477e-05f * kL, -6.19073477e-05f * kL));
+    q = fma_f2(q, s, pack_f2(-2.45941020e-04f * kL, -2.45941020e-04f * kL));
+    q = fma_f2(q, s, pack_f2(7.29314157e-02f * kL, 7.29314157e-02f * kL));
+    q = fma_f2(q, s, pack_f2(1.59565838e+00f * kL, 1.59565838e+00f * kL));
+    float u0, u1;
+    unpack_f2(mul_f2(q, x), u0, u1);
+    const float r0 = rcp_fast(1.0f + ex2_fast(u0));
+    const float r1 = rcp_fast(1.0f + ex2_fast(u1));
+    unpack_f2(mul_f2(x, pack_f2(r0, r1)), x0, x1);
+}
+
+// ---------------------------------------------------------------------------------------
 // Warp helpers
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -194,9 +249,23 @@ __device__ __forceinline__ void tma_load_2d(const void* desc, uint64_t* bar, voi
         : "memory");
 }
 
+// 2D tile prefetch global -> L2 (no shared memory, no completion tracking): pulls DRAM latency out of the operand ring
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* desc, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(c0),
+                 "r"(c1)
+                 : "memory");
+}
+
 // 2D tile store shared -> global (bulk async-group completion); out-of-bounds parts of the box are clipped
 __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int32_t c0, int32_t c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// same, but global[box] += shared[box] element-wise (performed by the L2 in the tensor map's element type)
+__device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
                  :
                  : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                  : "memory");
@@ -300,6 +369,18 @@ __device__ __forceinline__ void tma_load_2d_pair(const void* desc, uint64_t* bar
         :
         : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
           "l"(hint)
+        : "memory");
+}
+// Same, multicast: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and each destination's bytes are
+// credited to the mbarrier at this offset in the leader (even) CTA of that destination's pair.
+__device__ __forceinline__ void tma_load_2d_pair_mcast(const void* desc, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1,
+                                                       uint16_t cta_mask, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%4, %5}], [%2], %3, %6;"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & kPeerBitMask), "h"(cta_mask), "r"(c0),
+          "r"(c1), "l"(hint)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {

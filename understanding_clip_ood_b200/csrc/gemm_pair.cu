@@ -1,0 +1,614 @@
+// CTA-pair tcgen05 GEMM for the CLIP towers:  C[M,N] = epilogue(A[M,K] · W[N,K]^T + bias)  (16-bit storage, fp32 accumulate).
+//
+// This is the kernel the block GEMMs (QKV, out-proj, c_fc, c_proj: >96 % of the tower FLOPs) run on.  B200-first design,
+// nothing of it exists in the reference (which calls F.linear, transformer.py:224-263):
+//   * thread-block clusters of 2 CTAs on one TPC drive ONE 256 x BLOCK_N UMMA tile (tcgen05.mma.cta_group::2): each CTA
+//     stages its own 128 rows of A and its own half of the W tile, so every operand byte is fetched into shared memory once
+//     per pair (shared-memory traffic per MAC is 2/3 of the single-CTA 128 x 256 tile that saturated at ~74 % tensor-active);
+//   * persistent: one cluster per SM pair, static tile walk in L2-friendly groups of M-tiles;
+//   * 12 warps with fixed roles: warp 0 TMA producer, warp 1 MMA issuer (leader CTA only), warp 2 TMEM allocator, warps 4..11
+//     epilogue;  mbarrier pipelines: smem full/empty (TMA <-> MMA; the full barrier lives in the leader CTA and is credited by
+//     both CTAs' TMA loads), TMEM full/empty (MMA <-> both CTAs' epilogues; double-buffered accumulators: the epilogue of
+//     tile i overlaps the MMAs of tile i+1);
+//   * epilogue: tcgen05.ld -> registers -> bias / GELU / residual -> 128B-swizzled shared-memory staging -> TMA store, so
+//     global writes are full 128-byte lines issued by the copy engine instead of per-thread 16-byte scatters.  The residual
+//     operand is TMA-loaded into the same staging buffer ahead of time (prefetched one chunk ahead) and updated in place.
+// Rounding points mirror the reference's bf16/fp16 eager path: (acc + bias) is rounded to the storage type before the
+// activation / residual add, which round again.
+#include "common.cuh"
+#include "internal.h"
+#include "tmap.h"
+
+#include <cstdlib>
+#include <mutex>
+
+namespace b200clip {
+
+namespace {
+
+constexpr int kBM = 128;          // rows of A per CTA; a pair tile has 256
+constexpr int kPairM = 256;
+constexpr int kBK = 64;           // 64 x 16-bit = one 128 B swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kAccStages = 2;
+constexpr int kAccStride = 256;   // TMEM columns between the two accumulator stages
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;      // two groups of 4 warps (one warp per TMEM lane quarter)
+constexpr int kChunkN = 64;       // epilogue / store granularity: 128 rows x 64 columns (128 B rows)
+constexpr int kChunkBytes = kBM * kChunkN * 2;
+// EPI values beyond the public ones: 5 = residual that aliases C (x += A W^T + b): the add is done by the L2 through a TMA
+// reduce-add store, so the residual never travels to the SM (no load, no shared-memory pass)
+constexpr int kEpiResidualInPlace = 5;
+
+struct PairParams {
+    const void* bias;
+    int M, N, K;
+    int m_tiles, n_tiles;  // in units of (PAIRS*256) x BLOCK_N cluster tiles
+    int group_m;
+    int pf_dist;           // L2 prefetch distance of the A operand, in K-blocks (0 = off)
+    int dbg;               // measurement-only switches (B200CLIP_GEMM_DBG): 1 = skip the epilogue, 2 = MMA without operand loads
+};
+
+// STG_BUFS = staging buffers per epilogue group (3 with a loaded residual: landing / in-place update / store draining)
+template <int BLOCK_N, int STG_BUFS> struct PairCfg {
+    static_assert(BLOCK_N % 64 == 0 && BLOCK_N >= 128 && BLOCK_N <= 256, "BLOCK_N must be 128, 192 or 256");
+    static constexpr int kABytes = kBM * kBK * 2;
+    static constexpr int kBBytes = (BLOCK_N / 2) * kBK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStgBufs = STG_BUFS;
+    static constexpr int kStagingBytes = 2 * kStgBufs * kChunkBytes;
+    static constexpr int kBarBytes = 256;
+    static constexpr int kBudget = 227 * 1024 - 1024 - kStagingBytes - kBarBytes;
+    static constexpr int kStagesFit = kBudget / kStageBytes;
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;
+    static constexpr int kChunks = BLOCK_N / kChunkN;
+    static_assert(kStages >= 3, "not enough shared memory for the operand ring");
+    static_assert((2 * kStages + 2 * kAccStages + 2 * kStgBufs) * 8 + 8 <= kBarBytes, "barrier block too small");
+};
+
+__device__ __forceinline__ void pair_tile_coords(int t, const PairParams& p, int& mt, int& nt) {
+    const int per_group = p.group_m * p.n_tiles;
+    const int g = t / per_group;
+    const int r = t - g * per_group;
+    const int m0 = g * p.group_m;
+    const int gm = min(p.group_m, p.m_tiles - m0);
+    nt = r / gm;
+    mt = m0 + (r - nt * gm);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// PAIRS = CTA pairs per cluster (cluster size = 2 * PAIRS).  PAIRS == 2: the two pairs own vertically adjacent 256-row
+// tiles of the same BLOCK_N columns; every CTA fetches one QUARTER of the W tile and TMA-multicasts it to the CTA of the
+// other pair that needs the same half, so the cluster reads each W byte from L2 once instead of twice (the single-pair
+// kernel is bound by the ~10 TB/s L2 -> SM read bandwidth, not by the tensor pipe: profiles/r1_gemm_pair_v1_ncu.md).
+template <typename T, int BLOCK_N, int EPI, int PAIRS>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, const PairParams p) {
+    using Cfg = PairCfg<BLOCK_N, EPI == 3 ? 3 : 2>;
+    using H = Half16<T>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kStgBufs = Cfg::kStgBufs;
+    constexpr int kClusterCtas = 2 * PAIRS;
+    constexpr int kClusterM = PAIRS * kPairM;
+
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024 B alignment.  The dynamic-smem base offset is the same in every CTA of the cluster, so the
+    // carve-up below puts every object at the same CTA-relative address in all of them (required by the pair MMA, the
+    // multicast TMA and the multicast commits).
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+    uint8_t* staging = smem + kStages * Cfg::kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full_bar = empty_bar + kStages;
+    uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
+    uint64_t* res_bar = tmem_empty_bar + kAccStages;  // [group][buffer]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * kStgBufs);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const uint32_t pair = cta_rank >> 1;           // which pair of the cluster
+    const uint32_t half = cta_rank & 1;            // which CTA of the pair (0 = leader: issues the MMAs, owns the barriers)
+    const uint32_t leader_rank = cta_rank & ~1u;
+    const bool is_leader = half == 0;
+    const int cluster_id = blockIdx.x / kClusterCtas;
+    const int num_clusters = gridDim.x / kClusterCtas;
+    const int num_tiles = p.m_tiles * p.n_tiles;
+    const int num_kb = (p.K + kBK - 1) / kBK;
+
+    // every CTA of the cluster must be resident before the pair-wide TMEM allocation / remote barrier traffic
+    cluster_sync_all();
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_c);
+        if constexpr (EPI == 3) tma_prefetch_desc(&tmap_r);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 2);       // leader: arrive.expect_tx, peer: remote arrive (+ the TMA bytes of both CTAs' buffers)
+            mbar_init(&empty_bar[i], PAIRS);  // one multicast tcgen05.commit from every pair leader of the cluster
+        }
+        for (int i = 0; i < kAccStages; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);                // multicast tcgen05.commit of this pair's leader
+            mbar_init(&tmem_empty_bar[i], 2 * kEpiWarps);   // every epilogue warp of both CTAs arrives at the leader
+        }
+        for (int i = 0; i < 2 * kStgBufs; ++i) mbar_init(&res_bar[i], 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(tmem_ptr_smem, 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer (every CTA) =====================
+        if (lane == 0 && !(p.dbg & 2)) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int row_in_cluster = static_cast<int>(pair) * kPairM + static_cast<int>(half) * kBM;
+            // L2 prefetch cursor: runs p.pf_dist K-blocks ahead of the shared-memory ring (across tile boundaries), so the
+            // ring only has to cover L2 latency, not the DRAM latency of the streamed activations
+            int pf_t = cluster_id, pf_kb = 0, pf_row = 0;
+            auto prefetch_next = [&]() {
+                if (pf_t >= num_tiles) return;
+                if (pf_kb == 0) {
+                    int pmt, pnt;
+                    pair_tile_coords(pf_t, p, pmt, pnt);
+                    pf_row = pmt * kClusterM + row_in_cluster;
+                }
+                tma_prefetch_l2_2d(&tmap_a, pf_kb * kBK, pf_row);
+                if (++pf_kb == num_kb) {
+                    pf_kb = 0;
+                    pf_t += num_clusters;
+                }
+            };
+            for (int i = 0; i < p.pf_dist; ++i) prefetch_next();
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                int mt, nt;
+                pair_tile_coords(t, p, mt, nt);
+                const int row_a = mt * kClusterM + row_in_cluster;
+                const int row_w = nt * BLOCK_N + static_cast<int>(half) * (BLOCK_N / 2);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (p.pf_dist > 0) prefetch_next();
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                    else mbar_arrive_remote(&full_bar[stage], leader_rank);
+                    tma_load_2d_pair(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBK, row_a, kCacheHintEvictNormal);
+                    if constexpr (PAIRS == 1) {
+                        tma_load_2d_pair(&tmap_w, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBK, row_w, kCacheHintEvictLast);
+                    } else {
+                        // my quarter of the W tile -> the CTAs holding W half `half` in both pairs
+                        constexpr int kQRows = BLOCK_N / 4;
+                        const uint16_t mask = static_cast<uint16_t>((1u << half) | (1u << (half + 2)));
+                        tma_load_2d_pair_mcast(&tmap_w, &full_bar[stage], smem_b + stage * Cfg::kBBytes + pair * (kQRows * kBK * 2),
+                                               kb * kBK, row_w + static_cast<int>(pair) * kQRows, mask, kCacheHintEvictLast);
+                    }
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (pair leaders only) =====================
+        if (is_leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(H::kUmmaFormat, kPairM, BLOCK_N);
+            constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << kClusterCtas) - 1);
+            const uint16_t pair_mask = static_cast<uint16_t>(0x3u << leader_rank);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * kAccStride;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (!(p.dbg & 2)) mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t desc_a = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
+                    const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k)
+                        umma_f16_pair(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0);
+                    // frees the slot in EVERY CTA of the cluster (each of them writes into some of the buffers just read)
+                    if (!(p.dbg & 2)) umma_commit_pair(&empty_bar[stage], kAllCtas);
+                    if (kb == num_kb - 1) umma_commit_pair(&tmem_full_bar[acc], pair_mask);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+            // drain: the peer's last remote arrivals must have landed before this CTA may exit
+            if (it > 0) {
+                const int last = it - 1;
+                mbar_wait(&tmem_empty_bar[last & 1], (last >> 1) & 1);
+                if (it > 1) {
+                    const int prev = it - 2;
+                    mbar_wait(&tmem_empty_bar[prev & 1], (prev >> 1) & 1);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= kEpiWarp0) {
+        // ===================== epilogue (every CTA) =====================
+        const int e = warp - kEpiWarp0;
+        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        const int grp = e >> 2;   // epilogue group: handles column chunks grp, grp+2, ...
+        const bool grp_leader = (e & 3) == 0 && lane == 0;
+        const int bar_id = 1 + grp;
+        const int r = q * 32 + lane;  // row inside this CTA's 128-row half
+        uint8_t* stg_ptr = staging + grp * kStgBufs * kChunkBytes;
+        const uint32_t stg_base = smem_u32(stg_ptr);
+        uint64_t* my_res_bar = res_bar + grp * kStgBufs;
+        const uint32_t row_off = static_cast<uint32_t>(r) * 128;
+        const uint32_t rx = static_cast<uint32_t>(r & 7);
+        const int row_in_cluster = static_cast<int>(pair) * kPairM + static_cast<int>(half) * kBM;
+        const T* bias = static_cast<const T*>(p.bias);
+        uint32_t bufc = 0;  // chunks processed by this group so far (buffer = bufc % kStgBufs)
+
+        // (tile, chunk) -> the next chunk this group processes
+        auto advance = [&](int& tile, int& chunk) {
+            chunk += 2;
+            if (chunk >= Cfg::kChunks) {
+                chunk = grp;
+                tile += num_clusters;
+            }
+        };
+        auto issue_residual = [&](int tile, int chunk, uint32_t use) {  // group leader only
+            int mt2, nt2;
+            pair_tile_coords(tile, p, mt2, nt2);
+            const uint32_t b = use % kStgBufs;
+            mbar_arrive_expect_tx(&my_res_bar[b], kChunkBytes);
+            tma_load_2d(&tmap_r, &my_res_bar[b], stg_ptr + b * kChunkBytes, nt2 * BLOCK_N + chunk * kChunkN,
+                        mt2 * kClusterM + row_in_cluster, kCacheHintEvictFirst);
+        };
+        // residual prefetch, two chunks ahead: the first two chunks of this group
+        if constexpr (EPI == 3) {
+            if (grp_leader && !(p.dbg & 1)) {
+                int pt = cluster_id, pc = grp;
+                if (pt < num_tiles) issue_residual(pt, pc, 0);
+                advance(pt, pc);
+                if (pt < num_tiles) issue_residual(pt, pc, 1);
+            }
+            __syncwarp();
+        }
+
+        int it = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+            int mt, nt;
+            pair_tile_coords(t, p, mt, nt);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int row0 = mt * kClusterM + row_in_cluster;
+            if constexpr (EPI == 3) {
+                // pull the residual tiles this group will need two tiles from now into L2
+                if (grp_leader && p.pf_dist > 0) {
+                    const int ft = t + 2 * num_clusters;
+                    if (ft < num_tiles) {
+                        int fm, fn;
+                        pair_tile_coords(ft, p, fm, fn);
+                        for (int c = grp; c < Cfg::kChunks; c += 2)
+                            tma_prefetch_l2_2d(&tmap_r, fn * BLOCK_N + c * kChunkN, fm * kClusterM + row_in_cluster);
+                    }
+                }
+                __syncwarp();
+            }
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            if (p.dbg & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], leader_rank);
+                continue;
+            }
+
+#pragma unroll 1
+            for (int c = grp; c < Cfg::kChunks; c += 2) {
+                const bool last_of_tile = c + 2 >= Cfg::kChunks;
+                const uint32_t buf = bufc % kStgBufs;
+                const uint32_t stg = stg_base + buf * kChunkBytes;
+                if constexpr (EPI == 3) {
+                    mbar_wait(&my_res_bar[buf], (bufc / kStgBufs) & 1);
+                } else {
+                    // the store that last used this buffer (kStgBufs chunks ago) must have finished reading it
+                    if (grp_leader) tma_store_wait_read<kStgBufs - 1>();
+                    __syncwarp();
+                    named_bar_sync(bar_id, 128);
+                }
+                const int col0 = nt * BLOCK_N + c * kChunkN;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride + c * kChunkN + hf * 32;
+                    tmem_ld_32x32(taddr, v);
+                    uint4 bvec[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int col = col0 + hf * 32 + g * 8;
+                        bvec[g] = make_uint4(0, 0, 0, 0);
+                        if (bias != nullptr && col < p.N) bvec[g] = ldg128(bias + col);
+                    }
+                    tmem_ld_wait();
+                    if (last_of_tile && hf == 1) {
+                        // last TMEM read of this tile: hand the accumulator stage back to the MMA issuer early
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], leader_rank);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t saddr = stg + row_off + (((static_cast<uint32_t>(hf * 4 + g)) ^ rx) << 4);
+                        const uint32_t bw[4] = {bvec[g].x, bvec[g].y, bvec[g].z, bvec[g].w};
+                        uint32_t rw[4] = {0, 0, 0, 0};
+                        if constexpr (EPI == 3) {
+                            const uint4 rv = lds128(saddr);
+                            rw[0] = rv.x; rw[1] = rv.y; rw[2] = rv.z; rw[3] = rv.w;
+                        }
+                        uint32_t ow[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 b2 = H::unpack(bw[j]);
+                            float x0, x1;
+                            unpack_f2(add_f2(pack_f2(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])),
+                                             pack_f2(b2.x, b2.y)), x0, x1);
+                            if constexpr (EPI != 0) {
+                                const float2 xr = H::unpack(H::pack(x0, x1));  // linear output rounded to the storage type
+                                x0 = xr.x;
+                                x1 = xr.y;
+                            }
+                            if constexpr (EPI == 1) {
+                                gelu_pair_fast(x0, x1);
+                            } else if constexpr (EPI == 2) {
+                                x0 = quick_gelu(x0);
+                                x1 = quick_gelu(x1);
+                            } else if constexpr (EPI == 3) {
+                                const float2 r2 = H::unpack(rw[j]);
+                                x0 += r2.x;
+                                x1 += r2.y;
+                            }
+                            ow[j] = H::pack(x0, x1);
+                        }
+                        sts128(saddr, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+                    }
+                }
+                fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
+                named_bar_sync(bar_id, 128);
+                if (grp_leader) {
+                    if constexpr (EPI == kEpiResidualInPlace) tma_reduce_add_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, row0);
+                    else tma_store_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, row0);
+                    tma_store_commit();
+                    if constexpr (EPI == 3) {
+                        // prefetch the residual of the chunk two steps ahead into the buffer whose store was committed one
+                        // step ago (everything but the store just committed must have released its buffer)
+                        int pt = t, pc = c;
+                        advance(pt, pc);
+                        advance(pt, pc);
+                        if (pt < num_tiles) {
+                            tma_store_wait_read<1>();
+                            issue_residual(pt, pc, bufc + 2);
+                        }
+                    }
+                }
+                __syncwarp();
+                ++bufc;
+            }
+        }
+        if (grp_leader) tma_store_wait_all<0>();  // global writes complete before the CTA retires
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+template <typename T, int BLOCK_N, int EPI, int PAIRS>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr, const PairParams& p,
+                cudaStream_t stream) {
+    using Cfg = PairCfg<BLOCK_N, EPI == 3 ? 3 : 2>;
+    auto kern = gemm_pair_kernel<T, BLOCK_N, EPI, PAIRS>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    static int max_clusters = 0;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2 * PAIRS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (attr_err != cudaSuccess) return;
+        // how many clusters of this shape the device can hold at once (clusters of 4 do not tile all 148 SMs)
+        cfg.gridDim = dim3(num_sms() / (2 * PAIRS) * (2 * PAIRS));
+        int n = 0;
+        attr_err = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        max_clusters = n;
+    });
+    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "gemm_pair: kernel attribute / cluster occupancy query");
+    B2C_CHECK_ARG(max_clusters > 0, "gemm_pair: the device cannot co-schedule a cluster of %d CTAs", 2 * PAIRS);
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    cfg.gridDim = dim3(2 * PAIRS * clusters);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tw, tc, tr, p);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_pair_kernel)");
+    B2C_LAUNCH_CHECK("gemm_pair_kernel");
+    return 0;
+}
+
+template <typename T, int BLOCK_N, int PAIRS>
+int launch_pair_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr,
+                    const PairParams& p, cudaStream_t s) {
+    switch (epi) {
+        case 0: return launch_pair<T, BLOCK_N, 0, PAIRS>(ta, tw, tc, tr, p, s);
+        case 1: return launch_pair<T, BLOCK_N, 1, PAIRS>(ta, tw, tc, tr, p, s);
+        case 2: return launch_pair<T, BLOCK_N, 2, PAIRS>(ta, tw, tc, tr, p, s);
+        case 3: return launch_pair<T, BLOCK_N, 3, PAIRS>(ta, tw, tc, tr, p, s);
+        case kEpiResidualInPlace: return launch_pair<T, BLOCK_N, kEpiResidualInPlace, PAIRS>(ta, tw, tc, tr, p, s);
+    }
+    set_last_error("gemm_pair: unsupported epilogue %d", epi);
+    return -1;
+}
+
+template <typename T, int PAIRS>
+int launch_pair_bn(int bn, int epi, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr,
+                   const PairParams& p, cudaStream_t s) {
+    switch (bn) {
+        case 256: return launch_pair_epi<T, 256, PAIRS>(epi, ta, tw, tc, tr, p, s);
+        case 192: return launch_pair_epi<T, 192, PAIRS>(epi, ta, tw, tc, tr, p, s);
+        case 128: return launch_pair_epi<T, 128, PAIRS>(epi, ta, tw, tc, tr, p, s);
+    }
+    set_last_error("gemm_pair: BLOCK_N must be 128, 192 or 256 (got %d)", bn);
+    return -1;
+}
+
+// B200CLIP_GEMM_PAIRS=1|2 overrides the cluster shape (A/B measurements); default: single pairs
+int default_gemm_pairs(int M) {
+    static const int forced = [] {
+        const char* e = getenv("B200CLIP_GEMM_PAIRS");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    if (forced == 1 || forced == 2) return forced;
+    (void)M;
+    return 1;
+}
+
+// B200CLIP_NO_REDUCE_STORE=1: in-place residual GEMMs load the residual instead of using the TMA reduce-add store
+bool no_reduce_store() {
+    static const bool v = [] {
+        const char* e = getenv("B200CLIP_NO_REDUCE_STORE");
+        return e != nullptr && e[0] == '1';
+    }();
+    return v;
+}
+
+int gemm_debug_switches() {
+    static const int v = [] {
+        const char* e = getenv("B200CLIP_GEMM_DBG");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    return v;
+}
+
+// B200CLIP_PF_DIST=<K-blocks> overrides the L2 prefetch distance of the A operand (0 disables it)
+int l2_prefetch_distance() {
+    static const int v = [] {
+        const char* e = getenv("B200CLIP_PF_DIST");
+        const int d = e != nullptr ? atoi(e) : 0;
+        return d < 0 ? 0 : (d > 64 ? 64 : d);
+    }();
+    return v;
+}
+
+}  // namespace
+
+// Tile-shape choice: the persistent grid runs ceil(tiles / clusters) rounds; pick the N tile that minimises
+// rounds x tile cost (a 256-wide tile is the most efficient per MAC, narrower ones waste less of the last round).
+int pick_pair_block_n(int M, int N, int pairs) {
+    const int clusters = pairs == 2 ? 33 : num_sms() / 2;
+    const long mt = (M + pairs * kPairM - 1) / (pairs * kPairM);
+    double best_cost = 1e30;
+    int best = 256;
+    const int cands[3] = {256, 192, 128};
+    const double eff[3] = {1.0, 1.04, 1.10};
+    for (int i = 0; i < 3; ++i) {
+        const int bn = cands[i];
+        const long nt = (N + bn - 1) / bn;
+        const long tiles = mt * nt;
+        const long rounds = (tiles + clusters - 1) / clusters;
+        const double cost = static_cast<double>(rounds) * bn * eff[i];
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = bn;
+        }
+    }
+    return best;
+}
+
+// pairs: 1 = clusters of 2 CTAs, 2 = clusters of 4 with W multicast, 0 = choose
+int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
+              int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs,
+              cudaStream_t stream) {
+    B2C_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+    B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm_pair: unsupported epilogue %d", epilogue);
+    B2C_CHECK_ARG(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
+    B2C_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0,
+                  "gemm: K, lda, ldw, ldc must be multiples of 8 (16 B rows) K=%d lda=%lld ldw=%lld ldc=%lld", K,
+                  (long long)lda, (long long)ldw, (long long)ldc);
+    B2C_CHECK_ARG((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) % 16 == 0,
+                  "gemm: A, W, C must be 16-byte aligned");
+    B2C_CHECK_ARG(bias == nullptr || reinterpret_cast<uintptr_t>(bias) % 16 == 0, "gemm: bias must be 16-byte aligned");
+    if (epilogue == 3) {
+        B2C_CHECK_ARG(residual != nullptr && ldr % 8 == 0 && reinterpret_cast<uintptr_t>(residual) % 16 == 0,
+                      "gemm: residual epilogue needs an aligned residual pointer");
+    }
+    B2C_CHECK_ARG(pairs >= 0 && pairs <= 2, "gemm_pair: pairs must be 0, 1 or 2");
+    if (pairs == 0) pairs = default_gemm_pairs(M);
+    const int bn = force_block_n > 0 ? force_block_n : pick_pair_block_n(M, N, pairs);
+
+    CUtensorMap ta, tw, tc, tr;
+    if (make_tmap_2d(&ta, is_bf16, A, M, K, lda, kBM, kBK) != 0) return -1;
+    if (make_tmap_2d(&tw, is_bf16, W, N, K, ldw, pairs == 2 ? bn / 4 : bn / 2, kBK) != 0) return -1;
+    if (make_tmap_2d(&tc, is_bf16, C, M, N, ldc, kBM, kChunkN) != 0) return -1;
+    if (epilogue == 3 && residual == C && ldr == ldc && !no_reduce_store()) {
+        epilogue = kEpiResidualInPlace;
+        tr = tc;
+    } else if (epilogue == 3) {
+        if (make_tmap_2d(&tr, is_bf16, residual, M, N, ldr, kBM, kChunkN) != 0) return -1;
+    } else {
+        tr = tc;
+    }
+
+    PairParams p;
+    p.bias = bias;
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.m_tiles = (M + pairs * kPairM - 1) / (pairs * kPairM);
+    p.n_tiles = (N + bn - 1) / bn;
+    p.group_m = pairs == 2 ? 4 : 8;
+    p.pf_dist = l2_prefetch_distance();
+    p.dbg = gemm_debug_switches();
+    if (pairs == 2)
+        return is_bf16 ? launch_pair_bn<__nv_bfloat16, 2>(bn, epilogue, ta, tw, tc, tr, p, stream)
+                       : launch_pair_bn<__half, 2>(bn, epilogue, ta, tw, tc, tr, p, stream);
+    return is_bf16 ? launch_pair_bn<__nv_bfloat16, 1>(bn, epilogue, ta, tw, tc, tr, p, stream)
+                   : launch_pair_bn<__half, 1>(bn, epilogue, ta, tw, tc, tr, p, stream);
+}
+
+}  // namespace b200clip

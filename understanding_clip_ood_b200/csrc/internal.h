@@ -11,6 +11,10 @@ int gemm_tc(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw
             int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in, int g_out,
             int force_block_n, cudaStream_t stream);
 
+// CTA-pair (cta_group::2) variant with the TMA-store epilogue (gemm_pair.cu); epilogues 0..3
+int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
+              int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs, cudaStream_t stream);
+
 int gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* residual, int64_t ldr,
              float* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in, int g_out,
              cudaStream_t stream);

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -28,10 +29,47 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// Encoding a tensor map costs several microseconds of host time and the towers issue ~200 per forward with operands
+// (weights, workspace slices) that repeat from call to call: memoise by the full argument tuple.  The descriptor is a
+// pure function of the key, so a hit can never be stale.
+struct TmapKey {
+    const void* ptr;
+    uint64_t rows, cols, ld;
+    uint32_t box_rows, box_cols, is_bf16;
+    bool operator==(const TmapKey& o) const {
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols &&
+               is_bf16 == o.is_bf16;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+        auto mix = [&h](uint64_t v) { h = (h ^ v) * 0x9E3779B97F4A7C15ull; h ^= h >> 29; };
+        mix(k.rows); mix(k.cols); mix(k.ld); mix((uint64_t(k.box_rows) << 32) | (uint64_t(k.box_cols) << 1) | k.is_bf16);
+        return static_cast<size_t>(h);
+    }
+};
+constexpr size_t kTmapCacheMax = 8192;
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash>& tmap_cache() {
+    static auto* m = new std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash>();
+    return *m;
+}
+
 }  // namespace
 
 int make_tmap_2d(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                  uint32_t box_cols) {
+    const TmapKey key{ptr, rows, cols, ld, box_rows, box_cols, is_bf16 ? 1u : 0u};
+    {
+        std::lock_guard<std::mutex> lk(g_tmap_mu);
+        auto& c = tmap_cache();
+        auto it = c.find(key);
+        if (it != c.end()) {
+            *map = it->second;
+            return 0;
+        }
+    }
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) {
         set_last_error("cuTensorMapEncodeTiled not available from the driver");
@@ -48,6 +86,12 @@ int make_tmap_2d(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t rows,
         set_last_error("cuTensorMapEncodeTiled failed (CUresult %d) for ptr=%p rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r, ptr,
                        (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
         return -1;
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_tmap_mu);
+        auto& c = tmap_cache();
+        if (c.size() >= kTmapCacheMax) c.clear();
+        c.emplace(key, *map);
     }
     return 0;
 }
