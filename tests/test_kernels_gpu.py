@@ -194,7 +194,8 @@ def _attn_ref(qkv, B, Lq, H, causal):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
 @pytest.mark.parametrize("B,Lq,H,causal", [(3, 50, 12, False), (2, 77, 8, True), (2, 197, 12, False), (1, 257, 16, False),
-                                           (4, 16, 8, True), (2, 64, 2, True), (2, 130, 2, True)])
+                                           (4, 16, 8, True), (2, 64, 2, True), (2, 130, 2, True),
+                                           (700, 50, 12, False), (33, 7, 8, True), (5, 1, 8, False), (300, 33, 8, True)])
 def test_attention(dtype, B, Lq, H, causal):
     g = _gen(8)
     qkv = (torch.randn(B * Lq, 3 * H * 64, device=DEV, generator=g) * 1.5).to(dtype)

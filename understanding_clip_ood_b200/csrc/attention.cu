@@ -12,6 +12,10 @@
 // fp32 path (parity mode): SIMT, one warp per query row, fp32 everywhere.
 #include "common.cuh"
 #include "internal.h"
+#include "tmap.h"
+
+#include <cstdlib>
+#include <mutex>
 
 namespace b200clip {
 
@@ -225,6 +229,221 @@ attention_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int L, int 
     }
 }
 
+// ------------------------------- short-sequence fast path (L <= 64) -------------------------------
+// ViT-B/32 (L = 50) and EOT-truncated text run here.  One (batch, head) item fits a single 64 x 64 score tile, so the kernel
+// is a stream of small independent items and is bound by the qkv read / out write: persistent CTAs walk the items with a
+// 2-stage TMA ring (three CTAs per SM) (warp 4 = producer: three [L x 64] boxes per item straight out of the packed qkv matrix, 128B-swizzled;
+// warps 0-3 = consumers, 16 query rows each), so the loads of item i+1 are in flight while item i is computed, and the
+// output tile leaves through a TMA store (full 128-byte rows instead of 4-byte scatters).
+constexpr int kTileBytes = 64 * 128;
+constexpr int short_smem_bytes(int stages) { return stages * 3 * kTileBytes + 2 * kTileBytes + 128 + 1024; }
+
+// NKB = ceil(L / 8): number of 8-wide kv blocks that hold valid columns (compile-time so that every loop below unrolls
+// into straight-line code; a run-time bound made the compiler fall back to jump tables and local-memory arrays)
+template <typename T, bool CAUSAL, int NKB>
+__global__ void __launch_bounds__(160, 3)
+attention_short_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_out, int L, int heads,
+                       int items) {
+    using H = Half16<T>;
+    constexpr int kShortStages = 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;                                      // [stage][q|k|v][64 rows x 128 B]
+    uint8_t* obuf = smem + kShortStages * 3 * kTileBytes;      // [2][64 x 128 B]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(obuf + 2 * kTileBytes);
+    uint64_t* empty_bar = full_bar + kShortStages;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int W = heads * kHeadDim;
+
+    // rows [L, 64) of the tiles are never written by TMA: zero them once so masked lanes multiply finite values
+    for (int i = tid; i < (kShortStages * 3 + 2) * kTileBytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        for (int i = 0; i < kShortStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 4);
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&tmap_qkv);
+        tma_prefetch_desc(&tmap_out);
+    }
+    fence_proxy_async();  // the zero fill (generic proxy) is ordered before the TMA writes (async proxy)
+    __syncthreads();
+
+    const uint32_t tile_tx = static_cast<uint32_t>(L) * 128u;
+    if (warp == 4) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = blockIdx.x; it < items; it += gridDim.x) {
+                const int b = it / heads, h = it - b * heads;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full_bar[stage], 3 * tile_tx);
+                uint8_t* dst = ring + stage * 3 * kTileBytes;
+                tma_load_2d(&tmap_qkv, &full_bar[stage], dst, h * kHeadDim, b * L, kCacheHintEvictFirst);
+                tma_load_2d(&tmap_qkv, &full_bar[stage], dst + kTileBytes, W + h * kHeadDim, b * L, kCacheHintEvictFirst);
+                tma_load_2d(&tmap_qkv, &full_bar[stage], dst + 2 * kTileBytes, 2 * W + h * kHeadDim, b * L, kCacheHintEvictFirst);
+                if (++stage == kShortStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: warp w owns query rows [16w, 16w+16) ----
+    const float scale_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    const int qrow_a = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int row_lo = warp * 16 + (lane >> 2);
+    constexpr int nkb = NKB;             // 8-wide kv blocks that contain valid columns
+    constexpr int nkk = (NKB + 1) / 2;   // 16-deep kv steps of the P.V product
+    const bool warp_active = warp * 16 < L;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t oc = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++oc) {
+        const int b = it / heads, h = it - b * heads;
+        mbar_wait(&full_bar[stage], phase);
+        const uint32_t sq = smem_u32(ring + stage * 3 * kTileBytes);
+        const uint32_t sk = sq + kTileBytes, sv = sq + 2 * kTileBytes;
+        float o[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+        float inv0 = 0.f, inv1 = 0.f;
+        if (warp_active) {
+            uint32_t qf[4][4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) ldmatrix_x4(sq + swz(qrow_a, kk * 2 + (lane >> 4)), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+            float s[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+                for (int np = 0; np < 4; ++np) {
+                    if (np * 2 < nkb) {
+                        uint32_t b0, b1, b2, b3;
+                        const int krow = np * 16 + (lane & 7) + (lane >> 4) * 8;
+                        ldmatrix_x4(sk + swz(krow, kk * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+                        mma16816<T>(s[2 * np], qf[kk], b0, b1);
+                        if (np * 2 + 1 < nkb) mma16816<T>(s[2 * np + 1], qf[kk], b2, b3);
+                    }
+                }
+            }
+            // mask: only the last valid 8-wide block can contain columns >= L; the causal variant masks per element.
+            // Blocks >= nkb were never computed and are treated as -inf (probability 0) below.
+            if constexpr (CAUSAL) {
+#pragma unroll
+                for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = nb * 8 + (lane & 3) * 2 + (j & 1);
+                        const int row = row_lo + (j >> 1) * 8;
+                        if (col >= L || col > row) s[nb][j] = -INFINITY;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int nb = 0; nb < 8; ++nb) {
+                    if (nb == nkb - 1) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (nb * 8 + (lane & 3) * 2 + (j & 1) >= L) s[nb][j] = -INFINITY;
+                    }
+                }
+            }
+            float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                if (nb < nkb) {
+                    mx[0] = fmaxf(mx[0], fmaxf(s[nb][0], s[nb][1]));
+                    mx[1] = fmaxf(mx[1], fmaxf(s[nb][2], s[nb][3]));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+                mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            }
+            // p = 2^(s*c - max*c): one FFMA + one MUFU per element (column 0 is never masked, so max is finite)
+            const float nm0 = -mx[0] * scale_log2, nm1 = -mx[1] * scale_log2;
+            float rs[2] = {0.f, 0.f};
+            uint32_t pf[4][4];
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+                if (nb < nkb) {
+                    p0 = ex2_fast(fmaf(s[nb][0], scale_log2, nm0));
+                    p1 = ex2_fast(fmaf(s[nb][1], scale_log2, nm0));
+                    p2 = ex2_fast(fmaf(s[nb][2], scale_log2, nm1));
+                    p3 = ex2_fast(fmaf(s[nb][3], scale_log2, nm1));
+                    rs[0] += p0 + p1;
+                    rs[1] += p2 + p3;
+                }
+                pf[nb >> 1][(nb & 1) * 2 + 0] = H::pack(p0, p1);
+                pf[nb >> 1][(nb & 1) * 2 + 1] = H::pack(p2, p3);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+                rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+            }
+            inv0 = 1.f / rs[0];
+            inv1 = 1.f / rs[1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < nkk) {
+#pragma unroll
+                    for (int dp = 0; dp < 4; ++dp) {
+                        uint32_t b0, b1, b2, b3;
+                        const int vrow = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                        ldmatrix_x4_trans(sv + swz(vrow, dp * 2 + (lane >> 4)), b0, b1, b2, b3);
+                        mma16816<T>(o[2 * dp], pf[j], b0, b1);
+                        mma16816<T>(o[2 * dp + 1], pf[j], b2, b3);
+                    }
+                }
+            }
+        }
+        // all shared-memory reads of this stage are done: hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[stage]);
+        if (++stage == kShortStages) {
+            stage = 0;
+            phase ^= 1;
+        }
+
+        // ---- output tile: registers -> swizzled staging -> TMA store ----
+        const uint32_t ob = oc & 1;
+        if (tid == 0) tma_store_wait_read<1>();  // the store issued two items ago has released this buffer
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const uint32_t so = smem_u32(obuf + ob * kTileBytes);
+        if (warp_active) {
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+                const uint32_t off = static_cast<uint32_t>(lane & 3) * 4;
+                const uint32_t a0 = so + swz(row_lo, nb) + off;
+                const uint32_t a1 = so + swz(row_lo + 8, nb) + off;
+                const uint32_t w0 = H::pack(o[nb][0] * inv0, o[nb][1] * inv0);
+                const uint32_t w1 = H::pack(o[nb][2] * inv1, o[nb][3] * inv1);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(a0), "r"(w0) : "memory");
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(a1), "r"(w1) : "memory");
+            }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) {
+            tma_store_2d(&tmap_out, obuf + ob * kTileBytes, h * kHeadDim, b * L);
+            tma_store_commit();
+        }
+    }
+    if (tid == 0) tma_store_wait_all<0>();
+}
+
 // ------------------------------- fp32 parity path -------------------------------
 // One CTA per (batch, head); K and V of the head live in shared memory (row pitch 65 floats: conflict-free
 // for both the per-lane-row dot products and the per-lane-column P·V pass); one warp per query row.
@@ -286,6 +505,48 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
     }
 }
 
+template <typename T, bool CAUSAL, int NKB>
+int launch_short_one(int grid, const CUtensorMap& tq, const CUtensorMap& to, int L, int heads, int items, cudaStream_t stream) {
+    auto kern = attention_short_kernel<T, CAUSAL, NKB>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, short_smem_bytes(2)); });
+    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(attention_short smem)");
+    kern<<<grid, 160, short_smem_bytes(2), stream>>>(tq, to, L, heads, items);
+    return 0;
+}
+template <typename T, bool CAUSAL>
+int launch_short_nkb(int nkb, int grid, const CUtensorMap& tq, const CUtensorMap& to, int L, int heads, int items, cudaStream_t s) {
+    switch (nkb) {
+        case 1: return launch_short_one<T, CAUSAL, 1>(grid, tq, to, L, heads, items, s);
+        case 2: return launch_short_one<T, CAUSAL, 2>(grid, tq, to, L, heads, items, s);
+        case 3: return launch_short_one<T, CAUSAL, 3>(grid, tq, to, L, heads, items, s);
+        case 4: return launch_short_one<T, CAUSAL, 4>(grid, tq, to, L, heads, items, s);
+        case 5: return launch_short_one<T, CAUSAL, 5>(grid, tq, to, L, heads, items, s);
+        case 6: return launch_short_one<T, CAUSAL, 6>(grid, tq, to, L, heads, items, s);
+        case 7: return launch_short_one<T, CAUSAL, 7>(grid, tq, to, L, heads, items, s);
+        case 8: return launch_short_one<T, CAUSAL, 8>(grid, tq, to, L, heads, items, s);
+    }
+    set_last_error("attention: bad kv block count %d", nkb);
+    return -1;
+}
+int launch_short(bool is_bf16, bool causal, int nkb, int grid, const CUtensorMap& tq, const CUtensorMap& to, int L, int heads, int items,
+                 cudaStream_t s) {
+    if (is_bf16) return causal ? launch_short_nkb<__nv_bfloat16, true>(nkb, grid, tq, to, L, heads, items, s)
+                               : launch_short_nkb<__nv_bfloat16, false>(nkb, grid, tq, to, L, heads, items, s);
+    return causal ? launch_short_nkb<__half, true>(nkb, grid, tq, to, L, heads, items, s)
+                  : launch_short_nkb<__half, false>(nkb, grid, tq, to, L, heads, items, s);
+}
+
+// B200CLIP_ATTN_GENERIC=1 routes short sequences to the generic flash kernel too (A/B measurements)
+bool attention_force_generic() {
+    static const bool v = [] {
+        const char* e = getenv("B200CLIP_ATTN_GENERIC");
+        return e != nullptr && e[0] == '1';
+    }();
+    return v;
+}
+
 }  // namespace
 
 int attention(int dtype, const void* qkv, void* out, int batch, int seq_len, int heads, int causal, cudaStream_t stream) {
@@ -309,6 +570,19 @@ int attention(int dtype, const void* qkv, void* out, int batch, int seq_len, int
         return 0;
     }
     B2C_CHECK_ARG(bh <= 0x7fffffff, "attention: batch*heads too large");
+    if (seq_len <= 64 && (dtype == 1 || dtype == 2) && !attention_force_generic()) {
+        const int W = heads * kHeadDim;
+        const int64_t rows = static_cast<int64_t>(batch) * seq_len;
+        CUtensorMap tq, to;
+        if (make_tmap_2d(&tq, dtype == 1, qkv, rows, 3 * W, 3 * W, seq_len, kHeadDim) != 0) return -1;
+        if (make_tmap_2d(&to, dtype == 1, out, rows, W, W, seq_len, kHeadDim) != 0) return -1;
+        const int64_t max_ctas = 3 * static_cast<int64_t>(num_sms());
+        const int grid_s = static_cast<int>(bh < max_ctas ? bh : max_ctas);
+        const int rc = launch_short(dtype == 1, causal != 0, (seq_len + 7) / 8, grid_s, tq, to, seq_len, heads, static_cast<int>(bh), stream);
+        if (rc != 0) return rc;
+        B2C_LAUNCH_CHECK("attention_short_kernel");
+        return 0;
+    }
     dim3 grid(static_cast<unsigned>(bh), (seq_len + kBlockQ - 1) / kBlockQ);
     if (dtype == 1)
         attention_mma_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
