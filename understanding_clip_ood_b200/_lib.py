@@ -123,5 +123,15 @@ def require_cuda(*tensors) -> None:
             raise B200ClipError("b200clip kernels need CUDA tensors (no CPU fallback exists for this path)")
 
 
+_replayed_launches = 0
+
+
+def note_replayed(n: int) -> None:
+    """Kernels executed by replaying a captured CUDA graph (the C-side counter only sees them once, at capture)."""
+    global _replayed_launches
+    _replayed_launches += n
+
+
 def launch_count() -> int:
-    return int(load().b200clip_launch_count())
+    """Kernels of libb200clip.so launched by this process: direct launches + kernels inside replayed CUDA graphs."""
+    return int(load().b200clip_launch_count()) + _replayed_launches

@@ -545,7 +545,9 @@ int pick_pair_block_n(int M, int N, int pairs) {
     double best_cost = 1e30;
     int best = 256;
     const int cands[3] = {256, 192, 128};
-    const double eff[3] = {1.0, 1.04, 1.10};
+    // measured cost per MAC relative to the 256-wide tile (profiles/r1_gemm_variants_vs_cublas.txt): narrower tiles read
+    // more operand bytes per MAC through the shared-memory port that bounds the mainloop
+    const double eff[3] = {1.0, 1.18, 1.45};
     for (int i = 0; i < 3; ++i) {
         const int bn = cands[i];
         const long nt = (N + bn - 1) / bn;
