@@ -109,11 +109,22 @@ int b200clip_class_mean(int dtype, const void* txt_feat, void* prompt_feat, int 
  *   d_all_img, d_all_txt [N,D]: gradient through the gathered operands (reduce-scattered by the caller,
  *   as torch.distributed.nn.all_gather's backward does), d_scale: gradient of the logit scale.
  * Gradients are for `loss` with upstream gradient `grad_out` (device scalar, may be NULL = 1).
- * Any gradient pointer may be NULL (forward only when all are NULL).  workspace >= 2*n*N + 4*n floats. */
+ * Any gradient pointer may be NULL (forward only when all are NULL).  workspace >= 2*n*N + 8*n + 8 floats. */
 int b200clip_cliploss(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt,
                       const float* logit_scale, int rank, int n, int N, int D, float* loss, const float* grad_out,
                       float* d_img_loc, float* d_txt_loc, float* d_all_img, float* d_all_txt, float* d_scale,
                       float* workspace, void* stream);
+
+/* The same step split at the autograd boundary: `forward` writes the loss and leaves the raw logits and the per-row
+ * log-sum-exp in `workspace`; `backward` (same operands, same workspace, upstream gradient `grad_out` = device scalar or
+ * NULL for 1) turns them into the five gradients.  Two launches each; workspace as above. */
+int b200clip_cliploss_forward(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt,
+                              const float* logit_scale, int rank, int n, int N, int D, float* loss, float* workspace,
+                              void* stream);
+int b200clip_cliploss_backward(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt,
+                               const float* logit_scale, int rank, int n, int N, int D, const float* grad_out,
+                               float* d_img_loc, float* d_txt_loc, float* d_all_img, float* d_all_txt, float* d_scale,
+                               float* workspace, void* stream);
 
 /* ----- whole-tower drivers: one call per encode_image / encode_text ------------------------------ */
 

@@ -165,6 +165,18 @@ int b200clip_cliploss(const float* img_loc, const float* txt_loc, const float* a
                     d_all_txt, d_scale, workspace, S(stream));
 }
 
+int b200clip_cliploss_forward(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt,
+                              const float* logit_scale, int rank, int n, int N, int D, float* loss, float* workspace, void* stream) {
+    return cliploss_forward(img_loc, txt_loc, all_img, all_txt, logit_scale, rank, n, N, D, loss, workspace, S(stream));
+}
+
+int b200clip_cliploss_backward(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt,
+                               const float* logit_scale, int rank, int n, int N, int D, const float* grad_out, float* d_img_loc,
+                               float* d_txt_loc, float* d_all_img, float* d_all_txt, float* d_scale, float* workspace, void* stream) {
+    return cliploss_backward(img_loc, txt_loc, all_img, all_txt, logit_scale, rank, n, N, D, grad_out, d_img_loc, d_txt_loc, d_all_img,
+                             d_all_txt, d_scale, workspace, S(stream));
+}
+
 int64_t b200clip_workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {
     return workspace_bytes(cfg, batch, seq_len);
 }

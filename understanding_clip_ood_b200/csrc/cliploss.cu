@@ -3,20 +3,131 @@
 //   logits_per_image = s * img_loc @ all_txt^T          [n, N]
 //   logits_per_text  = s * txt_loc @ all_img^T          [n, N]
 //   labels_i = i + n * rank;   loss = (CE(logits_per_image) + CE(logits_per_text)) / 2
-// Round-1 structure: two fp32 logit GEMMs into a caller-provided workspace, one fused
-// softmax / cross-entropy / d-logits kernel (one CTA per logit row, the row is read once and
-// overwritten in place with s * dL/dlogit), a deterministic single-CTA reduction for the loss and
-// d(scale), and four fp32 GEMMs for the feature gradients.  world_size == 1 is the same code with
-// N == n and all_* == *_loc.
+// world_size == 1 is the same code with N == n and all_* == *_loc.
+//
+// The whole step is a few GFLOP on [256, 2048]-sized operands: it is bound by launch latency, not by any pipe.
+// So the structure is FOUR launches for forward + backward (the reference's eager path issues ~25):
+//   1. both logit blocks in one batched fp32 GEMM launch (64 x 64 tiles -> enough CTAs even at N = 256),
+//   2. row-wise log-sum-exp / cross-entropy, the loss reduction folded in through a last-CTA-done counter
+//      (deterministic: the last CTA sums the per-row terms in a fixed order),
+//   3. d(logits) in place (scaled by the upstream gradient read from device memory) + d(logit_scale), same fold,
+//   4. all four feature-gradient GEMMs in one batched launch.
+// fp32 FFMA with fp32 accumulation throughout: the loss / gradient parity gates are fp32 gates.
 #include "common.cuh"
 #include "internal.h"
 
 namespace b200clip {
 
-int gemm_f32_nt(bool ta, bool tb, const float* A, int64_t lda, const float* Bm, int64_t ldb, float* C, int64_t ldc, int M, int N,
-                int K, cudaStream_t stream);
-
 namespace {
+
+constexpr int kT = 64;    // output tile edge
+constexpr int kTK = 16;   // k step
+
+struct GemmProb {
+    const float* A;   // ta == 0: [M, K] (K contiguous);  ta == 1: stored [K, M]
+    const float* B;   // tb == 0: [N, K] (K contiguous);  tb == 1: stored [K, N]
+    float* C;         // [M, N]
+    int64_t lda, ldb, ldc;
+    int M, N, K, ta, tb;
+    int tiles_n, tile_begin;
+};
+struct GemmBatch {
+    GemmProb prob[4];
+    int count;
+};
+
+// stage a [kTK x 64] k-major tile of an operand stored with the contraction index contiguous ([rows, K]) ...
+__device__ __forceinline__ void stage_kc(float (*S)[kT + 4], const float* base, int64_t ld, int r0, int rows, int k0, int K, int tid) {
+    const int r = tid >> 2;
+    const int lk = (tid & 3) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 + r < rows && k0 + lk < K) a = *reinterpret_cast<const float4*>(base + static_cast<int64_t>(r0 + r) * ld + k0 + lk);
+    S[lk + 0][r] = a.x; S[lk + 1][r] = a.y; S[lk + 2][r] = a.z; S[lk + 3][r] = a.w;
+}
+// ... or with the output index contiguous ([K, rows])
+__device__ __forceinline__ void stage_mc(float (*S)[kT + 4], const float* base, int64_t ld, int r0, int rows, int k0, int K, int tid) {
+    const int k = tid >> 4;
+    const int r = (tid & 15) * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k0 + k < K && r0 + r < rows) a = *reinterpret_cast<const float4*>(base + static_cast<int64_t>(k0 + k) * ld + r0 + r);
+    *reinterpret_cast<float4*>(&S[k][r]) = a;
+}
+
+template <bool TA, bool TB>
+__device__ __forceinline__ void tile_gemm(const GemmProb& p, int m0, int n0, float (*As)[kT + 4], float (*Bs)[kT + 4]) {
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < p.K; k0 += kTK) {
+        if constexpr (TA) stage_mc(As, p.A, p.lda, m0, p.M, k0, p.K, tid);
+        else stage_kc(As, p.A, p.lda, m0, p.M, k0, p.K, tid);
+        if constexpr (TB) stage_mc(Bs, p.B, p.ldb, n0, p.N, k0, p.K, tid);
+        else stage_kc(Bs, p.B, p.ldb, n0, p.N, k0, p.K, tid);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kTK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = m0 + ty * 4 + i;
+        const int col = n0 + tx * 4;
+        if (row < p.M && col < p.N)  // N % 4 == 0 is checked on the host
+            *reinterpret_cast<float4*>(p.C + static_cast<int64_t>(row) * p.ldc + col) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+}
+
+__global__ void __launch_bounds__(256) batched_gemm_kernel(const GemmBatch batch) {
+    __shared__ __align__(16) float As[kTK][kT + 4];
+    __shared__ __align__(16) float Bs[kTK][kT + 4];
+    int pi = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (i < batch.count && static_cast<int>(blockIdx.x) >= batch.prob[i].tile_begin) pi = i;
+    const GemmProb& p = batch.prob[pi];
+    const int t = blockIdx.x - p.tile_begin;
+    const int m0 = (t / p.tiles_n) * kT, n0 = (t % p.tiles_n) * kT;
+    if (!p.ta && !p.tb) tile_gemm<false, false>(p, m0, n0, As, Bs);
+    else if (!p.ta && p.tb) tile_gemm<false, true>(p, m0, n0, As, Bs);
+    else if (p.ta && !p.tb) tile_gemm<true, false>(p, m0, n0, As, Bs);
+    else tile_gemm<true, true>(p, m0, n0, As, Bs);
+}
+
+int launch_batch(GemmBatch& b, cudaStream_t stream) {
+    int tiles = 0;
+    for (int i = 0; i < b.count; ++i) {
+        GemmProb& p = b.prob[i];
+        p.tiles_n = (p.N + kT - 1) / kT;
+        p.tile_begin = tiles;
+        tiles += p.tiles_n * ((p.M + kT - 1) / kT);
+    }
+    batched_gemm_kernel<<<tiles, 256, 0, stream>>>(b);
+    B2C_LAUNCH_CHECK("cliploss batched_gemm_kernel");
+    return 0;
+}
+
+GemmProb make_prob(const float* A, int64_t lda, bool ta, const float* B, int64_t ldb, bool tb, float* C, int64_t ldc, int M, int N, int K) {
+    GemmProb p;
+    p.A = A; p.B = B; p.C = C;
+    p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+    p.M = M; p.N = N; p.K = K;
+    p.ta = ta ? 1 : 0; p.tb = tb ? 1 : 0;
+    p.tiles_n = 0; p.tile_begin = 0;
+    return p;
+}
 
 __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -29,16 +140,45 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
     return r;
 }
 
-// rows [0,n): image->text logits; rows [n,2n): text->image logits.  `x` holds raw dot products.
+// True in exactly one CTA of the grid: the one that finishes last.  `counter` must be zero on entry and is reset to zero.
+__device__ __forceinline__ bool last_block_done(unsigned int* counter) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(counter, 1u);
+        is_last = prev == gridDim.x - 1;
+        if (is_last) *counter = 0u;
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+
+// workspace layout (floats): Li [n*N] | Lt [n*N] | row_loss [2n] | row_lse [2n] | row_ds [2n] | counter [4]
+struct Ws {
+    float *logits, *row_loss, *row_lse, *row_ds;
+    unsigned int* counter;
+};
+Ws carve(float* w, int n, int N) {
+    Ws s;
+    s.logits = w;
+    s.row_loss = w + 2 * static_cast<int64_t>(n) * N;
+    s.row_lse = s.row_loss + 2 * n;
+    s.row_ds = s.row_lse + 2 * n;
+    s.counter = reinterpret_cast<unsigned int*>(s.row_ds + 2 * n);
+    return s;
+}
+
+// rows [0,n): image->text logits; rows [n,2n): text->image logits.  `x` holds raw dot products (kept for the backward).
 __global__ void __launch_bounds__(256)
-ce_rows_kernel(float* __restrict__ x, const float* __restrict__ logit_scale, const float* __restrict__ grad_out, int n, int N,
-               int rank, int want_grad, float* __restrict__ row_loss, float* __restrict__ row_dscale) {
+ce_forward_kernel(const float* __restrict__ x, const float* __restrict__ logit_scale, int n, int N, int rank,
+                  float* __restrict__ row_loss, float* __restrict__ row_lse, unsigned int* counter, float* __restrict__ loss) {
     __shared__ float red[8];
     const int r = blockIdx.x;
-    float* xr = x + static_cast<int64_t>(r) * N;
+    const float* xr = x + static_cast<int64_t>(r) * N;
     const float s = *logit_scale;
     const int label = (r % n) + n * rank;
-
     float mx = -INFINITY;
     for (int j = threadIdx.x; j < N; j += blockDim.x) mx = fmaxf(mx, s * xr[j]);
     mx = block_reduce(mx, red, true);
@@ -46,11 +186,31 @@ ce_rows_kernel(float* __restrict__ x, const float* __restrict__ logit_scale, con
     for (int j = threadIdx.x; j < N; j += blockDim.x) sum += expf(s * xr[j] - mx);
     sum = block_reduce(sum, red, false);
     const float lse = mx + logf(sum);
-    if (threadIdx.x == 0) row_loss[r] = lse - s * xr[label];
-    if (!want_grad) return;
+    if (threadIdx.x == 0) {
+        row_lse[r] = lse;
+        row_loss[r] = lse - s * xr[label];
+    }
+    if (last_block_done(counter)) {
+        float a = 0.f;
+        for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) a += __ldcg(row_loss + i);
+        a = block_reduce(a, red, false);
+        if (threadIdx.x == 0) *loss = a / (2.f * static_cast<float>(n));
+    }
+}
+
+// x[r, j] <- s * dL/dlogit[r, j] in place;  d_scale = sum_rj dL/dlogit * raw (folded in like the loss)
+__global__ void __launch_bounds__(256)
+ce_backward_kernel(float* __restrict__ x, const float* __restrict__ logit_scale, const float* __restrict__ grad_out, int n, int N,
+                   int rank, const float* __restrict__ row_lse, float* __restrict__ row_ds, unsigned int* counter,
+                   float* __restrict__ d_scale) {
+    __shared__ float red[8];
+    const int r = blockIdx.x;
+    float* xr = x + static_cast<int64_t>(r) * N;
+    const float s = *logit_scale;
+    const int label = (r % n) + n * rank;
+    const float lse = row_lse[r];
     const float g = (grad_out != nullptr ? *grad_out : 1.f) / (2.f * static_cast<float>(n));
     float ds = 0.f;
-    __syncthreads();  // row_loss read of xr[label] happens before the in-place overwrite below
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
         const float raw = xr[j];
         const float p = expf(s * raw - lse);
@@ -59,56 +219,75 @@ ce_rows_kernel(float* __restrict__ x, const float* __restrict__ logit_scale, con
         xr[j] = s * dl;
     }
     ds = block_reduce(ds, red, false);
-    if (threadIdx.x == 0) row_dscale[r] = ds;
+    if (threadIdx.x == 0) row_ds[r] = ds;
+    if (last_block_done(counter)) {
+        float b = 0.f;
+        for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) b += __ldcg(row_ds + i);
+        b = block_reduce(b, red, false);
+        if (threadIdx.x == 0 && d_scale != nullptr) *d_scale = b;
+    }
 }
 
-__global__ void __launch_bounds__(256)
-loss_finalize_kernel(const float* __restrict__ row_loss, const float* __restrict__ row_dscale, int rows, float inv_rows,
-                     float* __restrict__ loss, float* __restrict__ d_scale) {
-    __shared__ float red[8];
-    float a = 0.f, b = 0.f;
-    for (int i = threadIdx.x; i < rows; i += blockDim.x) {
-        a += row_loss[i];
-        if (d_scale != nullptr) b += row_dscale[i];
-    }
-    a = block_reduce(a, red, false);
-    b = block_reduce(b, red, false);
-    if (threadIdx.x == 0) {
-        *loss = a * inv_rows;
-        if (d_scale != nullptr) *d_scale = b;
-    }
+int check_shapes(int rank, int n, int N, int D) {
+    B2C_CHECK_ARG(n > 0 && N >= n && D > 0 && N % n == 0, "cliploss: bad shape n=%d N=%d D=%d", n, N, D);
+    B2C_CHECK_ARG(rank >= 0 && (rank + 1) * n <= N, "cliploss: rank %d out of range for n=%d N=%d", rank, n, N);
+    B2C_CHECK_ARG(n % 4 == 0 && D % 4 == 0, "cliploss: n and D must be multiples of 4");
+    return 0;
 }
 
 }  // namespace
 
+int cliploss_forward(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt, const float* logit_scale,
+                     int rank, int n, int N, int D, float* loss, float* workspace, cudaStream_t stream) {
+    int rc;
+    if ((rc = check_shapes(rank, n, N, D)) != 0) return rc;
+    B2C_CHECK_ARG(img_loc && txt_loc && all_img && all_txt && logit_scale && loss && workspace, "cliploss: null pointer");
+    const Ws ws = carve(workspace, n, N);
+    B2C_CUDA(cudaMemsetAsync(ws.counter, 0, 16, stream));  // last-CTA-done counter (each kernel leaves it at zero again)
+    GemmBatch b;
+    b.count = 2;
+    b.prob[0] = make_prob(img_loc, D, false, all_txt, D, false, ws.logits, N, n, N, D);
+    b.prob[1] = make_prob(txt_loc, D, false, all_img, D, false, ws.logits + static_cast<int64_t>(n) * N, N, n, N, D);
+    if ((rc = launch_batch(b, stream)) != 0) return rc;
+    ce_forward_kernel<<<2 * n, 256, 0, stream>>>(ws.logits, logit_scale, n, N, rank, ws.row_loss, ws.row_lse, ws.counter, loss);
+    B2C_LAUNCH_CHECK("ce_forward_kernel");
+    return 0;
+}
+
+int cliploss_backward(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt, const float* logit_scale,
+                      int rank, int n, int N, int D, const float* grad_out, float* d_img_loc, float* d_txt_loc, float* d_all_img,
+                      float* d_all_txt, float* d_scale, float* workspace, cudaStream_t stream) {
+    int rc;
+    if ((rc = check_shapes(rank, n, N, D)) != 0) return rc;
+    B2C_CHECK_ARG(img_loc && txt_loc && all_img && all_txt && logit_scale && workspace, "cliploss: null pointer");
+    const Ws ws = carve(workspace, n, N);
+    ce_backward_kernel<<<2 * n, 256, 0, stream>>>(ws.logits, logit_scale, grad_out, n, N, rank, ws.row_lse, ws.row_ds, ws.counter, d_scale);
+    B2C_LAUNCH_CHECK("ce_backward_kernel");
+    // the workspace now holds s * dL/dlogits
+    float* Li = ws.logits;
+    float* Lt = ws.logits + static_cast<int64_t>(n) * N;
+    GemmBatch b;
+    b.count = 0;
+    if (d_img_loc) b.prob[b.count++] = make_prob(Li, N, false, all_txt, D, true, d_img_loc, D, n, D, N);
+    if (d_txt_loc) b.prob[b.count++] = make_prob(Lt, N, false, all_img, D, true, d_txt_loc, D, n, D, N);
+    if (d_all_txt) b.prob[b.count++] = make_prob(Li, N, true, img_loc, D, true, d_all_txt, D, N, D, n);
+    if (d_all_img) b.prob[b.count++] = make_prob(Lt, N, true, txt_loc, D, true, d_all_img, D, N, D, n);
+    if (b.count > 0 && (rc = launch_batch(b, stream)) != 0) return rc;
+    return 0;
+}
+
+// fused forward + backward (one call; used when the upstream gradient is already known or 1)
 int cliploss(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt, const float* logit_scale,
              int rank, int n, int N, int D, float* loss, const float* grad_out, float* d_img_loc, float* d_txt_loc,
              float* d_all_img, float* d_all_txt, float* d_scale, float* workspace, cudaStream_t stream) {
-    B2C_CHECK_ARG(n > 0 && N >= n && D > 0 && N % n == 0, "cliploss: bad shape n=%d N=%d D=%d", n, N, D);
-    B2C_CHECK_ARG(rank >= 0 && (rank + 1) * n <= N, "cliploss: rank %d out of range for n=%d N=%d", rank, n, N);
-    B2C_CHECK_ARG(n % 4 == 0 && D % 4 == 0, "cliploss: n and D must be multiples of 4");
-    B2C_CHECK_ARG(img_loc && txt_loc && all_img && all_txt && logit_scale && loss && workspace, "cliploss: null pointer");
-    const bool want_grad = d_img_loc || d_txt_loc || d_all_img || d_all_txt || d_scale;
-    float* Li = workspace;
-    float* Lt = workspace + static_cast<int64_t>(n) * N;
-    float* row_loss = Lt + static_cast<int64_t>(n) * N;
-    float* row_ds = row_loss + 2 * n;
-
     int rc;
-    if ((rc = gemm_f32_nt(false, false, img_loc, D, all_txt, D, Li, N, n, N, D, stream)) != 0) return rc;
-    if ((rc = gemm_f32_nt(false, false, txt_loc, D, all_img, D, Lt, N, n, N, D, stream)) != 0) return rc;
-    ce_rows_kernel<<<2 * n, 256, 0, stream>>>(workspace, logit_scale, grad_out, n, N, rank, want_grad ? 1 : 0, row_loss, row_ds);
-    B2C_LAUNCH_CHECK("ce_rows_kernel");
-    loss_finalize_kernel<<<1, 256, 0, stream>>>(row_loss, row_ds, 2 * n, 1.f / (2.f * static_cast<float>(n)), loss,
-                                                want_grad ? d_scale : nullptr);
-    B2C_LAUNCH_CHECK("loss_finalize_kernel");
+    B2C_CHECK_ARG(workspace != nullptr, "cliploss: null workspace");
+    if ((rc = check_shapes(rank, n, N, D)) != 0) return rc;
+    if ((rc = cliploss_forward(img_loc, txt_loc, all_img, all_txt, logit_scale, rank, n, N, D, loss, workspace, stream)) != 0) return rc;
+    const bool want_grad = d_img_loc || d_txt_loc || d_all_img || d_all_txt || d_scale;
     if (!want_grad) return 0;
-    // workspace now holds s * dL/dlogits
-    if (d_img_loc && (rc = gemm_f32_nt(false, true, Li, N, all_txt, D, d_img_loc, D, n, D, N, stream)) != 0) return rc;
-    if (d_all_txt && (rc = gemm_f32_nt(true, true, Li, N, img_loc, D, d_all_txt, D, N, D, n, stream)) != 0) return rc;
-    if (d_txt_loc && (rc = gemm_f32_nt(false, true, Lt, N, all_img, D, d_txt_loc, D, n, D, N, stream)) != 0) return rc;
-    if (d_all_img && (rc = gemm_f32_nt(true, true, Lt, N, txt_loc, D, d_all_img, D, N, D, n, stream)) != 0) return rc;
-    return 0;
+    return cliploss_backward(img_loc, txt_loc, all_img, all_txt, logit_scale, rank, n, N, D, grad_out, d_img_loc, d_txt_loc, d_all_img,
+                             d_all_txt, d_scale, workspace, stream);
 }
 
 }  // namespace b200clip

@@ -49,6 +49,13 @@ int cliploss(const float* img_loc, const float* txt_loc, const float* all_img, c
              int rank, int n, int N, int D, float* loss, const float* grad_out, float* d_img_loc, float* d_txt_loc,
              float* d_all_img, float* d_all_txt, float* d_scale, float* workspace, cudaStream_t stream);
 
+// split form of `cliploss`: forward leaves the raw logits + per-row log-sum-exp in the workspace for the backward
+int cliploss_forward(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt, const float* logit_scale,
+                     int rank, int n, int N, int D, float* loss, float* workspace, cudaStream_t stream);
+int cliploss_backward(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt, const float* logit_scale,
+                      int rank, int n, int N, int D, const float* grad_out, float* d_img_loc, float* d_txt_loc, float* d_all_img,
+                      float* d_all_txt, float* d_scale, float* workspace, cudaStream_t stream);
+
 inline int dtype_size(int dtype) { return dtype == 0 ? 4 : 2; }
 
 }  // namespace b200clip

@@ -82,32 +82,43 @@ def gather_features(image_features, text_features, local_loss=False, gather_with
     return gathered[:, :D], gathered[:, D:]
 
 
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
 class _FusedClipLoss(torch.autograd.Function):
-    """loss (+ all five gradients) from one C-ABI call; backward only rescales by the upstream gradient."""
+    """forward = `b200clip_cliploss_forward` (2 launches; keeps raw logits + row log-sum-exp in a workspace),
+    backward = `b200clip_cliploss_backward` (2 launches; reads the upstream gradient from device memory)."""
 
     @staticmethod
     def forward(ctx, img_loc, txt_loc, all_img, all_txt, logit_scale, rank: int):
-        needs = [t.requires_grad for t in (img_loc, txt_loc, all_img, all_txt, logit_scale)]
-        f32 = [t.detach().float().contiguous() for t in (img_loc, txt_loc, all_img, all_txt)]
-        scale = logit_scale.detach().float().reshape(()).contiguous()
-        loss, grads = ops.cliploss_fwd_bwd(*f32, scale, rank, want_grad=any(needs))
+        ops_f32 = [_f32c(t) for t in (img_loc, txt_loc, all_img, all_txt)]
+        scale = _f32c(logit_scale).reshape(())
+        loss, ws = ops.cliploss_forward(*ops_f32, scale, rank)
+        ctx.rank = rank
         ctx.dtypes = [t.dtype for t in (img_loc, txt_loc, all_img, all_txt, logit_scale)]
         ctx.scale_shape = logit_scale.shape
-        ctx.save_for_backward(*(grads if grads is not None else ()))
+        ctx.save_for_backward(*ops_f32, scale, ws)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        grads = ctx.saved_tensors
-        if not grads:
+        *ops_f32, scale, ws = ctx.saved_tensors
+        needs = list(ctx.needs_input_grad[:5])
+        if not any(needs):
             return (None,) * 6
+        grads = ops.cliploss_backward(*ops_f32, scale, ctx.rank, ws, _f32c(g).reshape(()), needs)
         out = []
         for i, (gr, dt) in enumerate(zip(grads, ctx.dtypes)):
-            if not ctx.needs_input_grad[i]:
+            if gr is None:
                 out.append(None)
                 continue
-            gi = (gr * g).to(dt)
-            out.append(gi.reshape(ctx.scale_shape) if i == 4 else gi)
+            if gr.dtype != dt:
+                gr = gr.to(dt)
+            out.append(gr.reshape(ctx.scale_shape) if i == 4 else gr)
         return (*out, None)
 
 

@@ -145,6 +145,36 @@ def class_mean(txt_feat: torch.Tensor, classes: int, templates: int) -> torch.Te
     return out
 
 
+def cliploss_workspace_floats(n: int, N: int) -> int:
+    return 2 * n * N + 8 * n + 8
+
+
+def cliploss_forward(img_loc, txt_loc, all_img, all_txt, logit_scale, rank: int):
+    """fp32, contiguous CUDA operands (checked by the caller).  -> (loss 0-dim, workspace) ; see b200clip_cliploss_forward."""
+    n, D = img_loc.shape
+    N = all_img.shape[0]
+    loss = torch.empty((), dtype=torch.float32, device=img_loc.device)
+    ws = torch.empty((cliploss_workspace_floats(n, N),), dtype=torch.float32, device=img_loc.device)
+    rc = L.load().b200clip_cliploss_forward(img_loc.data_ptr(), txt_loc.data_ptr(), all_img.data_ptr(), all_txt.data_ptr(),
+                                            logit_scale.data_ptr(), rank, n, N, D, loss.data_ptr(), ws.data_ptr(), L.stream_ptr())
+    L.check(rc, "b200clip_cliploss_forward")
+    return loss, ws
+
+
+def cliploss_backward(img_loc, txt_loc, all_img, all_txt, logit_scale, rank: int, ws, grad_out, needs):
+    """-> [d_img_loc, d_txt_loc, d_all_img, d_all_txt, d_scale] (None where `needs[i]` is False)."""
+    n, D = img_loc.shape
+    N = all_img.shape[0]
+    dev = img_loc.device
+    shapes = ((n, D), (n, D), (N, D), (N, D), ())
+    grads = [torch.empty(sh, dtype=torch.float32, device=dev) if need else None for sh, need in zip(shapes, needs)]
+    rc = L.load().b200clip_cliploss_backward(img_loc.data_ptr(), txt_loc.data_ptr(), all_img.data_ptr(), all_txt.data_ptr(),
+                                             logit_scale.data_ptr(), rank, n, N, D, L.ptr(grad_out), L.ptr(grads[0]), L.ptr(grads[1]),
+                                             L.ptr(grads[2]), L.ptr(grads[3]), L.ptr(grads[4]), ws.data_ptr(), L.stream_ptr())
+    L.check(rc, "b200clip_cliploss_backward")
+    return grads
+
+
 def cliploss_fwd_bwd(img_loc: torch.Tensor, txt_loc: torch.Tensor, all_img: torch.Tensor, all_txt: torch.Tensor,
                      logit_scale: torch.Tensor, rank: int, *, want_grad: bool = True, grad_out: torch.Tensor | None = None):
     """fp32 features.  -> loss (0-dim), (d_img_loc, d_txt_loc, d_all_img, d_all_txt, d_scale) or None."""
@@ -157,7 +187,7 @@ def cliploss_fwd_bwd(img_loc: torch.Tensor, txt_loc: torch.Tensor, all_img: torc
     N = all_img.shape[0]
     dev = img_loc.device
     loss = torch.empty((), dtype=torch.float32, device=dev)
-    ws = torch.empty((2 * n * N + 4 * n,), dtype=torch.float32, device=dev)
+    ws = torch.empty((cliploss_workspace_floats(n, N),), dtype=torch.float32, device=dev)
     grads = None
     if want_grad:
         grads = (torch.empty_like(img_loc), torch.empty_like(txt_loc), torch.empty_like(all_img), torch.empty_like(all_txt),
