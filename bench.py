@@ -190,22 +190,25 @@ def workload_config(n_gpus: int, extra: dict | None = None) -> dict:
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
 def time_gemm_roofline(ops, L, peaks) -> dict:
-    """Dominant kernel timed alone with CUDA events on the launching stream: the c_fc GEMM (+bias+GELU epilogue) of one
-    layer at the benchmark's token count (M = 1024*50).  Operands (78 MB in, 314 MB out) exceed the L2."""
+    """Dominant kernel timed alone with CUDA events on the launching stream: the c_fc GEMM of one layer at the benchmark's
+    token count (M = 1024*50) exactly as the tower runs it — LayerNorm folded into the epilogue (+bias +GELU), fed by the
+    un-normalised residual stream.  Operands (78 MB in, 314 MB out) exceed the L2."""
     M, N, K = BATCH * 50, 3072, 768
     g = torch.Generator(device="cuda").manual_seed(7)
-    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    x = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
     w = (torch.randn(N, K, device="cuda", generator=g) * 0.04).bfloat16()
     b = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
+    wf, colsum, bf = ops.fold_layernorm(w, b, torch.ones(K, device="cuda"), torch.zeros(K, device="cuda"), torch.bfloat16)
+    stats = ops.row_stats(x)
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     for _ in range(3):
-        ops.gemm(a, w, b, epilogue=L.EPI_GELU, out=out)
+        ops.gemm_ln(x, wf, colsum, bf, stats, epilogue=L.EPI_GELU, out=out)
     iters = 20
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for _ in range(iters):
-        ops.gemm(a, w, b, epilogue=L.EPI_GELU, out=out)
+        ops.gemm_ln(x, wf, colsum, bf, stats, epilogue=L.EPI_GELU, out=out)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
@@ -214,10 +217,10 @@ def time_gemm_roofline(ops, L, peaks) -> dict:
     traffic = None
     tp = ROOT / "profiles" / "roofline_traffic.json"
     if tp.exists():
-        traffic = json.loads(tp.read_text()).get("gemm_tc_cfc_bytes_per_launch")
+        traffic = json.loads(tp.read_text()).get("gemm_pair_cfc_bytes_per_launch")
     return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
             "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
-            "kernel": f"gemm_tc_kernel<bf16, EPI_GELU> M={M} N={N} K={K} (mlp.c_fc of one layer at batch {BATCH})",
+            "kernel": f"gemm_pair_kernel<bf16, 256, LN-fold+GELU> M={M} N={N} K={K} (ln_2 + mlp.c_fc + GELU of one layer at batch {BATCH})",
             "ms_per_launch": ms, "flops_per_launch": flops, "peak_source": f"{peaks['source']} burst bf16 GEMM (MEASURED_PEAKS.json)"}
 
 

@@ -54,6 +54,18 @@ int b200clip_gemm(int dtype, const void* A, int64_t lda, const void* W, int64_t 
                   const void* residual, int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue,
                   const float* pos, int g_in, int g_out, void* stream);
 
+/* LayerNorm folded into the following GEMM (16-bit dtypes): C = act(LN(x) W^T + b) computed WITHOUT materialising LN(x):
+ *   C[m,n] = act( rstd_m * (x W'^T)[m,n] - rstd_m * mean_m * colsum[n] + bias_f32[n] )
+ * with W' = W diag(gamma) in `dtype`, colsum[n] = sum_k W'[n,k] and bias_f32 = b + W beta (both fp32, prepared once by
+ * the caller) and rowstats[m] = (mean_m, rstd_m) from b200clip_row_stats.  `epilogue` is EPI_BIAS / EPI_GELU / EPI_QUICKGELU.
+ * Replaces ln_1 + in_proj and ln_2 + c_fc (+ activation) of ResidualAttentionBlock (transformer.py:253-264). */
+int b200clip_gemm_ln(int dtype, const void* x, int64_t ldx, const void* Wf, int64_t ldw, const float* colsum,
+                     const float* bias_f32, const float* rowstats, void* C, int64_t ldc, int M, int N, int K, int epilogue,
+                     void* stream);
+
+/* stats[r] = (mean, rstd = 1/sqrt(var + eps)) of row r of x, fp32 pairs (biased variance, like F.layer_norm). */
+int b200clip_row_stats(int dtype, const void* x, int64_t ldx, float* stats, int rows, int width, float eps, void* stream);
+
 /* y[r,:] = LayerNorm(x[row_index(r),:]) * gamma + beta, fp32 statistics, eps as given (1e-5).
  * `row_stride_rows` > 0 selects every row_stride_rows-th row starting at row_offset (CLS pooling:
  * stride L, offset 0); `row_idx` (int32, may be NULL) adds a per-output-row offset (EOT pooling).
@@ -141,6 +153,7 @@ typedef struct b200clip_tower_cfg {
     int32_t patch_size;  /* vision only */
     int32_t patch_kpad;  /* vision only: 3*P*P rounded up to a multiple of 64 */
     int32_t vocab_size;  /* text only */
+    int32_t fold_ln;     /* 16-bit dtypes: run ln_1 / ln_2 folded into the QKV / c_fc GEMMs (needs the *_f weights below) */
 } b200clip_tower_cfg;
 
 /* per-layer weights, all device pointers.  16-bit modes: matrices/biases in `dtype`, LN params fp32. */
@@ -150,6 +163,9 @@ typedef struct b200clip_block_weights {
     const void *out_proj_w, *out_proj_b; /* [W,W],  [W]  */
     const void *fc_w, *fc_b;             /* [4W,W], [4W] */
     const void *proj_w, *proj_b;         /* [W,4W], [W]  */
+    /* LN-fold operands (cfg.fold_ln; may be NULL otherwise): W diag(gamma) in dtype, its row sums and b + W beta in fp32 */
+    const void* in_proj_wf;  const float *in_proj_c, *in_proj_bf;   /* [3W,W], [3W], [3W] */
+    const void* fc_wf;       const float *fc_c, *fc_bf;             /* [4W,W], [4W], [4W] */
 } b200clip_block_weights;
 
 typedef struct b200clip_vit_weights {

@@ -181,6 +181,35 @@ def test_normalize(dtype):
     assert out[5].abs().sum().item() == 0
 
 
+# ------------------------------------------------------------------ LN folded into the GEMM -----------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K,epi", [(6400, 2304, 768, L.EPI_BIAS), (6400, 3072, 768, L.EPI_GELU), (1000, 1536, 512, L.EPI_QUICKGELU),
+                                       (77, 264, 72, L.EPI_BIAS), (51200, 768, 768, L.EPI_GELU)])
+def test_gemm_with_folded_layernorm(dtype, M, N, K, epi):
+    """act(LN(x) W^T + b) through row_stats + gemm_ln vs fp32 torch on the same (16-bit) operands."""
+    g = _gen(21)
+    x = (torch.randn(M, K, device=DEV, generator=g) * 1.7 + 0.3).to(dtype)
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.05).to(dtype)
+    b = (torch.randn(N, device=DEV, generator=g) * 0.1).to(dtype)
+    gamma = 1.0 + 0.2 * torch.randn(K, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(K, device=DEV, generator=g)
+    stats = ops.row_stats(x)
+    xf = x.float()
+    mean = xf.mean(dim=1)
+    rstd = torch.rsqrt(xf.var(dim=1, unbiased=False) + 1e-5)
+    assert torch.allclose(stats[:, 0], mean, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(stats[:, 1], rstd, atol=1e-6, rtol=1e-5)
+    wf, colsum, bf = ops.fold_layernorm(w, b, gamma, beta, dtype)
+    out = ops.gemm_ln(x, wf, colsum, bf, stats, epilogue=epi)
+    ref = torch.nn.functional.layer_norm(xf, (K,), gamma, beta, 1e-5) @ w.float().t() + b.float()
+    if epi == L.EPI_GELU:
+        ref = torch.nn.functional.gelu(ref)
+    elif epi == L.EPI_QUICKGELU:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < (1e-2 if dtype == torch.bfloat16 else 3e-3)
+
+
 # ------------------------------------------------------------------ attention ------------------------
 def _attn_ref(qkv, B, Lq, H, causal):
     W = H * 64

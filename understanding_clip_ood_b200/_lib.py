@@ -26,13 +26,13 @@ class B200ClipError(RuntimeError):
 class TowerCfg(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "dtype", "width", "layers", "heads", "mlp_width", "embed_dim", "seq_len", "quick_gelu",
-        "image_size", "patch_size", "patch_kpad", "vocab_size")]
+        "image_size", "patch_size", "patch_kpad", "vocab_size", "fold_ln")]
 
 
 class BlockWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "ln1_g", "ln1_b", "ln2_g", "ln2_b", "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b",
-        "fc_w", "fc_b", "proj_w", "proj_b")]
+        "fc_w", "fc_b", "proj_w", "proj_b", "in_proj_wf", "in_proj_c", "in_proj_bf", "fc_wf", "fc_c", "fc_bf")]
 
 
 class VitWeights(C.Structure):
@@ -54,6 +54,8 @@ SIGNATURES = {
     "b200clip_last_error": (C.c_char_p, []),
     "b200clip_launch_count": (C.c_uint64, []),
     "b200clip_gemm": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "b200clip_gemm_ln": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "b200clip_row_stats": (C.c_int, [_I, _P, _L, _P, _I, _I, _F, _P]),
     "b200clip_layernorm": (C.c_int, [_I, _P, _L, _P, _P, _P, _L, _I, _I, _F, _I, _P, _P]),
     "b200clip_attention": (C.c_int, [_I, _P, _P, _I, _I, _I, _I, _P]),
     "b200clip_patchify": (C.c_int, [_I, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P]),

@@ -113,6 +113,20 @@ int b200clip_gemm_tile(int dtype, const void* A, int64_t lda, const void* W, int
                    S(stream));
 }
 
+int b200clip_gemm_ln(int dtype, const void* x, int64_t ldx, const void* Wf, int64_t ldw, const float* colsum, const float* bias_f32,
+                     const float* rowstats, void* C, int64_t ldc, int M, int N, int K, int epilogue, void* stream) {
+    B2C_CHECK_ARG(x && Wf && colsum && bias_f32 && rowstats && C, "gemm_ln: null pointer");
+    B2C_CHECK_ARG(dtype == B200CLIP_BF16 || dtype == B200CLIP_F16, "gemm_ln: 16-bit dtypes only (the fp32 mode keeps the LayerNorm kernel)");
+    B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 2, "gemm_ln: epilogue must be BIAS, GELU or QUICKGELU");
+    return gemm_pair(dtype == B200CLIP_BF16, x, ldx, Wf, ldw, bias_f32, nullptr, 0, C, ldc, M, N, K, epilogue, 0, 0, S(stream), colsum,
+                     rowstats);
+}
+
+int b200clip_row_stats(int dtype, const void* x, int64_t ldx, float* stats, int rows, int width, float eps, void* stream) {
+    B2C_CHECK_ARG(x && stats, "row_stats: null pointer");
+    return row_stats(dtype, x, ldx, stats, rows, width, eps, S(stream));
+}
+
 int b200clip_layernorm(int dtype, const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
                        int rows, int width, float eps, int row_stride_rows, const int32_t* row_idx, void* stream) {
     B2C_CHECK_ARG(x && gamma && beta && y, "layernorm: null pointer");

@@ -40,9 +40,16 @@ constexpr int kChunkBytes = kBM * kChunkN * 2;
 // EPI values beyond the public ones: 5 = residual that aliases C (x += A W^T + b): the add is done by the L2 through a TMA
 // reduce-add store, so the residual never travels to the SM (no load, no shared-memory pass)
 constexpr int kEpiResidualInPlace = 5;
+// 6, 7, 8 = "LN-fold" + {bias, GELU, QuickGELU}: the GEMM runs on the UN-normalised rows x and the LayerNorm is applied to
+// the accumulator:  LN(x) W^T + b = rstd_m * (x W'^T)[m,n] - rstd_m * mean_m * c[n] + b'[n]   with  W' = W diag(gamma),
+// c[n] = sum_k W'[n,k],  b' = b + W beta  (prepared once on the host; c, b' fp32).  Per-row (mean, rstd) come from
+// row_stats_kernel.  The normalised activations never exist in memory.
+constexpr int kEpiLnFold = 6;
 
 struct PairParams {
-    const void* bias;
+    const void* bias;      // storage-type bias [N]; LN-fold epilogues: fp32 b'[N]
+    const float* colsum;   // LN-fold: c[N]
+    const float2* rowstats; // LN-fold: (mean, rstd) per row of A
     int M, N, K;
     int m_tiles, n_tiles;  // in units of (PAIRS*256) x BLOCK_N cluster tiles
     int group_m;
@@ -102,6 +109,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     using H = Half16<T>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kStgBufs = Cfg::kStgBufs;
+    constexpr bool kLn = EPI >= kEpiLnFold;
+    constexpr int kAct = kLn ? EPI - kEpiLnFold : (EPI == 1 || EPI == 2 ? EPI : 0);  // 0 none, 1 GELU, 2 QuickGELU
     constexpr int kClusterCtas = 2 * PAIRS;
     constexpr int kClusterM = PAIRS * kPairM;
 
@@ -271,6 +280,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t rx = static_cast<uint32_t>(r & 7);
         const int row_in_cluster = static_cast<int>(pair) * kPairM + static_cast<int>(half) * kBM;
         const T* bias = static_cast<const T*>(p.bias);
+        const float* bias_f32 = static_cast<const float*>(p.bias);
         uint32_t bufc = 0;  // chunks processed by this group so far (buffer = bufc % kStgBufs)
 
         // (tile, chunk) -> the next chunk this group processes
@@ -307,6 +317,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int row0 = mt * kClusterM + row_in_cluster;
+            float ln_rstd = 0.f, ln_nmr = 0.f;
+            if constexpr (kLn) {
+                if (row0 + r < p.M) {
+                    const float2 st = __ldg(p.rowstats + row0 + r);
+                    ln_rstd = st.y;
+                    ln_nmr = -st.x * st.y;
+                }
+            }
             if constexpr (EPI == 3) {
                 // pull the residual tiles this group will need two tiles from now into L2
                 if (grp_leader && p.pf_dist > 0) {
@@ -349,11 +367,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride + c * kChunkN + hf * 32;
                     tmem_ld_32x32(taddr, v);
                     uint4 bvec[4];
+                    if constexpr (!kLn) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int col = col0 + hf * 32 + g * 8;
-                        bvec[g] = make_uint4(0, 0, 0, 0);
-                        if (bias != nullptr && col < p.N) bvec[g] = ldg128(bias + col);
+                        for (int g = 0; g < 4; ++g) {
+                            const int col = col0 + hf * 32 + g * 8;
+                            bvec[g] = make_uint4(0, 0, 0, 0);
+                            if (bias != nullptr && col < p.N) bvec[g] = ldg128(bias + col);
+                        }
                     }
                     tmem_ld_wait();
                     if (last_of_tile && hf == 1) {
@@ -372,20 +392,39 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             rw[0] = rv.x; rw[1] = rv.y; rw[2] = rv.z; rw[3] = rv.w;
                         }
                         uint32_t ow[4];
+                        float cf[8], bf[8];
+                        if constexpr (kLn) {
+                            const int col = col0 + hf * 32 + g * 8;
+                            const bool ok = col < p.N;
+#pragma unroll
+                            for (int q4 = 0; q4 < 2; ++q4) {
+                                const float4 c4 = ok ? __ldg(reinterpret_cast<const float4*>(p.colsum + col) + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float4 b4 = ok ? __ldg(reinterpret_cast<const float4*>(bias_f32 + col) + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                cf[q4 * 4 + 0] = c4.x; cf[q4 * 4 + 1] = c4.y; cf[q4 * 4 + 2] = c4.z; cf[q4 * 4 + 3] = c4.w;
+                                bf[q4 * 4 + 0] = b4.x; bf[q4 * 4 + 1] = b4.y; bf[q4 * 4 + 2] = b4.z; bf[q4 * 4 + 3] = b4.w;
+                            }
+                        }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float2 b2 = H::unpack(bw[j]);
                             float x0, x1;
-                            unpack_f2(add_f2(pack_f2(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])),
-                                             pack_f2(b2.x, b2.y)), x0, x1);
-                            if constexpr (EPI != 0) {
+                            if constexpr (kLn) {
+                                // rstd * acc + (b' - rstd * mean * c): two packed FMAs per pair
+                                const uint64_t t = fma_f2(pack_f2(ln_nmr, ln_nmr), pack_f2(cf[2 * j], cf[2 * j + 1]), pack_f2(bf[2 * j], bf[2 * j + 1]));
+                                unpack_f2(fma_f2(pack_f2(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])),
+                                                 pack_f2(ln_rstd, ln_rstd), t), x0, x1);
+                            } else {
+                                const float2 b2 = H::unpack(bw[j]);
+                                unpack_f2(add_f2(pack_f2(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])),
+                                                 pack_f2(b2.x, b2.y)), x0, x1);
+                            }
+                            if constexpr (kAct != 0 || EPI == 3 || EPI == kEpiResidualInPlace) {
                                 const float2 xr = H::unpack(H::pack(x0, x1));  // linear output rounded to the storage type
                                 x0 = xr.x;
                                 x1 = xr.y;
                             }
-                            if constexpr (EPI == 1) {
+                            if constexpr (kAct == 1) {
                                 gelu_pair_fast(x0, x1);
-                            } else if constexpr (EPI == 2) {
+                            } else if constexpr (kAct == 2) {
                                 x0 = quick_gelu(x0);
                                 x1 = quick_gelu(x1);
                             } else if constexpr (EPI == 3) {
@@ -480,6 +519,9 @@ int launch_pair_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tw, const
         case 2: return launch_pair<T, BLOCK_N, 2, PAIRS>(ta, tw, tc, tr, p, s);
         case 3: return launch_pair<T, BLOCK_N, 3, PAIRS>(ta, tw, tc, tr, p, s);
         case kEpiResidualInPlace: return launch_pair<T, BLOCK_N, kEpiResidualInPlace, PAIRS>(ta, tw, tc, tr, p, s);
+        case kEpiLnFold + 0: return launch_pair<T, BLOCK_N, kEpiLnFold + 0, PAIRS>(ta, tw, tc, tr, p, s);
+        case kEpiLnFold + 1: return launch_pair<T, BLOCK_N, kEpiLnFold + 1, PAIRS>(ta, tw, tc, tr, p, s);
+        case kEpiLnFold + 2: return launch_pair<T, BLOCK_N, kEpiLnFold + 2, PAIRS>(ta, tw, tc, tr, p, s);
     }
     set_last_error("gemm_pair: unsupported epilogue %d", epi);
     return -1;
@@ -565,9 +607,17 @@ int pick_pair_block_n(int M, int N, int pairs) {
 // pairs: 1 = clusters of 2 CTAs, 2 = clusters of 4 with W multicast, 0 = choose
 int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
               int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs,
-              cudaStream_t stream) {
+              cudaStream_t stream, const float* ln_colsum, const float* ln_rowstats) {
     B2C_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm_pair: unsupported epilogue %d", epilogue);
+    const bool ln = ln_colsum != nullptr || ln_rowstats != nullptr;
+    if (ln) {
+        B2C_CHECK_ARG(ln_colsum != nullptr && ln_rowstats != nullptr && bias != nullptr && epilogue <= 2,
+                      "gemm_ln: needs colsum, rowstats, an fp32 bias and a bias/GELU/QuickGELU epilogue");
+        B2C_CHECK_ARG((reinterpret_cast<uintptr_t>(ln_colsum) | reinterpret_cast<uintptr_t>(bias)) % 16 == 0 &&
+                          reinterpret_cast<uintptr_t>(ln_rowstats) % 8 == 0,
+                      "gemm_ln: colsum / bias must be 16-byte aligned, rowstats 8-byte aligned");
+    }
     B2C_CHECK_ARG(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
     B2C_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0,
                   "gemm: K, lda, ldw, ldc must be multiples of 8 (16 B rows) K=%d lda=%lld ldw=%lld ldc=%lld", K,
@@ -596,8 +646,11 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
         tr = tc;
     }
 
+    if (ln) epilogue += kEpiLnFold;
     PairParams p;
     p.bias = bias;
+    p.colsum = ln_colsum;
+    p.rowstats = reinterpret_cast<const float2*>(ln_rowstats);
     p.M = M;
     p.N = N;
     p.K = K;

@@ -13,7 +13,11 @@ int gemm_tc(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw
 
 // CTA-pair (cta_group::2) variant with the TMA-store epilogue (gemm_pair.cu); epilogues 0..3
 int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
-              int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs, cudaStream_t stream);
+              int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs, cudaStream_t stream,
+              const float* ln_colsum = nullptr, const float* ln_rowstats = nullptr);
+
+// per-row LayerNorm statistics (mean, rstd) as float2 (rowwise.cu)
+int row_stats(int dtype, const void* x, int64_t ldx, float* stats, int rows, int width, float eps, cudaStream_t stream);
 
 int gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, const float* residual, int64_t ldr,
              float* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in, int g_out,

@@ -116,6 +116,48 @@ layernorm_kernel(const T* x, int64_t ldx, const float* __restrict__ gamma, const
     }
 }
 
+// Per-row LayerNorm statistics only: stats[r] = (mean, rstd) in fp32.  Used when the LayerNorm itself is folded into the
+// following GEMM (csrc/gemm_pair.cu, "LN-fold" epilogues): the GEMM then reads the un-normalised residual stream directly
+// and the normalised activations are never written to / re-read from HBM.  Read-only stream: one pass over x.
+template <typename T, int VPL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+row_stats_kernel(const T* __restrict__ x, int64_t ldx, float2* __restrict__ stats, int rows, int width, float eps) {
+    constexpr int E = Vec16<T>::kElems;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kWarpsPerBlock + warp;
+    if (r >= rows) return;
+    const T* xr = x + static_cast<int64_t>(r) * ldx;
+    const int nvec = width / E;
+    float v[VPL][E];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+            load_vec<T>(xr + vi * E, v[i]);
+#pragma unroll
+            for (int e = 0; e < E; ++e) sum += v[i][e];
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) v[i][e] = 0.f;
+        }
+    }
+    const float mean = warp_sum(sum) / static_cast<float>(width);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        if (lane + i * 32 < nvec) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const float d = v[i][e] - mean;
+                sq += d * d;
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(width) + eps);
+    if (lane == 0) stats[r] = make_float2(mean, rstd);
+}
+
 template <typename T, int VPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 normalize_kernel(const T* x, int64_t ldx, T* y, int64_t ldy, int rows, int dim, float eps) {
@@ -196,7 +238,40 @@ int launch_norm(const void* x, int64_t ldx, void* y, int64_t ldy, int rows, int 
     return 0;
 }
 
+template <typename T>
+int launch_stats(const void* x, int64_t ldx, float* stats, int rows, int width, float eps, cudaStream_t stream) {
+    constexpr int E = Vec16<T>::kElems;
+    const int vpl = (width / E + 31) / 32;
+    const int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const T* xp = static_cast<const T*>(x);
+    float2* sp = reinterpret_cast<float2*>(stats);
+#define ST_CASE(V) \
+    case V: row_stats_kernel<T, V><<<grid, kWarpsPerBlock * 32, 0, stream>>>(xp, ldx, sp, rows, width, eps); break;
+    switch (vpl) {
+        ST_CASE(1) ST_CASE(2) ST_CASE(3) ST_CASE(4) ST_CASE(5) ST_CASE(6) ST_CASE(7) ST_CASE(8)
+        default: set_last_error("row_stats: width %d too large", width); return -1;
+    }
+#undef ST_CASE
+    B2C_LAUNCH_CHECK("row_stats_kernel");
+    return 0;
+}
+
 }  // namespace
+
+int row_stats(int dtype, const void* x, int64_t ldx, float* stats, int rows, int width, float eps, cudaStream_t stream) {
+    B2C_CHECK_ARG(rows > 0 && width > 0, "row_stats: empty input rows=%d width=%d", rows, width);
+    const int e = 16 / dtype_size(dtype);
+    B2C_CHECK_ARG(width % e == 0 && ldx % e == 0, "row_stats: width/ld must be multiples of %d", e);
+    B2C_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(stats) % 8 == 0,
+                  "row_stats: x must be 16-byte and stats 8-byte aligned");
+    switch (dtype) {
+        case 0: return launch_stats<float>(x, ldx, stats, rows, width, eps, stream);
+        case 1: return launch_stats<__nv_bfloat16>(x, ldx, stats, rows, width, eps, stream);
+        case 2: return launch_stats<__half>(x, ldx, stats, rows, width, eps, stream);
+    }
+    set_last_error("row_stats: unknown dtype %d", dtype);
+    return -1;
+}
 
 int layernorm(int dtype, const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy, int rows,
               int width, float eps, int row_stride_rows, const int32_t* row_idx, cudaStream_t stream) {

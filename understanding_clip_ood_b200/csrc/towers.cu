@@ -30,6 +30,7 @@ struct Workspace {
     char* mlp;
     char* pooled;
     int32_t* eot;
+    float* stats;   // [rows, 2] (mean, rstd) for the LN-fold GEMMs
     int64_t total;
 };
 
@@ -52,6 +53,7 @@ Workspace carve(const b200clip_tower_cfg& c, int batch, int seq_len, void* base)
     w.mlp = take(rows * mlp_cols * es);
     w.pooled = take(static_cast<int64_t>(batch) * c.width * es);
     w.eot = reinterpret_cast<int32_t*>(take(static_cast<int64_t>(batch) * 4));
+    w.stats = reinterpret_cast<float*>(take(rows * 2 * 4));
     w.total = off;
     return w;
 }
@@ -74,17 +76,33 @@ int run_blocks(const b200clip_tower_cfg& c, const b200clip_block_weights* blocks
     const int W = c.width;
     const int act = c.quick_gelu ? B200CLIP_EPI_QUICKGELU : B200CLIP_EPI_GELU;
     int rc;
+    const bool fold = c.fold_ln != 0 && dt != B200CLIP_F32;
     for (int l = 0; l < c.layers; ++l) {
         const b200clip_block_weights& bw = blocks[l];
-        if ((rc = layernorm(dt, ws.x, W, bw.ln1_g, bw.ln1_b, ws.h, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
-        if ((rc = gemm_any(dt, ws.h, W, bw.in_proj_w, W, bw.in_proj_b, nullptr, 0, ws.qkv, 3 * W, M, 3 * W, W, B200CLIP_EPI_BIAS,
-                           nullptr, 0, 0, s)) != 0) return rc;
+        if (fold) {
+            // LN-fold: per-row statistics of the residual stream, then the GEMM reads x itself
+            B2C_CHECK_ARG(bw.in_proj_wf && bw.in_proj_c && bw.in_proj_bf && bw.fc_wf && bw.fc_c && bw.fc_bf,
+                          "tower: cfg.fold_ln is set but layer %d has no folded weights", l);
+            if ((rc = row_stats(dt, ws.x, W, ws.stats, M, W, 1e-5f, s)) != 0) return rc;
+            if ((rc = gemm_pair(dt == B200CLIP_BF16, ws.x, W, bw.in_proj_wf, W, bw.in_proj_bf, nullptr, 0, ws.qkv, 3 * W, M, 3 * W, W,
+                                B200CLIP_EPI_BIAS, 0, 0, s, bw.in_proj_c, ws.stats)) != 0) return rc;
+        } else {
+            if ((rc = layernorm(dt, ws.x, W, bw.ln1_g, bw.ln1_b, ws.h, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
+            if ((rc = gemm_any(dt, ws.h, W, bw.in_proj_w, W, bw.in_proj_b, nullptr, 0, ws.qkv, 3 * W, M, 3 * W, W, B200CLIP_EPI_BIAS,
+                               nullptr, 0, 0, s)) != 0) return rc;
+        }
         if ((rc = attention(dt, ws.qkv, ws.h, batch, L, c.heads, causal, s)) != 0) return rc;
         if ((rc = gemm_any(dt, ws.h, W, bw.out_proj_w, W, bw.out_proj_b, ws.x, W, ws.x, W, M, W, W, B200CLIP_EPI_RESIDUAL, nullptr, 0,
                            0, s)) != 0) return rc;
-        if ((rc = layernorm(dt, ws.x, W, bw.ln2_g, bw.ln2_b, ws.h, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
-        if ((rc = gemm_any(dt, ws.h, W, bw.fc_w, W, bw.fc_b, nullptr, 0, ws.mlp, c.mlp_width, M, c.mlp_width, W, act, nullptr, 0, 0,
-                           s)) != 0) return rc;
+        if (fold) {
+            if ((rc = row_stats(dt, ws.x, W, ws.stats, M, W, 1e-5f, s)) != 0) return rc;
+            if ((rc = gemm_pair(dt == B200CLIP_BF16, ws.x, W, bw.fc_wf, W, bw.fc_bf, nullptr, 0, ws.mlp, c.mlp_width, M, c.mlp_width, W,
+                                act, 0, 0, s, bw.fc_c, ws.stats)) != 0) return rc;
+        } else {
+            if ((rc = layernorm(dt, ws.x, W, bw.ln2_g, bw.ln2_b, ws.h, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
+            if ((rc = gemm_any(dt, ws.h, W, bw.fc_w, W, bw.fc_b, nullptr, 0, ws.mlp, c.mlp_width, M, c.mlp_width, W, act, nullptr, 0, 0,
+                               s)) != 0) return rc;
+        }
         if ((rc = gemm_any(dt, ws.mlp, c.mlp_width, bw.proj_w, c.mlp_width, bw.proj_b, ws.x, W, ws.x, W, M, W, c.mlp_width,
                            B200CLIP_EPI_RESIDUAL, nullptr, 0, 0, s)) != 0) return rc;
     }

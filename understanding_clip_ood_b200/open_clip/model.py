@@ -227,10 +227,19 @@ def _as(t: Optional[torch.Tensor], dtype: torch.dtype, keep: list) -> Optional[i
     return t.data_ptr()
 
 
-def _pack_blocks(stack: _Stack, dtype: torch.dtype, keep: list):
+def _pack_blocks(stack: _Stack, dtype: torch.dtype, keep: list, fold_ln: bool = False):
+    from .. import ops
     arr = (L.BlockWeights * stack.layers)()
     for i, blk in enumerate(stack.resblocks):
         b = arr[i]
+        if fold_ln:
+            for dst, w, bias, ln in (("in_proj", blk.attn.in_proj_weight, blk.attn.in_proj_bias, blk.ln_1),
+                                     ("fc", blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, blk.ln_2)):
+                wf, cs, bf = ops.fold_layernorm(w, bias, ln.weight, ln.bias, dtype)
+                keep.extend((wf, cs, bf))
+                setattr(b, dst + "_wf", wf.data_ptr())
+                setattr(b, dst + "_c", cs.data_ptr())
+                setattr(b, dst + "_bf", bf.data_ptr())
         b.ln1_g, b.ln1_b = _f32(blk.ln_1.weight, keep), _f32(blk.ln_1.bias, keep)
         b.ln2_g, b.ln2_b = _f32(blk.ln_2.weight, keep), _f32(blk.ln_2.bias, keep)
         b.in_proj_w, b.in_proj_b = _as(blk.attn.in_proj_weight, dtype, keep), _as(blk.attn.in_proj_bias, dtype, keep)
@@ -282,6 +291,8 @@ class VisionTower(nn.Module):
         self._engine = _Engine()
         #: replay the forward as a CUDA graph when the same input buffer is presented again (see _Engine.run_graphed)
         self.use_cuda_graphs = True
+        #: 16-bit modes: fold ln_1 / ln_2 into the QKV / c_fc GEMM epilogues (no normalised activations in HBM)
+        self.fold_layernorm = True
 
     # -- reference API surface ---------------------------------------------------------------
     def set_grad_checkpointing(self, enable: bool = True):
@@ -315,7 +326,8 @@ class VisionTower(nn.Module):
         keep.append(conv)
         proj_t = self.proj.detach().to(dt).t().contiguous()
         keep.append(proj_t)
-        blocks = _pack_blocks(self.transformer, dt, keep)
+        fold = bool(self.fold_layernorm) and dt != torch.float32
+        blocks = _pack_blocks(self.transformer, dt, keep, fold)
         w = L.VitWeights()
         w.conv1_w = conv.data_ptr()
         w.class_emb = _f32(self.class_embedding, keep)
@@ -327,7 +339,7 @@ class VisionTower(nn.Module):
         cfg = L.TowerCfg(dtype=L.dtype_code(dt), width=W, layers=self.transformer.layers, heads=self.transformer.heads,
                          mlp_width=self.transformer.mlp_width, embed_dim=self.output_dim,
                          seq_len=self.grid_size[0] * self.grid_size[1] + 1, quick_gelu=int(self.quick_gelu),
-                         image_size=self.image_size[0], patch_size=P, patch_kpad=kpad, vocab_size=0)
+                         image_size=self.image_size[0], patch_size=P, patch_kpad=kpad, vocab_size=0, fold_ln=int(fold))
         eng.sig, eng.keep, eng.blocks, eng.weights, eng.cfg = sig, keep, blocks, w, cfg
         eng.graphs.clear()      # captured graphs hold the old weight pointers
         return eng
@@ -426,6 +438,8 @@ class CLIP(nn.Module):
         # exact causal truncation of encode_text at max(EOT)+1; off = run all `context_length`
         # positions like the reference.  Costs one small device->host read per call.
         self.truncate_text_at_eot = False
+        #: 16-bit modes: fold ln_1 / ln_2 of the text blocks into the QKV / c_fc GEMM epilogues
+        self.fold_layernorm = True
         self._text_engine = _Engine()
 
     def _init_text_parameters(self) -> None:
@@ -466,7 +480,8 @@ class CLIP(nn.Module):
         keep: list = []
         proj_t = self.text_projection.detach().to(dt).t().contiguous()
         keep.append(proj_t)
-        blocks = _pack_blocks(self.transformer, dt, keep)
+        fold = bool(self.fold_layernorm) and dt != torch.float32
+        blocks = _pack_blocks(self.transformer, dt, keep, fold)
         w = L.TextWeights()
         w.tok_emb = _f32(self.token_embedding.weight, keep)
         w.pos_emb = _f32(self.positional_embedding, keep)
@@ -476,7 +491,7 @@ class CLIP(nn.Module):
         st = self.transformer
         cfg = L.TowerCfg(dtype=L.dtype_code(dt), width=st.width, layers=st.layers, heads=st.heads, mlp_width=st.mlp_width,
                          embed_dim=self.text_projection.shape[1], seq_len=self.context_length, quick_gelu=int(self.quick_gelu),
-                         image_size=0, patch_size=0, patch_kpad=0, vocab_size=self.vocab_size)
+                         image_size=0, patch_size=0, patch_kpad=0, vocab_size=self.vocab_size, fold_ln=int(fold))
         eng.sig, eng.keep, eng.blocks, eng.weights, eng.cfg = sig, keep, blocks, w, cfg
         return eng
 

@@ -40,6 +40,45 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, 
     return out
 
 
+def row_stats(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """-> [rows, 2] fp32 (mean, rstd) per row; see b200clip_row_stats."""
+    L.require_cuda(x)
+    x = _c(x)
+    x2 = x.view(-1, x.shape[-1])
+    stats = torch.empty((x2.shape[0], 2), dtype=torch.float32, device=x.device)
+    rc = L.load().b200clip_row_stats(L.dtype_code(x.dtype), x2.data_ptr(), x2.stride(0), stats.data_ptr(), x2.shape[0], x2.shape[1],
+                                     eps, L.stream_ptr())
+    L.check(rc, "b200clip_row_stats")
+    return stats
+
+
+def fold_layernorm(weight: torch.Tensor, bias: torch.Tensor | None, gamma: torch.Tensor, beta: torch.Tensor, dtype: torch.dtype):
+    """Host-side preparation of the LN-fold operands of `gemm_ln`: -> (W diag(gamma) in `dtype`, row sums fp32, b + W beta fp32)."""
+    w32 = weight.detach().float()
+    wf = (w32 * gamma.detach().float()[None, :]).to(dtype).contiguous()
+    colsum = wf.float().sum(dim=1).contiguous()
+    bf = w32 @ beta.detach().float()
+    if bias is not None:
+        bf = bf + bias.detach().float()
+    return wf, colsum, bf.contiguous()
+
+
+def gemm_ln(x: torch.Tensor, wf: torch.Tensor, colsum: torch.Tensor, bias_f32: torch.Tensor, stats: torch.Tensor, *,
+            epilogue: int = L.EPI_BIAS, out: torch.Tensor | None = None) -> torch.Tensor:
+    """act(LayerNorm(x) W^T + b) with the LayerNorm folded into the GEMM epilogue; see b200clip_gemm_ln."""
+    L.require_cuda(x, wf, colsum, bias_f32, stats, out)
+    x, wf = _c(x), _c(wf)
+    M, K = x.shape
+    N = wf.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    rc = L.load().b200clip_gemm_ln(L.dtype_code(x.dtype), x.data_ptr(), x.stride(0), wf.data_ptr(), wf.stride(0), colsum.data_ptr(),
+                                   bias_f32.data_ptr(), stats.data_ptr(), out.data_ptr(), out.stride(0), M, N, K, epilogue,
+                                   L.stream_ptr())
+    L.check(rc, "b200clip_gemm_ln")
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, *, rows: int | None = None,
               row_stride_rows: int = 1, row_idx: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     L.require_cuda(x, gamma, beta, row_idx, out)
