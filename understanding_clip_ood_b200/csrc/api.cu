@@ -29,6 +29,14 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
 
+bool pdl_enabled() {
+    static const bool v = [] {
+        const char* e = getenv("B200CLIP_NO_PDL");
+        return !(e != nullptr && e[0] == '1');
+    }();
+    return v;
+}
+
 int num_sms() {
     // per-device cache: one process drives one GPU, but stay correct if the current device changes
     static int cached_dev = -1;

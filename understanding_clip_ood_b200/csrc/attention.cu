@@ -268,7 +268,9 @@ attention_short_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __gri
         tma_prefetch_desc(&tmap_out);
     }
     fence_proxy_async();  // the zero fill (generic proxy) is ordered before the TMA writes (async proxy)
+    pdl_launch_dependents();
     __syncthreads();
+    pdl_wait();  // the qkv matrix is the previous kernel's output; everything above overlapped its tail
 
     const uint32_t tile_tx = static_cast<uint32_t>(L) * 128u;
     if (warp == 4) {
@@ -512,7 +514,18 @@ int launch_short_one(int grid, const CUtensorMap& tq, const CUtensorMap& to, int
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, short_smem_bytes(2)); });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(attention_short smem)");
-    kern<<<grid, 160, short_smem_bytes(2), stream>>>(tq, to, L, heads, items);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(160);
+    cfg.dynamicSmemBytes = short_smem_bytes(2);
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tq, to, L, heads, items);
+    if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(attention_short_kernel)");
     return 0;
 }
 template <typename T, bool CAUSAL>

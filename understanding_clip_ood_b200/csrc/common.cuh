@@ -43,6 +43,8 @@ void count_launch(int n);
     } while (0)
 
 int num_sms();
+// false when B200CLIP_NO_PDL=1: kernels are then launched without the programmatic-dependent-launch attribute
+bool pdl_enabled();
 
 // ---------------------------------------------------------------------------------------
 // 16-bit storage types: bf16 (F=1) and fp16 (F=0) share every kernel through this trait.
@@ -159,6 +161,16 @@ __device__ __forceinline__ void gelu_pair_fast(float& x0, float& x1) {
     const float r1 = rcp_fast(1.0f + ex2_fast(u1));
     unpack_f2(mul_f2(x, pack_f2(r0, r1)), x0, x1);
 }
+
+// ---------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while
+// its predecessor in the stream is still draining; everything before pdl_wait() (barrier init, TMEM allocation, descriptor
+// prefetch, shared-memory zero fill) overlaps the predecessor's tail, pdl_wait() blocks until the predecessor has completed
+// and its writes are visible.  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon as this kernel's
+// CTAs free their SMs.  Both are no-ops when the launch did not use the attribute.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------
 // Warp helpers

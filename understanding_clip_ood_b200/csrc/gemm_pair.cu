@@ -143,6 +143,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     // every CTA of the cluster must be resident before the pair-wide TMEM allocation / remote barrier traffic
     cluster_sync_all();
+    pdl_launch_dependents();  // the next kernel's CTAs may take over this SM as soon as this CTA retires
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -170,6 +171,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // everything above overlapped the previous kernel's tail; its outputs (our A operand / residual) are needed from here on
+    pdl_wait();
 
     if (warp == 0) {
         // ===================== TMA producer (every CTA) =====================
@@ -480,16 +483,18 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
     static cudaError_t attr_err = cudaSuccess;
     static int max_clusters = 0;
     cudaLaunchConfig_t cfg = {};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2 * PAIRS;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     std::call_once(once, [&] {
         attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (attr_err != cudaSuccess) return;

@@ -125,6 +125,8 @@ row_stats_kernel(const T* __restrict__ x, int64_t ldx, float2* __restrict__ stat
     constexpr int E = Vec16<T>::kElems;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = blockIdx.x * kWarpsPerBlock + warp;
+    pdl_launch_dependents();
+    pdl_wait();
     if (r >= rows) return;
     const T* xr = x + static_cast<int64_t>(r) * ldx;
     const int nvec = width / E;
@@ -245,13 +247,24 @@ int launch_stats(const void* x, int64_t ldx, float* stats, int rows, int width, 
     const int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const T* xp = static_cast<const T*>(x);
     float2* sp = reinterpret_cast<float2*>(stats);
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kWarpsPerBlock * 32);
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t le = cudaSuccess;
 #define ST_CASE(V) \
-    case V: row_stats_kernel<T, V><<<grid, kWarpsPerBlock * 32, 0, stream>>>(xp, ldx, sp, rows, width, eps); break;
+    case V: le = cudaLaunchKernelEx(&cfg, row_stats_kernel<T, V>, xp, ldx, sp, rows, width, eps); break;
     switch (vpl) {
         ST_CASE(1) ST_CASE(2) ST_CASE(3) ST_CASE(4) ST_CASE(5) ST_CASE(6) ST_CASE(7) ST_CASE(8)
         default: set_last_error("row_stats: width %d too large", width); return -1;
     }
 #undef ST_CASE
+    if (le != cudaSuccess) return cuda_fail(le, "cudaLaunchKernelEx(row_stats_kernel)");
     B2C_LAUNCH_CHECK("row_stats_kernel");
     return 0;
 }
