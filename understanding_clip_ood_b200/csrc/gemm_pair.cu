@@ -355,14 +355,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const bool last_of_tile = c + 2 >= Cfg::kChunks;
                 const uint32_t buf = bufc % kStgBufs;
                 const uint32_t stg = stg_base + buf * kChunkBytes;
-                if constexpr (EPI == 3) {
-                    mbar_wait(&my_res_bar[buf], (bufc / kStgBufs) & 1);
-                } else {
-                    // the store that last used this buffer (kStgBufs chunks ago) must have finished reading it
-                    if (grp_leader) tma_store_wait_read<kStgBufs - 1>();
-                    __syncwarp();
-                    named_bar_sync(bar_id, 128);
-                }
+                // Staging buffer `buf` is free here: the group leader drains its outstanding TMA store before it joins the
+                // barrier that ends each chunk (below), so the store issued kStgBufs chunks ago finished reading long ago.
+                if constexpr (EPI == 3) mbar_wait(&my_res_bar[buf], (bufc / kStgBufs) & 1);
                 const int col0 = nt * BLOCK_N + c * kChunkN;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
@@ -441,6 +436,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
                 fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
+                if constexpr (EPI != 3) {
+                    // every store but (at most) the previous chunk's has long completed; waiting for that one too BEFORE the
+                    // barrier tells the whole group that the other staging buffer is free for the next chunk
+                    if (grp_leader) tma_store_wait_read<0>();
+                    __syncwarp();
+                }
                 named_bar_sync(bar_id, 128);
                 if (grp_leader) {
                     if constexpr (EPI == kEpiResidualInPlace) tma_reduce_add_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, row0);
