@@ -69,9 +69,9 @@ __device__ __forceinline__ void load_tile(uint32_t smem_tile, const T* base, int
     }
 }
 
-template <typename T>
+template <typename T, bool CAUSAL>
 __global__ void __launch_bounds__(128)
-attention_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int L, int heads, int causal) {
+attention_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int L, int heads) {
     using H = Half16<T>;
     __shared__ __align__(128) uint8_t sQ[kBlockQ * 128];
     __shared__ __align__(128) uint8_t sK[2][kBlockKV * 128];
@@ -92,7 +92,7 @@ attention_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int L, int 
     constexpr uint32_t kTileBytes = kBlockKV * 128;
 
     int kv_end = L;
-    if (causal) kv_end = min(L, q0 + kBlockQ);
+    if (CAUSAL) kv_end = min(L, q0 + kBlockQ);
     const int nblk = (kv_end + kBlockKV - 1) / kBlockKV;
 
     load_tile<T>(sq, qbase, ld, q0, L, tid);
@@ -148,39 +148,46 @@ attention_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out, int L, int 
             }
         }
 
-        // mask + online softmax
+        // mask (only the block holding the sequence tail and, for the causal variant, the diagonal block need it)
         const int kv0 = blk * kBlockKV;
+        const bool need_mask = kv0 + kBlockKV > L || (CAUSAL && kv0 + kBlockKV > q0);
+        if (need_mask) {
+#pragma unroll
+            for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int col = kv0 + nb * 8 + (lane & 3) * 2 + (j & 1);
+                    const int row = row_lo + (j >> 1) * 8;
+                    if (col >= L || (CAUSAL && col > row)) s[nb][j] = -INFINITY;
+                }
+            }
+        }
+        // online softmax on the raw scores: p = 2^(s*c - m*c) is one FFMA + one MUFU per element
         float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int col = kv0 + nb * 8 + (lane & 3) * 2 + (j & 1);
-                const int row = row_lo + (j >> 1) * 8;
-                const bool masked = col >= L || (causal && col > row);
-                const float v = masked ? -INFINITY : s[nb][j] * scale_log2;
-                s[nb][j] = v;
-                mx[j >> 1] = fmaxf(mx[j >> 1], v);
-            }
+            mx[0] = fmaxf(mx[0], fmaxf(s[nb][0], s[nb][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[nb][2], s[nb][3]));
         }
-        float corr[2];
+        float corr[2], nm[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
             mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-            const float m_new = fmaxf(m_run[r], mx[r]);
-            corr[r] = exp2f(m_run[r] - m_new);  // m_new is finite: kv 0 is never masked
+            const float m_new = fmaxf(m_run[r], mx[r]);  // finite: kv column 0 is never masked
+            corr[r] = ex2_fast((m_run[r] - m_new) * scale_log2);
             m_run[r] = m_new;
+            nm[r] = -m_new * scale_log2;
             l_run[r] *= corr[r];
         }
         float rs[2] = {0.f, 0.f};
         uint32_t pf[4][4];
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
-            const float p0 = exp2f(s[nb][0] - m_run[0]);
-            const float p1 = exp2f(s[nb][1] - m_run[0]);
-            const float p2 = exp2f(s[nb][2] - m_run[1]);
-            const float p3 = exp2f(s[nb][3] - m_run[1]);
+            const float p0 = ex2_fast(fmaf(s[nb][0], scale_log2, nm[0]));
+            const float p1 = ex2_fast(fmaf(s[nb][1], scale_log2, nm[0]));
+            const float p2 = ex2_fast(fmaf(s[nb][2], scale_log2, nm[1]));
+            const float p3 = ex2_fast(fmaf(s[nb][3], scale_log2, nm[1]));
             rs[0] += p0 + p1;
             rs[1] += p2 + p3;
             // accumulator (row, 2 cols) pairs are exactly the A-fragment registers of the P·V product
@@ -597,12 +604,12 @@ int attention(int dtype, const void* qkv, void* out, int batch, int seq_len, int
         return 0;
     }
     dim3 grid(static_cast<unsigned>(bh), (seq_len + kBlockQ - 1) / kBlockQ);
-    if (dtype == 1)
-        attention_mma_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv),
-                                                                      static_cast<__nv_bfloat16*>(out), seq_len, heads, causal);
-    else if (dtype == 2)
-        attention_mma_kernel<__half><<<grid, 128, 0, stream>>>(static_cast<const __half*>(qkv), static_cast<__half*>(out),
-                                                               seq_len, heads, causal);
+    const __nv_bfloat16* qb = static_cast<const __nv_bfloat16*>(qkv);
+    const __half* qh = static_cast<const __half*>(qkv);
+    if (dtype == 1 && causal) attention_mma_kernel<__nv_bfloat16, true><<<grid, 128, 0, stream>>>(qb, static_cast<__nv_bfloat16*>(out), seq_len, heads);
+    else if (dtype == 1) attention_mma_kernel<__nv_bfloat16, false><<<grid, 128, 0, stream>>>(qb, static_cast<__nv_bfloat16*>(out), seq_len, heads);
+    else if (dtype == 2 && causal) attention_mma_kernel<__half, true><<<grid, 128, 0, stream>>>(qh, static_cast<__half*>(out), seq_len, heads);
+    else if (dtype == 2) attention_mma_kernel<__half, false><<<grid, 128, 0, stream>>>(qh, static_cast<__half*>(out), seq_len, heads);
     else {
         set_last_error("attention: unknown dtype %d", dtype);
         return -1;
