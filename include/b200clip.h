@@ -111,6 +111,13 @@ int b200clip_zeroshot(int dtype, const void* img_feat, const void* prompt_feat, 
                       float* topk_val, int B, int C, int D, int k, int normalize_img, float logit_scale,
                       void* stream);
 
+/* Per-row top-k of a materialised logit matrix x[B,C] (row pitch ldx elements, C <= 1024): topk_idx[B,k] int64 descending,
+ * ties to the lower class index; topk_val[B,k] fp32 (may be NULL); logits_out[B,C] fp32 copy of the rows (may be NULL; k may
+ * then be 0).  The 16-bit zero-shot path computes x with b200clip_gemm(img_feat, prompt_feat) on the tensor cores and ends
+ * here.  Replaces argmax / topk of xclip/zero_shot.py:103-109 and training/zero_shot.py:11-14. */
+int b200clip_topk(int dtype, const void* x, int64_t ldx, int B, int C, int k, int64_t* topk_idx, float* topk_val,
+                  float* logits_out, void* stream);
+
 /* prompt_feat[c,:] = normalize(mean_t normalize(txt_feat[c*T + t, :])) (xclip/zero_shot.py:231-234). */
 int b200clip_class_mean(int dtype, const void* txt_feat, void* prompt_feat, int classes, int templates, int D,
                         void* stream);

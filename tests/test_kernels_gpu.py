@@ -291,6 +291,25 @@ def test_zeroshot_tie_break_and_prenormalized():
     assert torch.allclose(logits2, 2 * torch.ones_like(logits2))
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_zeroshot_16bit_route_ties_and_logit_copy(dtype):
+    """16-bit route = tcgen05 logits GEMM + per-row warp top-k (b200clip_topk): ties -> lower index, fp32 logit copy exact."""
+    D, C = 64, 345
+    prm = torch.zeros(C, D, device=DEV, dtype=dtype)
+    prm[:, 0] = 1.0
+    prm[100:103, 1] = 0.5                # three classes share the (strictly larger) best logit
+    img = torch.zeros(9, D, device=DEV, dtype=dtype)
+    img[:, 0] = 1.0
+    img[:, 1] = 1.0
+    logits, idx, val = ops.zeroshot(img, prm, 5, normalize_img=False)
+    assert idx.tolist() == [[100, 101, 102, 0, 1]] * 9
+    assert torch.equal(val, torch.gather(logits, 1, idx))
+    ref = (img.float() @ prm.float().t()).to(dtype).float()
+    assert torch.equal(logits, ref)
+    only_logits, none_idx, _ = ops.zeroshot(img, prm, 0, normalize_img=False)
+    assert none_idx is None and torch.equal(only_logits, ref)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_class_mean(dtype):
     g = _gen(11)

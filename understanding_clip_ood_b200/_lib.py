@@ -63,6 +63,7 @@ SIGNATURES = {
     "b200clip_eot_argmax": (C.c_int, [_P, _I, _P, _I, _P]),
     "b200clip_normalize": (C.c_int, [_I, _P, _L, _P, _L, _I, _I, _F, _P]),
     "b200clip_zeroshot": (C.c_int, [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
+    "b200clip_topk": (C.c_int, [_I, _P, _L, _I, _I, _I, _P, _P, _P, _P]),
     "b200clip_class_mean": (C.c_int, [_I, _P, _P, _I, _I, _I, _P]),
     "b200clip_cliploss": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200clip_cliploss_forward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),

@@ -174,6 +174,11 @@ int b200clip_zeroshot(int dtype, const void* img_feat, const void* prompt_feat, 
     return zeroshot(dtype, img_feat, prompt_feat, logits, topk_idx, topk_val, B, C, D, k, normalize_img, logit_scale, S(stream));
 }
 
+int b200clip_topk(int dtype, const void* x, int64_t ldx, int B, int C, int k, int64_t* topk_idx, float* topk_val, float* logits_out,
+                  void* stream) {
+    return topk_rows(dtype, x, ldx, B, C, k, topk_idx, topk_val, logits_out, S(stream));
+}
+
 int b200clip_class_mean(int dtype, const void* txt_feat, void* prompt_feat, int classes, int templates, int D, void* stream) {
     B2C_CHECK_ARG(txt_feat && prompt_feat, "class_mean: null pointer");
     return class_mean(dtype, txt_feat, prompt_feat, classes, templates, D, S(stream));

@@ -624,7 +624,7 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
                           reinterpret_cast<uintptr_t>(ln_rowstats) % 8 == 0,
                       "gemm_ln: colsum / bias must be 16-byte aligned, rowstats 8-byte aligned");
     }
-    B2C_CHECK_ARG(N % 8 == 0, "gemm: N=%d must be a multiple of 8", N);
+    B2C_CHECK_ARG(N % 8 == 0 || (bias == nullptr && epilogue == 0), "gemm: N=%d must be a multiple of 8 (unless bias-free)", N);
     B2C_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0,
                   "gemm: K, lda, ldw, ldc must be multiples of 8 (16 B rows) K=%d lda=%lld ldw=%lld ldc=%lld", K,
                   (long long)lda, (long long)ldw, (long long)ldc);

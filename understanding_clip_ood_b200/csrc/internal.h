@@ -47,6 +47,9 @@ int normalize_rows(int dtype, const void* x, int64_t ldx, void* y, int64_t ldy, 
 int zeroshot(int dtype, const void* img_feat, const void* prompt_feat, float* logits, int64_t* topk_idx, float* topk_val,
              int B, int C, int D, int k, int normalize_img, float logit_scale, cudaStream_t stream);
 
+int topk_rows(int dtype, const void* x, int64_t ldx, int B, int C, int k, int64_t* topk_idx, float* topk_val, float* logits_out,
+              cudaStream_t stream);
+
 int class_mean(int dtype, const void* txt_feat, void* prompt_feat, int classes, int templates, int D, cudaStream_t stream);
 
 int cliploss(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt, const float* logit_scale,

@@ -126,6 +126,80 @@ zeroshot_kernel(const T* __restrict__ img, const T* __restrict__ prompt, float* 
     }
 }
 
+// Per-row warp-level top-k over a materialised logit matrix x[B, C] (row pitch ldx): the 16-bit zero-shot path computes
+// the logits with the tcgen05 GEMM (csrc/gemm_pair.cu) and finishes here.  One warp per row; the row (<= 1024 classes:
+// 32 per lane) lives in registers, each of the k rounds is a lane-local scan + a 5-step shuffle arg-max; ties go to the
+// lower class index like torch.argmax / torch.topk.  Optionally also emits the row as fp32 (`logits_out`, pitch C).
+constexpr int kTopkWarps = 8;
+template <typename T, int VPL>
+__global__ void __launch_bounds__(kTopkWarps * 32)
+topk_rows_kernel(const T* __restrict__ x, int64_t ldx, int B, int C, int k, int64_t* __restrict__ topk_idx,
+                 float* __restrict__ topk_val, float* __restrict__ logits_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * kTopkWarps + warp;
+    if (r >= B) return;
+    const T* xr = x + static_cast<int64_t>(r) * ldx;
+    float v[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = lane + i * 32;
+        v[i] = c < C ? ld_as_f<T>(xr + c) : -INFINITY;
+        if (logits_out != nullptr && c < C) logits_out[static_cast<int64_t>(r) * C + c] = v[i];
+    }
+    if (topk_idx == nullptr) return;
+    for (int it = 0; it < k; ++it) {
+        float best = -INFINITY;
+        int best_c = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int c = lane + i * 32;
+            if (c < C && (v[i] > best || (v[i] == best && c < best_c))) {
+                best = v[i];
+                best_c = c;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+            if (ov > best || (ov == best && oc < best_c)) {
+                best = ov;
+                best_c = oc;
+            }
+        }
+        if (best_c == 0x7fffffff) best_c = 0;  // all remaining entries are -inf / NaN
+        if (lane == 0) {
+            topk_idx[static_cast<int64_t>(r) * k + it] = best_c;
+            if (topk_val != nullptr) topk_val[static_cast<int64_t>(r) * k + it] = best;
+        }
+        // the winning lane retires its element (c = lane + i*32  ->  i = c / 32)
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+            if (lane + i * 32 == best_c) v[i] = -INFINITY;
+    }
+}
+
+template <typename T>
+int topk_rows_t(const void* x, int64_t ldx, int B, int C, int k, int64_t* idx, float* val, float* logits_out, cudaStream_t stream) {
+    const int vpl = (C + 31) / 32;
+    const int grid = (B + kTopkWarps - 1) / kTopkWarps;
+    const T* xp = static_cast<const T*>(x);
+#define TK_CASE(V) \
+    topk_rows_kernel<T, V><<<grid, kTopkWarps * 32, 0, stream>>>(xp, ldx, B, C, k, idx, val, logits_out)
+    if (vpl <= 4) TK_CASE(4);
+    else if (vpl <= 8) TK_CASE(8);
+    else if (vpl <= 12) TK_CASE(12);
+    else if (vpl <= 16) TK_CASE(16);
+    else if (vpl <= 32) TK_CASE(32);
+    else {
+        set_last_error("topk_rows: C=%d exceeds the 1024 classes of the register-resident path", C);
+        return -1;
+    }
+#undef TK_CASE
+    B2C_LAUNCH_CHECK("topk_rows_kernel");
+    return 0;
+}
+
 // one CTA (128 threads) per class
 template <typename T>
 __global__ void __launch_bounds__(128)
@@ -191,6 +265,22 @@ int class_mean_t(const void* txt, void* out, int classes, int templates, int D, 
 }
 
 }  // namespace
+
+int topk_rows(int dtype, const void* x, int64_t ldx, int B, int C, int k, int64_t* topk_idx, float* topk_val, float* logits_out,
+              cudaStream_t stream) {
+    B2C_CHECK_ARG(x != nullptr && B > 0 && C > 0 && ldx >= C, "topk_rows: bad input B=%d C=%d ld=%lld", B, C, (long long)ldx);
+    B2C_CHECK_ARG(k >= 0 && k <= 8 && k <= C, "topk_rows: k=%d must be in [0, min(8, C)]", k);
+    B2C_CHECK_ARG(k == 0 || topk_idx != nullptr, "topk_rows: k > 0 needs topk_idx");
+    B2C_CHECK_ARG(topk_idx != nullptr || logits_out != nullptr, "topk_rows: nothing to write");
+    if (k == 0) topk_idx = nullptr;
+    switch (dtype) {
+        case 0: return topk_rows_t<float>(x, ldx, B, C, k, topk_idx, topk_val, logits_out, stream);
+        case 1: return topk_rows_t<__nv_bfloat16>(x, ldx, B, C, k, topk_idx, topk_val, logits_out, stream);
+        case 2: return topk_rows_t<__half>(x, ldx, B, C, k, topk_idx, topk_val, logits_out, stream);
+    }
+    set_last_error("topk_rows: unknown dtype %d", dtype);
+    return -1;
+}
 
 int zeroshot(int dtype, const void* img_feat, const void* prompt_feat, float* logits, int64_t* topk_idx, float* topk_val, int B,
              int C, int D, int k, int normalize_img, float logit_scale, cudaStream_t stream) {

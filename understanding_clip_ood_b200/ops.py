@@ -167,6 +167,20 @@ def zeroshot(img_feat: torch.Tensor, prompt_feat: torch.Tensor, k: int = 1, *, n
     logits = torch.empty((B, Cn), dtype=torch.float32, device=dev) if want_logits else None
     idx = torch.empty((B, k), dtype=torch.int64, device=dev) if k > 0 else None
     val = torch.empty((B, k), dtype=torch.float32, device=dev) if k > 0 else None
+    if img_feat.dtype != torch.float32 and logit_scale == 1.0 and Cn <= 1024 and D % 8 == 0 and (k > 0 or want_logits):
+        # 16-bit path: logits on the tensor cores (bf16/fp16 operands, fp32 accumulation, rounded to the storage type — the
+        # reference's own bf16 `tensordot` semantics), then the per-row warp top-k.  fp32 keeps the fused FFMA kernel below
+        # (index-exact parity gate).
+        feat = normalize(img_feat) if normalize_img else img_feat
+        ld = (Cn + 7) // 8 * 8
+        lg = torch.empty((B, ld), dtype=img_feat.dtype, device=dev)
+        lib = L.load()
+        rc = lib.b200clip_gemm(L.dtype_code(feat.dtype), feat.data_ptr(), feat.stride(0), prompt_feat.data_ptr(), prompt_feat.stride(0),
+                               None, None, 0, lg.data_ptr(), ld, B, Cn, D, L.EPI_BIAS, None, 0, 0, L.stream_ptr())
+        L.check(rc, "b200clip_gemm (zero-shot logits)")
+        rc = lib.b200clip_topk(L.dtype_code(lg.dtype), lg.data_ptr(), ld, B, Cn, k, L.ptr(idx), L.ptr(val), L.ptr(logits), L.stream_ptr())
+        L.check(rc, "b200clip_topk")
+        return logits, idx, val
     rc = L.load().b200clip_zeroshot(L.dtype_code(img_feat.dtype), img_feat.data_ptr(), prompt_feat.data_ptr(), L.ptr(logits),
                                     L.ptr(idx), L.ptr(val), B, Cn, D, k, int(normalize_img), logit_scale, L.stream_ptr())
     L.check(rc, "b200clip_zeroshot")
