@@ -123,41 +123,52 @@ template <typename T, int VPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 row_stats_kernel(const T* __restrict__ x, int64_t ldx, float2* __restrict__ stats, int rows, int width, float eps) {
     constexpr int E = Vec16<T>::kElems;
+    constexpr int R = VPL <= 4 ? 2 : 1;  // rows per warp, all of their loads in flight before the first reduction
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = blockIdx.x * kWarpsPerBlock + warp;
+    const int r0 = (blockIdx.x * kWarpsPerBlock + warp) * R;
     pdl_launch_dependents();
     pdl_wait();
-    if (r >= rows) return;
-    const T* xr = x + static_cast<int64_t>(r) * ldx;
+    if (r0 >= rows) return;
     const int nvec = width / E;
-    float v[VPL][E];
-    float sum = 0.f;
+    float v[R][VPL][E];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int vi = lane + i * 32;
-        if (vi < nvec) {
-            load_vec<T>(xr + vi * E, v[i]);
+    for (int j = 0; j < R; ++j) {
+        const int r = min(r0 + j, rows - 1);
+        const T* xr = x + static_cast<int64_t>(r) * ldx;
 #pragma unroll
-            for (int e = 0; e < E; ++e) sum += v[i][e];
-        } else {
+        for (int i = 0; i < VPL; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < nvec) {
+                load_vec<T>(xr + vi * E, v[j][i]);
+            } else {
 #pragma unroll
-            for (int e = 0; e < E; ++e) v[i][e] = 0.f;
-        }
-    }
-    const float mean = warp_sum(sum) / static_cast<float>(width);
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        if (lane + i * 32 < nvec) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const float d = v[i][e] - mean;
-                sq += d * d;
+                for (int e = 0; e < E; ++e) v[j][i][e] = 0.f;
             }
         }
     }
-    const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(width) + eps);
-    if (lane == 0) stats[r] = make_float2(mean, rstd);
+    const float inv_w = 1.0f / static_cast<float>(width);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i)
+#pragma unroll
+            for (int e = 0; e < E; ++e) sum += v[j][i][e];
+        const float mean = warp_sum(sum) * inv_w;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            if (lane + i * 32 < nvec) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const float d = v[j][i][e] - mean;
+                    sq += d * d;
+                }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) * inv_w + eps);
+        if (lane == 0 && r0 + j < rows) stats[r0 + j] = make_float2(mean, rstd);
+    }
 }
 
 template <typename T, int VPL>
@@ -244,7 +255,9 @@ template <typename T>
 int launch_stats(const void* x, int64_t ldx, float* stats, int rows, int width, float eps, cudaStream_t stream) {
     constexpr int E = Vec16<T>::kElems;
     const int vpl = (width / E + 31) / 32;
-    const int grid = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int rows_per_warp = vpl <= 4 ? 2 : 1;   // must match R in row_stats_kernel
+    const int warps = (rows + rows_per_warp - 1) / rows_per_warp;
+    const int grid = (warps + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const T* xp = static_cast<const T*>(x);
     float2* sp = reinterpret_cast<float2*>(stats);
     cudaLaunchConfig_t cfg = {};
