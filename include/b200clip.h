@@ -182,6 +182,9 @@ typedef struct b200clip_vit_weights {
     const float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
     const void* proj_t;       /* [D, W]: visual.proj transposed, dtype */
     const b200clip_block_weights* blocks_host; /* HOST array of `layers` entries */
+    /* 16-bit modes, optional: [L, W] fp32 = pos_emb with row 0 replaced by dtype(class_emb) + dtype(pos_emb[0]); when set the
+     * patch embedding runs as one token-layout GEMM on the CTA-pair kernel */
+    const float* pos_cls;
 } b200clip_vit_weights;
 
 typedef struct b200clip_text_weights {

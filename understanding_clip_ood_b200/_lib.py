@@ -38,7 +38,7 @@ class BlockWeights(C.Structure):
 class VitWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "conv1_w", "class_emb", "pos_emb", "ln_pre_g", "ln_pre_b", "ln_post_g", "ln_post_b", "proj_t",
-        "blocks_host")]
+        "blocks_host", "pos_cls")]
 
 
 class TextWeights(C.Structure):

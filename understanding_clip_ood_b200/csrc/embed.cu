@@ -24,22 +24,24 @@ template <typename T> __device__ __forceinline__ float rt(float v) { return cast
 // VEC elements (16 bytes) per thread when the patch size allows it, else 1.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
-patchify_kernel(const T* __restrict__ image, T* __restrict__ patches, int batch, int S, int P, int g, int kpad) {
+patchify_kernel(const T* __restrict__ image, T* __restrict__ patches, int batch, int S, int P, int g, int kpad, int cls_slot) {
+    // cls_slot = 1: token layout, g*g+1 rows per image with an all-zero row in the class-token slot (row 0)
     const int kreal = 3 * P * P;
     const int vec_per_row = kpad / VEC;
-    const int64_t total = static_cast<int64_t>(batch) * g * g * vec_per_row;
+    const int rows_per_img = g * g + cls_slot;
+    const int64_t total = static_cast<int64_t>(batch) * rows_per_img * vec_per_row;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const int64_t row = i / vec_per_row;
         const int col = static_cast<int>(i - row * vec_per_row) * VEC;
         T* dst = patches + row * kpad + col;
-        if (col >= kreal) {
+        const int b = static_cast<int>(row / rows_per_img);
+        const int pr = static_cast<int>(row - static_cast<int64_t>(b) * rows_per_img) - cls_slot;
+        if (col >= kreal || pr < 0) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) dst[e] = cast_from_f<T>(0.f);
             continue;
         }
-        const int b = static_cast<int>(row / (g * g));
-        const int pr = static_cast<int>(row - static_cast<int64_t>(b) * g * g);
         const int gy = pr / g, gx = pr - gy * g;
         const int c = col / (P * P);
         const int rem = col - c * P * P;
@@ -112,20 +114,20 @@ __global__ void eot_kernel(const int64_t* __restrict__ text, int ctx, int32_t* _
 
 template <typename T>
 int patchify_t(const void* image, void* patches, int batch, int S, int P, int kpad, const float* class_emb, const float* pos,
-               void* x, int width, cudaStream_t stream) {
+               void* x, int width, int cls_slot, cudaStream_t stream) {
     const int g = S / P;
     constexpr int V = 16 / sizeof(T);
     const bool vec_ok = (P % V == 0) && (S % V == 0) && (kpad % V == 0) &&
                         (reinterpret_cast<uintptr_t>(image) % 16 == 0) && (reinterpret_cast<uintptr_t>(patches) % 16 == 0);
-    const int64_t total = static_cast<int64_t>(batch) * g * g * (vec_ok ? kpad / V : kpad);
+    const int64_t total = static_cast<int64_t>(batch) * (g * g + cls_slot) * (vec_ok ? kpad / V : kpad);
     int64_t blocks = (total + 255) / 256;
     if (blocks > static_cast<int64_t>(num_sms()) * 32) blocks = static_cast<int64_t>(num_sms()) * 32;
     if (vec_ok)
         patchify_kernel<T, V><<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const T*>(image), static_cast<T*>(patches),
-                                                                            batch, S, P, g, kpad);
+                                                                            batch, S, P, g, kpad, cls_slot);
     else
         patchify_kernel<T, 1><<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const T*>(image), static_cast<T*>(patches),
-                                                                            batch, S, P, g, kpad);
+                                                                            batch, S, P, g, kpad, cls_slot);
     B2C_LAUNCH_CHECK("patchify_kernel");
     if (x != nullptr) {
         const int64_t tot2 = static_cast<int64_t>(batch) * width;
@@ -154,15 +156,15 @@ int text_embed_t(const int64_t* text, int ctx, const float* tok_emb, const float
 }  // namespace
 
 int patchify(int dtype, const void* image, void* patches, int batch, int image_size, int patch, int kpad,
-             const float* class_emb, const float* pos, void* x, int width, cudaStream_t stream) {
+             const float* class_emb, const float* pos, void* x, int width, cudaStream_t stream, int cls_slot) {
     B2C_CHECK_ARG(batch > 0 && image_size > 0 && patch > 0 && image_size % patch == 0,
                   "patchify: bad geometry batch=%d image=%d patch=%d", batch, image_size, patch);
     B2C_CHECK_ARG(kpad >= 3 * patch * patch, "patchify: kpad=%d smaller than 3*P*P=%d", kpad, 3 * patch * patch);
     B2C_CHECK_ARG(x == nullptr || (class_emb != nullptr && pos != nullptr), "patchify: class rows need class_emb and pos");
     switch (dtype) {
-        case 0: return patchify_t<float>(image, patches, batch, image_size, patch, kpad, class_emb, pos, x, width, stream);
-        case 1: return patchify_t<__nv_bfloat16>(image, patches, batch, image_size, patch, kpad, class_emb, pos, x, width, stream);
-        case 2: return patchify_t<__half>(image, patches, batch, image_size, patch, kpad, class_emb, pos, x, width, stream);
+        case 0: return patchify_t<float>(image, patches, batch, image_size, patch, kpad, class_emb, pos, x, width, cls_slot, stream);
+        case 1: return patchify_t<__nv_bfloat16>(image, patches, batch, image_size, patch, kpad, class_emb, pos, x, width, cls_slot, stream);
+        case 2: return patchify_t<__half>(image, patches, batch, image_size, patch, kpad, class_emb, pos, x, width, cls_slot, stream);
     }
     set_last_error("patchify: unknown dtype %d", dtype);
     return -1;

@@ -45,11 +45,16 @@ constexpr int kEpiResidualInPlace = 5;
 // c[n] = sum_k W'[n,k],  b' = b + W beta  (prepared once on the host; c, b' fp32).  Per-row (mean, rstd) come from
 // row_stats_kernel.  The normalised activations never exist in memory.
 constexpr int kEpiLnFold = 6;
+// 9 = token-layout patch embedding: C[m,n] = round(acc) + round(pos[m % period, n]) with an fp32 table whose row 0 already
+// holds class_embedding + positional_embedding[0] (the class-token rows of A are all zero), transformer.py:602-609
+constexpr int kEpiPosAdd = 9;
 
 struct PairParams {
     const void* bias;      // storage-type bias [N]; LN-fold epilogues: fp32 b'[N]
     const float* colsum;   // LN-fold: c[N]
     const float2* rowstats; // LN-fold: (mean, rstd) per row of A
+    const float* pos;      // pos-add: fp32 table [period, N]
+    int pos_period;
     int M, N, K;
     int m_tiles, n_tiles;  // in units of (PAIRS*256) x BLOCK_N cluster tiles
     int group_m;
@@ -109,7 +114,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     using H = Half16<T>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kStgBufs = Cfg::kStgBufs;
-    constexpr bool kLn = EPI >= kEpiLnFold;
+    constexpr bool kLn = EPI >= kEpiLnFold && EPI < kEpiPosAdd;
+    constexpr bool kPos = EPI == kEpiPosAdd;
     constexpr int kAct = kLn ? EPI - kEpiLnFold : (EPI == 1 || EPI == 2 ? EPI : 0);  // 0 none, 1 GELU, 2 QuickGELU
     constexpr int kClusterCtas = 2 * PAIRS;
     constexpr int kClusterM = PAIRS * kPairM;
@@ -320,6 +326,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int row0 = mt * kClusterM + row_in_cluster;
+            const float* pos_row = nullptr;
+            if constexpr (kPos) pos_row = p.pos + static_cast<int64_t>((row0 + r) % p.pos_period) * p.N;
             float ln_rstd = 0.f, ln_nmr = 0.f;
             if constexpr (kLn) {
                 if (row0 + r < p.M) {
@@ -391,6 +399,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                         uint32_t ow[4];
                         float cf[8], bf[8];
+                        if constexpr (kPos) {
+                            const int col = col0 + hf * 32 + g * 8;
+                            const bool ok = col < p.N;
+#pragma unroll
+                            for (int q4 = 0; q4 < 2; ++q4) {
+                                const float4 b4 = ok ? __ldg(reinterpret_cast<const float4*>(pos_row + col) + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                bf[q4 * 4 + 0] = b4.x; bf[q4 * 4 + 1] = b4.y; bf[q4 * 4 + 2] = b4.z; bf[q4 * 4 + 3] = b4.w;
+                            }
+                        }
                         if constexpr (kLn) {
                             const int col = col0 + hf * 32 + g * 8;
                             const bool ok = col < p.N;
@@ -410,6 +427,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 const uint64_t t = fma_f2(pack_f2(ln_nmr, ln_nmr), pack_f2(cf[2 * j], cf[2 * j + 1]), pack_f2(bf[2 * j], bf[2 * j + 1]));
                                 unpack_f2(fma_f2(pack_f2(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])),
                                                  pack_f2(ln_rstd, ln_rstd), t), x0, x1);
+                            } else if constexpr (kPos) {
+                                // conv output and table entry are each rounded to the storage type before the add
+                                const float2 a2 = H::unpack(H::pack(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])));
+                                const float2 p2 = H::unpack(H::pack(bf[2 * j], bf[2 * j + 1]));
+                                x0 = a2.x + p2.x;
+                                x1 = a2.y + p2.y;
                             } else {
                                 const float2 b2 = H::unpack(bw[j]);
                                 unpack_f2(add_f2(pack_f2(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])),
@@ -528,6 +551,7 @@ int launch_pair_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tw, const
         case kEpiLnFold + 0: return launch_pair<T, BLOCK_N, kEpiLnFold + 0, PAIRS>(ta, tw, tc, tr, p, s);
         case kEpiLnFold + 1: return launch_pair<T, BLOCK_N, kEpiLnFold + 1, PAIRS>(ta, tw, tc, tr, p, s);
         case kEpiLnFold + 2: return launch_pair<T, BLOCK_N, kEpiLnFold + 2, PAIRS>(ta, tw, tc, tr, p, s);
+        case kEpiPosAdd: return launch_pair<T, BLOCK_N, kEpiPosAdd, PAIRS>(ta, tw, tc, tr, p, s);
     }
     set_last_error("gemm_pair: unsupported epilogue %d", epi);
     return -1;
@@ -613,7 +637,7 @@ int pick_pair_block_n(int M, int N, int pairs) {
 // pairs: 1 = clusters of 2 CTAs, 2 = clusters of 4 with W multicast, 0 = choose
 int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
               int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs,
-              cudaStream_t stream, const float* ln_colsum, const float* ln_rowstats) {
+              cudaStream_t stream, const float* ln_colsum, const float* ln_rowstats, const float* pos_table, int pos_period) {
     B2C_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm_pair: unsupported epilogue %d", epilogue);
     const bool ln = ln_colsum != nullptr || ln_rowstats != nullptr;
@@ -653,10 +677,17 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     }
 
     if (ln) epilogue += kEpiLnFold;
+    if (pos_table != nullptr) {
+        B2C_CHECK_ARG(!ln && epilogue == 0 && bias == nullptr && pos_period > 0 && reinterpret_cast<uintptr_t>(pos_table) % 16 == 0,
+                      "gemm_pos: needs a bias-free plain epilogue, an aligned fp32 table and period > 0");
+        epilogue = kEpiPosAdd;
+    }
     PairParams p;
     p.bias = bias;
     p.colsum = ln_colsum;
     p.rowstats = reinterpret_cast<const float2*>(ln_rowstats);
+    p.pos = pos_table;
+    p.pos_period = pos_period;
     p.M = M;
     p.N = N;
     p.K = K;

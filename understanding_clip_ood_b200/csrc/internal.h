@@ -14,7 +14,7 @@ int gemm_tc(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw
 // CTA-pair (cta_group::2) variant with the TMA-store epilogue (gemm_pair.cu); epilogues 0..3
 int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
               int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs, cudaStream_t stream,
-              const float* ln_colsum = nullptr, const float* ln_rowstats = nullptr);
+              const float* ln_colsum = nullptr, const float* ln_rowstats = nullptr, const float* pos_table = nullptr, int pos_period = 0);
 
 // per-row LayerNorm statistics (mean, rstd) as float2 (rowwise.cu)
 int row_stats(int dtype, const void* x, int64_t ldx, float* stats, int rows, int width, float eps, cudaStream_t stream);
@@ -34,7 +34,7 @@ int layernorm(int dtype, const void* x, int64_t ldx, const float* gamma, const f
 int attention(int dtype, const void* qkv, void* out, int batch, int seq_len, int heads, int causal, cudaStream_t stream);
 
 int patchify(int dtype, const void* image, void* patches, int batch, int image_size, int patch, int kpad,
-             const float* class_emb, const float* pos, void* x, int width, cudaStream_t stream);
+             const float* class_emb, const float* pos, void* x, int width, cudaStream_t stream, int cls_slot = 0);
 
 int text_embed(int dtype, const int64_t* text, int ctx, const float* tok_emb, const float* pos_emb, void* x, int32_t* eot,
                int T, int L, int width, cudaStream_t stream);

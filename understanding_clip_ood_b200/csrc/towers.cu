@@ -139,12 +139,22 @@ int vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, co
     const int W = c.width;
     const int M = batch * L;
 
-    // patch embedding: im2col -> GEMM whose epilogue scatters to token rows 1..L-1 and adds the positional embedding
-    if ((rc = patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s)) != 0)
-        return rc;
-    if ((rc = gemm_any(dt, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, batch * g * g, W,
-                       c.patch_kpad, B200CLIP_EPI_PATCH, w->pos_emb, g * g, L, s)) != 0)
-        return rc;
+    if (dt != B200CLIP_F32 && w->pos_cls != nullptr) {
+        // patch embedding in token layout: im2col with an all-zero row in every class-token slot, then ONE CTA-pair GEMM over
+        // all B*L rows whose epilogue adds the (class + positional) table row of each token
+        if ((rc = patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, nullptr, nullptr, nullptr, W, s, 1)) != 0)
+            return rc;
+        if ((rc = gemm_pair(dt == B200CLIP_BF16, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, M, W,
+                            c.patch_kpad, B200CLIP_EPI_BIAS, 0, 0, s, nullptr, nullptr, w->pos_cls, L)) != 0)
+            return rc;
+    } else {
+        // im2col -> GEMM whose epilogue scatters to token rows 1..L-1 and adds the positional embedding
+        if ((rc = patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s)) != 0)
+            return rc;
+        if ((rc = gemm_any(dt, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, batch * g * g, W,
+                           c.patch_kpad, B200CLIP_EPI_PATCH, w->pos_emb, g * g, L, s)) != 0)
+            return rc;
+    }
     if ((rc = layernorm(dt, ws.x, W, w->ln_pre_g, w->ln_pre_b, ws.x, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
     if ((rc = run_blocks(c, w->blocks_host, ws, batch, L, 0, s)) != 0) return rc;
     // pool_type 'tok': ln_post on the class token only (LN is per-row, so pooling first is exact), then @ proj

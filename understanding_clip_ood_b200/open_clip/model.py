@@ -336,6 +336,14 @@ class VisionTower(nn.Module):
         w.ln_post_g, w.ln_post_b = _f32(self.ln_post.weight, keep), _f32(self.ln_post.bias, keep)
         w.proj_t = proj_t.data_ptr()
         w.blocks_host = C.cast(blocks, C.c_void_p)
+        if dt != torch.float32:
+            # token-layout patch embedding: the class-token row of the additive table holds dtype(class_emb) + dtype(pos[0])
+            # (an exact fp32 sum of two 16-bit values), the other rows are the fp32 positional embedding
+            pos_cls = self.positional_embedding.detach().float().clone()
+            pos_cls[0] = self.class_embedding.detach().to(dt).float() + self.positional_embedding.detach()[0].to(dt).float()
+            pos_cls = pos_cls.contiguous()
+            keep.append(pos_cls)
+            w.pos_cls = pos_cls.data_ptr()
         cfg = L.TowerCfg(dtype=L.dtype_code(dt), width=W, layers=self.transformer.layers, heads=self.transformer.heads,
                          mlp_width=self.transformer.mlp_width, embed_dim=self.output_dim,
                          seq_len=self.grid_size[0] * self.grid_size[1] + 1, quick_gelu=int(self.quick_gelu),
