@@ -145,6 +145,17 @@ int b200clip_cliploss_backward(const float* img_loc, const float* txt_loc, const
                                float* d_img_loc, float* d_txt_loc, float* d_all_img, float* d_all_txt, float* d_scale,
                                float* workspace, void* stream);
 
+/* Distributed form (--local-loss --gather-with-grad, world_size > 1): `gathered` [N, 2D] fp32 is the payload of the ONE
+ * all-gather the host issues (row r*n + i = img_i | txt_i of rank r; loss.py:49-50 gathers the two halves separately); the
+ * local operands are its rows [rank*n, rank*n + n).  `backward` writes d_gathered [N, 2D], the gradient w.r.t. every
+ * gathered row with the local-row terms already added in, i.e. the input of the reduce-scatter(SUM) that completes
+ * torch.distributed.nn.all_gather's backward.  workspace as for b200clip_cliploss. */
+int b200clip_cliploss_packed_forward(const float* gathered, const float* logit_scale, int rank, int n, int N, int D,
+                                     float* loss, float* workspace, void* stream);
+int b200clip_cliploss_packed_backward(const float* gathered, const float* logit_scale, int rank, int n, int N, int D,
+                                      const float* grad_out, float* d_gathered, float* d_scale, float* workspace,
+                                      void* stream);
+
 /* ----- whole-tower drivers: one call per encode_image / encode_text ------------------------------ */
 
 typedef struct b200clip_tower_cfg {

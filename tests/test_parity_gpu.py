@@ -147,6 +147,34 @@ def test_cliploss_matches_reference_two_rank_local_loss():
         assert float(res[r][4]) == pytest.approx(float(g["w2"][r]["d_scale"]), rel=1e-4)
 
 
+def test_cliploss_packed_distributed_form_matches_reference_two_rank():
+    """Packed (img | txt) form used by the NCCL path: same golden two-rank run; the reduce-scatter is emulated as the sum of
+    both ranks' d_gathered, whose rows [r*n, r*n+n) must equal rank r's feature gradients (local-row terms folded in)."""
+    g = torch.load(GOLD / "cliploss.pt", weights_only=False)
+    img, txt = g["img"].to(DEV), g["txt"].to(DEV)
+    scale = torch.tensor(g["scale"], device=DEV)
+    n, D = img.shape[0] // 2, img.shape[1]
+    gathered = torch.cat([img, txt], dim=1).contiguous()
+    d_sum = torch.zeros_like(gathered)
+    d_scales = []
+    for r in range(2):
+        loss, ws = ops.cliploss_packed_forward(gathered, scale, r, n)
+        assert abs(float(loss) - float(g["w2"][r]["loss"])) / float(g["w2"][r]["loss"]) < 1e-5
+        d_g, d_s = ops.cliploss_packed_backward(gathered, scale, r, n, ws, None)
+        d_sum += d_g
+        d_scales.append(float(d_s))
+    for r in range(2):
+        assert rel(d_sum[r * n:(r + 1) * n, :D], g["w2"][r]["d_img"]) < 1e-4
+        assert rel(d_sum[r * n:(r + 1) * n, D:], g["w2"][r]["d_txt"]) < 1e-4
+        assert d_scales[r] == pytest.approx(float(g["w2"][r]["d_scale"]), rel=1e-4)
+    # upstream gradient is read from device memory
+    loss, ws = ops.cliploss_packed_forward(gathered, scale, 0, n)
+    d_g2, d_s2 = ops.cliploss_packed_backward(gathered, scale, 0, n, ws, torch.tensor(0.5, device=DEV))
+    loss, ws = ops.cliploss_packed_forward(gathered, scale, 0, n)
+    d_g1, d_s1 = ops.cliploss_packed_backward(gathered, scale, 0, n, ws, None)
+    assert rel(d_g2, 0.5 * d_g1) < 1e-6 and float(d_s2) == pytest.approx(0.5 * float(d_s1), rel=1e-6)
+
+
 # ------------------------------------------------------------------ BASELINE config 1 at full size ---
 def _domainnet_tokens():
     z = np.load(GOLD / "domainnet_prompts.npz")

@@ -204,6 +204,16 @@ int b200clip_cliploss_backward(const float* img_loc, const float* txt_loc, const
                              d_all_txt, d_scale, workspace, S(stream));
 }
 
+int b200clip_cliploss_packed_forward(const float* gathered, const float* logit_scale, int rank, int n, int N, int D, float* loss,
+                                     float* workspace, void* stream) {
+    return cliploss_packed_forward(gathered, logit_scale, rank, n, N, D, loss, workspace, S(stream));
+}
+
+int b200clip_cliploss_packed_backward(const float* gathered, const float* logit_scale, int rank, int n, int N, int D,
+                                      const float* grad_out, float* d_gathered, float* d_scale, float* workspace, void* stream) {
+    return cliploss_packed_backward(gathered, logit_scale, rank, n, N, D, grad_out, d_gathered, d_scale, workspace, S(stream));
+}
+
 int64_t b200clip_workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {
     return workspace_bytes(cfg, batch, seq_len);
 }

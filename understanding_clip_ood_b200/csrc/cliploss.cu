@@ -29,6 +29,7 @@ struct GemmProb {
     float* C;         // [M, N]
     int64_t lda, ldb, ldc;
     int M, N, K, ta, tb;
+    int accumulate;   // C += A B instead of C = A B
     int tiles_n, tile_begin;
 };
 struct GemmBatch {
@@ -85,8 +86,15 @@ __device__ __forceinline__ void tile_gemm(const GemmProb& p, int m0, int n0, flo
     for (int i = 0; i < 4; ++i) {
         const int row = m0 + ty * 4 + i;
         const int col = n0 + tx * 4;
-        if (row < p.M && col < p.N)  // N % 4 == 0 is checked on the host
-            *reinterpret_cast<float4*>(p.C + static_cast<int64_t>(row) * p.ldc + col) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (row < p.M && col < p.N) {  // N % 4 == 0 is checked on the host
+            float4* dst = reinterpret_cast<float4*>(p.C + static_cast<int64_t>(row) * p.ldc + col);
+            float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+            if (p.accumulate) {
+                const float4 c = *dst;
+                o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+            }
+            *dst = o;
+        }
     }
 }
 
@@ -119,12 +127,14 @@ int launch_batch(GemmBatch& b, cudaStream_t stream) {
     return 0;
 }
 
-GemmProb make_prob(const float* A, int64_t lda, bool ta, const float* B, int64_t ldb, bool tb, float* C, int64_t ldc, int M, int N, int K) {
+GemmProb make_prob(const float* A, int64_t lda, bool ta, const float* B, int64_t ldb, bool tb, float* C, int64_t ldc, int M, int N, int K,
+                   bool accumulate = false) {
     GemmProb p;
     p.A = A; p.B = B; p.C = C;
     p.lda = lda; p.ldb = ldb; p.ldc = ldc;
     p.M = M; p.N = N; p.K = K;
     p.ta = ta ? 1 : 0; p.tb = tb ? 1 : 0;
+    p.accumulate = accumulate ? 1 : 0;
     p.tiles_n = 0; p.tile_begin = 0;
     return p;
 }
@@ -235,31 +245,38 @@ int check_shapes(int rank, int n, int N, int D) {
     return 0;
 }
 
-}  // namespace
+// Operand views with explicit row pitches: the contiguous API passes pitch D everywhere, the packed (img | txt) API of the
+// distributed path passes pitch 2D and column offsets.
+struct LossOperands {
+    const float *img_loc, *txt_loc, *all_img, *all_txt;
+    int64_t ld_loc, ld_all;
+};
 
-int cliploss_forward(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt, const float* logit_scale,
-                     int rank, int n, int N, int D, float* loss, float* workspace, cudaStream_t stream) {
+int forward_impl(const LossOperands& o, const float* logit_scale, int rank, int n, int N, int D, float* loss, float* workspace,
+                 cudaStream_t stream) {
     int rc;
     if ((rc = check_shapes(rank, n, N, D)) != 0) return rc;
-    B2C_CHECK_ARG(img_loc && txt_loc && all_img && all_txt && logit_scale && loss && workspace, "cliploss: null pointer");
+    B2C_CHECK_ARG(o.img_loc && o.txt_loc && o.all_img && o.all_txt && logit_scale && loss && workspace, "cliploss: null pointer");
     const Ws ws = carve(workspace, n, N);
     B2C_CUDA(cudaMemsetAsync(ws.counter, 0, 16, stream));  // last-CTA-done counter (each kernel leaves it at zero again)
     GemmBatch b;
     b.count = 2;
-    b.prob[0] = make_prob(img_loc, D, false, all_txt, D, false, ws.logits, N, n, N, D);
-    b.prob[1] = make_prob(txt_loc, D, false, all_img, D, false, ws.logits + static_cast<int64_t>(n) * N, N, n, N, D);
+    b.prob[0] = make_prob(o.img_loc, o.ld_loc, false, o.all_txt, o.ld_all, false, ws.logits, N, n, N, D);
+    b.prob[1] = make_prob(o.txt_loc, o.ld_loc, false, o.all_img, o.ld_all, false, ws.logits + static_cast<int64_t>(n) * N, N, n, N, D);
     if ((rc = launch_batch(b, stream)) != 0) return rc;
     ce_forward_kernel<<<2 * n, 256, 0, stream>>>(ws.logits, logit_scale, n, N, rank, ws.row_loss, ws.row_lse, ws.counter, loss);
     B2C_LAUNCH_CHECK("ce_forward_kernel");
     return 0;
 }
 
-int cliploss_backward(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt, const float* logit_scale,
-                      int rank, int n, int N, int D, const float* grad_out, float* d_img_loc, float* d_txt_loc, float* d_all_img,
-                      float* d_all_txt, float* d_scale, float* workspace, cudaStream_t stream) {
+// d_*_loc == nullptr with `fold_local`: the local-row gradients are ADDED into rows [rank*n, rank*n + n) of d_all_* (second
+// launch), which is what a following reduce-scatter needs
+int backward_impl(const LossOperands& o, const float* logit_scale, int rank, int n, int N, int D, const float* grad_out,
+                  float* d_img_loc, float* d_txt_loc, int64_t ld_dloc, float* d_all_img, float* d_all_txt, int64_t ld_dall,
+                  bool fold_local, float* d_scale, float* workspace, cudaStream_t stream) {
     int rc;
     if ((rc = check_shapes(rank, n, N, D)) != 0) return rc;
-    B2C_CHECK_ARG(img_loc && txt_loc && all_img && all_txt && logit_scale && workspace, "cliploss: null pointer");
+    B2C_CHECK_ARG(o.img_loc && o.txt_loc && o.all_img && o.all_txt && logit_scale && workspace, "cliploss: null pointer");
     const Ws ws = carve(workspace, n, N);
     ce_backward_kernel<<<2 * n, 256, 0, stream>>>(ws.logits, logit_scale, grad_out, n, N, rank, ws.row_lse, ws.row_ds, ws.counter, d_scale);
     B2C_LAUNCH_CHECK("ce_backward_kernel");
@@ -268,12 +285,58 @@ int cliploss_backward(const float* img_loc, const float* txt_loc, const float* a
     float* Lt = ws.logits + static_cast<int64_t>(n) * N;
     GemmBatch b;
     b.count = 0;
-    if (d_img_loc) b.prob[b.count++] = make_prob(Li, N, false, all_txt, D, true, d_img_loc, D, n, D, N);
-    if (d_txt_loc) b.prob[b.count++] = make_prob(Lt, N, false, all_img, D, true, d_txt_loc, D, n, D, N);
-    if (d_all_txt) b.prob[b.count++] = make_prob(Li, N, true, img_loc, D, true, d_all_txt, D, N, D, n);
-    if (d_all_img) b.prob[b.count++] = make_prob(Lt, N, true, txt_loc, D, true, d_all_img, D, N, D, n);
+    if (!fold_local) {
+        if (d_img_loc) b.prob[b.count++] = make_prob(Li, N, false, o.all_txt, o.ld_all, true, d_img_loc, ld_dloc, n, D, N);
+        if (d_txt_loc) b.prob[b.count++] = make_prob(Lt, N, false, o.all_img, o.ld_all, true, d_txt_loc, ld_dloc, n, D, N);
+    }
+    if (d_all_txt) b.prob[b.count++] = make_prob(Li, N, true, o.img_loc, o.ld_loc, true, d_all_txt, ld_dall, N, D, n);
+    if (d_all_img) b.prob[b.count++] = make_prob(Lt, N, true, o.txt_loc, o.ld_loc, true, d_all_img, ld_dall, N, D, n);
     if (b.count > 0 && (rc = launch_batch(b, stream)) != 0) return rc;
+    if (fold_local) {
+        B2C_CHECK_ARG(d_all_img && d_all_txt, "cliploss: folding the local gradients needs d_all_img and d_all_txt");
+        GemmBatch f;
+        f.count = 2;
+        f.prob[0] = make_prob(Li, N, false, o.all_txt, o.ld_all, true, d_all_img + static_cast<int64_t>(rank) * n * ld_dall, ld_dall, n, D, N, true);
+        f.prob[1] = make_prob(Lt, N, false, o.all_img, o.ld_all, true, d_all_txt + static_cast<int64_t>(rank) * n * ld_dall, ld_dall, n, D, N, true);
+        if ((rc = launch_batch(f, stream)) != 0) return rc;
+    }
     return 0;
+}
+
+}  // namespace
+
+int cliploss_forward(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt, const float* logit_scale,
+                     int rank, int n, int N, int D, float* loss, float* workspace, cudaStream_t stream) {
+    const LossOperands o{img_loc, txt_loc, all_img, all_txt, D, D};
+    return forward_impl(o, logit_scale, rank, n, N, D, loss, workspace, stream);
+}
+
+int cliploss_backward(const float* img_loc, const float* txt_loc, const float* all_img, const float* all_txt, const float* logit_scale,
+                      int rank, int n, int N, int D, const float* grad_out, float* d_img_loc, float* d_txt_loc, float* d_all_img,
+                      float* d_all_txt, float* d_scale, float* workspace, cudaStream_t stream) {
+    const LossOperands o{img_loc, txt_loc, all_img, all_txt, D, D};
+    return backward_impl(o, logit_scale, rank, n, N, D, grad_out, d_img_loc, d_txt_loc, D, d_all_img, d_all_txt, D, false, d_scale,
+                         workspace, stream);
+}
+
+// Packed layout of the distributed path: `gathered` [N, 2D] holds img | txt of every rank (the ONE all-gather payload), the
+// local rows are rows [rank*n, rank*n + n) of it.  backward writes d_gathered [N, 2D] = gradient w.r.t. every gathered row
+// INCLUDING the local-row terms, i.e. exactly the input of the reduce-scatter that finishes gather_with_grad.
+int cliploss_packed_forward(const float* gathered, const float* logit_scale, int rank, int n, int N, int D, float* loss,
+                            float* workspace, cudaStream_t stream) {
+    B2C_CHECK_ARG(gathered != nullptr, "cliploss: null pointer");
+    const float* loc = gathered + static_cast<int64_t>(rank) * n * 2 * D;
+    const LossOperands o{loc, loc + D, gathered, gathered + D, 2 * static_cast<int64_t>(D), 2 * static_cast<int64_t>(D)};
+    return forward_impl(o, logit_scale, rank, n, N, D, loss, workspace, stream);
+}
+
+int cliploss_packed_backward(const float* gathered, const float* logit_scale, int rank, int n, int N, int D, const float* grad_out,
+                             float* d_gathered, float* d_scale, float* workspace, cudaStream_t stream) {
+    B2C_CHECK_ARG(gathered != nullptr && d_gathered != nullptr, "cliploss: null pointer");
+    const float* loc = gathered + static_cast<int64_t>(rank) * n * 2 * D;
+    const LossOperands o{loc, loc + D, gathered, gathered + D, 2 * static_cast<int64_t>(D), 2 * static_cast<int64_t>(D)};
+    return backward_impl(o, logit_scale, rank, n, N, D, grad_out, nullptr, nullptr, 0, d_gathered, d_gathered + D,
+                         2 * static_cast<int64_t>(D), true, d_scale, workspace, stream);
 }
 
 // fused forward + backward (one call; used when the upstream gradient is already known or 1)

@@ -63,6 +63,11 @@ int cliploss_backward(const float* img_loc, const float* txt_loc, const float* a
                       int rank, int n, int N, int D, const float* grad_out, float* d_img_loc, float* d_txt_loc, float* d_all_img,
                       float* d_all_txt, float* d_scale, float* workspace, cudaStream_t stream);
 
+int cliploss_packed_forward(const float* gathered, const float* logit_scale, int rank, int n, int N, int D, float* loss,
+                            float* workspace, cudaStream_t stream);
+int cliploss_packed_backward(const float* gathered, const float* logit_scale, int rank, int n, int N, int D, const float* grad_out,
+                             float* d_gathered, float* d_scale, float* workspace, cudaStream_t stream);
+
 inline int dtype_size(int dtype) { return dtype == 0 ? 4 : 2; }
 
 }  // namespace b200clip

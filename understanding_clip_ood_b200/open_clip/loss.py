@@ -122,6 +122,39 @@ class _FusedClipLoss(torch.autograd.Function):
         return (*out, None)
 
 
+class _DistLocalClipLoss(torch.autograd.Function):
+    """--local-loss --gather-with-grad on world_size > 1 as ONE autograd node: pack img | txt, one all-gather, the packed
+    forward kernels; backward = packed backward kernels (local-row gradients folded into the gathered gradient) + one
+    reduce-scatter.  Same values as gather_features + the generic node, without the slice / cat / add kernels in between."""
+
+    @staticmethod
+    def forward(ctx, image_features, text_features, logit_scale, rank: int, world_size: int, group):
+        n, D = image_features.shape
+        both = torch.cat([_f32c(image_features), _f32c(text_features)], dim=1)          # [n, 2D]
+        gathered = torch.empty((world_size * n, 2 * D), dtype=torch.float32, device=both.device)
+        if both.is_cuda:
+            dist.all_gather_into_tensor(gathered, both, group=group)
+        else:  # pragma: no cover  (the kernels below need CUDA; kept so the failure is the loud one from ops)
+            dist.all_gather(list(gathered.chunk(world_size, dim=0)), both, group=group)
+        scale = _f32c(logit_scale).reshape(())
+        loss, ws = ops.cliploss_packed_forward(gathered, scale, rank, n)
+        ctx.meta = (rank, n, D, group, image_features.dtype, text_features.dtype, logit_scale.dtype, logit_scale.shape)
+        ctx.save_for_backward(gathered, scale, ws)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        gathered, scale, ws = ctx.saved_tensors
+        rank, n, D, group, dt_i, dt_t, dt_s, s_shape = ctx.meta
+        d_g, d_s = ops.cliploss_packed_backward(gathered, scale, rank, n, ws, _f32c(g).reshape(()), ctx.needs_input_grad[2])
+        d_both = torch.empty((n, 2 * D), dtype=torch.float32, device=d_g.device)
+        dist.reduce_scatter_tensor(d_both, d_g, op=dist.ReduceOp.SUM, group=group)
+        d_i = d_both[:, :D].to(dt_i) if ctx.needs_input_grad[0] else None
+        d_t = d_both[:, D:].to(dt_t) if ctx.needs_input_grad[1] else None
+        d_sc = d_s.to(dt_s).reshape(s_shape) if d_s is not None else None
+        return d_i, d_t, d_sc, None, None, None
+
+
 class ClipLoss(nn.Module):
     def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1, use_horovod=False):
         super().__init__()
@@ -168,6 +201,9 @@ class ClipLoss(nn.Module):
             raise L.B200ClipError("ClipLoss: CUDA feature tensors required — this path has no CPU fallback")
         if not torch.is_tensor(logit_scale):
             logit_scale = torch.tensor(float(logit_scale), device=image_features.device)
-        rows_i, rows_t, all_img, all_txt, rank = self._operands(image_features, text_features)
-        total_loss = _FusedClipLoss.apply(rows_i, rows_t, all_img, all_txt, logit_scale, rank)
+        if self.world_size > 1 and self.local_loss and self.gather_with_grad and not self.use_horovod:
+            total_loss = _DistLocalClipLoss.apply(image_features, text_features, logit_scale, self.rank, self.world_size, None)
+        else:
+            rows_i, rows_t, all_img, all_txt, rank = self._operands(image_features, text_features)
+            total_loss = _FusedClipLoss.apply(rows_i, rows_t, all_img, all_txt, logit_scale, rank)
         return {"contrastive_loss": total_loss} if output_dict else total_loss

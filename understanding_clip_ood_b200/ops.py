@@ -228,6 +228,29 @@ def cliploss_backward(img_loc, txt_loc, all_img, all_txt, logit_scale, rank: int
     return grads
 
 
+def cliploss_packed_forward(gathered: torch.Tensor, logit_scale: torch.Tensor, rank: int, n: int):
+    """gathered [N, 2D] fp32 (img | txt of every rank).  -> (loss 0-dim, workspace); see b200clip_cliploss_packed_forward."""
+    N, D2 = gathered.shape
+    loss = torch.empty((), dtype=torch.float32, device=gathered.device)
+    ws = torch.empty((cliploss_workspace_floats(n, N),), dtype=torch.float32, device=gathered.device)
+    rc = L.load().b200clip_cliploss_packed_forward(gathered.data_ptr(), logit_scale.data_ptr(), rank, n, N, D2 // 2, loss.data_ptr(),
+                                                   ws.data_ptr(), L.stream_ptr())
+    L.check(rc, "b200clip_cliploss_packed_forward")
+    return loss, ws
+
+
+def cliploss_packed_backward(gathered: torch.Tensor, logit_scale: torch.Tensor, rank: int, n: int, ws: torch.Tensor,
+                             grad_out: torch.Tensor | None, want_scale: bool = True):
+    """-> (d_gathered [N, 2D] incl. the local-row terms, d_scale 0-dim | None); see b200clip_cliploss_packed_backward."""
+    N, D2 = gathered.shape
+    d_g = torch.empty_like(gathered)
+    d_s = torch.empty((), dtype=torch.float32, device=gathered.device) if want_scale else None
+    rc = L.load().b200clip_cliploss_packed_backward(gathered.data_ptr(), logit_scale.data_ptr(), rank, n, N, D2 // 2, L.ptr(grad_out),
+                                                    d_g.data_ptr(), L.ptr(d_s), ws.data_ptr(), L.stream_ptr())
+    L.check(rc, "b200clip_cliploss_packed_backward")
+    return d_g, d_s
+
+
 def cliploss_fwd_bwd(img_loc: torch.Tensor, txt_loc: torch.Tensor, all_img: torch.Tensor, all_txt: torch.Tensor,
                      logit_scale: torch.Tensor, rank: int, *, want_grad: bool = True, grad_out: torch.Tensor | None = None):
     """fp32 features.  -> loss (0-dim), (d_img_loc, d_txt_loc, d_all_img, d_all_txt, d_scale) or None."""
