@@ -7,7 +7,7 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from understanding_clip_ood_b200 import ops  # noqa: E402
 
-for (B, L, H, causal) in [(1024, 50, 12, False), (128, 50, 12, False), (4096, 16, 8, True), (1024, 77, 8, True), (256, 197, 12, False)]:
+for (B, L, H, causal) in [(1024, 50, 12, False), (128, 50, 12, False), (4096, 16, 8, True), (1024, 77, 8, True), (256, 197, 12, False), (128, 257, 16, False)]:
     W = H * 64
     g = torch.Generator(device="cuda").manual_seed(0)
     qkv = torch.randn(B * L, 3 * W, device="cuda", generator=g).bfloat16()

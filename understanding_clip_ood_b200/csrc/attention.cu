@@ -19,6 +19,8 @@
 
 namespace b200clip {
 
+int attention_tc(int dtype, const void* qkv, void* out, int batch, int L, int heads, int causal, cudaStream_t stream);
+
 namespace {
 
 constexpr int kHeadDim = 64;
@@ -602,6 +604,11 @@ int attention(int dtype, const void* qkv, void* out, int batch, int seq_len, int
         if (rc != 0) return rc;
         B2C_LAUNCH_CHECK("attention_short_kernel");
         return 0;
+    }
+    if (!attention_force_generic()) {
+        // 64 < L <= 288: tcgen05 kernel (attention_tc.cu); returns 1 when the shape is outside its range
+        const int rc = attention_tc(dtype, qkv, out, batch, seq_len, heads, causal, stream);
+        if (rc != 1) return rc;
     }
     dim3 grid(static_cast<unsigned>(bh), (seq_len + kBlockQ - 1) / kBlockQ);
     const __nv_bfloat16* qb = static_cast<const __nv_bfloat16*>(qkv);
