@@ -225,9 +225,12 @@ def _attn_ref(qkv, B, Lq, H, causal):
 @pytest.mark.parametrize("B,Lq,H,causal", [(3, 50, 12, False), (2, 77, 8, True), (2, 197, 12, False), (1, 257, 16, False),
                                            (4, 16, 8, True), (2, 64, 2, True), (2, 130, 2, True),
                                            (700, 50, 12, False), (33, 7, 8, True), (5, 1, 8, False), (300, 33, 8, True),
-                                           # tcgen05 kernel (64 < L <= 288): tile-exact, tail, two-accumulator-group and persistent cases
+                                           # tcgen05 kernel (64 < L <= 257): tile-exact, M=128 / M=64 tail tiles, the CUDA-core key of
+                                           # L = 257, persistent multi-item CTAs; L > 257 falls back to the generic kernel
                                            (3, 128, 4, False), (2, 256, 2, True), (2, 288, 2, False), (3, 65, 3, True), (2, 288, 1, True),
-                                           (40, 197, 12, False), (64, 77, 8, True), (1, 300, 2, False)])
+                                           (40, 197, 12, False), (64, 77, 8, True), (1, 300, 2, False), (20, 257, 16, False),
+                                           (3, 257, 2, True), (2, 192, 3, False), (2, 129, 2, True), (2, 193, 1, False), (150, 80, 3, True),
+                                           (149, 257, 1, False)])
 def test_attention(dtype, B, Lq, H, causal):
     g = _gen(8)
     qkv = (torch.randn(B * Lq, 3 * H * 64, device=DEV, generator=g) * 1.5).to(dtype)
