@@ -25,6 +25,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
+    # experiment switches (-DNAME=value), e.g. B200CLIP_NVCC_EXTRA="-DB2C_ATTN_NO_PIPE=1"
+    *os.environ.get("B200CLIP_NVCC_EXTRA", "").split(),
 ]
 
 

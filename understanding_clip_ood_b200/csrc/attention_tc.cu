@@ -35,12 +35,13 @@ namespace {
 constexpr int kHd = 64;
 constexpr int kQT = 128;               // query rows per tile
 constexpr int kTileQBytes = kQT * 128;
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;   // 2 softmax warpgroups + 1 warpgroup holding the TMA and MMA threads
 constexpr int kTmemCols = 512;
 constexpr int kMaxSmem = 227 * 1024;
 
 struct AttnTcParams {
     int L, heads, q_tiles, items, tail_rows, n_cols, kv_stage_bytes;
+    int nq, nkv;   // ring depths: query-tile slots (2..4), K/V stages (2..6), as many as shared memory holds
 };
 
 // tcgen05.mma with the A operand in tensor memory (lane = row, one 32-bit column = two consecutive K elements)
@@ -65,8 +66,7 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// tcgen05.wait::ld + a register dependency on the loaded values: with loads kept in flight across the arithmetic of the
-// previous chunk, nothing may be scheduled on `v` before the wait.
+// tcgen05.wait::ld + a register dependency on the loaded values: nothing may be scheduled on `v` before the wait.
 __device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
@@ -91,6 +91,11 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_bmn(uint32_t fmt, uint32_t
     return (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -98,7 +103,8 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 
 // barrier slots
-enum { kKvFull = 0, kKvEmpty = 2, kQFull = 4, kQEmpty = 6, kSFull = 8, kPFull = 10, kOFull = 12, kSEmpty = 14, kNumBars = 16 };
+constexpr int kMaxQ = 4, kMaxKv = 6;
+enum { kKvFull = 0, kKvEmpty = 6, kQFull = 12, kQEmpty = 16, kSFull = 20, kPFull = 22, kOFull = 24, kSEmpty = 26, kNumBars = 28 };
 
 template <typename T, bool CAUSAL, bool EXTRA>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -108,10 +114,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     using H = Half16<T>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* s_q = smem;                       // 2 x [128 x 64] query tiles
-    uint8_t* s_o = s_q + 2 * kTileQBytes;      // 2 x [128 x 64] output staging tiles (one per softmax warpgroup)
-    uint8_t* s_kv = s_o + 2 * kTileQBytes;     // 2 stages x (K rows | V rows)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + 4 * p.kv_stage_bytes);
+    uint8_t* s_o = smem;                          // 2 x [128 x 64] output staging tiles (one per softmax warpgroup)
+    uint8_t* s_q = s_o + 2 * kTileQBytes;         // nq x [128 x 64] query tiles
+    uint8_t* s_kv = s_q + p.nq * kTileQBytes;     // nkv stages x (K rows | V rows)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + 2 * p.nkv * p.kv_stage_bytes);
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -122,13 +128,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int n_tiles = n_items * q_tiles;
 
     // K / V rows beyond L are never written by TMA: zero the ring once (masked probabilities multiply finite values)
-    for (int i = tid; i < (4 * p.kv_stage_bytes) / 16; i += kThreads) reinterpret_cast<uint4*>(s_kv)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < (2 * p.nkv * p.kv_stage_bytes) / 16; i += kThreads) reinterpret_cast<uint4*>(s_kv)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < kMaxKv; ++s) {
             mbar_init(bars + kKvFull + s, 1);
             mbar_init(bars + kKvEmpty + s, EXTRA ? 1 + 128 * q_tiles : 1);
+        }
+        for (int s = 0; s < kMaxQ; ++s) {
             mbar_init(bars + kQFull + s, 1);
             mbar_init(bars + kQEmpty + s, EXTRA ? 128 : 1);
+        }
+        for (int s = 0; s < 2; ++s) {
             mbar_init(bars + kSFull + s, 1);
             mbar_init(bars + kPFull + s, 128);
             mbar_init(bars + kOFull + s, 1);
@@ -155,19 +165,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const int kv_tail = L - full_kv_boxes * 128;
     const bool tail_m64 = p.tail_rows <= 64;
 
+    // 168 registers per thread at launch; the producer warpgroup hands 128 x 112 of them to the two softmax warpgroups
+    // (each role branch issues its own setmaxnreg so that ptxas budgets the branch accordingly)
     if (warp == 8) {
         // ===================== TMA producer (one thread) =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (lane == 0) {
             int t = 0;
             for (int il = 0; il < n_items; ++il) {
                 const int it = static_cast<int>(blockIdx.x) + il * static_cast<int>(gridDim.x);
                 const int b = it / p.heads, h = it - b * p.heads;
                 const int row0 = b * L;
-                const int st = il & 1;
+                const int st = il % p.nkv;
                 uint8_t* sk = s_kv + st * 2 * p.kv_stage_bytes;
                 uint8_t* sv = sk + p.kv_stage_bytes;
                 uint64_t* kv_full = bars + kKvFull + st;
-                mbar_wait(bars + kKvEmpty + st, ((il >> 1) & 1) ^ 1);
+                mbar_wait(bars + kKvEmpty + st, ((il / p.nkv) & 1) ^ 1);
                 mbar_arrive_expect_tx(kv_full, static_cast<uint32_t>(2 * L * 128));
                 for (int bx = 0; bx < full_kv_boxes; ++bx) {
                     tma_load_2d(&tmap_q, kv_full, sk + bx * kTileQBytes, W + h * kHd, row0 + bx * 128, kCacheHintEvictFirst);
@@ -180,21 +193,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                                 kCacheHintEvictFirst);
                 }
                 for (int qt = 0; qt < q_tiles; ++qt, ++t) {
-                    const int g = t & 1;
-                    mbar_wait(bars + kQEmpty + g, ((t >> 1) & 1) ^ 1);
-                    mbar_arrive_expect_tx(bars + kQFull + g, kTileQBytes);
-                    tma_load_2d(&tmap_q, bars + kQFull + g, s_q + g * kTileQBytes, h * kHd, row0 + qt * kQT, kCacheHintEvictFirst);
+                    const int qs = t % p.nq;
+                    mbar_wait(bars + kQEmpty + qs, ((t / p.nq) & 1) ^ 1);
+                    mbar_arrive_expect_tx(bars + kQFull + qs, kTileQBytes);
+                    tma_load_2d(&tmap_q, bars + kQFull + qs, s_q + qs * kTileQBytes, h * kHd, row0 + qt * kQT, kCacheHintEvictFirst);
                 }
             }
         }
         __syncwarp();
     } else if (warp == 9) {
         // ===================== MMA issue (one thread) =====================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (lane == 0) {
             auto issue_pv = [&](int t) {
                 const int g = t & 1;
                 const int il = t / q_tiles, qt = t - il * q_tiles;
-                const int st = il & 1;
+                const int st = il % p.nkv;
                 const bool m64 = tail_m64 && qt == q_tiles - 1;
                 const int ncols = CAUSAL ? min(p.n_cols, kQT * (qt + 1)) : p.n_cols;
                 const uint32_t idesc_o = make_idesc_f16_bmn(H::kUmmaFormat, m64 ? 64 : 128, kHd);
@@ -211,34 +225,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             for (int t = 0; t < n_tiles; ++t) {
                 const int g = t & 1;
                 const int il = t / q_tiles, qt = t - il * q_tiles;
-                const int st = il & 1;
+                const int st = il % p.nkv, qs = t % p.nq;
                 const bool m64 = tail_m64 && qt == q_tiles - 1;
                 const int ncols = CAUSAL ? min(p.n_cols, kQT * (qt + 1)) : p.n_cols;
                 const uint32_t idesc_s = make_idesc_f16(H::kUmmaFormat, m64 ? 64 : 128, static_cast<uint32_t>(ncols));
-                const uint64_t desc_q = make_sw128_kmajor_desc(smem_u32(s_q + g * kTileQBytes));
+                const uint64_t desc_q = make_sw128_kmajor_desc(smem_u32(s_q + qs * kTileQBytes));
                 const uint64_t desc_k = make_sw128_kmajor_desc(smem_u32(s_kv + st * 2 * p.kv_stage_bytes));
                 const uint32_t tm = tmem_base + static_cast<uint32_t>(g * 256);
                 mbar_wait(bars + kSEmpty + g, ((t >> 1) & 1) ^ 1);      // O of tile t-2 has been drained from this TMEM half
-                if (qt == 0) mbar_wait(bars + kKvFull + st, (il >> 1) & 1);
-                mbar_wait(bars + kQFull + g, (t >> 1) & 1);
+                if (qt == 0) mbar_wait(bars + kKvFull + st, (il / p.nkv) & 1);
+                mbar_wait(bars + kQFull + qs, (t / p.nq) & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < kHd / 16; ++k) umma_f16(tm, desc_q + 2 * k, desc_k + 2 * k, idesc_s, k != 0);
                 umma_commit(bars + kSFull + g);
-                if (!EXTRA) umma_commit(bars + kQEmpty + g);
+                if (!EXTRA) umma_commit(bars + kQEmpty + qs);
                 if (t > 0) issue_pv(t - 1);
             }
             if (n_tiles > 0) issue_pv(n_tiles - 1);
         }
         __syncwarp();
-    } else {
+    } else if (warp < 8) {
         // ===================== softmax + output (thread = query row; warpgroup g owns tiles t = g, g+2, ...) =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         const int g = warp >> 2, wq = warp & 3;
         const int gtid = tid & 127;
         const uint32_t tm = tmem_base + static_cast<uint32_t>(g * 256) + (static_cast<uint32_t>(wq * 32) << 16);
         const float c = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
         const uint32_t so = smem_u32(s_o + g * kTileQBytes);
-        const uint32_t sq = smem_u32(s_q + g * kTileQBytes);
         uint64_t* s_full = bars + kSFull + g;
         uint64_t* p_full = bars + kPFull + g;
         uint64_t* o_full = bars + kOFull + g;
@@ -248,7 +262,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const int il = t / q_tiles, qt = t - il * q_tiles;
             const int it = static_cast<int>(blockIdx.x) + il * static_cast<int>(gridDim.x);
             const int b = it / p.heads, h = it - b * p.heads;
-            const int st = il & 1;
+            const int st = il % p.nkv, qs = t % p.nq;
             const bool last = qt == q_tiles - 1;
             const bool m64 = tail_m64 && last;
             const int vr = last ? p.tail_rows : kQT;                      // valid rows of this tile
@@ -275,18 +289,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                             mx = fmaxf(mx, s);
                         }
                     } else {
-                        float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
-                        float m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+                        float m0 = mx, m1 = __uint_as_float(v[0]);   // two FMNMX3 chains
 #pragma unroll
-                        for (int j = 4; j < 32; j += 4) {
-                            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
-                            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+                        for (int j = 0; j < 32; j += 4) {
+                            m0 = fmax3(m0, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                            m1 = fmax3(m1, __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                         }
-                        mx = fmaxf(mx, fmaxf(m0, m1));
+                        mx = fmaxf(m0, m1);
                     }
                 };
                 {
+                    // NOT unrolled over the chunks (the unrolled form overflowed the instruction cache: stall_no_inst), and the
+                    // next chunk's tcgen05.ld is not kept in flight under this chunk's arithmetic: measured slower (113 vs 101 us
+                    // at L = 197), the second softmax warpgroup on the same scheduler already fills the load latency.
                     uint32_t va[32];
+#pragma unroll 1
                     for (int ch = 0; ch < nch; ++ch) {
                         tmem_ld_32x32(tm + ch * 32, va);
                         tmem_ld_wait_on(va);
@@ -295,7 +312,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 }
                 if (EXTRA) {
                     // key 256 on the CUDA cores: s_x = q_row . k_256 (row 256 of the K stage: 256 % 8 == 0, so it is not swizzled)
-                    const uint32_t qa = sq + static_cast<uint32_t>(r) * 128, rx = static_cast<uint32_t>(r & 7);
+                    const uint32_t qa = smem_u32(s_q + qs * kTileQBytes) + static_cast<uint32_t>(r) * 128, rx = static_cast<uint32_t>(r & 7);
                     const uint32_t ka = skv + 256u * 128u;
                     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
@@ -313,46 +330,63 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     s_x = (CAUSAL && 256 > qrow) ? -INFINITY : a0 + a1;
                     mx = fmaxf(mx, s_x);
                 }
-                if (EXTRA) mbar_arrive(bars + kQEmpty + g);
+                if (EXTRA) mbar_arrive(bars + kQEmpty + qs);
                 // column 0 is valid for every row (causal: col 0 <= row), so mx is finite unless the scores themselves are not
                 const float nm = -mx * c;
                 // ---- pass 2: p = 2^(s*c - m*c), row sum, P (16-bit) over the S columns this thread has already consumed
                 float sum0 = 0.f, sum1 = 0.f;
+                uint64_t sum2a = 0ull, sum2b = 0ull;   // packed fp32x2 partial sums (FADD2)
+                const uint64_t c2 = pack_f2(c, c), nm2 = pack_f2(nm, nm);
                 auto exp_chunk = [&](const uint32_t (&v)[32], int ch) {
                     const int c0 = ch * 32;
-                    const bool need_mask = c0 + 32 > L || (CAUSAL && c0 + 32 > qrow + 1);
                     uint32_t pk[16];
+                    if (c0 + 32 > L || (CAUSAL && c0 + 32 > qrow + 1)) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float p0 = ex2_fast(fmaf(__uint_as_float(v[2 * j]), c, nm));
-                        float p1 = ex2_fast(fmaf(__uint_as_float(v[2 * j + 1]), c, nm));
-                        if (need_mask) {
+                        for (int j = 0; j < 16; ++j) {
+                            float p0 = ex2_fast(fmaf(__uint_as_float(v[2 * j]), c, nm));
+                            float p1 = ex2_fast(fmaf(__uint_as_float(v[2 * j + 1]), c, nm));
                             const int col = c0 + 2 * j;
                             if (col >= L || (CAUSAL && col > qrow)) p0 = 0.f;
                             if (col + 1 >= L || (CAUSAL && col + 1 > qrow)) p1 = 0.f;
+                            sum0 += p0;
+                            sum1 += p1;
+                            pk[j] = H::pack(p0, p1);
                         }
-                        sum0 += p0;
-                        sum1 += p1;
-                        pk[j] = H::pack(p0, p1);
+                    } else {
+                        // FFMA2 for the exponent argument and FADD2 for the row sum: 2.5 issue slots per element instead of 3.5
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float x0, x1;
+                            unpack_f2(fma_f2(pack_f2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), c2, nm2), x0, x1);
+                            const float p0 = ex2_fast(x0), p1 = ex2_fast(x1);
+                            if (j & 1) sum2b = add_f2(sum2b, pack_f2(p0, p1));
+                            else sum2a = add_f2(sum2a, pack_f2(p0, p1));
+                            pk[j] = H::pack(p0, p1);
+                        }
                     }
                     tmem_st_32x16(tm + ch * 16, pk);
                 };
                 {
                     uint32_t va[32];
+#pragma unroll 1
                     for (int ch = 0; ch < nch; ++ch) {
                         tmem_ld_32x32(tm + ch * 32, va);
                         tmem_ld_wait_on(va);
                         exp_chunk(va, ch);
                     }
                 }
-                sum = sum0 + sum1;
+                {
+                    float s0, s1;
+                    unpack_f2(add_f2(sum2a, sum2b), s0, s1);
+                    sum = (sum0 + sum1) + (s0 + s1);
+                }
                 if (EXTRA) {
                     p_x = ex2_fast(fmaf(s_x, c, nm));   // 2^(-inf) = 0 for the causally masked case
                     sum += p_x;
                 }
                 tmem_st_wait();
             } else if (EXTRA) {
-                mbar_arrive(bars + kQEmpty + g);
+                mbar_arrive(bars + kQEmpty + qs);
             }
             tc_fence_before();
             mbar_arrive(p_full);
@@ -409,6 +443,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
         }
         if (gtid == 0) tma_store_wait_all<0>();
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     }
 
     tc_fence_before();
@@ -459,7 +495,14 @@ int attention_tc(int dtype, const void* qkv, void* out, int batch, int L, int he
     if (make_tmap_2d(&to, bf, out, rows, W, W, kQT, kHd) != 0) return -1;
     if (make_tmap_2d(&tot, bf, out, rows, W, W, p.tail_rows, kHd) != 0) return -1;
 
-    const int smem_bytes = 4 * kTileQBytes + 4 * p.kv_stage_bytes + kNumBars * 8 + 16 + 1024;
+    // ring depths: the minimum is 2 + 2; query slots first (their prefetch distance is one tile), then K/V stages
+    const int fixed_bytes = 2 * kTileQBytes + kNumBars * 8 + 16 + 1024;
+    p.nq = 2;
+    p.nkv = 2;
+    auto total = [&](int nq, int nkv) { return fixed_bytes + nq * kTileQBytes + 2 * nkv * p.kv_stage_bytes; };
+    while (p.nq < kMaxQ && total(p.nq + 1, p.nkv) <= kMaxSmem) ++p.nq;
+    while (p.nkv < kMaxKv && total(p.nq, p.nkv + 1) <= kMaxSmem) ++p.nkv;
+    const int smem_bytes = total(p.nq, p.nkv);
     B2C_CHECK_ARG(smem_bytes <= kMaxSmem, "attention_tc: shared memory budget exceeded");
     const int grid = static_cast<int>(items < num_sms() ? items : num_sms());
 
