@@ -156,6 +156,27 @@ int b200clip_cliploss_packed_backward(const float* gathered, const float* logit_
                                       const float* grad_out, float* d_gathered, float* d_scale, float* workspace,
                                       void* stream);
 
+/* ----- peer-memory form of the distributed step (NVLink / NVSwitch stores instead of the NCCL all-gather and reduce-scatter
+ * of loss.py:49-50 and its autograd backward).  The host maps one symmetric allocation per rank (torch symmetric memory) and
+ * passes DEVICE arrays of `world` pre-offset pointers; flags are uint32 words holding a monotonically increasing epoch.
+ *
+ * b200clip_p2p_allgather: rows img | txt (dtype B200CLIP_*, [n, D] each) -> fp32 [n, 2D] written into peer_dst[p] for every
+ *   rank p (= slot `rank` of p's gather buffer), then *peer_flag[p] = epoch (release, system scope), then waits until
+ *   my_flags[q] >= epoch for all q: when the call's kernel has finished, the local gather buffer holds every rank's rows.
+ *   `counters`: `world` zero-initialised uint32 in local memory (left at zero).
+ * b200clip_cliploss_packed_backward_p2p: as b200clip_cliploss_packed_backward, but the gradient block of rank j's rows
+ *   ([n, 2D]) is stored to d_slots[j] (= slot `rank` of j's receive buffer): the GEMM epilogue is the scatter.
+ * b200clip_p2p_reduce_finish: *peer_flag[p] = epoch for every p, wait my_flags[q] >= epoch for all q, then
+ *   out[elems] = sum over q of recv[q * elems ...] (recv = the local receive buffer, `world` slots). */
+int b200clip_p2p_allgather(int dtype, const void* img, const void* txt, int n, int D, float* const* peer_dst,
+                           uint32_t* const* peer_flag, const uint32_t* my_flags, uint32_t* counters, int world,
+                           uint32_t epoch, void* stream);
+int b200clip_cliploss_packed_backward_p2p(const float* gathered, const float* logit_scale, int rank, int n, int N, int D,
+                                          const float* grad_out, float* const* d_slots, float* d_scale, float* workspace,
+                                          void* stream);
+int b200clip_p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag,
+                               const uint32_t* my_flags, int world, uint32_t epoch, void* stream);
+
 /* ----- whole-tower drivers: one call per encode_image / encode_text ------------------------------ */
 
 typedef struct b200clip_tower_cfg {

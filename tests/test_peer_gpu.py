@@ -1,0 +1,93 @@
+"""Distributed ClipLoss over peer memory (csrc/p2p.cu, open_clip/peer.py) on >= 2 GPUs of one node: one process per GPU,
+NCCL for the rendezvous only.  Checked against the CPU oracle evaluated on the global batch (identities of SURVEY §8c:
+mean_r loss_r == global loss, grad_r == global grad / world ... here per-rank values directly) and against the NCCL form."""
+import os
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_rank(all_img, all_txt, scale, rank, n):
+    """loss and d(img_r), d(txt_r), d(scale) of rank `rank`'s local loss INCLUDING the reduce-scattered terms of every other
+    rank's loss (what --gather-with-grad delivers), from the CPU oracle."""
+    from oracle import clip_oracle as O
+    world = all_img.shape[0] // n
+    loss = float(O.clip_loss_local(all_img[rank * n:(rank + 1) * n], all_txt[rank * n:(rank + 1) * n], all_img, all_txt, scale, rank))
+    d_img = torch.zeros(n, all_img.shape[1], dtype=torch.float64)
+    d_txt = torch.zeros_like(d_img)
+    d_scale = 0.0
+    for q in range(world):
+        gi, gt, gai, gat, gs = O.clip_loss_local_grads(all_img[q * n:(q + 1) * n], all_txt[q * n:(q + 1) * n], all_img, all_txt, scale, q)
+        d_img += gai[rank * n:(rank + 1) * n]
+        d_txt += gat[rank * n:(rank + 1) * n]
+        if q == rank:
+            d_img += gi
+            d_txt += gt
+            d_scale = gs
+    return loss, d_img, d_txt, d_scale
+
+
+def _worker(rank, world, port, n, D, dtype_name, steps, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from understanding_clip_ood_b200 import open_clip
+        from understanding_clip_ood_b200.open_clip import loss as loss_mod, peer
+        dtype = getattr(torch, dtype_name)
+        errs = []
+        loss_fn = open_clip.ClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world)
+        for step in range(steps):
+            g = torch.Generator().manual_seed(100 + step)
+            all_img = torch.nn.functional.normalize(torch.randn(world * n, D, generator=g), dim=-1).to(dtype)
+            all_txt = torch.nn.functional.normalize(torch.randn(world * n, D, generator=g), dim=-1).to(dtype)
+            scale = 1 / 0.07 + step
+            img = all_img[rank * n:(rank + 1) * n].to(dev).requires_grad_(True)
+            txt = all_txt[rank * n:(rank + 1) * n].to(dev).requires_grad_(True)
+            ls = torch.tensor(scale, device=dev, requires_grad=True)
+            if step == 1:     # a forward that never gets a backward (ring slot released when the graph dies)
+                with torch.no_grad():
+                    loss_fn(img, txt, ls)
+                dropped = loss_fn(img, txt, ls)
+                del dropped
+            loss = loss_fn(img, txt, ls)
+            assert type(loss.grad_fn).__name__.startswith("_PeerLocalClipLoss"), type(loss.grad_fn).__name__
+            (loss * 2.0).backward()              # upstream gradient != 1
+            want_loss, want_di, want_dt, want_ds = _oracle_rank(all_img.float(), all_txt.float(), scale, rank, n)
+            tol = 1e-4 if dtype == torch.float32 else 2e-2
+            errs.append(abs(float(loss) - want_loss) / abs(want_loss))
+            errs.append(float((img.grad.double().cpu() / 2 - want_di).norm() / want_di.norm()) * (1e-4 / tol))
+            errs.append(float((txt.grad.double().cpu() / 2 - want_dt).norm() / want_dt.norm()) * (1e-4 / tol))
+            errs.append(abs(float(ls.grad) / 2 - want_ds) / abs(want_ds))
+            # the NCCL form of the same node gives the same numbers
+            img2, txt2, ls2 = [t.detach().clone().requires_grad_(True) for t in (img, txt, ls)]
+            loss2 = loss_mod._DistLocalClipLoss.apply(img2, txt2, ls2, rank, world, None)
+            (loss2 * 2.0).backward()
+            errs.append(abs(float(loss2) - float(loss)) / abs(float(loss)))
+            errs.append(float((img2.grad.float() - img.grad.float()).norm() / img.grad.float().norm()) * (1e-4 / tol) * 0.1)
+        torch.cuda.synchronize()
+        ret[rank] = max(errs)
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs on one node")
+@pytest.mark.parametrize("n,D,dtype_name", [(256, 512, "float32"), (36, 64, "float32"), (128, 512, "bfloat16")])
+def test_peer_cliploss_matches_oracle(n, D, dtype_name):
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 8)
+    ret = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_worker, args=(world, 29600 + (n % 97), n, D, dtype_name, 7, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    assert max(ret.values()) < 1e-3, dict(ret)

@@ -70,6 +70,9 @@ SIGNATURES = {
     "b200clip_cliploss_backward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200clip_cliploss_packed_forward": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "b200clip_cliploss_packed_backward": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "b200clip_p2p_allgather": (C.c_int, [_I, _P, _P, _I, _I, _P, _P, _P, _P, _I, C.c_uint32, _P]),
+    "b200clip_cliploss_packed_backward_p2p": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "b200clip_p2p_reduce_finish": (C.c_int, [_P, _P, _L, _P, _P, _I, C.c_uint32, _P]),
     "b200clip_workspace_bytes": (C.c_int64, [C.POINTER(TowerCfg), _I, _I]),
     "b200clip_vit_forward": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(VitWeights), _P, _P, _I, _I, _P, _L, _P]),
     "b200clip_text_forward": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(TextWeights), _P, _P, _I, _I, _I, _P, _L, _P]),
@@ -121,7 +124,9 @@ def ptr(t) -> int | None:
 
 
 def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of torch's current stream on the current device (the C-level query: `torch.cuda.current_stream()`
+    costs ~10 us of Python per call, which showed up as a sixth of the ClipLoss step)."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def require_cuda(*tensors) -> None:

@@ -214,6 +214,23 @@ int b200clip_cliploss_packed_backward(const float* gathered, const float* logit_
     return cliploss_packed_backward(gathered, logit_scale, rank, n, N, D, grad_out, d_gathered, d_scale, workspace, S(stream));
 }
 
+int b200clip_p2p_allgather(int dtype, const void* img, const void* txt, int n, int D, float* const* peer_dst,
+                           uint32_t* const* peer_flag, const uint32_t* my_flags, uint32_t* counters, int world, uint32_t epoch,
+                           void* stream) {
+    return p2p_allgather(dtype, img, txt, n, D, peer_dst, peer_flag, my_flags, counters, world, epoch, S(stream));
+}
+
+int b200clip_cliploss_packed_backward_p2p(const float* gathered, const float* logit_scale, int rank, int n, int N, int D,
+                                          const float* grad_out, float* const* d_slots, float* d_scale, float* workspace,
+                                          void* stream) {
+    return cliploss_packed_backward_p2p(gathered, logit_scale, rank, n, N, D, grad_out, d_slots, d_scale, workspace, S(stream));
+}
+
+int b200clip_p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag, const uint32_t* my_flags,
+                               int world, uint32_t epoch, void* stream) {
+    return p2p_reduce_finish(recv, out, elems, peer_flag, my_flags, world, epoch, S(stream));
+}
+
 int64_t b200clip_workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {
     return workspace_bytes(cfg, batch, seq_len);
 }

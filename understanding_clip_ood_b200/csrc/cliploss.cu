@@ -31,6 +31,10 @@ struct GemmProb {
     int M, N, K, ta, tb;
     int accumulate;   // C += A B instead of C = A B
     int tiles_n, tile_begin;
+    // slot-addressed output (peer-memory scatter of the distributed backward, p2p.cu): row r of C lives at
+    // slots[(slot_row0 + r) / slot_rows] + ((slot_row0 + r) % slot_rows) * ldc + slot_col0; C itself is unused then
+    float* const* slots;
+    int slot_rows, slot_row0, slot_col0;
 };
 struct GemmBatch {
     GemmProb prob[4];
@@ -87,7 +91,14 @@ __device__ __forceinline__ void tile_gemm(const GemmProb& p, int m0, int n0, flo
         const int row = m0 + ty * 4 + i;
         const int col = n0 + tx * 4;
         if (row < p.M && col < p.N) {  // N % 4 == 0 is checked on the host
-            float4* dst = reinterpret_cast<float4*>(p.C + static_cast<int64_t>(row) * p.ldc + col);
+            float4* dst;
+            if (p.slots != nullptr) {
+                const int gr = p.slot_row0 + row;
+                const int sl = gr / p.slot_rows;
+                dst = reinterpret_cast<float4*>(p.slots[sl] + static_cast<int64_t>(gr - sl * p.slot_rows) * p.ldc + p.slot_col0 + col);
+            } else {
+                dst = reinterpret_cast<float4*>(p.C + static_cast<int64_t>(row) * p.ldc + col);
+            }
             float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
             if (p.accumulate) {
                 const float4 c = *dst;
@@ -136,6 +147,11 @@ GemmProb make_prob(const float* A, int64_t lda, bool ta, const float* B, int64_t
     p.ta = ta ? 1 : 0; p.tb = tb ? 1 : 0;
     p.accumulate = accumulate ? 1 : 0;
     p.tiles_n = 0; p.tile_begin = 0;
+    p.slots = nullptr; p.slot_rows = 1; p.slot_row0 = 0; p.slot_col0 = 0;
+    return p;
+}
+GemmProb to_slots(GemmProb p, float* const* slots, int slot_rows, int row0, int col0) {
+    p.slots = slots; p.slot_rows = slot_rows; p.slot_row0 = row0; p.slot_col0 = col0;
     return p;
 }
 
@@ -273,7 +289,7 @@ int forward_impl(const LossOperands& o, const float* logit_scale, int rank, int 
 // launch), which is what a following reduce-scatter needs
 int backward_impl(const LossOperands& o, const float* logit_scale, int rank, int n, int N, int D, const float* grad_out,
                   float* d_img_loc, float* d_txt_loc, int64_t ld_dloc, float* d_all_img, float* d_all_txt, int64_t ld_dall,
-                  bool fold_local, float* d_scale, float* workspace, cudaStream_t stream) {
+                  bool fold_local, float* d_scale, float* workspace, cudaStream_t stream, float* const* d_slots = nullptr) {
     int rc;
     if ((rc = check_shapes(rank, n, N, D)) != 0) return rc;
     B2C_CHECK_ARG(o.img_loc && o.txt_loc && o.all_img && o.all_txt && logit_scale && workspace, "cliploss: null pointer");
@@ -288,6 +304,18 @@ int backward_impl(const LossOperands& o, const float* logit_scale, int rank, int
     if (!fold_local) {
         if (d_img_loc) b.prob[b.count++] = make_prob(Li, N, false, o.all_txt, o.ld_all, true, d_img_loc, ld_dloc, n, D, N);
         if (d_txt_loc) b.prob[b.count++] = make_prob(Lt, N, false, o.all_img, o.ld_all, true, d_txt_loc, ld_dloc, n, D, N);
+    }
+    if (d_slots != nullptr) {
+        // peer-memory scatter: the packed [n, 2D] gradient block of rank j's rows goes to d_slots[j] (img half | txt half)
+        B2C_CHECK_ARG(fold_local, "cliploss: the slot-addressed backward is the packed (fold_local) form");
+        b.prob[b.count++] = to_slots(make_prob(Li, N, true, o.img_loc, o.ld_loc, true, nullptr, ld_dall, N, D, n), d_slots, n, 0, D);
+        b.prob[b.count++] = to_slots(make_prob(Lt, N, true, o.txt_loc, o.ld_loc, true, nullptr, ld_dall, N, D, n), d_slots, n, 0, 0);
+        if ((rc = launch_batch(b, stream)) != 0) return rc;
+        GemmBatch f;
+        f.count = 2;
+        f.prob[0] = to_slots(make_prob(Li, N, false, o.all_txt, o.ld_all, true, nullptr, ld_dall, n, D, N, true), d_slots, n, rank * n, 0);
+        f.prob[1] = to_slots(make_prob(Lt, N, false, o.all_img, o.ld_all, true, nullptr, ld_dall, n, D, N, true), d_slots, n, rank * n, D);
+        return launch_batch(f, stream);
     }
     if (d_all_txt) b.prob[b.count++] = make_prob(Li, N, true, o.img_loc, o.ld_loc, true, d_all_txt, ld_dall, N, D, n);
     if (d_all_img) b.prob[b.count++] = make_prob(Lt, N, true, o.txt_loc, o.ld_loc, true, d_all_img, ld_dall, N, D, n);
@@ -337,6 +365,17 @@ int cliploss_packed_backward(const float* gathered, const float* logit_scale, in
     const LossOperands o{loc, loc + D, gathered, gathered + D, 2 * static_cast<int64_t>(D), 2 * static_cast<int64_t>(D)};
     return backward_impl(o, logit_scale, rank, n, N, D, grad_out, nullptr, nullptr, 0, d_gathered, d_gathered + D,
                          2 * static_cast<int64_t>(D), true, d_scale, workspace, stream);
+}
+
+// Same, with the reduce-scatter's scatter half folded into the GEMM epilogue: d_slots[j] (device array of N/n pointers) is
+// where the [n, 2D] gradient block of rank j's rows goes — slot `rank` of rank j's receive buffer in peer memory.
+int cliploss_packed_backward_p2p(const float* gathered, const float* logit_scale, int rank, int n, int N, int D, const float* grad_out,
+                                 float* const* d_slots, float* d_scale, float* workspace, cudaStream_t stream) {
+    B2C_CHECK_ARG(gathered != nullptr && d_slots != nullptr, "cliploss: null pointer");
+    const float* loc = gathered + static_cast<int64_t>(rank) * n * 2 * D;
+    const LossOperands o{loc, loc + D, gathered, gathered + D, 2 * static_cast<int64_t>(D), 2 * static_cast<int64_t>(D)};
+    return backward_impl(o, logit_scale, rank, n, N, D, grad_out, nullptr, nullptr, 0, nullptr, nullptr, 2 * static_cast<int64_t>(D), true,
+                         d_scale, workspace, stream, d_slots);
 }
 
 // fused forward + backward (one call; used when the upstream gradient is already known or 1)

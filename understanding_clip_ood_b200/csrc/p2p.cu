@@ -1,0 +1,149 @@
+// Peer-memory exchange of the distributed ClipLoss (--local-loss --gather-with-grad, world_size > 1): replaces the two
+// collectives of the reference step — torch.distributed.nn.all_gather of the features (deps/open_clip/src/open_clip/
+// loss.py:49-50) and the reduce-scatter(SUM) of its autograd backward (torch/distributed/nn/functional.py:_AllGather) — by
+// stores into the peers' HBM over NVLink / NVSwitch plus flag words, so a step is six small launches without a NCCL
+// collective on its latency path:
+//   forward   p2p_allgather_kernel   every rank converts its img | txt rows to fp32 and writes them into slot `rank` of EVERY
+//                                    rank's gather buffer, raises its flag on each peer, then waits for all flags on itself
+//             (packed forward kernels of cliploss.cu read the local gather buffer)
+//   backward  the feature-gradient GEMM writes the [n, 2D] gradient block of rank j's rows straight into slot `rank` of rank
+//             j's receive buffer (slot-addressed epilogue in cliploss.cu: the store IS the scatter)
+//             p2p_reduce_finish_kernel   raises the "my blocks are written" flag on every peer, waits for all peers, sums
+//                                        the `world` received blocks -> gradient of the local rows.
+// The buffers are symmetric allocations mapped by the host (torch symmetric memory); this file only sees raw pointers.
+// Flags carry a monotonically increasing epoch; a waiter accepts any value >= its epoch (a peer may already be one step on).
+#include "common.cuh"
+#include "internal.h"
+
+namespace b200clip {
+
+namespace {
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// bounded spin (a dead peer becomes a trap the host reports, not a hung GPU): ~2^33 cycles is > 4 s at any B200 clock
+__device__ __forceinline__ void wait_flag(const uint32_t* flag, uint32_t epoch) {
+    if (static_cast<int32_t>(ld_acquire_sys(flag) - epoch) >= 0) return;
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ld_acquire_sys(flag) - epoch) < 0) {
+        if (clock64() - t0 > (1ll << 33)) {
+            printf("b200clip: peer flag wait timed out (block %d thread %d epoch %u)\n", (int)blockIdx.x, (int)threadIdx.x, epoch);
+            __trap();
+        }
+    }
+}
+
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = Half16<__nv_bfloat16>::unpack(u.x), b = Half16<__nv_bfloat16>::unpack(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <> __device__ __forceinline__ float4 load4<__half>(const __half* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = Half16<__half>::unpack(u.x), b = Half16<__half>::unpack(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// grid (chunks, world): block (c, p) writes chunk c of this rank's packed [n, 2D] fp32 rows into peer p's gather slot
+template <typename T>
+__global__ void __launch_bounds__(256)
+p2p_allgather_kernel(const T* __restrict__ img, const T* __restrict__ txt, int n, int D, float* const* __restrict__ peer_dst,
+                     uint32_t* const* __restrict__ peer_flag, const uint32_t* __restrict__ my_flags, uint32_t* counters, int world,
+                     uint32_t epoch) {
+    const int p = blockIdx.y;
+    float* dst = peer_dst[p];
+    const int quads_per_row = D / 2;   // float4 per packed row (2D floats)
+    const int64_t total = static_cast<int64_t>(n) * quads_per_row;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / quads_per_row), q = static_cast<int>(i - static_cast<int64_t>(r) * quads_per_row);
+        const int col = q * 4;
+        const float4 v = col < D ? load4<T>(img + static_cast<int64_t>(r) * D + col) : load4<T>(txt + static_cast<int64_t>(r) * D + (col - D));
+        *reinterpret_cast<float4*>(dst + static_cast<int64_t>(r) * 2 * D + col) = v;
+    }
+    // last block done for peer p publishes the slot
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(counters + p, 1u);
+        if (prev == gridDim.x - 1) {
+            counters[p] = 0u;
+            __threadfence_system();
+            st_release_sys(peer_flag[p], epoch);
+        }
+    }
+    // every rank's slot in MY buffer must have landed before the kernel (and with it the stream) moves on
+    if (threadIdx.x < world) wait_flag(my_flags + threadIdx.x, epoch);
+    __syncthreads();
+}
+
+// recv [world][elems] (slot q written by rank q's backward GEMM) -> out[elems] = sum over q
+__global__ void __launch_bounds__(256)
+p2p_reduce_finish_kernel(const float* __restrict__ recv, float* __restrict__ out, int64_t elems, uint32_t* const* __restrict__ peer_flag,
+                         const uint32_t* __restrict__ my_flags, int world, uint32_t epoch) {
+    // the stores of the preceding kernel on this stream (the slot-addressed GEMM epilogue) are complete; publish them
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        __threadfence_system();
+        st_release_sys(peer_flag[threadIdx.x], epoch);
+    }
+    if (threadIdx.x < world) wait_flag(my_flags + threadIdx.x, epoch);
+    __syncthreads();
+    const int64_t quads = elems / 4;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < quads; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float4 a = __ldcv(reinterpret_cast<const float4*>(recv) + i);
+        for (int q = 1; q < world; ++q) {
+            const float4 b = __ldcv(reinterpret_cast<const float4*>(recv + static_cast<int64_t>(q) * elems) + i);
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        reinterpret_cast<float4*>(out)[i] = a;
+    }
+}
+
+}  // namespace
+
+int p2p_allgather(int dtype, const void* img, const void* txt, int n, int D, float* const* peer_dst, uint32_t* const* peer_flag,
+                  const uint32_t* my_flags, uint32_t* counters, int world, uint32_t epoch, cudaStream_t stream) {
+    B2C_CHECK_ARG(img && txt && peer_dst && peer_flag && my_flags && counters, "p2p_allgather: null pointer");
+    B2C_CHECK_ARG(n > 0 && D > 0 && D % 4 == 0 && world >= 1 && world <= 16, "p2p_allgather: bad shape n=%d D=%d world=%d", n, D, world);
+    const int64_t quads = static_cast<int64_t>(n) * (D / 2);
+    int chunks = static_cast<int>((quads + 2047) / 2048);            // 8 float4 per thread
+    const int max_chunks = num_sms() / world > 0 ? num_sms() / world : 1;   // all blocks co-resident: the flag waits cannot starve a writer
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    dim3 grid(chunks, world);
+    if (dtype == 0)
+        p2p_allgather_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(img), static_cast<const float*>(txt), n, D, peer_dst,
+                                                              peer_flag, my_flags, counters, world, epoch);
+    else if (dtype == 1)
+        p2p_allgather_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(img), static_cast<const __nv_bfloat16*>(txt),
+                                                                      n, D, peer_dst, peer_flag, my_flags, counters, world, epoch);
+    else if (dtype == 2)
+        p2p_allgather_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<const __half*>(img), static_cast<const __half*>(txt), n, D, peer_dst,
+                                                               peer_flag, my_flags, counters, world, epoch);
+    else
+        B2C_CHECK_ARG(false, "p2p_allgather: bad dtype %d", dtype);
+    B2C_LAUNCH_CHECK("p2p_allgather_kernel");
+    return 0;
+}
+
+int p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag, const uint32_t* my_flags, int world,
+                      uint32_t epoch, cudaStream_t stream) {
+    B2C_CHECK_ARG(recv && out && peer_flag && my_flags, "p2p_reduce_finish: null pointer");
+    B2C_CHECK_ARG(elems > 0 && elems % 4 == 0 && world >= 1 && world <= 16, "p2p_reduce_finish: bad shape elems=%lld world=%d",
+                  static_cast<long long>(elems), world);
+    int blocks = static_cast<int>((elems / 4 + 1023) / 1024);
+    if (blocks > num_sms()) blocks = num_sms();
+    if (blocks < 1) blocks = 1;
+    p2p_reduce_finish_kernel<<<blocks, 256, 0, stream>>>(recv, out, elems, peer_flag, my_flags, world, epoch);
+    B2C_LAUNCH_CHECK("p2p_reduce_finish_kernel");
+    return 0;
+}
+
+}  // namespace b200clip

@@ -1,7 +1,9 @@
 """ClipLoss with the reference's constructor / forward signature (deps/open_clip/src/open_clip/loss.py:66-131),
-computed by the fused forward+backward CUDA path (`b200clip_cliploss`) and, for world_size > 1, ONE NCCL
-all-gather of the concatenated img‖txt features (the reference issues two, loss.py:49-50) whose autograd backward
-is one reduce-scatter — the same semantics as torch.distributed.nn.all_gather.
+computed by the fused forward+backward CUDA path (`b200clip_cliploss`).  For world_size > 1 the feature exchange of
+--local-loss --gather-with-grad (the reference issues two all-gathers, loss.py:49-50, whose autograd backward is two
+reduce-scatters) runs over peer memory: NVLink stores + flags inside our own kernels (`_PeerLocalClipLoss`, csrc/p2p.cu).
+Where symmetric memory is unavailable (or B200CLIP_P2P=0) it is ONE NCCL all-gather of the concatenated img‖txt features and
+one reduce-scatter in the backward (`_DistLocalClipLoss`) — the same semantics as torch.distributed.nn.all_gather.
 
 There is no PyTorch-op fallback for the loss arithmetic: CPU feature tensors raise.
 """
@@ -19,6 +21,7 @@ except ImportError:  # pragma: no cover
 
 from .. import _lib as L
 from .. import ops
+from . import peer
 
 __all__ = ["ClipLoss", "gather_features", "local_labels"]
 
@@ -155,6 +158,45 @@ class _DistLocalClipLoss(torch.autograd.Function):
         return d_i, d_t, d_sc, None, None, None
 
 
+class _PeerLocalClipLoss(torch.autograd.Function):
+    """The same node over peer memory (csrc/p2p.cu, open_clip/peer.py): no NCCL collective on the step.  forward: every
+    rank stores its fp32 img | txt rows into all gather buffers and waits on flags (one launch) + the packed forward kernels;
+    backward: the gradient GEMM stores each rank's block straight into that rank's receive buffer, one launch publishes /
+    waits / sums.  Values are those of `_DistLocalClipLoss` (the sum over ranks is taken in rank order instead of NCCL's)."""
+
+    @staticmethod
+    def forward(ctx, image_features, text_features, logit_scale, rank: int, world_size: int, ex):
+        n, D = image_features.shape
+        img, txt = image_features.detach(), text_features.detach()
+        if img.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            img = img.float()
+        if txt.dtype != img.dtype:
+            txt = txt.to(img.dtype)
+        gathered, slot = ex.all_gather(img.contiguous(), txt.contiguous())
+        scale = _f32c(logit_scale).reshape(())
+        loss, ws = ops.cliploss_packed_forward(gathered, scale, rank, n, ws=ex.ws[slot])
+        ctx.meta = (rank, n, D, slot, image_features.dtype, text_features.dtype, logit_scale.dtype, logit_scale.shape)
+        ctx.ex = ex
+        ctx.token = peer._SlotToken(ex, slot) if any(ctx.needs_input_grad[:3]) else None
+        ctx.save_for_backward(scale)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        scale, = ctx.saved_tensors
+        rank, n, D, slot, dt_i, dt_t, dt_s, s_shape = ctx.meta
+        ex = ctx.ex
+        ws = ex.ws[slot]
+        d_s = ops.cliploss_packed_backward_p2p(ex.gathered_view(slot), scale, rank, n, ws, _f32c(g).reshape(()), ex.rs_dst[slot],
+                                               ctx.needs_input_grad[2])
+        d_both = ex.reduce_scatter_finish(slot)
+        ctx.token = None                       # the ring slot may be reused by a later forward
+        d_i = d_both[:, :D].to(dt_i) if ctx.needs_input_grad[0] else None
+        d_t = d_both[:, D:].to(dt_t) if ctx.needs_input_grad[1] else None
+        d_sc = d_s.to(dt_s).reshape(s_shape) if d_s is not None else None
+        return d_i, d_t, d_sc, None, None, None
+
+
 class ClipLoss(nn.Module):
     def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1, use_horovod=False):
         super().__init__()
@@ -202,7 +244,14 @@ class ClipLoss(nn.Module):
         if not torch.is_tensor(logit_scale):
             logit_scale = torch.tensor(float(logit_scale), device=image_features.device)
         if self.world_size > 1 and self.local_loss and self.gather_with_grad and not self.use_horovod:
-            total_loss = _DistLocalClipLoss.apply(image_features, text_features, logit_scale, self.rank, self.world_size, None)
+            ex = None
+            if dist.get_backend() == "nccl":
+                n, D = image_features.shape
+                ex = peer.get_exchange(n, D, self.rank, self.world_size, image_features.device)
+            if ex is not None:
+                total_loss = _PeerLocalClipLoss.apply(image_features, text_features, logit_scale, self.rank, self.world_size, ex)
+            else:
+                total_loss = _DistLocalClipLoss.apply(image_features, text_features, logit_scale, self.rank, self.world_size, None)
         else:
             rows_i, rows_t, all_img, all_txt, rank = self._operands(image_features, text_features)
             total_loss = _FusedClipLoss.apply(rows_i, rows_t, all_img, all_txt, logit_scale, rank)

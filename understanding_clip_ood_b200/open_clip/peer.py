@@ -1,0 +1,127 @@
+"""Host side of the peer-memory ClipLoss exchange (csrc/p2p.cu): symmetric buffers, pointer tables, epochs.
+
+PyTorch is plumbing here: `torch.distributed._symmetric_memory` allocates one buffer per rank and maps every peer's copy
+into this process; the kernels only ever see the raw, pre-offset pointers collected in the small device tables below.
+
+Buffer layout per rank (fp32 words, S = n * 2D = one rank's packed img | txt rows, W = world * S):
+    [ gather ring: RING x W ][ receive ring: RING x W ]
+Sync pad per rank (uint32 words): [0, 16) all-gather flags (word q = epoch last published by rank q), [16, 32) reduce-scatter
+flags, [32, 48) block counters of the local all-gather kernel.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+
+import torch
+
+from .. import _lib as L
+
+RING = 4          # forward passes whose gathered features may be alive (saved for a backward) at the same time
+MAX_WORLD = 16
+
+
+def enabled() -> bool:
+    return os.environ.get("B200CLIP_P2P", "1") != "0"
+
+
+class _SlotToken:
+    """Held by an autograd ctx: the ring slot is released when the ctx dies (after its backward, or when the graph is freed)."""
+
+    def __init__(self, state: "PeerExchange", slot: int):
+        self.state, self.slot = state, slot
+        state.inflight.add(slot)
+
+    def __del__(self):
+        self.state.inflight.discard(self.slot)
+
+
+class PeerExchange:
+    def __init__(self, n: int, D: int, rank: int, world: int, device: torch.device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        if world > MAX_WORLD:
+            raise L.B200ClipError(f"peer exchange supports up to {MAX_WORLD} ranks, got {world}")
+        group = group if group is not None else dist.group.WORLD
+        self.n, self.D, self.rank, self.world, self.device = n, D, rank, world, device
+        self.S = n * 2 * D
+        self.W = world * self.S
+        self.data = symm_mem.empty(2 * RING * self.W, dtype=torch.float32, device=device)
+        self.sync = symm_mem.empty(64, dtype=torch.int32, device=device)
+        self.sync.zero_()
+        torch.cuda.synchronize(device)
+        hd = symm_mem.rendezvous(self.data, group.group_name)
+        hs = symm_mem.rendezvous(self.sync, group.group_name)
+        dptr, sptr = [int(p) for p in hd.buffer_ptrs], [int(p) for p in hs.buffer_ptrs]
+
+        def table(vals):
+            return torch.tensor(vals, dtype=torch.int64, device=device)
+
+        # where THIS rank's rows go on every peer p (slot `rank` of p's gather buffer), per ring slot
+        self.ag_dst = [table([dptr[p] + 4 * (s * self.W + rank * self.S) for p in range(world)]) for s in range(RING)]
+        # where the gradient block of rank j's rows goes (slot `rank` of j's receive buffer), per ring slot
+        self.rs_dst = [table([dptr[j] + 4 * ((RING + s) * self.W + rank * self.S) for j in range(world)]) for s in range(RING)]
+        self.ag_flag = table([sptr[p] + 4 * rank for p in range(world)])
+        self.rs_flag = table([sptr[p] + 4 * (16 + rank) for p in range(world)])
+        base = self.sync.data_ptr()
+        self.my_ag_flags, self.my_rs_flags, self.counters = base, base + 64, base + 128
+        # loss workspace (raw logits, row statistics) per ring slot: lives exactly as long as the slot is held
+        self.ws = [torch.empty((2 * n * world * n + 8 * n + 8,), dtype=torch.float32, device=device) for _ in range(RING)]
+        self.ag_epoch = 0
+        self.rs_epoch = 0
+        self.inflight: set[int] = set()
+        dist.barrier(group=group)            # every rank's sync pad is zeroed and mapped before anyone signals
+        torch.cuda.synchronize(device)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def gathered_view(self, slot: int) -> torch.Tensor:
+        return self.data[slot * self.W:(slot + 1) * self.W].view(self.world * self.n, 2 * self.D)
+
+    def recv_view(self, slot: int) -> torch.Tensor:
+        return self.data[(RING + slot) * self.W:(RING + slot + 1) * self.W]
+
+    def all_gather(self, img: torch.Tensor, txt: torch.Tensor) -> tuple[torch.Tensor, int]:
+        """img, txt [n, D] (fp32 / bf16 / fp16, contiguous) -> (gathered [N, 2D] fp32 view of the local ring slot, slot)."""
+        self.ag_epoch += 1
+        slot = self.ag_epoch % RING
+        if slot in self.inflight:
+            raise L.B200ClipError(f"ClipLoss peer exchange: more than {RING - 1} forward passes are waiting for their backward")
+        rc = L.load().b200clip_p2p_allgather(L.dtype_code(img.dtype), img.data_ptr(), txt.data_ptr(), self.n, self.D,
+                                             self.ag_dst[slot].data_ptr(), self.ag_flag.data_ptr(), self.my_ag_flags, self.counters,
+                                             self.world, self.ag_epoch & 0xFFFFFFFF, L.stream_ptr())
+        L.check(rc, "b200clip_p2p_allgather")
+        return self.gathered_view(slot), slot
+
+    def reduce_scatter_finish(self, slot: int) -> torch.Tensor:
+        """After the slot-addressed backward GEMM of every rank: -> d(img | txt) [n, 2D] of the local rows."""
+        self.rs_epoch += 1
+        out = torch.empty((self.n, 2 * self.D), dtype=torch.float32, device=self.device)
+        rc = L.load().b200clip_p2p_reduce_finish(self.recv_view(slot).data_ptr(), out.data_ptr(), self.S, self.rs_flag.data_ptr(),
+                                                 self.my_rs_flags, self.world, self.rs_epoch & 0xFFFFFFFF, L.stream_ptr())
+        L.check(rc, "b200clip_p2p_reduce_finish")
+        return out
+
+
+_states: dict = {}
+_failed = False
+
+
+def get_exchange(n: int, D: int, rank: int, world: int, device: torch.device, group=None):
+    """One PeerExchange per (shape, device, group); None when peer memory is unavailable (the caller then uses NCCL)."""
+    global _failed
+    if _failed or not enabled():
+        return None
+    key = (n, D, rank, world, device.index, id(group))
+    st = _states.get(key)
+    if st is None:
+        try:
+            st = PeerExchange(n, D, rank, world, device, group)
+        except L.B200ClipError:
+            raise
+        except Exception as e:  # symmetric memory not supported on this system: every rank takes the same branch
+            _failed = True
+            warnings.warn(f"b200clip: peer-memory ClipLoss exchange unavailable ({type(e).__name__}: {e}); using NCCL collectives")
+            return None
+        _states[key] = st
+    return st

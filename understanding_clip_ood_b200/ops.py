@@ -228,11 +228,12 @@ def cliploss_backward(img_loc, txt_loc, all_img, all_txt, logit_scale, rank: int
     return grads
 
 
-def cliploss_packed_forward(gathered: torch.Tensor, logit_scale: torch.Tensor, rank: int, n: int):
+def cliploss_packed_forward(gathered: torch.Tensor, logit_scale: torch.Tensor, rank: int, n: int, ws: torch.Tensor | None = None):
     """gathered [N, 2D] fp32 (img | txt of every rank).  -> (loss 0-dim, workspace); see b200clip_cliploss_packed_forward."""
     N, D2 = gathered.shape
     loss = torch.empty((), dtype=torch.float32, device=gathered.device)
-    ws = torch.empty((cliploss_workspace_floats(n, N),), dtype=torch.float32, device=gathered.device)
+    if ws is None:
+        ws = torch.empty((cliploss_workspace_floats(n, N),), dtype=torch.float32, device=gathered.device)
     rc = L.load().b200clip_cliploss_packed_forward(gathered.data_ptr(), logit_scale.data_ptr(), rank, n, N, D2 // 2, loss.data_ptr(),
                                                    ws.data_ptr(), L.stream_ptr())
     L.check(rc, "b200clip_cliploss_packed_forward")
@@ -249,6 +250,18 @@ def cliploss_packed_backward(gathered: torch.Tensor, logit_scale: torch.Tensor, 
                                                     d_g.data_ptr(), L.ptr(d_s), ws.data_ptr(), L.stream_ptr())
     L.check(rc, "b200clip_cliploss_packed_backward")
     return d_g, d_s
+
+
+def cliploss_packed_backward_p2p(gathered: torch.Tensor, logit_scale: torch.Tensor, rank: int, n: int, ws: torch.Tensor,
+                                 grad_out: torch.Tensor | None, d_slots: torch.Tensor, want_scale: bool = True):
+    """Slot-addressed form: the gradient block of rank j's rows is stored to the address in d_slots[j] (int64 device table of
+    peer-memory pointers, see open_clip/peer.py).  -> d_scale 0-dim | None; see b200clip_cliploss_packed_backward_p2p."""
+    N, D2 = gathered.shape
+    d_s = torch.empty((), dtype=torch.float32, device=gathered.device) if want_scale else None
+    rc = L.load().b200clip_cliploss_packed_backward_p2p(gathered.data_ptr(), logit_scale.data_ptr(), rank, n, N, D2 // 2, L.ptr(grad_out),
+                                                        d_slots.data_ptr(), L.ptr(d_s), ws.data_ptr(), L.stream_ptr())
+    L.check(rc, "b200clip_cliploss_packed_backward_p2p")
+    return d_s
 
 
 def cliploss_fwd_bwd(img_loc: torch.Tensor, txt_loc: torch.Tensor, all_img: torch.Tensor, all_txt: torch.Tensor,
