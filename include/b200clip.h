@@ -165,9 +165,10 @@ int b200clip_cliploss_packed_backward(const float* gathered, const float* logit_
  *   my_flags[q] >= epoch for all q: when the call's kernel has finished, the local gather buffer holds every rank's rows.
  *   `counters`: `world` zero-initialised uint32 in local memory (left at zero).
  * b200clip_cliploss_packed_backward_p2p: as b200clip_cliploss_packed_backward, but the gradient block of rank j's rows
- *   ([n, 2D]) is stored to d_slots[j] (= slot `rank` of j's receive buffer): the GEMM epilogue is the scatter.
- * b200clip_p2p_reduce_finish: *peer_flag[p] = epoch for every p, wait my_flags[q] >= epoch for all q, then
- *   out[elems] = sum over q of recv[q * elems ...] (recv = the local receive buffer, `world` slots). */
+ *   ([n, 2D]) is stored to d_slots[j], j < world (= slot `rank` of j's receive buffer): the GEMM epilogue is the scatter.
+ *   d_slots[world], d_slots[world + 1]: two LOCAL [n, 2D] slots for the two K halves of the local-row terms.
+ * b200clip_p2p_reduce_finish: *peer_flag[p] = epoch for every p, wait my_flags[q] >= epoch for all q < world, then
+ *   out[elems] = sum over s < slots of recv[s * elems ...] (recv = the local receive buffer; slots = world + 2 here). */
 int b200clip_p2p_allgather(int dtype, const void* img, const void* txt, int n, int D, float* const* peer_dst,
                            uint32_t* const* peer_flag, const uint32_t* my_flags, uint32_t* counters, int world,
                            uint32_t epoch, void* stream);
@@ -175,7 +176,7 @@ int b200clip_cliploss_packed_backward_p2p(const float* gathered, const float* lo
                                           const float* grad_out, float* const* d_slots, float* d_scale, float* workspace,
                                           void* stream);
 int b200clip_p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag,
-                               const uint32_t* my_flags, int world, uint32_t epoch, void* stream);
+                               const uint32_t* my_flags, int world, int slots, uint32_t epoch, void* stream);
 
 /* ----- whole-tower drivers: one call per encode_image / encode_text ------------------------------ */
 

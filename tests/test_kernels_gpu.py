@@ -354,3 +354,79 @@ def test_cliploss_fwd_bwd(n, world, rank, D):
     g_out = torch.tensor(0.25, device=DEV)
     _, grads3 = ops.cliploss_fwd_bwd(img_loc, txt_loc, all_img, all_txt, scale, rank, grad_out=g_out)
     assert _rel(grads3[0], 0.25 * il.grad) < 1e-4
+
+
+# ------------------------------------------------------------------ peer-memory exchange kernels (csrc/p2p.cu) on ONE device -
+# The multi-process form runs in tests/test_peer_gpu.py (>= 2 GPUs).  Here the "peers" are local buffers and the flags of
+# the other ranks are set by hand, which exercises the same kernels, addressing and flag protocol.
+def _ptr_table(ptrs):
+    return torch.tensor(ptrs, dtype=torch.int64, device=DEV)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n,D,world,rank", [(256, 512, 2, 1), (36, 64, 3, 0), (128, 512, 8, 5), (4, 4, 1, 0)])
+def test_p2p_allgather_kernel(dtype, n, D, world, rank):
+    g = _gen(21)
+    img = torch.randn(n, D, device=DEV, generator=g).to(dtype)
+    txt = torch.randn(n, D, device=DEV, generator=g).to(dtype)
+    S = n * 2 * D
+    bufs = [torch.full((world * S,), float("nan"), device=DEV) for _ in range(world)]       # every rank's gather buffer
+    pads = [torch.zeros(64, dtype=torch.int32, device=DEV) for _ in range(world)]
+    epoch = 7
+    pads[rank][:world] = epoch            # the other ranks "have already published" into this rank's pad
+    pads[rank][rank] = 0                  # ... except this rank itself: set by the kernel
+    dst = _ptr_table([bufs[p].data_ptr() + 4 * rank * S for p in range(world)])
+    flag = _ptr_table([pads[p].data_ptr() + 4 * rank for p in range(world)])
+    rc = L.load().b200clip_p2p_allgather(L.dtype_code(dtype), img.data_ptr(), txt.data_ptr(), n, D, dst.data_ptr(), flag.data_ptr(),
+                                         pads[rank].data_ptr(), pads[rank].data_ptr() + 128, world, epoch, L.stream_ptr())
+    L.check(rc, "b200clip_p2p_allgather")
+    torch.cuda.synchronize()
+    want = torch.cat([img.float(), txt.float()], dim=1)
+    for p in range(world):
+        got = bufs[p].view(world, n, 2 * D)
+        assert torch.equal(got[rank], want)                              # bit-exact fp32 conversion, every peer
+        assert torch.isnan(got[[q for q in range(world) if q != rank]]).all()   # nothing else touched
+        assert int(pads[p][rank]) == epoch                               # flag published on every peer
+    assert int(pads[rank][32:48].abs().sum()) == 0                       # block counters left at zero
+
+
+@pytest.mark.parametrize("n,D,world,rank", [(256, 512, 2, 1), (36, 64, 3, 0), (128, 512, 8, 5), (64, 512, 1, 0)])
+def test_slot_addressed_backward_and_reduce_finish(n, D, world, rank):
+    """b200clip_cliploss_packed_backward_p2p + b200clip_p2p_reduce_finish against b200clip_cliploss_packed_backward:
+    slot j must hold the gathered-row terms of rank j's block, the two local slots the local-row terms."""
+    g = _gen(22)
+    N = n * world
+    gathered = F.normalize(torch.randn(N, 2 * D, device=DEV, generator=g), dim=-1)
+    scale = torch.tensor(1 / 0.07, device=DEV)
+    gout = torch.tensor(0.7, device=DEV)
+    loss, ws = ops.cliploss_packed_forward(gathered, scale, rank, n)
+    d_ref, ds_ref = ops.cliploss_packed_backward(gathered, scale, rank, n, ws.clone(), gout, True)
+    S = n * 2 * D
+    # rank j's receive buffer: world + 2 slots; this rank writes slot `rank` of each, and its own two local slots
+    recv = [torch.zeros((world + 2) * S, device=DEV) for _ in range(world)]
+    slots = _ptr_table([recv[j].data_ptr() + 4 * rank * S for j in range(world)] +
+                       [recv[rank].data_ptr() + 4 * (world + h) * S for h in range(2)])
+    ds = ops.cliploss_packed_backward_p2p(gathered, scale, rank, n, ws, gout, slots, True)
+    torch.cuda.synchronize()
+    assert float((ds - ds_ref).abs()) <= 1e-6 * max(1.0, float(ds_ref.abs()))
+    for j in range(world):
+        got = recv[j].view(world + 2, n, 2 * D)[rank]
+        if j == rank:
+            got = got + recv[rank].view(world + 2, n, 2 * D)[world:].sum(0)
+        want = d_ref[j * n:(j + 1) * n]
+        assert float((got - want).norm() / want.norm()) < 2e-6, j
+    # reduce-finish on this rank's buffer (the other ranks' flags set by hand)
+    pad = torch.zeros(64, dtype=torch.int32, device=DEV)
+    others = [torch.zeros(64, dtype=torch.int32, device=DEV) for _ in range(world)]
+    others[rank] = pad
+    epoch = 3
+    pad[16:16 + world] = epoch
+    pad[16 + rank] = 0
+    flag = _ptr_table([others[p].data_ptr() + 4 * (16 + rank) for p in range(world)])
+    out = torch.empty(n, 2 * D, device=DEV)
+    rc = L.load().b200clip_p2p_reduce_finish(recv[rank].data_ptr(), out.data_ptr(), S, flag.data_ptr(), pad.data_ptr() + 64, world,
+                                             world + 2, epoch, L.stream_ptr())
+    L.check(rc, "b200clip_p2p_reduce_finish")
+    torch.cuda.synchronize()
+    assert torch.allclose(out, recv[rank].view(world + 2, n, 2 * D).sum(0), rtol=1e-6, atol=1e-7)
+    assert all(int(others[p][16 + rank]) == epoch for p in range(world))

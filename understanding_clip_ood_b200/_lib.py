@@ -72,7 +72,7 @@ SIGNATURES = {
     "b200clip_cliploss_packed_backward": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "b200clip_p2p_allgather": (C.c_int, [_I, _P, _P, _I, _I, _P, _P, _P, _P, _I, C.c_uint32, _P]),
     "b200clip_cliploss_packed_backward_p2p": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "b200clip_p2p_reduce_finish": (C.c_int, [_P, _P, _L, _P, _P, _I, C.c_uint32, _P]),
+    "b200clip_p2p_reduce_finish": (C.c_int, [_P, _P, _L, _P, _P, _I, _I, C.c_uint32, _P]),
     "b200clip_workspace_bytes": (C.c_int64, [C.POINTER(TowerCfg), _I, _I]),
     "b200clip_vit_forward": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(VitWeights), _P, _P, _I, _I, _P, _L, _P]),
     "b200clip_text_forward": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(TextWeights), _P, _P, _I, _I, _I, _P, _L, _P]),

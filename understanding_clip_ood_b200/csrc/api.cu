@@ -227,8 +227,8 @@ int b200clip_cliploss_packed_backward_p2p(const float* gathered, const float* lo
 }
 
 int b200clip_p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag, const uint32_t* my_flags,
-                               int world, uint32_t epoch, void* stream) {
-    return p2p_reduce_finish(recv, out, elems, peer_flag, my_flags, world, epoch, S(stream));
+                               int world, int slots, uint32_t epoch, void* stream) {
+    return p2p_reduce_finish(recv, out, elems, peer_flag, my_flags, world, slots, epoch, S(stream));
 }
 
 int64_t b200clip_workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {

@@ -36,8 +36,9 @@ struct GemmProb {
     float* const* slots;
     int slot_rows, slot_row0, slot_col0;
 };
+constexpr int kMaxProbs = 6;
 struct GemmBatch {
-    GemmProb prob[4];
+    GemmProb prob[kMaxProbs];
     int count;
 };
 
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) batched_gemm_kernel(const GemmBatch batch
     __shared__ __align__(16) float Bs[kTK][kT + 4];
     int pi = 0;
 #pragma unroll
-    for (int i = 1; i < 4; ++i)
+    for (int i = 1; i < kMaxProbs; ++i)
         if (i < batch.count && static_cast<int>(blockIdx.x) >= batch.prob[i].tile_begin) pi = i;
     const GemmProb& p = batch.prob[pi];
     const int t = blockIdx.x - p.tile_begin;
@@ -306,16 +307,24 @@ int backward_impl(const LossOperands& o, const float* logit_scale, int rank, int
         if (d_txt_loc) b.prob[b.count++] = make_prob(Lt, N, false, o.all_img, o.ld_all, true, d_txt_loc, ld_dloc, n, D, N);
     }
     if (d_slots != nullptr) {
-        // peer-memory scatter: the packed [n, 2D] gradient block of rank j's rows goes to d_slots[j] (img half | txt half)
+        // Peer-memory scatter, ONE launch.  The local-row terms (contraction over all N gathered rows: few tiles, long K) come
+        // first in the grid and are split in two K halves, each written to its own local slot (d_slots[world], [world + 1]);
+        // the gathered-row terms (many tiles, K = n) follow and store rank j's [n, 2D] block to d_slots[j] in j's memory.
+        // b200clip_p2p_reduce_finish sums all world + 2 slots, so nothing is accumulated in place and nothing is ordered.
         B2C_CHECK_ARG(fold_local, "cliploss: the slot-addressed backward is the packed (fold_local) form");
+        const int world = N / n;
+        const int kh = (N / 2 + 3) / 4 * 4;   // K split point (multiple of 4: float4 staging)
+        for (int h = 0; h < 2; ++h) {
+            const int k0 = h * kh, kn = h == 0 ? kh : N - kh;
+            if (kn <= 0) continue;
+            b.prob[b.count++] = to_slots(make_prob(Li + k0, N, false, o.all_txt + static_cast<int64_t>(k0) * o.ld_all, o.ld_all, true, nullptr,
+                                                   ld_dall, n, D, kn), d_slots, n, (world + h) * n, 0);
+            b.prob[b.count++] = to_slots(make_prob(Lt + k0, N, false, o.all_img + static_cast<int64_t>(k0) * o.ld_all, o.ld_all, true, nullptr,
+                                                   ld_dall, n, D, kn), d_slots, n, (world + h) * n, D);
+        }
         b.prob[b.count++] = to_slots(make_prob(Li, N, true, o.img_loc, o.ld_loc, true, nullptr, ld_dall, N, D, n), d_slots, n, 0, D);
         b.prob[b.count++] = to_slots(make_prob(Lt, N, true, o.txt_loc, o.ld_loc, true, nullptr, ld_dall, N, D, n), d_slots, n, 0, 0);
-        if ((rc = launch_batch(b, stream)) != 0) return rc;
-        GemmBatch f;
-        f.count = 2;
-        f.prob[0] = to_slots(make_prob(Li, N, false, o.all_txt, o.ld_all, true, nullptr, ld_dall, n, D, N, true), d_slots, n, rank * n, 0);
-        f.prob[1] = to_slots(make_prob(Lt, N, false, o.all_img, o.ld_all, true, nullptr, ld_dall, n, D, N, true), d_slots, n, rank * n, D);
-        return launch_batch(f, stream);
+        return launch_batch(b, stream);
     }
     if (d_all_txt) b.prob[b.count++] = make_prob(Li, N, true, o.img_loc, o.ld_loc, true, d_all_txt, ld_dall, N, D, n);
     if (d_all_img) b.prob[b.count++] = make_prob(Lt, N, true, o.txt_loc, o.ld_loc, true, d_all_img, ld_dall, N, D, n);
@@ -367,8 +376,9 @@ int cliploss_packed_backward(const float* gathered, const float* logit_scale, in
                          2 * static_cast<int64_t>(D), true, d_scale, workspace, stream);
 }
 
-// Same, with the reduce-scatter's scatter half folded into the GEMM epilogue: d_slots[j] (device array of N/n pointers) is
-// where the [n, 2D] gradient block of rank j's rows goes — slot `rank` of rank j's receive buffer in peer memory.
+// Same, with the reduce-scatter's scatter half folded into the GEMM epilogue: d_slots[j], j < world = N/n, is where the [n, 2D]
+// gradient block of rank j's rows goes — slot `rank` of rank j's receive buffer in peer memory; d_slots[world] and
+// d_slots[world + 1] are two LOCAL [n, 2D] slots that receive the two K halves of the local-row terms.
 int cliploss_packed_backward_p2p(const float* gathered, const float* logit_scale, int rank, int n, int N, int D, const float* grad_out,
                                  float* const* d_slots, float* d_scale, float* workspace, cudaStream_t stream) {
     B2C_CHECK_ARG(gathered != nullptr && d_slots != nullptr, "cliploss: null pointer");

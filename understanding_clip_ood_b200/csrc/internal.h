@@ -75,7 +75,7 @@ int cliploss_packed_backward_p2p(const float* gathered, const float* logit_scale
 int p2p_allgather(int dtype, const void* img, const void* txt, int n, int D, float* const* peer_dst, uint32_t* const* peer_flag,
                   const uint32_t* my_flags, uint32_t* counters, int world, uint32_t epoch, cudaStream_t stream);
 int p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag, const uint32_t* my_flags, int world,
-                      uint32_t epoch, cudaStream_t stream);
+                      int slots, uint32_t epoch, cudaStream_t stream);
 
 inline int dtype_size(int dtype) { return dtype == 0 ? 4 : 2; }
 

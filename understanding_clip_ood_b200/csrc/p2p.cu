@@ -84,10 +84,10 @@ p2p_allgather_kernel(const T* __restrict__ img, const T* __restrict__ txt, int n
     __syncthreads();
 }
 
-// recv [world][elems] (slot q written by rank q's backward GEMM) -> out[elems] = sum over q
+// recv [slots][elems] (slot q < world written by rank q's backward GEMM, slots >= world by the local one) -> out[elems] = sum
 __global__ void __launch_bounds__(256)
 p2p_reduce_finish_kernel(const float* __restrict__ recv, float* __restrict__ out, int64_t elems, uint32_t* const* __restrict__ peer_flag,
-                         const uint32_t* __restrict__ my_flags, int world, uint32_t epoch) {
+                         const uint32_t* __restrict__ my_flags, int world, int slots, uint32_t epoch) {
     // the stores of the preceding kernel on this stream (the slot-addressed GEMM epilogue) are complete; publish them
     if (blockIdx.x == 0 && threadIdx.x < world) {
         __threadfence_system();
@@ -98,7 +98,7 @@ p2p_reduce_finish_kernel(const float* __restrict__ recv, float* __restrict__ out
     const int64_t quads = elems / 4;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < quads; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         float4 a = __ldcv(reinterpret_cast<const float4*>(recv) + i);
-        for (int q = 1; q < world; ++q) {
+        for (int q = 1; q < slots; ++q) {
             const float4 b = __ldcv(reinterpret_cast<const float4*>(recv + static_cast<int64_t>(q) * elems) + i);
             a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         }
@@ -134,14 +134,14 @@ int p2p_allgather(int dtype, const void* img, const void* txt, int n, int D, flo
 }
 
 int p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag, const uint32_t* my_flags, int world,
-                      uint32_t epoch, cudaStream_t stream) {
+                      int slots, uint32_t epoch, cudaStream_t stream) {
     B2C_CHECK_ARG(recv && out && peer_flag && my_flags, "p2p_reduce_finish: null pointer");
-    B2C_CHECK_ARG(elems > 0 && elems % 4 == 0 && world >= 1 && world <= 16, "p2p_reduce_finish: bad shape elems=%lld world=%d",
-                  static_cast<long long>(elems), world);
+    B2C_CHECK_ARG(elems > 0 && elems % 4 == 0 && world >= 1 && world <= 16 && slots >= world,
+                  "p2p_reduce_finish: bad shape elems=%lld world=%d slots=%d", static_cast<long long>(elems), world, slots);
     int blocks = static_cast<int>((elems / 4 + 1023) / 1024);
     if (blocks > num_sms()) blocks = num_sms();
     if (blocks < 1) blocks = 1;
-    p2p_reduce_finish_kernel<<<blocks, 256, 0, stream>>>(recv, out, elems, peer_flag, my_flags, world, epoch);
+    p2p_reduce_finish_kernel<<<blocks, 256, 0, stream>>>(recv, out, elems, peer_flag, my_flags, world, slots, epoch);
     B2C_LAUNCH_CHECK("p2p_reduce_finish_kernel");
     return 0;
 }

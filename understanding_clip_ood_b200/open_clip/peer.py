@@ -3,8 +3,9 @@
 PyTorch is plumbing here: `torch.distributed._symmetric_memory` allocates one buffer per rank and maps every peer's copy
 into this process; the kernels only ever see the raw, pre-offset pointers collected in the small device tables below.
 
-Buffer layout per rank (fp32 words, S = n * 2D = one rank's packed img | txt rows, W = world * S):
-    [ gather ring: RING x W ][ receive ring: RING x W ]
+Buffer layout per rank (fp32 words, S = n * 2D = one rank's packed img | txt rows, W = world * S, R = (world + 2) * S):
+    [ gather ring: RING x W ][ receive ring: RING x R ]
+A receive buffer has one slot per rank plus two local slots (the two K halves of the local-row gradient terms).
 Sync pad per rank (uint32 words): [0, 16) all-gather flags (word q = epoch last published by rank q), [16, 32) reduce-scatter
 flags, [32, 48) block counters of the local all-gather kernel.
 """
@@ -47,7 +48,8 @@ class PeerExchange:
         self.n, self.D, self.rank, self.world, self.device = n, D, rank, world, device
         self.S = n * 2 * D
         self.W = world * self.S
-        self.data = symm_mem.empty(2 * RING * self.W, dtype=torch.float32, device=device)
+        self.R = (world + 2) * self.S
+        self.data = symm_mem.empty(RING * (self.W + self.R), dtype=torch.float32, device=device)
         self.sync = symm_mem.empty(64, dtype=torch.int32, device=device)
         self.sync.zero_()
         torch.cuda.synchronize(device)
@@ -61,7 +63,9 @@ class PeerExchange:
         # where THIS rank's rows go on every peer p (slot `rank` of p's gather buffer), per ring slot
         self.ag_dst = [table([dptr[p] + 4 * (s * self.W + rank * self.S) for p in range(world)]) for s in range(RING)]
         # where the gradient block of rank j's rows goes (slot `rank` of j's receive buffer), per ring slot
-        self.rs_dst = [table([dptr[j] + 4 * ((RING + s) * self.W + rank * self.S) for j in range(world)]) for s in range(RING)]
+        # (+ this rank's two local slots)
+        self.rs_dst = [table([dptr[j] + 4 * (RING * self.W + s * self.R + rank * self.S) for j in range(world)] +
+                             [dptr[rank] + 4 * (RING * self.W + s * self.R + (world + h) * self.S) for h in range(2)]) for s in range(RING)]
         self.ag_flag = table([sptr[p] + 4 * rank for p in range(world)])
         self.rs_flag = table([sptr[p] + 4 * (16 + rank) for p in range(world)])
         base = self.sync.data_ptr()
@@ -79,7 +83,8 @@ class PeerExchange:
         return self.data[slot * self.W:(slot + 1) * self.W].view(self.world * self.n, 2 * self.D)
 
     def recv_view(self, slot: int) -> torch.Tensor:
-        return self.data[(RING + slot) * self.W:(RING + slot + 1) * self.W]
+        off = RING * self.W + slot * self.R
+        return self.data[off:off + self.R]
 
     def all_gather(self, img: torch.Tensor, txt: torch.Tensor) -> tuple[torch.Tensor, int]:
         """img, txt [n, D] (fp32 / bf16 / fp16, contiguous) -> (gathered [N, 2D] fp32 view of the local ring slot, slot)."""
@@ -98,7 +103,7 @@ class PeerExchange:
         self.rs_epoch += 1
         out = torch.empty((self.n, 2 * self.D), dtype=torch.float32, device=self.device)
         rc = L.load().b200clip_p2p_reduce_finish(self.recv_view(slot).data_ptr(), out.data_ptr(), self.S, self.rs_flag.data_ptr(),
-                                                 self.my_rs_flags, self.world, self.rs_epoch & 0xFFFFFFFF, L.stream_ptr())
+                                                 self.my_rs_flags, self.world, self.world + 2, self.rs_epoch & 0xFFFFFFFF, L.stream_ptr())
         L.check(rc, "b200clip_p2p_reduce_finish")
         return out
 
