@@ -231,6 +231,9 @@ int b200clip_p2p_reduce_finish(const float* recv, float* out, int64_t elems, uin
     return p2p_reduce_finish(recv, out, elems, peer_flag, my_flags, world, slots, epoch, S(stream));
 }
 
+// not part of the public header: timeline capture of the tcgen05 attention kernel (tools/attn_timeline.py)
+void b200clip_attention_debug(long long* buf) { attention_tc_set_debug(buf); }
+
 int64_t b200clip_workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {
     return workspace_bytes(cfg, batch, seq_len);
 }

@@ -42,7 +42,11 @@ constexpr int kMaxSmem = 227 * 1024;
 struct AttnTcParams {
     int L, heads, q_tiles, items, tail_rows, n_cols, kv_stage_bytes;
     int nq, nkv;   // ring depths: query-tile slots (2..4), K/V stages (2..6), as many as shared memory holds
+    long long* dbg; // timeline capture of CTA 0 (tools/attn_timeline.py); nullptr in normal operation
 };
+
+// event e of tile t of CTA 0 -> dbg[t * 8 + e] (clock64)
+#define B2C_STAMP(e, t) do { if (p.dbg != nullptr && blockIdx.x == 0 && (t) < 64) p.dbg[(t) * 8 + (e)] = clock64(); } while (0)
 
 // tcgen05.mma with the A operand in tensor memory (lane = row, one 32-bit column = two consecutive K elements)
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -216,11 +220,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 const uint32_t tm = tmem_base + static_cast<uint32_t>(g * 256);
                 mbar_wait(bars + kPFull + g, (t >> 1) & 1);
                 tc_fence_after();
+                B2C_STAMP(2, t);
                 const int ksteps = ncols / 16;
                 for (int j = 0; j < ksteps; ++j)
                     umma_f16_ts(tm + 128, tm + 8 * j, desc_v + static_cast<uint64_t>(j) * ((16u * 128u) >> 4), idesc_o, j != 0);
                 umma_commit(bars + kOFull + g);
                 if (qt == q_tiles - 1) umma_commit(bars + kKvEmpty + st);
+                B2C_STAMP(7, t);
             };
             for (int t = 0; t < n_tiles; ++t) {
                 const int g = t & 1;
@@ -236,6 +242,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 if (qt == 0) mbar_wait(bars + kKvFull + st, (il / p.nkv) & 1);
                 mbar_wait(bars + kQFull + qs, (t / p.nq) & 1);
                 tc_fence_after();
+                B2C_STAMP(0, t);
 #pragma unroll
                 for (int k = 0; k < kHd / 16; ++k) umma_f16(tm, desc_q + 2 * k, desc_k + 2 * k, idesc_s, k != 0);
                 umma_commit(bars + kSFull + g);
@@ -275,6 +282,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
             mbar_wait(s_full, ph);
             tc_fence_after();
+            if (gtid == 0) B2C_STAMP(1, t);
             float sum = 0.f, s_x = 0.f, p_x = 0.f;
             if (warp_live) {
                 // ---- pass 1: row maximum over the valid columns (loads kept one chunk ahead of the arithmetic)
@@ -389,11 +397,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 mbar_arrive(bars + kQEmpty + qs);
             }
             tc_fence_before();
+            if (gtid == 0) B2C_STAMP(3, t);
             mbar_arrive(p_full);
 
             // ---- O: TMEM -> registers -> * 1/sum -> swizzled staging -> TMA store
             mbar_wait(o_full, ph);
             tc_fence_after();
+            if (gtid == 0) B2C_STAMP(4, t);
             uint32_t o0[32], o1[32];
             if (warp_live) {
                 tmem_ld_32x32(tm + 128, o0);
@@ -403,6 +413,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             }
             tc_fence_before();
             mbar_arrive(s_empty);
+            if (gtid == 0) B2C_STAMP(5, t);
             if (gtid == 0) tma_store_wait_read<0>();   // this warpgroup's previous store has released the staging tile
             asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
             if (warp_live && (!m64 || lane < 16)) {
@@ -440,6 +451,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 const bool tail = last && p.tail_rows != kQT;
                 tma_store_2d(tail ? &tmap_o_tail : &tmap_o, s_o + g * kTileQBytes, h * kHd, b * L + qt * kQT);
                 tma_store_commit();
+                B2C_STAMP(6, t);
             }
         }
         if (gtid == 0) tma_store_wait_all<0>();
@@ -469,6 +481,9 @@ cudaError_t launch_tc(const cudaLaunchConfig_t& cfg, const CUtensorMap& tq, cons
 
 }  // namespace
 
+static long long* g_attn_dbg = nullptr;
+void attention_tc_set_debug(long long* buf) { g_attn_dbg = buf; }
+
 // qkv [batch*L, 3*heads*64] -> out [batch*L, heads*64]; 16-bit dtypes, 64 < L <= 257.  Returns 1 when the shape is outside
 // this kernel's range (the caller then uses the generic path), 0 on success, < 0 / CUDA code on error.
 int attention_tc(int dtype, const void* qkv, void* out, int batch, int L, int heads, int causal, cudaStream_t stream) {
@@ -486,6 +501,7 @@ int attention_tc(int dtype, const void* qkv, void* out, int batch, int L, int he
     p.tail_rows = L - (p.q_tiles - 1) * kQT;
     p.n_cols = extra ? 256 : (L + 15) / 16 * 16;
     p.kv_stage_bytes = (extra ? 264 : p.n_cols) * 128;
+    p.dbg = g_attn_dbg;
     const int kv_tail = L % 128;
 
     const bool bf = dtype == 1;

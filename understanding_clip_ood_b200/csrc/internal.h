@@ -31,6 +31,7 @@ int gemm_any(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, 
 int layernorm(int dtype, const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy, int rows,
               int width, float eps, int row_stride_rows, const int32_t* row_idx, cudaStream_t stream);
 
+void attention_tc_set_debug(long long* buf);
 int attention(int dtype, const void* qkv, void* out, int batch, int seq_len, int heads, int causal, cudaStream_t stream);
 
 int patchify(int dtype, const void* image, void* patches, int batch, int image_size, int patch, int kpad,
