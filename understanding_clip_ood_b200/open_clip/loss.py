@@ -209,6 +209,7 @@ class ClipLoss(nn.Module):
         # cache state (kept for API compatibility; the fused kernel derives labels from (n, rank) itself)
         self.prev_num_logits = 0
         self.labels = {}
+        self._nccl = None      # backend of the default process group, looked up once
 
     def get_ground_truth(self, device, num_logits) -> torch.Tensor:
         if self.prev_num_logits != num_logits or device not in self.labels:
@@ -245,7 +246,9 @@ class ClipLoss(nn.Module):
             logit_scale = torch.tensor(float(logit_scale), device=image_features.device)
         if self.world_size > 1 and self.local_loss and self.gather_with_grad and not self.use_horovod:
             ex = None
-            if dist.get_backend() == "nccl":
+            if self._nccl is None:
+                self._nccl = dist.get_backend() == "nccl"
+            if self._nccl:
                 n, D = image_features.shape
                 ex = peer.get_exchange(n, D, self.rank, self.world_size, image_features.device)
             if ex is not None:
