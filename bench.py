@@ -192,6 +192,38 @@ def workload_config(n_gpus: int, extra: dict | None = None) -> dict:
     return cfg
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Multi-rank runs: keep this process (and with it the pinned host batches it allocates, first-touch) on the NUMA node
+    the GPU's PCIe root hangs off, so that the per-step H2D copy of every rank does not cross the socket interconnect.
+    Best effort: returns the node or None and never raises."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        idx = local_rank
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                idx = int(ids[local_rank])
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        node = int((Path("/sys/bus/pci/devices") / f"{dom[-4:]}:{rest}".lower() / "numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in (Path("/sys/devices/system/node") / f"node{node}" / "cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if len(allowed) >= 2:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
@@ -243,9 +275,12 @@ def run_ours(args) -> None:
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     L.load()
     peaks = measured_peaks()
@@ -397,7 +432,7 @@ def run_ours(args) -> None:
                 "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 2, "d2h_bytes_per_step": BATCH * 8,
                         "what": "ZeroShotClassifier.predict(images) from pinned host bf16 batches, H2D double-buffered on two copy streams, "
-                                "int64 predictions copied back to pinned host memory"},
+                                "int64 predictions copied back to pinned host memory", "numa_node_rank0": numa_node},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                 "per_gpu": {"images_per_s": value / world, "algorithmic_tflops": tower_tflops,
                             "frac_of_bf16_peak_burst": tower_tflops / peaks["bf16_tflops"],
