@@ -63,6 +63,21 @@ int b200clip_gemm_ln(int dtype, const void* x, int64_t ldx, const void* Wf, int6
                      const float* bias_f32, const float* rowstats, void* C, int64_t ldc, int M, int N, int K, int epilogue,
                      void* stream);
 
+/* The row statistics can also come out of the GEMM that WROTE the rows (the residual GEMMs of the block, whose output is the
+ * input of the next LayerNorm), which removes the separate statistics pass over the residual stream:
+ *   b200clip_gemm_residual_stats: C = round(A W^T + bias) + residual (EPI_RESIDUAL semantics; residual may alias C) and
+ *     partials[m][s] = (sum, sum of squares) of the stored values of row m over the columns epilogue slot s covered,
+ *     s < b200clip_gemm_stats_slots(M, N) (fp32 pairs, fixed slots: deterministic).
+ *   b200clip_gemm_ln_partials: b200clip_gemm_ln with (mean_m, rstd_m) derived from those `slots` pairs per row:
+ *     mean = sum / K, rstd = 1/sqrt(max(sumsq / K - mean^2, 0) + eps). */
+int b200clip_gemm_stats_slots(int M, int N);
+int b200clip_gemm_residual_stats(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
+                                 const void* residual, int64_t ldr, void* C, int64_t ldc, int M, int N, int K,
+                                 float* partials, void* stream);
+int b200clip_gemm_ln_partials(int dtype, const void* x, int64_t ldx, const void* Wf, int64_t ldw, const float* colsum,
+                              const float* bias_f32, const float* partials, int slots, float eps, void* C, int64_t ldc,
+                              int M, int N, int K, int epilogue, void* stream);
+
 /* stats[r] = (mean, rstd = 1/sqrt(var + eps)) of row r of x, fp32 pairs (biased variance, like F.layer_norm). */
 int b200clip_row_stats(int dtype, const void* x, int64_t ldx, float* stats, int rows, int width, float eps, void* stream);
 

@@ -210,6 +210,46 @@ def test_gemm_with_folded_layernorm(dtype, M, N, K, epi):
     assert _rel(out, ref) < (1e-2 if dtype == torch.bfloat16 else 3e-3)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K,N2,epi", [(6400, 768, 768, 3072, L.EPI_GELU), (6400, 768, 3072, 2304, L.EPI_BIAS), (1000, 512, 512, 1536, L.EPI_QUICKGELU),
+                                          (300, 1024, 256, 512, L.EPI_BIAS), (51200, 768, 768, 768, L.EPI_GELU)])
+def test_row_statistics_fused_into_the_residual_gemm(dtype, M, N, K, N2, epi):
+    """x += a W^T + b with the LayerNorm partial sums coming out of the same epilogue (b200clip_gemm_residual_stats), then
+    act(LN(x) W2^T + b2) from those sums (b200clip_gemm_ln_partials): the stored rows are bit-identical to the plain residual
+    GEMM, the statistics match a two-pass fp32 computation on them, and the LN-fold result matches torch."""
+    g = _gen(31)
+    a = (torch.randn(M, K, device=DEV, generator=g) * 0.8).to(dtype)
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.05).to(dtype)
+    b = (torch.randn(N, device=DEV, generator=g) * 0.1).to(dtype)
+    x0 = (torch.randn(M, N, device=DEV, generator=g) * 1.5 + 0.4).to(dtype)
+    x0[:, 5] += 30.0                                      # an outlier channel, as real CLIP residual streams have
+    x_plain = x0.clone()
+    ops.gemm(a, w, b, epilogue=L.EPI_RESIDUAL, residual=x_plain, out=x_plain)       # TMA reduce-add route
+    x = x0.clone()
+    _, partials = ops.gemm_residual_stats(a, w, b, x, out=x)
+    assert torch.equal(x, x_plain)
+    xf = x.float()
+    sums = partials.double().sum(dim=1)
+    assert torch.allclose(sums[:, 0], xf.double().sum(dim=1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(sums[:, 1], (xf.double() ** 2).sum(dim=1), rtol=1e-5, atol=1e-3)
+    # consumer
+    w2 = (torch.randn(N2, N, device=DEV, generator=g) * 0.05).to(dtype)
+    b2 = (torch.randn(N2, device=DEV, generator=g) * 0.1).to(dtype)
+    gamma = 1.0 + 0.2 * torch.randn(N, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(N, device=DEV, generator=g)
+    wf, colsum, bf = ops.fold_layernorm(w2, b2, gamma, beta, dtype)
+    out = ops.gemm_ln_partials(x, wf, colsum, bf, partials, epilogue=epi)
+    out_two_pass = ops.gemm_ln(x, wf, colsum, bf, ops.row_stats(x), epilogue=epi)
+    ref = torch.nn.functional.layer_norm(xf, (N,), gamma, beta, 1e-5) @ w2.float().t() + b2.float()
+    if epi == L.EPI_GELU:
+        ref = torch.nn.functional.gelu(ref)
+    elif epi == L.EPI_QUICKGELU:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < (1e-2 if dtype == torch.bfloat16 else 3e-3)
+    assert _rel(out, out_two_pass.float()) < (4e-3 if dtype == torch.bfloat16 else 1e-3)
+
+
 # ------------------------------------------------------------------ attention ------------------------
 def _attn_ref(qkv, B, Lq, H, causal):
     W = H * 64

@@ -55,6 +55,9 @@ SIGNATURES = {
     "b200clip_launch_count": (C.c_uint64, []),
     "b200clip_gemm": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _P, _I, _I, _P]),
     "b200clip_gemm_ln": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "b200clip_gemm_stats_slots": (C.c_int, [_I, _I]),
+    "b200clip_gemm_residual_stats": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _P, _P]),
+    "b200clip_gemm_ln_partials": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _P, _I, _F, _P, _L, _I, _I, _I, _I, _P]),
     "b200clip_row_stats": (C.c_int, [_I, _P, _L, _P, _I, _I, _F, _P]),
     "b200clip_layernorm": (C.c_int, [_I, _P, _L, _P, _P, _P, _L, _I, _I, _F, _I, _P, _P]),
     "b200clip_attention": (C.c_int, [_I, _P, _P, _I, _I, _I, _I, _P]),

@@ -130,6 +130,30 @@ int b200clip_gemm_ln(int dtype, const void* x, int64_t ldx, const void* Wf, int6
                      rowstats);
 }
 
+int b200clip_gemm_stats_slots(int M, int N) {
+    B2C_CHECK_ARG(M > 0 && N > 0, "gemm_stats_slots: empty problem");
+    return gemm_pair_stats_slots(M, N);
+}
+
+int b200clip_gemm_residual_stats(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
+                                 const void* residual, int64_t ldr, void* C, int64_t ldc, int M, int N, int K, float* partials,
+                                 void* stream) {
+    B2C_CHECK_ARG(A && W && C && residual && partials, "gemm_residual_stats: null pointer");
+    B2C_CHECK_ARG(dtype == B200CLIP_BF16 || dtype == B200CLIP_F16, "gemm_residual_stats: 16-bit dtypes only");
+    return gemm_pair(dtype == B200CLIP_BF16, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, B200CLIP_EPI_RESIDUAL, 0, 0, S(stream),
+                     nullptr, nullptr, nullptr, 0, partials);
+}
+
+int b200clip_gemm_ln_partials(int dtype, const void* x, int64_t ldx, const void* Wf, int64_t ldw, const float* colsum,
+                              const float* bias_f32, const float* partials, int slots, float eps, void* C, int64_t ldc, int M, int N,
+                              int K, int epilogue, void* stream) {
+    B2C_CHECK_ARG(x && Wf && colsum && bias_f32 && partials && C, "gemm_ln_partials: null pointer");
+    B2C_CHECK_ARG(dtype == B200CLIP_BF16 || dtype == B200CLIP_F16, "gemm_ln_partials: 16-bit dtypes only");
+    B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 2, "gemm_ln_partials: epilogue must be BIAS, GELU or QUICKGELU");
+    return gemm_pair(dtype == B200CLIP_BF16, x, ldx, Wf, ldw, bias_f32, nullptr, 0, C, ldc, M, N, K, epilogue, 0, 0, S(stream), colsum,
+                     nullptr, nullptr, 0, nullptr, partials, slots, eps);
+}
+
 int b200clip_row_stats(int dtype, const void* x, int64_t ldx, float* stats, int rows, int width, float eps, void* stream) {
     B2C_CHECK_ARG(x && stats, "row_stats: null pointer");
     return row_stats(dtype, x, ldx, stats, rows, width, eps, S(stream));

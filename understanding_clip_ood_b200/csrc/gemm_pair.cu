@@ -48,11 +48,21 @@ constexpr int kEpiLnFold = 6;
 // 9 = token-layout patch embedding: C[m,n] = round(acc) + round(pos[m % period, n]) with an fp32 table whose row 0 already
 // holds class_embedding + positional_embedding[0] (the class-token rows of A are all zero), transformer.py:602-609
 constexpr int kEpiPosAdd = 9;
+// 10 = residual (TMA-loaded, also when it aliases C) + LayerNorm statistics of the OUTPUT rows: every epilogue thread sums
+// x and x^2 of the rounded values it stores (its row, its chunks of this N tile) and writes the pair to
+// stats_out[row][n_tile * 2 + group].  The next LN-fold GEMM adds the slots of a row up and derives (mean, rstd) itself, so
+// the separate row-statistics pass over the residual stream (one more read of x per LayerNorm) disappears.  Deterministic:
+// fixed slots, fixed summation order, no atomics.
+constexpr int kEpiResidualStats = 10;
 
 struct PairParams {
     const void* bias;      // storage-type bias [N]; LN-fold epilogues: fp32 b'[N]
     const float* colsum;   // LN-fold: c[N]
-    const float2* rowstats; // LN-fold: (mean, rstd) per row of A
+    const float2* rowstats; // LN-fold: (mean, rstd) per row of A ...
+    const float2* stats_part; // ... or, when stats_slots > 0, `stats_slots` partial (sum x, sum x^2) pairs per row (epilogue 10)
+    float2* stats_out;      // epilogue 10: [M][stats_slots] partial sums of the output rows
+    int stats_slots;
+    float ln_eps;
     const float* pos;      // pos-add: fp32 table [period, N]
     int pos_period;
     int M, N, K;
@@ -110,7 +120,9 @@ template <typename T, int BLOCK_N, int EPI, int PAIRS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, const PairParams p) {
-    using Cfg = PairCfg<BLOCK_N, EPI == 3 ? 3 : 2>;
+    constexpr bool kRes = EPI == 3 || EPI == kEpiResidualStats;   // residual operand TMA-loaded into the staging ring
+    constexpr bool kStats = EPI == kEpiResidualStats;
+    using Cfg = PairCfg<BLOCK_N, kRes ? 3 : 2>;
     using H = Half16<T>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kStgBufs = Cfg::kStgBufs;
@@ -155,7 +167,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_c);
-        if constexpr (EPI == 3) tma_prefetch_desc(&tmap_r);
+        if constexpr (kRes) tma_prefetch_desc(&tmap_r);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
@@ -309,7 +321,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         mt2 * kClusterM + row_in_cluster, kCacheHintEvictFirst);
         };
         // residual prefetch, two chunks ahead: the first two chunks of this group
-        if constexpr (EPI == 3) {
+        if constexpr (kRes) {
             if (grp_leader && !(p.dbg & 1)) {
                 int pt = cluster_id, pc = grp;
                 if (pt < num_tiles) issue_residual(pt, pc, 0);
@@ -331,12 +343,29 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             float ln_rstd = 0.f, ln_nmr = 0.f;
             if constexpr (kLn) {
                 if (row0 + r < p.M) {
-                    const float2 st = __ldg(p.rowstats + row0 + r);
+                    float2 st;
+                    if (p.stats_slots > 0) {
+                        // partial (sum, sum of squares) pairs written by the epilogue-10 GEMM that produced these rows
+                        const float2* sp = p.stats_part + static_cast<int64_t>(row0 + r) * p.stats_slots;
+                        float sx = 0.f, sq = 0.f;
+                        for (int i = 0; i < p.stats_slots; ++i) {
+                            const float2 v2 = __ldg(sp + i);
+                            sx += v2.x;
+                            sq += v2.y;
+                        }
+                        const float inv_k = 1.0f / static_cast<float>(p.K);
+                        const float mean = sx * inv_k;
+                        st.x = mean;
+                        st.y = rsqrtf(fmaxf(fmaf(-mean, mean, sq * inv_k), 0.f) + p.ln_eps);
+                    } else {
+                        st = __ldg(p.rowstats + row0 + r);
+                    }
                     ln_rstd = st.y;
                     ln_nmr = -st.x * st.y;
                 }
             }
-            if constexpr (EPI == 3) {
+            float st_s = 0.f, st_q = 0.f;   // epilogue 10: this thread's share of sum x / sum x^2 of its output row
+            if constexpr (kRes) {
                 // pull the residual tiles this group will need two tiles from now into L2
                 if (grp_leader && p.pf_dist > 0) {
                     const int ft = t + 2 * num_clusters;
@@ -365,7 +394,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const uint32_t stg = stg_base + buf * kChunkBytes;
                 // Staging buffer `buf` is free here: the group leader drains its outstanding TMA store before it joins the
                 // barrier that ends each chunk (below), so the store issued kStgBufs chunks ago finished reading long ago.
-                if constexpr (EPI == 3) mbar_wait(&my_res_bar[buf], (bufc / kStgBufs) & 1);
+                if constexpr (kRes) mbar_wait(&my_res_bar[buf], (bufc / kStgBufs) & 1);
                 const int col0 = nt * BLOCK_N + c * kChunkN;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
@@ -393,7 +422,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         const uint32_t saddr = stg + row_off + (((static_cast<uint32_t>(hf * 4 + g)) ^ rx) << 4);
                         const uint32_t bw[4] = {bvec[g].x, bvec[g].y, bvec[g].z, bvec[g].w};
                         uint32_t rw[4] = {0, 0, 0, 0};
-                        if constexpr (EPI == 3) {
+                        if constexpr (kRes) {
                             const uint4 rv = lds128(saddr);
                             rw[0] = rv.x; rw[1] = rv.y; rw[2] = rv.z; rw[3] = rv.w;
                         }
@@ -438,7 +467,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 unpack_f2(add_f2(pack_f2(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])),
                                                  pack_f2(b2.x, b2.y)), x0, x1);
                             }
-                            if constexpr (kAct != 0 || EPI == 3 || EPI == kEpiResidualInPlace) {
+                            if constexpr (kAct != 0 || kRes || EPI == kEpiResidualInPlace) {
                                 const float2 xr = H::unpack(H::pack(x0, x1));  // linear output rounded to the storage type
                                 x0 = xr.x;
                                 x1 = xr.y;
@@ -448,18 +477,23 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             } else if constexpr (kAct == 2) {
                                 x0 = quick_gelu(x0);
                                 x1 = quick_gelu(x1);
-                            } else if constexpr (EPI == 3) {
+                            } else if constexpr (kRes) {
                                 const float2 r2 = H::unpack(rw[j]);
                                 x0 += r2.x;
                                 x1 += r2.y;
                             }
                             ow[j] = H::pack(x0, x1);
+                            if constexpr (kStats) {
+                                const float2 rr = H::unpack(ow[j]);   // the values the next GEMM will read
+                                st_s += rr.x + rr.y;
+                                st_q = fmaf(rr.x, rr.x, fmaf(rr.y, rr.y, st_q));
+                            }
                         }
                         sts128(saddr, make_uint4(ow[0], ow[1], ow[2], ow[3]));
                     }
                 }
                 fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
-                if constexpr (EPI != 3) {
+                if constexpr (!kRes) {
                     // every store but (at most) the previous chunk's has long completed; waiting for that one too BEFORE the
                     // barrier tells the whole group that the other staging buffer is free for the next chunk
                     if (grp_leader) tma_store_wait_read<0>();
@@ -470,7 +504,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if constexpr (EPI == kEpiResidualInPlace) tma_reduce_add_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, row0);
                     else tma_store_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, row0);
                     tma_store_commit();
-                    if constexpr (EPI == 3) {
+                    if constexpr (kRes) {
                         // prefetch the residual of the chunk two steps ahead into the buffer whose store was committed one
                         // step ago (everything but the store just committed must have released its buffer)
                         int pt = t, pc = c;
@@ -484,6 +518,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 __syncwarp();
                 ++bufc;
+            }
+            if constexpr (kStats) {
+                if (row0 + r < p.M)
+                    p.stats_out[static_cast<int64_t>(row0 + r) * p.stats_slots + nt * 2 + grp] = make_float2(st_s, st_q);
             }
         }
         if (grp_leader) tma_store_wait_all<0>();  // global writes complete before the CTA retires
@@ -501,7 +539,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 template <typename T, int BLOCK_N, int EPI, int PAIRS>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr, const PairParams& p,
                 cudaStream_t stream) {
-    using Cfg = PairCfg<BLOCK_N, EPI == 3 ? 3 : 2>;
+    using Cfg = PairCfg<BLOCK_N, (EPI == 3 || EPI == kEpiResidualStats) ? 3 : 2>;
     auto kern = gemm_pair_kernel<T, BLOCK_N, EPI, PAIRS>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -552,6 +590,9 @@ int launch_pair_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tw, const
         case kEpiLnFold + 1: return launch_pair<T, BLOCK_N, kEpiLnFold + 1, PAIRS>(ta, tw, tc, tr, p, s);
         case kEpiLnFold + 2: return launch_pair<T, BLOCK_N, kEpiLnFold + 2, PAIRS>(ta, tw, tc, tr, p, s);
         case kEpiPosAdd: return launch_pair<T, BLOCK_N, kEpiPosAdd, PAIRS>(ta, tw, tc, tr, p, s);
+        case kEpiResidualStats:
+            if constexpr (PAIRS == 1) return launch_pair<T, BLOCK_N, kEpiResidualStats, 1>(ta, tw, tc, tr, p, s);
+            break;
     }
     set_last_error("gemm_pair: unsupported epilogue %d", epi);
     return -1;
@@ -634,20 +675,28 @@ int pick_pair_block_n(int M, int N, int pairs) {
     return best;
 }
 
+// Partial-sum slots per row that an epilogue-10 GEMM of this shape writes (2 per N tile); the consumer passes it back.
+int gemm_pair_stats_slots(int M, int N) { return 2 * ((N + pick_pair_block_n(M, N, 1) - 1) / pick_pair_block_n(M, N, 1)); }
+
 // pairs: 1 = clusters of 2 CTAs, 2 = clusters of 4 with W multicast, 0 = choose
 int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
               int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs,
-              cudaStream_t stream, const float* ln_colsum, const float* ln_rowstats, const float* pos_table, int pos_period) {
+              cudaStream_t stream, const float* ln_colsum, const float* ln_rowstats, const float* pos_table, int pos_period,
+              float* stats_out, const float* stats_part, int stats_slots, float ln_eps) {
     B2C_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm_pair: unsupported epilogue %d", epilogue);
-    const bool ln = ln_colsum != nullptr || ln_rowstats != nullptr;
+    const bool ln = ln_colsum != nullptr || ln_rowstats != nullptr || stats_part != nullptr;
     if (ln) {
-        B2C_CHECK_ARG(ln_colsum != nullptr && ln_rowstats != nullptr && bias != nullptr && epilogue <= 2,
-                      "gemm_ln: needs colsum, rowstats, an fp32 bias and a bias/GELU/QuickGELU epilogue");
+        B2C_CHECK_ARG(ln_colsum != nullptr && (ln_rowstats != nullptr) != (stats_part != nullptr) && bias != nullptr && epilogue <= 2,
+                      "gemm_ln: needs colsum, rowstats OR partial sums, an fp32 bias and a bias/GELU/QuickGELU epilogue");
         B2C_CHECK_ARG((reinterpret_cast<uintptr_t>(ln_colsum) | reinterpret_cast<uintptr_t>(bias)) % 16 == 0 &&
-                          reinterpret_cast<uintptr_t>(ln_rowstats) % 8 == 0,
+                          (reinterpret_cast<uintptr_t>(ln_rowstats) | reinterpret_cast<uintptr_t>(stats_part)) % 8 == 0,
                       "gemm_ln: colsum / bias must be 16-byte aligned, rowstats 8-byte aligned");
+        B2C_CHECK_ARG(stats_part == nullptr || (stats_slots > 0 && stats_slots <= 64), "gemm_ln: bad partial-sum slot count %d", stats_slots);
     }
+    if (stats_out != nullptr)
+        B2C_CHECK_ARG(epilogue == 3 && !ln && pos_table == nullptr && reinterpret_cast<uintptr_t>(stats_out) % 8 == 0,
+                      "gemm_stats: row statistics are produced by the residual epilogue only");
     B2C_CHECK_ARG(N % 8 == 0 || (bias == nullptr && epilogue == 0), "gemm: N=%d must be a multiple of 8 (unless bias-free)", N);
     B2C_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0,
                   "gemm: K, lda, ldw, ldc must be multiples of 8 (16 B rows) K=%d lda=%lld ldw=%lld ldc=%lld", K,
@@ -661,13 +710,17 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     }
     B2C_CHECK_ARG(pairs >= 0 && pairs <= 2, "gemm_pair: pairs must be 0, 1 or 2");
     if (pairs == 0) pairs = default_gemm_pairs(M);
+    if (stats_out != nullptr) pairs = 1;
     const int bn = force_block_n > 0 ? force_block_n : pick_pair_block_n(M, N, pairs);
 
     CUtensorMap ta, tw, tc, tr;
     if (make_tmap_2d(&ta, is_bf16, A, M, K, lda, kBM, kBK) != 0) return -1;
     if (make_tmap_2d(&tw, is_bf16, W, N, K, ldw, pairs == 2 ? bn / 4 : bn / 2, kBK) != 0) return -1;
     if (make_tmap_2d(&tc, is_bf16, C, M, N, ldc, kBM, kChunkN) != 0) return -1;
-    if (epilogue == 3 && residual == C && ldr == ldc && !no_reduce_store()) {
+    if (stats_out != nullptr) {
+        if (make_tmap_2d(&tr, is_bf16, residual, M, N, ldr, kBM, kChunkN) != 0) return -1;
+        epilogue = kEpiResidualStats;
+    } else if (epilogue == 3 && residual == C && ldr == ldc && !no_reduce_store()) {
         epilogue = kEpiResidualInPlace;
         tr = tc;
     } else if (epilogue == 3) {
@@ -686,6 +739,10 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     p.bias = bias;
     p.colsum = ln_colsum;
     p.rowstats = reinterpret_cast<const float2*>(ln_rowstats);
+    p.stats_part = reinterpret_cast<const float2*>(stats_part);
+    p.stats_out = reinterpret_cast<float2*>(stats_out);
+    p.stats_slots = stats_out != nullptr ? 2 * ((N + bn - 1) / bn) : (stats_part != nullptr ? stats_slots : 0);
+    p.ln_eps = ln_eps;
     p.pos = pos_table;
     p.pos_period = pos_period;
     p.M = M;

@@ -14,7 +14,12 @@ int gemm_tc(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw
 // CTA-pair (cta_group::2) variant with the TMA-store epilogue (gemm_pair.cu); epilogues 0..3
 int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
               int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs, cudaStream_t stream,
-              const float* ln_colsum = nullptr, const float* ln_rowstats = nullptr, const float* pos_table = nullptr, int pos_period = 0);
+              const float* ln_colsum = nullptr, const float* ln_rowstats = nullptr, const float* pos_table = nullptr, int pos_period = 0,
+              float* stats_out = nullptr, const float* stats_part = nullptr, int stats_slots = 0, float ln_eps = 1e-5f);
+// LayerNorm statistics fused into the residual GEMMs: `stats_out` ([M][gemm_pair_stats_slots(M, N)] float2 partial (sum x,
+// sum x^2) of the output rows) is written by a residual-epilogue GEMM and read back through `stats_part` / `stats_slots` by
+// the LN-fold GEMM that consumes those rows, instead of (mean, rstd) from row_stats.
+int gemm_pair_stats_slots(int M, int N);
 
 // per-row LayerNorm statistics (mean, rstd) as float2 (rowwise.cu)
 int row_stats(int dtype, const void* x, int64_t ldx, float* stats, int rows, int width, float eps, cudaStream_t stream);

@@ -8,11 +8,15 @@
 // no synchronisation, so a whole forward is CUDA-graph capturable.  Per layer: LN1 -> QKV GEMM(+bias) ->
 // attention -> out-proj GEMM(+bias+residual, in place on x) -> LN2 -> c_fc GEMM(+bias+GELU) -> c_proj
 // GEMM(+bias+residual, in place) = 7 launches, residual adds / activations / bias all fused in GEMM epilogues.
+// 16-bit modes with folded LayerNorms: both LayerNorms live in the QKV / c_fc GEMM epilogues; their row statistics come from
+// row_stats_kernel (default) or from the epilogue of the residual GEMM that wrote those rows (B200CLIP_FUSED_STATS=1).
 // Token layout is batch-major [B*L, W] (the reference's LND transpose, transformer.py:351, is an
 // implementation detail of nn.MultiheadAttention, not a contract).
 #include "../../include/b200clip.h"
 #include "common.cuh"
 #include "internal.h"
+
+#include <cstdlib>
 
 namespace b200clip {
 
@@ -30,7 +34,8 @@ struct Workspace {
     char* mlp;
     char* pooled;
     int32_t* eot;
-    float* stats;   // [rows, 2] (mean, rstd) for the LN-fold GEMMs
+    float* stats;   // [rows, 2] (mean, rstd) for the LN-fold GEMM of the first layer
+    float* part[2]; // [rows, slots, 2] partial (sum x, sum x^2) written by the residual GEMMs (after attention / after the MLP)
     int64_t total;
 };
 
@@ -54,6 +59,9 @@ Workspace carve(const b200clip_tower_cfg& c, int batch, int seq_len, void* base)
     w.pooled = take(static_cast<int64_t>(batch) * c.width * es);
     w.eot = reinterpret_cast<int32_t*>(take(static_cast<int64_t>(batch) * 4));
     w.stats = reinterpret_cast<float*>(take(rows * 2 * 4));
+    const int64_t max_slots = c.width / 64 + 2;   // >= 2 * ceil(width / 128), the narrowest N tile
+    w.part[0] = reinterpret_cast<float*>(take(rows * max_slots * 8));
+    w.part[1] = reinterpret_cast<float*>(take(rows * max_slots * 8));
     w.total = off;
     return w;
 }
@@ -77,34 +85,64 @@ int run_blocks(const b200clip_tower_cfg& c, const b200clip_block_weights* blocks
     const int act = c.quick_gelu ? B200CLIP_EPI_QUICKGELU : B200CLIP_EPI_GELU;
     int rc;
     const bool fold = c.fold_ln != 0 && dt != B200CLIP_F32;
+    const bool bf = dt == B200CLIP_BF16;
+    // B200CLIP_FUSED_STATS=1: take the LayerNorm statistics out of the residual GEMMs' epilogues instead of running the
+    // row-statistics kernel in front of every LN-fold GEMM (5 launches per layer instead of 7).  Off by default: the
+    // epilogue then has to LOAD the residual (the default in-place form lets the L2 do the add through a TMA reduce-add
+    // store), and that extra L2 -> SM traffic costs the out-proj / c_proj GEMMs what the two statistics passes cost
+    // (ViT-B/32 batch 1024: 9.65 ms either way; ViT-L/14: 43.2 vs 43.8 ms; ViT-B/16 batch 256: 9.79 vs 9.61 ms).
+    static const bool fused_stats = [] {
+        const char* e = getenv("B200CLIP_FUSED_STATS");
+        return e != nullptr && e[0] == '1';
+    }();
+    const int slots = fold ? gemm_pair_stats_slots(M, W) : 0;
+    B2C_CHECK_ARG(slots <= W / 64 + 2, "tower: statistics slot count %d exceeds the workspace carve-up", slots);
     for (int l = 0; l < c.layers; ++l) {
         const b200clip_block_weights& bw = blocks[l];
         if (fold) {
-            // LN-fold: per-row statistics of the residual stream, then the GEMM reads x itself
+            // LN-fold: the GEMM reads x itself; per-row statistics come from row_stats (first layer) or from the epilogue of the
+            // c_proj GEMM of the previous layer
             B2C_CHECK_ARG(bw.in_proj_wf && bw.in_proj_c && bw.in_proj_bf && bw.fc_wf && bw.fc_c && bw.fc_bf,
                           "tower: cfg.fold_ln is set but layer %d has no folded weights", l);
-            if ((rc = row_stats(dt, ws.x, W, ws.stats, M, W, 1e-5f, s)) != 0) return rc;
-            if ((rc = gemm_pair(dt == B200CLIP_BF16, ws.x, W, bw.in_proj_wf, W, bw.in_proj_bf, nullptr, 0, ws.qkv, 3 * W, M, 3 * W, W,
-                                B200CLIP_EPI_BIAS, 0, 0, s, bw.in_proj_c, ws.stats)) != 0) return rc;
+            const bool have = fused_stats && l > 0;
+            if (!have && (rc = row_stats(dt, ws.x, W, ws.stats, M, W, 1e-5f, s)) != 0) return rc;
+            if ((rc = gemm_pair(bf, ws.x, W, bw.in_proj_wf, W, bw.in_proj_bf, nullptr, 0, ws.qkv, 3 * W, M, 3 * W, W, B200CLIP_EPI_BIAS, 0,
+                                0, s, bw.in_proj_c, have ? nullptr : ws.stats, nullptr, 0, nullptr, have ? ws.part[1] : nullptr, slots,
+                                1e-5f)) != 0)
+                return rc;
         } else {
             if ((rc = layernorm(dt, ws.x, W, bw.ln1_g, bw.ln1_b, ws.h, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
             if ((rc = gemm_any(dt, ws.h, W, bw.in_proj_w, W, bw.in_proj_b, nullptr, 0, ws.qkv, 3 * W, M, 3 * W, W, B200CLIP_EPI_BIAS,
                                nullptr, 0, 0, s)) != 0) return rc;
         }
         if ((rc = attention(dt, ws.qkv, ws.h, batch, L, c.heads, causal, s)) != 0) return rc;
-        if ((rc = gemm_any(dt, ws.h, W, bw.out_proj_w, W, bw.out_proj_b, ws.x, W, ws.x, W, M, W, W, B200CLIP_EPI_RESIDUAL, nullptr, 0,
-                           0, s)) != 0) return rc;
+        if (fold && fused_stats) {
+            if ((rc = gemm_pair(bf, ws.h, W, bw.out_proj_w, W, bw.out_proj_b, ws.x, W, ws.x, W, M, W, W, B200CLIP_EPI_RESIDUAL, 0, 0, s,
+                                nullptr, nullptr, nullptr, 0, ws.part[0])) != 0)
+                return rc;
+        } else if ((rc = gemm_any(dt, ws.h, W, bw.out_proj_w, W, bw.out_proj_b, ws.x, W, ws.x, W, M, W, W, B200CLIP_EPI_RESIDUAL, nullptr,
+                                  0, 0, s)) != 0) {
+            return rc;
+        }
         if (fold) {
-            if ((rc = row_stats(dt, ws.x, W, ws.stats, M, W, 1e-5f, s)) != 0) return rc;
-            if ((rc = gemm_pair(dt == B200CLIP_BF16, ws.x, W, bw.fc_wf, W, bw.fc_bf, nullptr, 0, ws.mlp, c.mlp_width, M, c.mlp_width, W,
-                                act, 0, 0, s, bw.fc_c, ws.stats)) != 0) return rc;
+            if (!fused_stats && (rc = row_stats(dt, ws.x, W, ws.stats, M, W, 1e-5f, s)) != 0) return rc;
+            if ((rc = gemm_pair(bf, ws.x, W, bw.fc_wf, W, bw.fc_bf, nullptr, 0, ws.mlp, c.mlp_width, M, c.mlp_width, W, act, 0, 0, s, bw.fc_c,
+                                fused_stats ? nullptr : ws.stats, nullptr, 0, nullptr, fused_stats ? ws.part[0] : nullptr, slots,
+                                1e-5f)) != 0)
+                return rc;
         } else {
             if ((rc = layernorm(dt, ws.x, W, bw.ln2_g, bw.ln2_b, ws.h, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
             if ((rc = gemm_any(dt, ws.h, W, bw.fc_w, W, bw.fc_b, nullptr, 0, ws.mlp, c.mlp_width, M, c.mlp_width, W, act, nullptr, 0, 0,
                                s)) != 0) return rc;
         }
-        if ((rc = gemm_any(dt, ws.mlp, c.mlp_width, bw.proj_w, c.mlp_width, bw.proj_b, ws.x, W, ws.x, W, M, W, c.mlp_width,
-                           B200CLIP_EPI_RESIDUAL, nullptr, 0, 0, s)) != 0) return rc;
+        if (fold && fused_stats && l + 1 < c.layers) {
+            if ((rc = gemm_pair(bf, ws.mlp, c.mlp_width, bw.proj_w, c.mlp_width, bw.proj_b, ws.x, W, ws.x, W, M, W, c.mlp_width,
+                                B200CLIP_EPI_RESIDUAL, 0, 0, s, nullptr, nullptr, nullptr, 0, ws.part[1])) != 0)
+                return rc;
+        } else if ((rc = gemm_any(dt, ws.mlp, c.mlp_width, bw.proj_w, c.mlp_width, bw.proj_b, ws.x, W, ws.x, W, M, W, c.mlp_width,
+                                  B200CLIP_EPI_RESIDUAL, nullptr, 0, 0, s)) != 0) {
+            return rc;
+        }
     }
     return 0;
 }

@@ -79,6 +79,42 @@ def gemm_ln(x: torch.Tensor, wf: torch.Tensor, colsum: torch.Tensor, bias_f32: t
     return out
 
 
+def gemm_residual_stats(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, residual: torch.Tensor, *,
+                        out: torch.Tensor | None = None):
+    """out = round(a W^T + bias) + residual (residual may be `out`) and the LayerNorm partial sums of the stored rows.
+    -> (out [M, N], partials [M, slots, 2] fp32); see b200clip_gemm_residual_stats."""
+    L.require_cuda(a, w, bias, residual, out)
+    a, w = _c(a), _c(w)
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    lib = L.load()
+    slots = lib.b200clip_gemm_stats_slots(M, N)
+    partials = torch.empty((M, slots, 2), dtype=torch.float32, device=a.device)
+    rc = lib.b200clip_gemm_residual_stats(L.dtype_code(a.dtype), a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), L.ptr(bias),
+                                          residual.data_ptr(), residual.stride(0), out.data_ptr(), out.stride(0), M, N, K,
+                                          partials.data_ptr(), L.stream_ptr())
+    L.check(rc, "b200clip_gemm_residual_stats")
+    return out, partials
+
+
+def gemm_ln_partials(x: torch.Tensor, wf: torch.Tensor, colsum: torch.Tensor, bias_f32: torch.Tensor, partials: torch.Tensor, *,
+                     eps: float = 1e-5, epilogue: int = L.EPI_BIAS, out: torch.Tensor | None = None) -> torch.Tensor:
+    """gemm_ln with the row statistics derived from the partial sums a residual GEMM left behind; see b200clip_gemm_ln_partials."""
+    L.require_cuda(x, wf, colsum, bias_f32, partials, out)
+    x, wf = _c(x), _c(wf)
+    M, K = x.shape
+    N = wf.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    rc = L.load().b200clip_gemm_ln_partials(L.dtype_code(x.dtype), x.data_ptr(), x.stride(0), wf.data_ptr(), wf.stride(0),
+                                            colsum.data_ptr(), bias_f32.data_ptr(), partials.data_ptr(), partials.shape[1], eps,
+                                            out.data_ptr(), out.stride(0), M, N, K, epilogue, L.stream_ptr())
+    L.check(rc, "b200clip_gemm_ln_partials")
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, *, rows: int | None = None,
               row_stride_rows: int = 1, row_idx: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     L.require_cuda(x, gamma, beta, row_idx, out)
