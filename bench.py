@@ -158,7 +158,7 @@ def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 64
+    sample = int(os.environ.get("B200CLIP_REF_SAMPLE", "64"))      # images per step (a bounded sample of the 1024-image batch)
     sd, image, prompt = cpu_setup(sample)
     for _ in range(max(args.warmup, 1)):
         cpu_hot_path(sd, image[:4], prompt)

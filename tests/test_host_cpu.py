@@ -232,3 +232,23 @@ def test_gather_features_two_rank_gloo():
         assert torch.allclose(r["d_img"], torch.full_like(r["d_img"], 3.0))
         assert torch.allclose(r["d_txt"], torch.full_like(r["d_txt"], 6.0))
     assert r0["labels"].tolist() == [0, 1, 2, 3] and r1["labels"].tolist() == [4, 5, 6, 7]   # loss.py:92-94
+
+
+# ------------------------------------------------------------------ bench.py contract (reference arm runs on CPU) ---
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` = the CPU oracle port timed on the host cores; one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, B200CLIP_REF_SAMPLE="2")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "zero_shot_images_per_sec" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
