@@ -42,20 +42,32 @@ struct GemmBatch {
     int count;
 };
 
-// stage a [kTK x 64] k-major tile of an operand stored with the contraction index contiguous ([rows, K]) ...
-__device__ __forceinline__ void stage_kc(float (*S)[kT + 4], const float* base, int64_t ld, int r0, int rows, int k0, int K, int tid) {
+// One k-step of an operand tile: [kTK x 64] in shared memory, k-major.  The global read and the shared-memory write are
+// separate so that the next k-step's global loads are in flight while this one is multiplied (register double buffering).
+// operand stored with the contraction index contiguous ([rows, K]) ...
+__device__ __forceinline__ float4 load_kc(const float* base, int64_t ld, int r0, int rows, int k0, int K, int tid) {
     const int r = tid >> 2;
     const int lk = (tid & 3) * 4;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r0 + r < rows && k0 + lk < K) a = *reinterpret_cast<const float4*>(base + static_cast<int64_t>(r0 + r) * ld + k0 + lk);
+    return a;
+}
+__device__ __forceinline__ void store_kc(float (*S)[kT + 4], float4 a, int tid) {
+    const int r = tid >> 2;
+    const int lk = (tid & 3) * 4;
     S[lk + 0][r] = a.x; S[lk + 1][r] = a.y; S[lk + 2][r] = a.z; S[lk + 3][r] = a.w;
 }
 // ... or with the output index contiguous ([K, rows])
-__device__ __forceinline__ void stage_mc(float (*S)[kT + 4], const float* base, int64_t ld, int r0, int rows, int k0, int K, int tid) {
+__device__ __forceinline__ float4 load_mc(const float* base, int64_t ld, int r0, int rows, int k0, int K, int tid) {
     const int k = tid >> 4;
     const int r = (tid & 15) * 4;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k0 + k < K && r0 + r < rows) a = *reinterpret_cast<const float4*>(base + static_cast<int64_t>(k0 + k) * ld + r0 + r);
+    return a;
+}
+__device__ __forceinline__ void store_mc(float (*S)[kT + 4], float4 a, int tid) {
+    const int k = tid >> 4;
+    const int r = (tid & 15) * 4;
     *reinterpret_cast<float4*>(&S[k][r]) = a;
 }
 
@@ -68,12 +80,19 @@ __device__ __forceinline__ void tile_gemm(const GemmProb& p, int m0, int n0, flo
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    auto load_a = [&](int k0) { return TA ? load_mc(p.A, p.lda, m0, p.M, k0, p.K, tid) : load_kc(p.A, p.lda, m0, p.M, k0, p.K, tid); };
+    auto load_b = [&](int k0) { return TB ? load_mc(p.B, p.ldb, n0, p.N, k0, p.K, tid) : load_kc(p.B, p.ldb, n0, p.N, k0, p.K, tid); };
+    float4 ra = load_a(0), rb = load_b(0);
     for (int k0 = 0; k0 < p.K; k0 += kTK) {
-        if constexpr (TA) stage_mc(As, p.A, p.lda, m0, p.M, k0, p.K, tid);
-        else stage_kc(As, p.A, p.lda, m0, p.M, k0, p.K, tid);
-        if constexpr (TB) stage_mc(Bs, p.B, p.ldb, n0, p.N, k0, p.K, tid);
-        else stage_kc(Bs, p.B, p.ldb, n0, p.N, k0, p.K, tid);
+        if constexpr (TA) store_mc(As, ra, tid);
+        else store_kc(As, ra, tid);
+        if constexpr (TB) store_mc(Bs, rb, tid);
+        else store_kc(Bs, rb, tid);
         __syncthreads();
+        if (k0 + kTK < p.K) {   // next k-step's operands: in flight under the FMAs below
+            ra = load_a(k0 + kTK);
+            rb = load_b(k0 + kTK);
+        }
 #pragma unroll
         for (int k = 0; k < kTK; ++k) {
             const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
