@@ -354,45 +354,55 @@ def run_ours(args) -> None:
     value = BATCH * world * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region ---------
-    host_img = [torch.randn(BATCH, 3, 224, 224, generator=torch.Generator().manual_seed(11 + i)).bfloat16().pin_memory() for i in range(2)]
-    host_pred = torch.empty((BATCH,), dtype=torch.int64).pin_memory()
     copy_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-    dev_img = [torch.empty_like(image), torch.empty_like(image)]
-    ready = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
     half = BATCH // 2
 
-    def upload(i):
-        # two halves on two copy streams: 47 -> 55 GB/s on a Gen5 x16 link (tools/h2d_bench.py)
-        for k, cs in enumerate(copy_streams):
-            with torch.cuda.stream(cs):
-                cs.wait_event(consumed[i % 2])
-                dev_img[i % 2][k * half:(k + 1) * half].copy_(host_img[i % 2][k * half:(k + 1) * half], non_blocking=True)
-                ready[i % 2][k].record(cs)
+    def e2e_measure(host_img):
+        """predict() on pinned host batches: H2D (two halves on two copy streams, double-buffered) + D2H of the predictions
+        inside the timed region.  -> images/s over all ranks (max wall time over ranks)."""
+        host_pred = torch.empty((BATCH,), dtype=torch.int64).pin_memory()
+        dev_img = [torch.empty_like(host_img[0], device=dev), torch.empty_like(host_img[0], device=dev)]
+        ready = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_run(steps):
-        for ev in consumed:
-            ev.record()
-        upload(0)
-        for i in range(steps):
-            if i + 1 < steps:
-                upload(i + 1)                                    # next batch's H2D overlaps this batch's compute
-            for ev in ready[i % 2]:
-                torch.cuda.current_stream().wait_event(ev)
-            pred = classifier.predict(dev_img[i % 2])["pred"]    # the call a user makes (xclip.zero_shot API)
-            consumed[i % 2].record()
-            host_pred.copy_(pred, non_blocking=True)
-        torch.cuda.synchronize()
+        def upload(i):
+            # two halves on two copy streams: 47 -> 55 GB/s on a Gen5 x16 link (tools/h2d_bench.py)
+            for k, cs in enumerate(copy_streams):
+                with torch.cuda.stream(cs):
+                    cs.wait_event(consumed[i % 2])
+                    dev_img[i % 2][k * half:(k + 1) * half].copy_(host_img[i % 2][k * half:(k + 1) * half], non_blocking=True)
+                    ready[i % 2][k].record(cs)
 
-    e2e_run(3)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_run(args.steps)
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = BATCH * world * args.steps / float(t)
+        def e2e_run(steps):
+            for ev in consumed:
+                ev.record()
+            upload(0)
+            for i in range(steps):
+                if i + 1 < steps:
+                    upload(i + 1)                                    # next batch's H2D overlaps this batch's compute
+                for ev in ready[i % 2]:
+                    torch.cuda.current_stream().wait_event(ev)
+                pred = classifier.predict(dev_img[i % 2])["pred"]    # the call a user makes (xclip.zero_shot API)
+                consumed[i % 2].record()
+                host_pred.copy_(pred, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_run(3)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(args.steps)
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return BATCH * world * args.steps / float(t)
+
+    # (a) the reference's input contract: images already preprocessed on the host and cast to the tower dtype (16 bit)
+    e2e_value = e2e_measure([torch.randn(BATCH, 3, 224, 224, generator=torch.Generator().manual_seed(11 + i)).bfloat16().pin_memory()
+                             for i in range(2)])
+    # (b) uint8 pixel batches: ToTensor + Normalize fused into the im2col kernel, half the H2D bytes
+    e2e_u8_value = e2e_measure([torch.randint(0, 256, (BATCH, 3, 224, 224), generator=torch.Generator().manual_seed(21 + i),
+                                              dtype=torch.uint8).pin_memory() for i in range(2)])
 
     # ---- ClipLoss step (BASELINE config 4 shape: 256 local rows per rank), reported next to the headline ---------
     n_loc = 256
@@ -433,6 +443,9 @@ def run_ours(args) -> None:
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 2, "d2h_bytes_per_step": BATCH * 8,
                         "what": "ZeroShotClassifier.predict(images) from pinned host bf16 batches, H2D double-buffered on two copy streams, "
                                 "int64 predictions copied back to pinned host memory", "numa_node_rank0": numa_node},
+                "e2e_uint8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 224 * 224, "d2h_bytes_per_step": BATCH * 8,
+                              "what": "same call with uint8 pixel batches (resized / cropped on the host): ToTensor + Normalize run "
+                                      "inside the im2col kernel (b200clip_vit_forward_u8)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                 "per_gpu": {"images_per_s": value / world, "algorithmic_tflops": tower_tflops,
                             "frac_of_bf16_peak_burst": tower_tflops / peaks["bf16_tflops"],

@@ -246,6 +246,17 @@ typedef struct b200clip_text_weights {
 /* bytes of scratch a forward of `batch` items needs (seq_len from cfg; text may pass a truncated L) */
 int64_t b200clip_workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len);
 
+/* The same forward from uint8 pixels [B,3,S,S] (0..255, already resized / centre-cropped): the preprocessing tail of the
+ * reference — ToTensor (x / 255) and Normalize((x - mean) / std), deps/open_clip/src/open_clip/transform.py:274-392 with
+ * constants.py:1-2 — runs inside the im2col, in fp32 with the reference's operation order, followed by the one rounding to
+ * the tower dtype that `.half()` / `.to(bfloat16)` performs in the evaluation scripts.  `mean`, `std`: 3 HOST floats each.
+ * b200clip_patchify_u8 is the im2col alone (patches [B*g*g, kpad]). */
+int b200clip_vit_forward_u8(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const uint8_t* image,
+                            const float* mean, const float* std, void* out, int batch, int normalize, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+int b200clip_patchify_u8(int dtype, const uint8_t* image, const float* mean, const float* std, void* patches, int batch,
+                         int image_size, int patch, int kpad, void* stream);
+
 /* VisionTransformer.forward (transformer.py:601-643): image [B,3,S,S] dtype -> out [B,D] dtype
  * (L2-normalised when `normalize` != 0, CLIP.encode_image model.py:265-267). */
 int b200clip_vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out,

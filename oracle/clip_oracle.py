@@ -209,3 +209,12 @@ def clip_loss_local_grads(img_loc, txt_loc, all_img, all_txt, logit_scale, rank:
         d_scale += float((dl * raw).sum())
     (d_img_loc, d_all_txt), (d_txt_loc, d_all_img) = out
     return d_img_loc, d_txt_loc, d_all_img, d_all_txt, d_scale
+
+
+def preprocess_u8(image_u8: torch.Tensor, mean, std) -> torch.Tensor:
+    """ToTensor + Normalize on already resized / cropped uint8 pixels [B,3,H,W] (deps/open_clip/src/open_clip/transform.py:
+    274-392: `ToTensor()` = x.float().div(255), `Normalize(mean, std)` = (x - mean) / std), fp32."""
+    x = image_u8.float().div(255.0)
+    m = torch.tensor(mean, dtype=torch.float32).view(1, 3, 1, 1)
+    s = torch.tensor(std, dtype=torch.float32).view(1, 3, 1, 1)
+    return x.sub(m).div(s)

@@ -396,6 +396,20 @@ def test_cliploss_fwd_bwd(n, world, rank, D):
     assert _rel(grads3[0], 0.25 * il.grad) < 1e-4
 
 
+# ------------------------------------------------------------------ uint8 preprocessing fused into the im2col --------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("S,P,kpad", [(224, 32, 3072), (224, 16, 768), (224, 14, 640), (64, 8, 192)])
+def test_patchify_u8_is_totensor_normalize_patchify(dtype, S, P, kpad):
+    from oracle import clip_oracle as O
+    from understanding_clip_ood_b200.open_clip import OPENAI_DATASET_MEAN as MEAN, OPENAI_DATASET_STD as STD
+    g = _gen(41)
+    img = torch.randint(0, 256, (5, 3, S, S), device=DEV, generator=g, dtype=torch.uint8)
+    got = ops.patchify_u8(img, P, kpad, dtype, MEAN, STD)
+    ref_img = O.preprocess_u8(img.cpu(), MEAN, STD).to(dtype).to(DEV)          # fp32 ToTensor + Normalize, one rounding
+    want = ops.patchify(ref_img, P, kpad)
+    assert torch.equal(got, want)
+
+
 # ------------------------------------------------------------------ peer-memory exchange kernels (csrc/p2p.cu) on ONE device -
 # The multi-process form runs in tests/test_peer_gpu.py (>= 2 GPUs).  Here the "peers" are local buffers and the flags of
 # the other ranks are set by hand, which exercises the same kernels, addressing and flag protocol.

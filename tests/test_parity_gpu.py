@@ -44,6 +44,30 @@ def tiny_model(tiny, precision="fp32", quick=False):
     return m.eval()
 
 
+# ------------------------------------------------------------------ uint8 pixel batches (preprocessing tail on the GPU)
+@pytest.mark.parametrize("precision,dtype", [("fp32", torch.float32), ("bf16", torch.bfloat16), ("fp16", torch.float16)])
+def test_uint8_images_equal_reference_preprocessing_then_forward(tiny, precision, dtype):
+    """encode_image(uint8 pixels) == encode_image(ToTensor + Normalize of the same pixels, cast like the scripts do): the
+    normalisation is fused into the im2col with the reference's operation order, so the two routes agree bit for bit; and
+    the fp32 route matches the CPU oracle run on the oracle-preprocessed image."""
+    m = tiny_model(tiny, precision)
+    S = m.visual.image_size[0]
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (6, 3, S, S), generator=g, dtype=torch.uint8)
+    pp = m.visual.preprocess_cfg
+    ref_img = O.preprocess_u8(u8, pp["mean"], pp["std"])
+    a = m.encode_image(u8.to(DEV))
+    b = m.encode_image(ref_img.to(dtype).to(DEV))
+    assert a.dtype == dtype and torch.equal(a, b)
+    a2 = m.encode_image(u8.to(DEV))                  # second sighting of the same buffer: CUDA-graph replay
+    assert torch.equal(a2, a)
+    if precision == "fp32":
+        want = O.vit_forward(tiny["state_dict"], ref_img)
+        assert row_rel(a, want) < 1e-4
+    clf = zs.ZeroShotClassifier(OpenCLIP(m), FakeTokenizer(300), [f"class {i}" for i in range(7)])
+    assert torch.equal(clf.predict(u8.to(DEV))["pred"], clf.predict(ref_img.to(dtype).to(DEV))["pred"])
+
+
 # ------------------------------------------------------------------ (1) golden vectors of the reference
 def test_tiny_fp32_embeddings_match_reference(tiny):
     m = tiny_model(tiny)

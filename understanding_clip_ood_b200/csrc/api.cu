@@ -82,6 +82,8 @@ int gemm_any(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, 
 int64_t workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len);
 int vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out, int batch,
                 int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s);
+int vit_forward_u8(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const uint8_t* image, const float* mean,
+                   const float* std, void* out, int batch, int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s);
 int text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
                  int seq_len, int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s);
 
@@ -265,6 +267,17 @@ int64_t b200clip_workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int s
 int b200clip_vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out, int batch,
                          int normalize, void* workspace, int64_t workspace_bytes, void* stream) {
     return vit_forward(cfg, w, image, out, batch, normalize, workspace, workspace_bytes, S(stream));
+}
+
+int b200clip_vit_forward_u8(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const uint8_t* image, const float* mean,
+                            const float* std, void* out, int batch, int normalize, void* workspace, int64_t workspace_bytes,
+                            void* stream) {
+    return vit_forward_u8(cfg, w, image, mean, std, out, batch, normalize, workspace, workspace_bytes, S(stream));
+}
+
+int b200clip_patchify_u8(int dtype, const uint8_t* image, const float* mean, const float* std, void* patches, int batch, int image_size,
+                         int patch, int kpad, void* stream) {
+    return patchify_u8(dtype, image, mean, std, patches, batch, image_size, patch, kpad, nullptr, nullptr, nullptr, 0, S(stream));
 }
 
 int b200clip_text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,

@@ -55,6 +55,62 @@ patchify_kernel(const T* __restrict__ image, T* __restrict__ patches, int batch,
     }
 }
 
+// uint8 pixels -> normalised activations inside the im2col: ToTensor (x / 255) and Normalize ((x - mean) / std) of the
+// reference's preprocessing (deps/open_clip/src/open_clip/transform.py:274-392, constants.py:1-2) with the same operation
+// order in fp32, then ONE rounding to the activation dtype (= `.half()` / `.to(bfloat16)` of the evaluation scripts).  The
+// host then uploads 1 byte per pixel instead of 2 or 4 and the normalised image never exists in memory.
+struct Norm3 {
+    float mean[3], std[3];
+};
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+patchify_u8_kernel(const uint8_t* __restrict__ image, T* __restrict__ patches, int batch, int S, int P, int g, int kpad, int cls_slot,
+                   const Norm3 nrm) {
+    const int kreal = 3 * P * P;
+    const int vec_per_row = kpad / VEC;
+    const int rows_per_img = g * g + cls_slot;
+    const int64_t total = static_cast<int64_t>(batch) * rows_per_img * vec_per_row;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t row = i / vec_per_row;
+        const int col = static_cast<int>(i - row * vec_per_row) * VEC;
+        T* dst = patches + row * kpad + col;
+        const int b = static_cast<int>(row / rows_per_img);
+        const int pr = static_cast<int>(row - static_cast<int64_t>(b) * rows_per_img) - cls_slot;
+        T vals[VEC];
+        if (col >= kreal || pr < 0) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) vals[e] = cast_from_f<T>(0.f);
+        } else {
+            const int gy = pr / g, gx = pr - gy * g;
+            const int c = col / (P * P);
+            const int rem = col - c * P * P;
+            const int ky = rem / P, kx = rem - ky * P;
+            const uint8_t* src = image + ((static_cast<int64_t>(b) * 3 + c) * S + (gy * P + ky)) * S + gx * P + kx;
+            uint8_t px[VEC];
+            if constexpr (VEC == 8) {
+                const uint2 u = __ldg(reinterpret_cast<const uint2*>(src));
+                const uint32_t w2[2] = {u.x, u.y};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) px[e] = static_cast<uint8_t>(w2[e >> 2] >> (8 * (e & 3)));
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) px[e] = src[e];
+            }
+            const float mean = nrm.mean[c], sd = nrm.std[c];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                vals[e] = cast_from_f<T>(__fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(px[e]), 255.0f), mean), sd));
+        }
+        if constexpr (VEC * sizeof(T) == 16) {
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(vals);
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) dst[e] = vals[e];
+        }
+    }
+}
+
 template <typename T>
 __global__ void cls_rows_kernel(const float* __restrict__ class_emb, const float* __restrict__ pos, T* __restrict__ x,
                                 int batch, int L, int width) {
@@ -140,6 +196,31 @@ int patchify_t(const void* image, void* patches, int batch, int S, int P, int kp
 }
 
 template <typename T>
+int patchify_u8_t(const uint8_t* image, const Norm3& nrm, void* patches, int batch, int S, int P, int kpad, const float* class_emb,
+                  const float* pos, void* x, int width, int cls_slot, cudaStream_t stream) {
+    const int g = S / P;
+    // 8 pixels (one 8-byte load, one 16-byte store for the 16-bit dtypes) per thread when a patch row allows it
+    const bool vec_ok = sizeof(T) == 2 && (P % 8 == 0) && (S % 8 == 0) && (kpad % 8 == 0) && (reinterpret_cast<uintptr_t>(image) % 8 == 0) &&
+                        (reinterpret_cast<uintptr_t>(patches) % 16 == 0);
+    const int64_t total = static_cast<int64_t>(batch) * (g * g + cls_slot) * (vec_ok ? kpad / 8 : kpad);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > static_cast<int64_t>(num_sms()) * 32) blocks = static_cast<int64_t>(num_sms()) * 32;
+    if (vec_ok)
+        patchify_u8_kernel<T, 8><<<static_cast<int>(blocks), 256, 0, stream>>>(image, static_cast<T*>(patches), batch, S, P, g, kpad, cls_slot, nrm);
+    else
+        patchify_u8_kernel<T, 1><<<static_cast<int>(blocks), 256, 0, stream>>>(image, static_cast<T*>(patches), batch, S, P, g, kpad, cls_slot, nrm);
+    B2C_LAUNCH_CHECK("patchify_u8_kernel");
+    if (x != nullptr) {
+        const int64_t tot2 = static_cast<int64_t>(batch) * width;
+        int blocks2 = static_cast<int>((tot2 + 255) / 256);
+        if (blocks2 > num_sms() * 8) blocks2 = num_sms() * 8;
+        cls_rows_kernel<T><<<blocks2, 256, 0, stream>>>(class_emb, pos, static_cast<T*>(x), batch, g * g + 1, width);
+        B2C_LAUNCH_CHECK("cls_rows_kernel");
+    }
+    return 0;
+}
+
+template <typename T>
 int text_embed_t(const int64_t* text, int ctx, const float* tok_emb, const float* pos_emb, void* x, int32_t* eot, int T_,
                  int L, int width, int vocab, cudaStream_t stream) {
     const int64_t rows = static_cast<int64_t>(T_) * L;
@@ -167,6 +248,28 @@ int patchify(int dtype, const void* image, void* patches, int batch, int image_s
         case 2: return patchify_t<__half>(image, patches, batch, image_size, patch, kpad, class_emb, pos, x, width, cls_slot, stream);
     }
     set_last_error("patchify: unknown dtype %d", dtype);
+    return -1;
+}
+
+int patchify_u8(int dtype, const uint8_t* image, const float* mean, const float* std, void* patches, int batch, int image_size, int patch,
+                int kpad, const float* class_emb, const float* pos, void* x, int width, cudaStream_t stream, int cls_slot) {
+    B2C_CHECK_ARG(image != nullptr && mean != nullptr && std != nullptr && patches != nullptr, "patchify_u8: null pointer");
+    B2C_CHECK_ARG(batch > 0 && image_size > 0 && patch > 0 && image_size % patch == 0,
+                  "patchify: bad geometry batch=%d image=%d patch=%d", batch, image_size, patch);
+    B2C_CHECK_ARG(kpad >= 3 * patch * patch, "patchify: kpad=%d smaller than 3*P*P=%d", kpad, 3 * patch * patch);
+    B2C_CHECK_ARG(x == nullptr || (class_emb != nullptr && pos != nullptr), "patchify: class rows need class_emb and pos");
+    Norm3 nrm;
+    for (int c = 0; c < 3; ++c) {
+        B2C_CHECK_ARG(std[c] > 0.f, "patchify_u8: std[%d] must be positive", c);
+        nrm.mean[c] = mean[c];
+        nrm.std[c] = std[c];
+    }
+    switch (dtype) {
+        case 0: return patchify_u8_t<float>(image, nrm, patches, batch, image_size, patch, kpad, class_emb, pos, x, width, cls_slot, stream);
+        case 1: return patchify_u8_t<__nv_bfloat16>(image, nrm, patches, batch, image_size, patch, kpad, class_emb, pos, x, width, cls_slot, stream);
+        case 2: return patchify_u8_t<__half>(image, nrm, patches, batch, image_size, patch, kpad, class_emb, pos, x, width, cls_slot, stream);
+    }
+    set_last_error("patchify_u8: unknown dtype %d", dtype);
     return -1;
 }
 

@@ -42,6 +42,10 @@ int attention(int dtype, const void* qkv, void* out, int batch, int seq_len, int
 int patchify(int dtype, const void* image, void* patches, int batch, int image_size, int patch, int kpad,
              const float* class_emb, const float* pos, void* x, int width, cudaStream_t stream, int cls_slot = 0);
 
+// same im2col from uint8 pixels with ToTensor + Normalize(mean, std) applied on the fly (mean / std: 3 host floats each)
+int patchify_u8(int dtype, const uint8_t* image, const float* mean, const float* std, void* patches, int batch, int image_size, int patch,
+                int kpad, const float* class_emb, const float* pos, void* x, int width, cudaStream_t stream, int cls_slot = 0);
+
 int text_embed(int dtype, const int64_t* text, int ctx, const float* tok_emb, const float* pos_emb, void* x, int32_t* eot,
                int T, int L, int width, cudaStream_t stream);
 

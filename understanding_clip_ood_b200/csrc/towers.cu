@@ -154,12 +154,15 @@ int64_t workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {
     return carve(*cfg, batch, seq_len, nullptr).total;
 }
 
-int vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out, int batch,
-                int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s) {
+// image_u8 != nullptr: uint8 pixels, ToTensor + Normalize(mean, std) fused into the im2col (`image` is ignored)
+static int vit_forward_impl(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, const uint8_t* image_u8,
+                            const float* mean, const float* std, void* out, int batch, int normalize, void* workspace,
+                            int64_t workspace_bytes_, cudaStream_t s) {
     int rc;
     if ((rc = check_cfg(cfg)) != 0) return rc;
     const b200clip_tower_cfg& c = *cfg;
-    B2C_CHECK_ARG(w != nullptr && image != nullptr && out != nullptr && workspace != nullptr && w->blocks_host != nullptr,
+    B2C_CHECK_ARG(w != nullptr && (image != nullptr || image_u8 != nullptr) && out != nullptr && workspace != nullptr &&
+                      w->blocks_host != nullptr,
                   "vit_forward: null pointer");
     B2C_CHECK_ARG(batch > 0, "vit_forward: empty batch");
     B2C_CHECK_ARG(c.patch_size > 0 && c.image_size % c.patch_size == 0, "vit_forward: image %d not divisible by patch %d",
@@ -180,15 +183,19 @@ int vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, co
     if (dt != B200CLIP_F32 && w->pos_cls != nullptr) {
         // patch embedding in token layout: im2col with an all-zero row in every class-token slot, then ONE CTA-pair GEMM over
         // all B*L rows whose epilogue adds the (class + positional) table row of each token
-        if ((rc = patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, nullptr, nullptr, nullptr, W, s, 1)) != 0)
-            return rc;
+        rc = image_u8 != nullptr
+                 ? patchify_u8(dt, image_u8, mean, std, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, nullptr, nullptr, nullptr, W, s, 1)
+                 : patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, nullptr, nullptr, nullptr, W, s, 1);
+        if (rc != 0) return rc;
         if ((rc = gemm_pair(dt == B200CLIP_BF16, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, M, W,
                             c.patch_kpad, B200CLIP_EPI_BIAS, 0, 0, s, nullptr, nullptr, w->pos_cls, L)) != 0)
             return rc;
     } else {
         // im2col -> GEMM whose epilogue scatters to token rows 1..L-1 and adds the positional embedding
-        if ((rc = patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s)) != 0)
-            return rc;
+        rc = image_u8 != nullptr
+                 ? patchify_u8(dt, image_u8, mean, std, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s)
+                 : patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s);
+        if (rc != 0) return rc;
         if ((rc = gemm_any(dt, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, batch * g * g, W,
                            c.patch_kpad, B200CLIP_EPI_PATCH, w->pos_emb, g * g, L, s)) != 0)
             return rc;
@@ -202,6 +209,18 @@ int vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, co
         return rc;
     if (normalize && (rc = normalize_rows(dt, out, c.embed_dim, out, c.embed_dim, batch, c.embed_dim, 1e-12f, s)) != 0) return rc;
     return 0;
+}
+
+int vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out, int batch,
+                int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s) {
+    B2C_CHECK_ARG(image != nullptr, "vit_forward: null image");
+    return vit_forward_impl(cfg, w, image, nullptr, nullptr, nullptr, out, batch, normalize, workspace, workspace_bytes_, s);
+}
+
+int vit_forward_u8(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const uint8_t* image, const float* mean,
+                   const float* std, void* out, int batch, int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s) {
+    B2C_CHECK_ARG(image != nullptr && mean != nullptr && std != nullptr, "vit_forward_u8: null pointer");
+    return vit_forward_impl(cfg, w, nullptr, image, mean, std, out, batch, normalize, workspace, workspace_bytes_, s);
 }
 
 int text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,

@@ -19,6 +19,9 @@ import numpy as np
 import torch
 from torch import nn
 
+OPENAI_DATASET_MEAN = (0.48145466, 0.4578275, 0.40821073)     # open_clip/constants.py:1-2
+OPENAI_DATASET_STD = (0.26862954, 0.26130258, 0.27577711)
+
 from .. import _lib as L
 
 __all__ = ["CLIP", "VisionTower", "convert_weights_to_lp", "get_cast_dtype", "get_input_dtype"]
@@ -357,9 +360,11 @@ class VisionTower(nn.Module):
         _check_device(image, "encode_image")
         _check_device(self.proj, "encode_image (model weights)")
         dt = self._compute_dtype()
-        if image.dtype != dt:
+        u8 = image.dtype == torch.uint8
+        if not u8 and image.dtype != dt:
             raise RuntimeError(f"Input type ({image.dtype}) and weight type ({dt}) should be the same "
-                               f"(cast the batch with get_input_dtype(precision), as the reference requires)")
+                               f"(cast the batch with get_input_dtype(precision), as the reference requires; uint8 pixel "
+                               f"batches are normalised on the GPU with visual.preprocess_cfg mean / std)")
         if image.ndim != 4 or image.shape[1] != 3 or tuple(image.shape[2:]) != self.image_size:
             raise RuntimeError(f"expected images of shape [B, 3, {self.image_size[0]}, {self.image_size[1]}], got {tuple(image.shape)}")
         image = image.contiguous()
@@ -372,14 +377,24 @@ class VisionTower(nn.Module):
             nbytes = lib.b200clip_workspace_bytes(C.byref(eng.cfg), B, eng.cfg.seq_len)
             ws = eng.workspace(nbytes, image.device)
 
+            if u8:
+                # uint8 pixels: ToTensor + Normalize (open_clip/transform.py:274-392) run inside the im2col kernel
+                pp = getattr(self, "preprocess_cfg", None) or {}
+                mean = (C.c_float * 3)(*[float(v) for v in pp.get("mean", OPENAI_DATASET_MEAN)])
+                std = (C.c_float * 3)(*[float(v) for v in pp.get("std", OPENAI_DATASET_STD)])
+
             def enqueue(dst: torch.Tensor) -> None:
-                rc = lib.b200clip_vit_forward(C.byref(eng.cfg), C.byref(eng.weights), image.data_ptr(), dst.data_ptr(), B,
-                                              int(normalize), ws.data_ptr(), ws.numel(), L.stream_ptr())
+                if u8:
+                    rc = lib.b200clip_vit_forward_u8(C.byref(eng.cfg), C.byref(eng.weights), image.data_ptr(), mean, std, dst.data_ptr(), B,
+                                                     int(normalize), ws.data_ptr(), ws.numel(), L.stream_ptr())
+                else:
+                    rc = lib.b200clip_vit_forward(C.byref(eng.cfg), C.byref(eng.weights), image.data_ptr(), dst.data_ptr(), B,
+                                                  int(normalize), ws.data_ptr(), ws.numel(), L.stream_ptr())
                 L.check(rc, "b200clip_vit_forward")
 
             if self.use_cuda_graphs and not torch.cuda.is_current_stream_capturing():
-                return eng.run_graphed((image.data_ptr(), B, int(normalize), ws.data_ptr()), enqueue,
-                                       (B, self.output_dim), dt, image.device)
+                key = (image.data_ptr(), B, int(normalize), ws.data_ptr(), int(u8), tuple(mean) + tuple(std) if u8 else ())
+                return eng.run_graphed(key, enqueue, (B, self.output_dim), dt, image.device)
             out = torch.empty((B, self.output_dim), dtype=dt, device=image.device)
             enqueue(out)
         return out

@@ -164,6 +164,25 @@ def patchify(image: torch.Tensor, patch: int, kpad: int, class_emb: torch.Tensor
     return patches
 
 
+def patchify_u8(image: torch.Tensor, patch: int, kpad: int, dtype: torch.dtype, mean, std) -> torch.Tensor:
+    """uint8 pixels [B,3,S,S] -> normalised patch matrix [B*g*g, kpad] in `dtype`; see b200clip_patchify_u8."""
+    L.require_cuda(image)
+    if image.dtype != torch.uint8:
+        raise L.B200ClipError("patchify_u8: uint8 image required")
+    image = _c(image)
+    B, Cc, S, S2 = image.shape
+    if Cc != 3 or S != S2:
+        raise L.B200ClipError("patchify: image must be [B,3,S,S]")
+    g = S // patch
+    patches = torch.empty((B * g * g, kpad), dtype=dtype, device=image.device)
+    import ctypes as C
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    sd = (C.c_float * 3)(*[float(v) for v in std])
+    rc = L.load().b200clip_patchify_u8(L.dtype_code(dtype), image.data_ptr(), m, sd, patches.data_ptr(), B, S, patch, kpad, L.stream_ptr())
+    L.check(rc, "b200clip_patchify_u8")
+    return patches
+
+
 def text_embed(text: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Tensor, dtype: torch.dtype, seq_len: int | None = None):
     L.require_cuda(text, tok_emb, pos_emb)
     text = _c(text)
