@@ -279,8 +279,8 @@ def run_ours(args) -> None:
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner there)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]          # the image sets it; NCCL prints its version banner to STDOUT, next to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     L.load()
     peaks = measured_peaks()
