@@ -21,11 +21,17 @@ template <> __device__ __forceinline__ float cast_to_f<__half>(__half v) { retur
 // value after a cast to the activation dtype (fp32 tables are cast at use in the 16-bit modes)
 template <typename T> __device__ __forceinline__ float rt(float v) { return cast_to_f<T>(cast_from_f<T>(v)); }
 
-// VEC elements (16 bytes) per thread when the patch size allows it, else 1.
-template <typename T, int VEC>
+// VEC elements (16 bytes) per thread when the patch size allows it, else 1.  PC / GC / KC > 0: patch size, grid and padded row
+// length known at compile time (the CLIP geometries), so that the five integer divisions per 16-byte vector become
+// multiply-shifts: the generic form was issue-bound (75 % of the issue slots at 51 % of the DRAM peak).
+template <typename T, int VEC, int PC = 0, int GC = 0, int KC = 0>
 __global__ void __launch_bounds__(256)
-patchify_kernel(const T* __restrict__ image, T* __restrict__ patches, int batch, int S, int P, int g, int kpad, int cls_slot) {
+patchify_kernel(const T* __restrict__ image, T* __restrict__ patches, int batch, int S_, int P_, int g_, int kpad_, int cls_slot) {
     // cls_slot = 1: token layout, g*g+1 rows per image with an all-zero row in the class-token slot (row 0)
+    const int P = PC > 0 ? PC : P_;
+    const int g = GC > 0 ? GC : g_;
+    const int kpad = KC > 0 ? KC : kpad_;
+    const int S = PC > 0 ? PC * GC : S_;
     const int kreal = 3 * P * P;
     const int vec_per_row = kpad / VEC;
     const int rows_per_img = g * g + cls_slot;
@@ -49,6 +55,8 @@ patchify_kernel(const T* __restrict__ image, T* __restrict__ patches, int batch,
         const T* src = image + ((static_cast<int64_t>(b) * 3 + c) * S + (gy * P + ky)) * S + gx * P + kx;
         if constexpr (VEC * sizeof(T) == 16) {
             *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(src));
+        } else if constexpr (VEC * sizeof(T) == 4 && VEC == 2) {
+            *reinterpret_cast<uint32_t*>(dst) = __ldg(reinterpret_cast<const uint32_t*>(src));
         } else {
             dst[0] = src[0];
         }
@@ -62,10 +70,22 @@ patchify_kernel(const T* __restrict__ image, T* __restrict__ patches, int batch,
 struct Norm3 {
     float mean[3], std[3];
 };
-template <typename T, int VEC>
+template <typename T, int VEC, int PC = 0, int GC = 0, int KC = 0>
 __global__ void __launch_bounds__(256)
-patchify_u8_kernel(const uint8_t* __restrict__ image, T* __restrict__ patches, int batch, int S, int P, int g, int kpad, int cls_slot,
+patchify_u8_kernel(const uint8_t* __restrict__ image, T* __restrict__ patches, int batch, int S_, int P_, int g_, int kpad_, int cls_slot,
                    const Norm3 nrm) {
+    // The result depends on (pixel value, channel) only: every block tabulates the 3 x 256 values once with the reference's
+    // operation order and IEEE divisions (two fp32 divisions per pixel made the straightforward form compute-bound).
+    __shared__ T lut[3][256];
+    for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
+        const int c = i >> 8, v = i & 255;
+        lut[c][v] = cast_from_f<T>(__fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), nrm.mean[c]), nrm.std[c]));
+    }
+    __syncthreads();
+    const int P = PC > 0 ? PC : P_;
+    const int g = GC > 0 ? GC : g_;
+    const int kpad = KC > 0 ? KC : kpad_;
+    const int S = PC > 0 ? PC * GC : S_;
     const int kreal = 3 * P * P;
     const int vec_per_row = kpad / VEC;
     const int rows_per_img = g * g + cls_slot;
@@ -93,17 +113,21 @@ patchify_u8_kernel(const uint8_t* __restrict__ image, T* __restrict__ patches, i
                 const uint32_t w2[2] = {u.x, u.y};
 #pragma unroll
                 for (int e = 0; e < 8; ++e) px[e] = static_cast<uint8_t>(w2[e >> 2] >> (8 * (e & 3)));
+            } else if constexpr (VEC == 2) {
+                const unsigned short u = __ldg(reinterpret_cast<const unsigned short*>(src));
+                px[0] = static_cast<uint8_t>(u & 0xff);
+                px[1] = static_cast<uint8_t>(u >> 8);
             } else {
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) px[e] = src[e];
             }
-            const float mean = nrm.mean[c], sd = nrm.std[c];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e)
-                vals[e] = cast_from_f<T>(__fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(px[e]), 255.0f), mean), sd));
+            for (int e = 0; e < VEC; ++e) vals[e] = lut[c][px[e]];
         }
         if constexpr (VEC * sizeof(T) == 16) {
             *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(vals);
+        } else if constexpr (VEC * sizeof(T) == 4) {
+            *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(vals);
         } else {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) dst[e] = vals[e];
@@ -175,12 +199,26 @@ int patchify_t(const void* image, void* patches, int batch, int S, int P, int kp
     constexpr int V = 16 / sizeof(T);
     const bool vec_ok = (P % V == 0) && (S % V == 0) && (kpad % V == 0) &&
                         (reinterpret_cast<uintptr_t>(image) % 16 == 0) && (reinterpret_cast<uintptr_t>(patches) % 16 == 0);
-    const int64_t total = static_cast<int64_t>(batch) * (g * g + cls_slot) * (vec_ok ? kpad / V : kpad);
+    // 16-bit types with an even patch size that is not a multiple of 8 (ViT-L/14): two elements (4 bytes) per thread
+    const bool vec2_ok = !vec_ok && sizeof(T) == 2 && (P % 2 == 0) && (S % 2 == 0) && (kpad % 2 == 0) &&
+                         (reinterpret_cast<uintptr_t>(image) % 4 == 0) && (reinterpret_cast<uintptr_t>(patches) % 4 == 0);
+    const int64_t total = static_cast<int64_t>(batch) * (g * g + cls_slot) * (vec_ok ? kpad / V : (vec2_ok ? kpad / 2 : kpad));
     int64_t blocks = (total + 255) / 256;
     if (blocks > static_cast<int64_t>(num_sms()) * 32) blocks = static_cast<int64_t>(num_sms()) * 32;
-    if (vec_ok)
+    const T* img = static_cast<const T*>(image);
+    T* pat = static_cast<T*>(patches);
+    const int nb = static_cast<int>(blocks);
+    if (vec_ok && S == 224 && P == 32 && kpad == 3072)        // ViT-B/32
+        patchify_kernel<T, V, 32, 7, 3072><<<nb, 256, 0, stream>>>(img, pat, batch, S, P, g, kpad, cls_slot);
+    else if (vec_ok && S == 224 && P == 16 && kpad == 768)    // ViT-B/16
+        patchify_kernel<T, V, 16, 14, 768><<<nb, 256, 0, stream>>>(img, pat, batch, S, P, g, kpad, cls_slot);
+    else if (vec_ok)
         patchify_kernel<T, V><<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const T*>(image), static_cast<T*>(patches),
                                                                             batch, S, P, g, kpad, cls_slot);
+    else if (vec2_ok && S == 224 && P == 14 && kpad == 640)   // ViT-L/14
+        patchify_kernel<T, 2, 14, 16, 640><<<nb, 256, 0, stream>>>(img, pat, batch, S, P, g, kpad, cls_slot);
+    else if (vec2_ok)
+        patchify_kernel<T, 2><<<nb, 256, 0, stream>>>(img, pat, batch, S, P, g, kpad, cls_slot);
     else
         patchify_kernel<T, 1><<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const T*>(image), static_cast<T*>(patches),
                                                                             batch, S, P, g, kpad, cls_slot);
@@ -199,16 +237,28 @@ template <typename T>
 int patchify_u8_t(const uint8_t* image, const Norm3& nrm, void* patches, int batch, int S, int P, int kpad, const float* class_emb,
                   const float* pos, void* x, int width, int cls_slot, cudaStream_t stream) {
     const int g = S / P;
-    // 8 pixels (one 8-byte load, one 16-byte store for the 16-bit dtypes) per thread when a patch row allows it
+    // 8 pixels (one 8-byte load, one 16-byte store for the 16-bit dtypes) per thread when a patch row allows it, else 2
     const bool vec_ok = sizeof(T) == 2 && (P % 8 == 0) && (S % 8 == 0) && (kpad % 8 == 0) && (reinterpret_cast<uintptr_t>(image) % 8 == 0) &&
                         (reinterpret_cast<uintptr_t>(patches) % 16 == 0);
-    const int64_t total = static_cast<int64_t>(batch) * (g * g + cls_slot) * (vec_ok ? kpad / 8 : kpad);
+    const bool vec2_ok = !vec_ok && sizeof(T) == 2 && (P % 2 == 0) && (S % 2 == 0) && (kpad % 2 == 0) &&
+                         (reinterpret_cast<uintptr_t>(image) % 2 == 0) && (reinterpret_cast<uintptr_t>(patches) % 4 == 0);
+    const int64_t total = static_cast<int64_t>(batch) * (g * g + cls_slot) * (vec_ok ? kpad / 8 : (vec2_ok ? kpad / 2 : kpad));
     int64_t blocks = (total + 255) / 256;
-    if (blocks > static_cast<int64_t>(num_sms()) * 32) blocks = static_cast<int64_t>(num_sms()) * 32;
-    if (vec_ok)
-        patchify_u8_kernel<T, 8><<<static_cast<int>(blocks), 256, 0, stream>>>(image, static_cast<T*>(patches), batch, S, P, g, kpad, cls_slot, nrm);
+    if (blocks > static_cast<int64_t>(num_sms()) * 16) blocks = static_cast<int64_t>(num_sms()) * 16;
+    const int nb = static_cast<int>(blocks);
+    T* pat = static_cast<T*>(patches);
+    if (vec_ok && S == 224 && P == 32 && kpad == 3072)
+        patchify_u8_kernel<T, 8, 32, 7, 3072><<<nb, 256, 0, stream>>>(image, pat, batch, S, P, g, kpad, cls_slot, nrm);
+    else if (vec_ok && S == 224 && P == 16 && kpad == 768)
+        patchify_u8_kernel<T, 8, 16, 14, 768><<<nb, 256, 0, stream>>>(image, pat, batch, S, P, g, kpad, cls_slot, nrm);
+    else if (vec_ok)
+        patchify_u8_kernel<T, 8><<<nb, 256, 0, stream>>>(image, pat, batch, S, P, g, kpad, cls_slot, nrm);
+    else if (vec2_ok && S == 224 && P == 14 && kpad == 640)
+        patchify_u8_kernel<T, 2, 14, 16, 640><<<nb, 256, 0, stream>>>(image, pat, batch, S, P, g, kpad, cls_slot, nrm);
+    else if (vec2_ok)
+        patchify_u8_kernel<T, 2><<<nb, 256, 0, stream>>>(image, pat, batch, S, P, g, kpad, cls_slot, nrm);
     else
-        patchify_u8_kernel<T, 1><<<static_cast<int>(blocks), 256, 0, stream>>>(image, static_cast<T*>(patches), batch, S, P, g, kpad, cls_slot, nrm);
+        patchify_u8_kernel<T, 1><<<nb, 256, 0, stream>>>(image, pat, batch, S, P, g, kpad, cls_slot, nrm);
     B2C_LAUNCH_CHECK("patchify_u8_kernel");
     if (x != nullptr) {
         const int64_t tot2 = static_cast<int64_t>(batch) * width;
