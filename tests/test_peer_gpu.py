@@ -63,12 +63,13 @@ def _worker(rank, world, port, n, D, dtype_name, steps, ret):
             loss = loss_fn(img, txt, ls)
             assert type(loss.grad_fn).__name__.startswith("_PeerLocalClipLoss"), type(loss.grad_fn).__name__
             (loss * 2.0).backward()              # upstream gradient != 1
-            want_loss, want_di, want_dt, want_ds = _oracle_rank(all_img.float(), all_txt.float(), scale, rank, n)
             tol = 1e-4 if dtype == torch.float32 else 2e-2
-            errs.append(abs(float(loss) - want_loss) / abs(want_loss))
-            errs.append(float((img.grad.double().cpu() / 2 - want_di).norm() / want_di.norm()) * (1e-4 / tol))
-            errs.append(float((txt.grad.double().cpu() / 2 - want_dt).norm() / want_dt.norm()) * (1e-4 / tol))
-            errs.append(abs(float(ls.grad) / 2 - want_ds) / abs(want_ds))
+            if step in (0, steps - 1) or world <= 2:     # the float64 CPU oracle is the slow part at 8 ranks: first and last step there
+                want_loss, want_di, want_dt, want_ds = _oracle_rank(all_img.float(), all_txt.float(), scale, rank, n)
+                errs.append(abs(float(loss) - want_loss) / abs(want_loss))
+                errs.append(float((img.grad.double().cpu() / 2 - want_di).norm() / want_di.norm()) * (1e-4 / tol))
+                errs.append(float((txt.grad.double().cpu() / 2 - want_dt).norm() / want_dt.norm()) * (1e-4 / tol))
+                errs.append(abs(float(ls.grad) / 2 - want_ds) / abs(want_ds))
             # the NCCL form of the same node gives the same numbers
             img2, txt2, ls2 = [t.detach().clone().requires_grad_(True) for t in (img, txt, ls)]
             loss2 = loss_mod._DistLocalClipLoss.apply(img2, txt2, ls2, rank, world, None)
