@@ -35,7 +35,7 @@ import torch
 
 __all__ = [
     "vit_forward", "text_forward", "normalize", "zero_shot_logits", "predict", "topk", "class_prompt_feat",
-    "clip_loss_local", "clip_loss_local_grads", "cfg_from_state_dict",
+    "clip_loss_local", "clip_loss_local_grads", "cfg_from_state_dict", "preprocess_u8", "train_step_grads",
 ]
 
 
@@ -104,8 +104,10 @@ def _f32(sd: dict) -> dict:
 
 def vit_forward(sd: dict, image: torch.Tensor, *, heads: int | None = None, quick_gelu: bool = False) -> torch.Tensor:
     """image [B,3,S,S] -> [B,D]   (transformer.py:601-643, pool_type 'tok', final_ln_after_pool False)."""
-    sd = _f32(sd)
-    x = image.detach().to(torch.float32).cpu()
+    return _vit(_f32(sd), image.detach().to(torch.float32).cpu(), heads, quick_gelu)
+
+
+def _vit(sd: dict, x: torch.Tensor, heads: int | None, quick_gelu: bool) -> torch.Tensor:
     conv = sd["visual.conv1.weight"]
     W, _, P, _ = conv.shape
     B, _, S, _ = x.shape
@@ -127,8 +129,10 @@ def text_forward(sd: dict, text: torch.Tensor, *, heads: int | None = None, quic
                  seq_len: int | None = None) -> torch.Tensor:
     """text int64 [T, ctx] -> [T, D]   (model.py:269-284; causal mask transformer.py:751-757; EOT pool :654).
     `seq_len` < ctx runs only the leading positions (exact when it exceeds every EOT index, by causality)."""
-    sd = _f32(sd)
-    text = text.detach().cpu().long()
+    return _text(_f32(sd), text.detach().cpu().long(), heads, quick_gelu, seq_len)
+
+
+def _text(sd: dict, text: torch.Tensor, heads: int | None, quick_gelu: bool, seq_len: int | None) -> torch.Tensor:
     Wt = sd["token_embedding.weight"].shape[1]
     heads = heads or Wt // 64
     L = text.shape[1] if seq_len is None else seq_len
@@ -218,3 +222,23 @@ def preprocess_u8(image_u8: torch.Tensor, mean, std) -> torch.Tensor:
     m = torch.tensor(mean, dtype=torch.float32).view(1, 3, 1, 1)
     s = torch.tensor(std, dtype=torch.float32).view(1, 3, 1, 1)
     return x.sub(m).div(s)
+
+
+def train_step_grads(sd: dict, image: torch.Tensor, text: torch.Tensor, *, quick_gelu: bool = False, dtype=torch.float32):
+    """Loss and parameter gradients of ONE contrastive training step on one rank without accumulation — `model(image, text)`
+    (CLIP.forward, model.py:295-315: both towers, F.normalize, logit_scale.exp()), ClipLoss.forward with world_size 1
+    (loss.py:120-131), `backward()` (training/train.py:115-183) — by autograd through the plain-op restatement above.
+    -> (loss float, {state_dict key: gradient}).  The checker for the tower backward of SURVEY §8(f)-1."""
+    leaf = {k: v.detach().to(dtype).cpu().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    img = _vit(leaf, image.detach().to(dtype).cpu(), None, quick_gelu)
+    txt = _text(leaf, text.detach().cpu().long(), None, quick_gelu, None)
+    img = img / img.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    txt = txt / txt.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    scale = leaf["logit_scale"].exp()
+    li = _log_softmax_rows(scale * img @ txt.t())
+    lt = _log_softmax_rows(scale * txt @ img.t())
+    n = img.shape[0]
+    rows = torch.arange(n)
+    loss = (-(li[rows, rows]).mean() - (lt[rows, rows]).mean()) / 2
+    loss.backward()
+    return float(loss), {k: v.grad.detach().clone() for k, v in leaf.items() if v.requires_grad and v.grad is not None}

@@ -10,6 +10,8 @@ Fixtures (all outputs of reference code on seeded inputs):
                       prompt features, logits and predictions, and `training.zero_shot.accuracy`-style top-5.
   cliploss.pt         reference `ClipLoss`: world_size 1 (loss + grads) and a 2-rank gloo run with
                       local_loss=True, gather_with_grad=True (per-rank loss, feature / logit_scale grads).
+  tiny_train_grads.pt reference training step on the tiny model (model(image, text) -> ClipLoss -> backward): loss and the
+                      gradient of every parameter; pins oracle.train_step_grads (checker of the tower backward).
   domainnet_prompts.npz   reference tokenizer output for the 345 DomainNet classes x 86 OpenAI templates
                       (class names = keys of data/in_to_dn_mapping.json, label order), truncated to the
                       first 24 context positions (max EOT index is 15), uint16.
@@ -217,18 +219,40 @@ def make_full(open_clip, zs, xo, skip_bf16: bool):
     print(f"vitb32_seed0_bf16.pt  reference bf16 vs fp32 top-1 agreement {agree:.3f}")
 
 
+def make_train_grads(open_clip):
+    """One training step of the reference on the tiny model: model(image, text) -> ClipLoss -> backward.  Stores the loss and
+    the gradient of every parameter (the golden vectors of the tower backward); inputs / weights are the ones
+    of tiny_clip.pt."""
+    tiny = torch.load(GOLD / "tiny_clip.pt", weights_only=False)
+    ref = open_clip.create_model("ViT-B-32", precision="fp32", **TINY)
+    ref.load_state_dict(tiny["state_dict"])
+    ref.train()
+    image, text = tiny["image"], tiny["text"][:6]
+    fi, ft, scale = ref(image, text)
+    loss = open_clip.ClipLoss()(fi, ft, scale)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in ref.named_parameters() if p.grad is not None}
+    torch.save({"loss": loss.detach().clone(), "grads": grads}, GOLD / "tiny_train_grads.pt")
+    print("tiny_train_grads.pt", float(loss), len(grads), "gradients,", sum(g.numel() for g in grads.values()), "values")
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--only-train-grads", action="store_true")
     ap.add_argument("--skip-full", action="store_true")
     ap.add_argument("--skip-bf16", action="store_true")
     ap.add_argument("--only-full", action="store_true")
     args = ap.parse_args()
     GOLD.mkdir(parents=True, exist_ok=True)
     open_clip, zs, xo = ref_loader.load()
+    if args.only_train_grads:
+        make_train_grads(open_clip)
+        return
     if not args.only_full:
         make_prompts(open_clip, zs)
         make_tiny(open_clip, zs, xo)
         make_cliploss(open_clip)
+        make_train_grads(open_clip)
     if not args.skip_full:
         make_full(open_clip, zs, xo, args.skip_bf16)
 
