@@ -252,3 +252,37 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_peer_exchange_ring_slot_bookkeeping():
+    """Host logic of the peer-memory ClipLoss exchange that needs no GPU: a ring slot is held while an autograd ctx that saved
+    it is alive, released by its backward (explicitly) or when the graph dies, and re-entering a held slot is refused."""
+    import gc
+    from understanding_clip_ood_b200.open_clip import peer
+
+    class FakeState:
+        def __init__(self):
+            self.inflight = set()
+
+    st = FakeState()
+    tokens = [peer._SlotToken(st, s) for s in (1, 2, 3)]
+    assert st.inflight == {1, 2, 3}
+    tokens[0] = None                  # what `ctx.token = None` does at the end of backward
+    gc.collect()
+    assert st.inflight == {2, 3}
+    del tokens                        # graphs that never ran backward
+    gc.collect()
+    assert st.inflight == set()
+    assert peer.RING >= 2 and peer.MAX_WORLD == 16
+    # B200CLIP_P2P=0 routes ClipLoss to the NCCL form
+    old = os.environ.get("B200CLIP_P2P")
+    try:
+        os.environ["B200CLIP_P2P"] = "0"
+        assert peer.enabled() is False and peer.get_exchange(4, 8, 0, 2, torch.device("cpu")) is None
+        os.environ["B200CLIP_P2P"] = "1"
+        assert peer.enabled() is True
+    finally:
+        if old is None:
+            os.environ.pop("B200CLIP_P2P", None)
+        else:
+            os.environ["B200CLIP_P2P"] = old
