@@ -286,3 +286,34 @@ def test_peer_exchange_ring_slot_bookkeeping():
             os.environ.pop("B200CLIP_P2P", None)
         else:
             os.environ["B200CLIP_P2P"] = old
+
+
+def test_built_library_is_blackwell_native_sass():
+    """The shipped kernels are sm_100a code on the Blackwell paths, not recompiled legacy kernels: SASS of the in-tree
+    libb200clip.so (cuobjdump; mnemonic table of /opt/skills/guides/B200_PROFILING.md) shows tcgen05 MMAs (UTCHMMA) fed by TMA
+    (UTMALDG) with TMEM loads / stores (LDTM / STTM) and TMA stores incl. the reduce-add form (UTMASTG / UTMAREDG) in the GEMM
+    and the long-sequence attention kernel, and system-scope release / acquire accesses in the peer-memory exchange."""
+    import collections
+    import shutil
+    import subprocess
+    from understanding_clip_ood_b200 import _lib
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not Path(tool).exists():
+        pytest.skip("cuobjdump not available")
+    _lib.load()
+    sass = subprocess.run([tool, "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True, timeout=600).stdout
+    per = collections.defaultdict(collections.Counter)
+    for part in re.split(r"\n\s*Function : ", sass)[1:]:
+        name = part.split("\n", 1)[0]
+        m = re.search(r"(gemm_pair_kernel|attention_tc_kernel|attention_short_kernel|p2p_allgather_kernel|p2p_reduce_finish_kernel)", name)
+        if not m:
+            continue
+        for mn in ("UTCHMMA", "UTMALDG", "UTMASTG", "UTMAREDG", "LDTM", "STTM", "HMMA", "USETMAXREG", "STG.E.STRONG.SYS", "LDG.E.STRONG.SYS"):
+            per[m.group(1)][mn] += len(re.findall(r"\b" + re.escape(mn), part))
+    g = per["gemm_pair_kernel"]
+    assert g["UTCHMMA"] > 0 and g["UTMALDG"] > 0 and g["UTMASTG"] > 0 and g["UTMAREDG"] > 0 and g["LDTM"] > 0 and g["HMMA"] == 0
+    a = per["attention_tc_kernel"]
+    assert a["UTCHMMA"] > 0 and a["UTMALDG"] > 0 and a["LDTM"] > 0 and a["STTM"] > 0 and a["USETMAXREG"] > 0 and a["HMMA"] == 0
+    assert per["attention_short_kernel"]["UTMALDG"] > 0 and per["attention_short_kernel"]["UTMASTG"] > 0
+    assert per["p2p_allgather_kernel"]["STG.E.STRONG.SYS"] > 0 and per["p2p_allgather_kernel"]["LDG.E.STRONG.SYS"] > 0
+    assert per["p2p_reduce_finish_kernel"]["STG.E.STRONG.SYS"] > 0 and per["p2p_reduce_finish_kernel"]["LDG.E.STRONG.SYS"] > 0
