@@ -28,3 +28,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """A fresh checkout has no libb200clip.so (built artefacts are git-ignored): build it once, in-tree, before the first
+    test needs it.  An existing library is used as it is (on the GPU box it travels with the snapshot)."""
+    from understanding_clip_ood_b200 import build as b
+    if not b.LIB_PATH.exists():
+        b.build(verbose=False)
+    yield
