@@ -317,3 +317,26 @@ def test_built_library_is_blackwell_native_sass():
     assert per["attention_short_kernel"]["UTMALDG"] > 0 and per["attention_short_kernel"]["UTMASTG"] > 0
     assert per["p2p_allgather_kernel"]["STG.E.STRONG.SYS"] > 0 and per["p2p_allgather_kernel"]["LDG.E.STRONG.SYS"] > 0
     assert per["p2p_reduce_finish_kernel"]["STG.E.STRONG.SYS"] > 0 and per["p2p_reduce_finish_kernel"]["LDG.E.STRONG.SYS"] > 0
+
+
+def test_training_mode_forward_warns_that_the_towers_are_forward_only():
+    """A training loop calling the towers with autograd on would silently train nothing: the first such call warns."""
+    import warnings as W
+    from understanding_clip_ood_b200 import _lib, open_clip
+    from understanding_clip_ood_b200.open_clip import model as M
+    m = open_clip.create_model("ViT-B-32", vision_cfg={"image_size": 64, "layers": 1, "width": 64, "patch_size": 32},
+                               text_cfg={"context_length": 77, "vocab_size": 64, "width": 64, "heads": 1, "layers": 1}, embed_dim=32)
+    m.train()
+    M._warned_no_backward = False
+    with W.catch_warnings(record=True) as rec:
+        W.simplefilter("always")
+        with pytest.raises(_lib.B200ClipError):          # CPU tensors: still the loud no-fallback error afterwards
+            m.encode_image(torch.zeros(1, 3, 64, 64))
+    assert any("forward-only" in str(w.message) for w in rec)
+    m.eval()
+    M._warned_no_backward = False
+    with W.catch_warnings(record=True) as rec:
+        W.simplefilter("always")
+        with pytest.raises(_lib.B200ClipError):
+            m.encode_image(torch.zeros(1, 3, 64, 64))
+    assert not any("forward-only" in str(w.message) for w in rec)

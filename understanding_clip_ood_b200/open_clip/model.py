@@ -16,6 +16,8 @@ import math
 from typing import Optional
 
 import numpy as np
+import warnings
+
 import torch
 from torch import nn
 
@@ -252,6 +254,23 @@ def _pack_blocks(stack: _Stack, dtype: torch.dtype, keep: list, fold_ln: bool = 
     return arr
 
 
+_warned_no_backward = False
+
+
+def _note_forward_only(module: nn.Module, what: str) -> None:
+    """The towers are forward kernels: their outputs carry no autograd graph.  A caller in training mode with gradients
+    enabled (the reference's train loop, training/train.py:115-183) would otherwise train nothing but logit_scale without
+    noticing — say so once, loudly.  (The tower backward is the next row of SURVEY §8f; ClipLoss itself has its backward.)"""
+    global _warned_no_backward
+    if _warned_no_backward or not module.training or not torch.is_grad_enabled():
+        return
+    if any(p.requires_grad for p in module.parameters()):
+        _warned_no_backward = True
+        warnings.warn(f"b200clip: {what} was called in training mode with autograd enabled, but the B200 towers are forward-only: "
+                      "the returned features do not propagate gradients to the tower parameters (use model.eval() / torch.no_grad() "
+                      "for inference; the tower backward is not implemented yet)", RuntimeWarning, stacklevel=3)
+
+
 def _check_device(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise L.B200ClipError(f"{what}: CUDA tensors required — this path has no CPU fallback (got {t.device})")
@@ -357,6 +376,7 @@ class VisionTower(nn.Module):
 
     def forward(self, image: torch.Tensor, normalize: bool = False) -> torch.Tensor:
         """[B,3,S,S] -> [B,D] (transformer.py:601-643); `normalize` fuses CLIP.encode_image's F.normalize."""
+        _note_forward_only(self, "encode_image")
         _check_device(image, "encode_image")
         _check_device(self.proj, "encode_image (model weights)")
         dt = self._compute_dtype()
@@ -520,6 +540,7 @@ class CLIP(nn.Module):
 
     def encode_text(self, text: torch.Tensor, normalize: bool = False) -> torch.Tensor:
         """[T, context_length] int64 -> [T, D] (model.py:269-284)."""
+        _note_forward_only(self, "encode_text")
         _check_device(text, "encode_text")
         _check_device(self.text_projection, "encode_text (model weights)")
         if text.ndim != 2 or text.shape[1] != self.context_length:
