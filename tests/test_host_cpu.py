@@ -340,3 +340,43 @@ def test_training_mode_forward_warns_that_the_towers_are_forward_only():
         with pytest.raises(_lib.B200ClipError):
             m.encode_image(torch.zeros(1, 3, 64, 64))
     assert not any("forward-only" in str(w.message) for w in rec)
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """Parameter COUNT and coarse kinds (pointer / 64-bit integer / 32-bit integer / float) of every ctypes signature against
+    the prototype in include/b200clip.h — a mismatch would not fail at load time, it would corrupt the call."""
+    import ctypes as C
+    from understanding_clip_ood_b200 import _lib
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    protos = dict(re.findall(r"\b(b200clip_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text))
+    assert set(protos) == set(_lib.SIGNATURES)
+
+    def kind_of_c(param: str) -> str:
+        p = param.strip()
+        if p in ("void", ""):
+            return "none"
+        if "*" in p:
+            return "ptr"
+        if re.search(r"\b(int64_t|uint64_t)\b", p):
+            return "i64"
+        if re.search(r"\bfloat\b", p):
+            return "f32"
+        if re.search(r"\b(int|int32_t|uint32_t)\b", p):
+            return "i32"
+        raise AssertionError(f"unrecognised parameter {p!r}")
+
+    def kind_of_ctypes(t) -> str:
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        if t in (C.c_int64, C.c_uint64):
+            return "i64"
+        if t is C.c_float:
+            return "f32"
+        if t in (C.c_int, C.c_int32, C.c_uint32):
+            return "i32"
+        raise AssertionError(f"unrecognised ctypes type {t}")
+
+    for name, params in protos.items():
+        want = [k for k in (kind_of_c(p) for p in params.split(",")) if k != "none"]
+        got = [kind_of_ctypes(t) for t in _lib.SIGNATURES[name][1]]
+        assert got == want, f"{name}: header {want} vs ctypes {got}"
