@@ -380,3 +380,32 @@ def test_ctypes_signatures_match_header_prototypes():
         want = [k for k in (kind_of_c(p) for p in params.split(",")) if k != "none"]
         got = [kind_of_ctypes(t) for t in _lib.SIGNATURES[name][1]]
         assert got == want, f"{name}: header {want} vs ctypes {got}"
+
+
+def test_openclip_from_pretrained_checkpoint_forms(tmp_path):
+    """xclip OpenCLIP.from_pretrained (reference: xclip/open_clip/model.py:30-56): bare state dict, training checkpoint
+    ({"state_dict": ...}) and DistributedDataParallel `module.` prefix all load; fp16 is the default precision; logit_scale is
+    exp(param) clamped to [0, 100]."""
+    import math
+    from understanding_clip_ood_b200 import open_clip
+    from understanding_clip_ood_b200.xclip.open_clip import OpenCLIP
+    kw = dict(vision_cfg={"image_size": 64, "layers": 1, "width": 64, "patch_size": 32},
+              text_cfg={"context_length": 77, "vocab_size": 64, "width": 64, "heads": 1, "layers": 1}, embed_dim=32)
+    torch.manual_seed(3)
+    src = open_clip.create_model("ViT-B-32", precision="fp32", **kw)
+    sd = {k: v.clone() for k, v in src.state_dict().items()}
+    forms = {"bare": sd, "wrapped": {"state_dict": sd, "epoch": 3}, "ddp": {"state_dict": {"module." + k: v for k, v in sd.items()}}}
+    for name, blob in forms.items():
+        path = tmp_path / f"{name}.pt"
+        torch.save(blob, path)
+        wrapper, pre_train, pre_val = OpenCLIP.from_pretrained("ViT-B-32", ckpt_path=str(path), precision="fp32", **kw)
+        got = wrapper.clip.state_dict()
+        assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd), name
+        assert callable(pre_train) and callable(pre_val)
+    wrapper, _, _ = OpenCLIP.from_pretrained("ViT-B-32", **kw)
+    assert wrapper.clip.visual.proj.dtype == torch.float16                       # default precision of the wrapper
+    wrapper.clip.logit_scale.data.fill_(10.0)
+    assert float(wrapper.logit_scale) == 100.0
+    wrapper.clip.logit_scale.data.fill_(1.0)
+    assert abs(float(wrapper.logit_scale) - math.e) < 1e-5
+    assert wrapper.vocab_size == 64 and wrapper.uses_one_hot_encoding is False
