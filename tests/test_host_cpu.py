@@ -409,3 +409,16 @@ def test_openclip_from_pretrained_checkpoint_forms(tmp_path):
     wrapper.clip.logit_scale.data.fill_(1.0)
     assert abs(float(wrapper.logit_scale) - math.e) < 1e-5
     assert wrapper.vocab_size == 64 and wrapper.uses_one_hot_encoding is False
+
+
+def test_statistics_slot_count_fits_the_workspace_carve_up():
+    """b200clip_gemm_stats_slots (2 per N tile of the tile shape the picker chooses; needs no device: the SM count defaults
+    to 148) stays within the W/64 + 2 slots per row that the tower workspace reserves, for every tower width and batch."""
+    from understanding_clip_ood_b200 import _lib
+    lib = _lib.load()
+    for W in (512, 768, 1024, 1280):
+        for rows in (77, 6400, 25600, 51200, 65792, 806912):
+            slots = lib.b200clip_gemm_stats_slots(rows, W)
+            assert slots >= 2 and slots % 2 == 0 and slots <= W // 64 + 2, (W, rows, slots)
+    assert lib.b200clip_gemm_stats_slots(51200, 768) == 6          # three 256-wide N tiles, two epilogue groups each
+    assert lib.b200clip_gemm_stats_slots(0, 768) < 0               # invalid argument -> error code, no crash
