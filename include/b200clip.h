@@ -183,15 +183,26 @@ int b200clip_cliploss_packed_backward(const float* gathered, const float* logit_
  *   ([n, 2D]) is stored to d_slots[j], j < world (= slot `rank` of j's receive buffer): the GEMM epilogue is the scatter.
  *   d_slots[world], d_slots[world + 1]: two LOCAL [n, 2D] slots for the two K halves of the local-row terms.
  * b200clip_p2p_reduce_finish: *peer_flag[p] = epoch for every p, wait my_flags[q] >= epoch for all q < world, then
- *   out[elems] = sum over s < slots of recv[s * elems ...] (recv = the local receive buffer; slots = world + 2 here). */
+ *   out[elems] = sum over s < slots of recv[s * elems ...] (recv = the local receive buffer; slots = world + 2 here).
+ *
+ * Ring-slot protection: `my_busy` (may be NULL) is this rank's busy word of the ring slot in use — the all-gather sets it to
+ * `epoch` when `hold` != 0 (a backward will read the gathered rows) or to 0, reduce_finish clears it; `peer_busy` (DEVICE array
+ * of `world` pointers, may be NULL) are the peers' busy words of the same slot: a rank stores into peer p's slot only once
+ * *peer_busy[p] is 0 or `epoch`.
+ * Waits are bounded in wall time.  b200clip_p2p_configure sets the bound (seconds; default 600, or the environment variable
+ * B200CLIP_P2P_TIMEOUT_S) and registers `error_word`, a DEVICE-ACCESSIBLE uint32 (pinned host memory; may be NULL): an expired
+ * wait stores a non-zero code there (1 = a peer's flag never arrived, 2 = a peer's ring slot was never released) and lets the
+ * kernel retire with undefined results — the host checks the word before trusting them.  Without an error word an expired
+ * wait traps (sticky CUDA error). */
+int b200clip_p2p_configure(double timeout_seconds, uint32_t* error_word);
 int b200clip_p2p_allgather(int dtype, const void* img, const void* txt, int n, int D, float* const* peer_dst,
                            uint32_t* const* peer_flag, const uint32_t* my_flags, uint32_t* counters, int world,
-                           uint32_t epoch, void* stream);
+                           uint32_t epoch, uint32_t* const* peer_busy, uint32_t* my_busy, int hold, void* stream);
 int b200clip_cliploss_packed_backward_p2p(const float* gathered, const float* logit_scale, int rank, int n, int N, int D,
                                           const float* grad_out, float* const* d_slots, float* d_scale, float* workspace,
                                           void* stream);
 int b200clip_p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag,
-                               const uint32_t* my_flags, int world, int slots, uint32_t epoch, void* stream);
+                               const uint32_t* my_flags, int world, int slots, uint32_t epoch, uint32_t* my_busy, void* stream);
 
 /* ----- whole-tower drivers: one call per encode_image / encode_text ------------------------------ */
 

@@ -2,6 +2,7 @@
 of the same op (these are floating-point kernels; tolerances are written next to each assert).
 Tower-level parity against the oracle / the reference's golden vectors lives in test_parity_gpu.py."""
 import math
+import time
 
 import pytest
 import torch
@@ -431,8 +432,13 @@ def test_p2p_allgather_kernel(dtype, n, D, world, rank):
     pads[rank][rank] = 0                  # ... except this rank itself: set by the kernel
     dst = _ptr_table([bufs[p].data_ptr() + 4 * rank * S for p in range(world)])
     flag = _ptr_table([pads[p].data_ptr() + 4 * rank for p in range(world)])
+    # ring-slot busy words (word 48 of every pad): free on the peers, one of them "already runs this epoch"
+    if world > 1:
+        pads[(rank + 1) % world][48] = epoch
+    busy = _ptr_table([pads[p].data_ptr() + 4 * 48 for p in range(world)])
     rc = L.load().b200clip_p2p_allgather(L.dtype_code(dtype), img.data_ptr(), txt.data_ptr(), n, D, dst.data_ptr(), flag.data_ptr(),
-                                         pads[rank].data_ptr(), pads[rank].data_ptr() + 128, world, epoch, L.stream_ptr())
+                                         pads[rank].data_ptr(), pads[rank].data_ptr() + 128, world, epoch, busy.data_ptr(),
+                                         pads[rank].data_ptr() + 4 * 48, 1, L.stream_ptr())
     L.check(rc, "b200clip_p2p_allgather")
     torch.cuda.synchronize()
     want = torch.cat([img.float(), txt.float()], dim=1)
@@ -442,6 +448,48 @@ def test_p2p_allgather_kernel(dtype, n, D, world, rank):
         assert torch.isnan(got[[q for q in range(world) if q != rank]]).all()   # nothing else touched
         assert int(pads[p][rank]) == epoch                               # flag published on every peer
     assert int(pads[rank][32:48].abs().sum()) == 0                       # block counters left at zero
+    assert int(pads[rank][48]) == epoch                                  # hold=1: this rank's slot is marked busy for its backward
+
+
+def test_p2p_wait_is_bounded_and_reported():
+    """A peer that never releases its ring slot / never publishes its flag must not hang or trap the GPU: the wait expires after
+    the configured wall time, the registered (pinned) error word is raised and the kernel retires."""
+    n, D, world, rank = 8, 16, 2, 0
+    lib = L.load()
+    err = torch.zeros(1, dtype=torch.int32).pin_memory()
+    L.check(lib.b200clip_p2p_configure(0.05, err.data_ptr()), "b200clip_p2p_configure")
+    try:
+        img = torch.randn(n, D, device=DEV)
+        txt = torch.randn(n, D, device=DEV)
+        S = n * 2 * D
+        bufs = [torch.zeros(world * S, device=DEV) for _ in range(world)]
+        pads = [torch.zeros(64, dtype=torch.int32, device=DEV) for _ in range(world)]
+        epoch = 9
+        dst = _ptr_table([bufs[p].data_ptr() + 4 * rank * S for p in range(world)])
+        flag = _ptr_table([pads[p].data_ptr() + 4 * rank for p in range(world)])
+        busy = _ptr_table([pads[p].data_ptr() + 4 * 48 for p in range(world)])
+        # (a) peer 1 still holds the slot for epoch 5 and never releases it -> code 2
+        pads[1][48] = 5
+        pads[rank][1] = epoch                  # its flag is there, only the slot is blocked
+        t0 = time.perf_counter()
+        L.check(lib.b200clip_p2p_allgather(L.F32, img.data_ptr(), txt.data_ptr(), n, D, dst.data_ptr(), flag.data_ptr(), pads[rank].data_ptr(),
+                                           pads[rank].data_ptr() + 128, world, epoch, busy.data_ptr(), pads[rank].data_ptr() + 4 * 48, 0,
+                                           L.stream_ptr()), "b200clip_p2p_allgather")
+        torch.cuda.synchronize()               # no sticky error: the context survives
+        assert time.perf_counter() - t0 < 5.0
+        assert int(err[0]) == 2
+        # (b) slot free, but peer 1's flag never arrives -> code 1
+        err.zero_()
+        pads[1][48] = 0
+        pads[rank][1] = 0
+        L.check(lib.b200clip_p2p_allgather(L.F32, img.data_ptr(), txt.data_ptr(), n, D, dst.data_ptr(), flag.data_ptr(), pads[rank].data_ptr(),
+                                           pads[rank].data_ptr() + 128, world, epoch + 1, busy.data_ptr(), pads[rank].data_ptr() + 4 * 48, 0,
+                                           L.stream_ptr()), "b200clip_p2p_allgather")
+        torch.cuda.synchronize()
+        assert int(err[0]) == 1
+        assert torch.isfinite(torch.ones(1, device=DEV) + 1).all()      # the device still works
+    finally:
+        L.check(lib.b200clip_p2p_configure(600.0, None), "b200clip_p2p_configure")
 
 
 @pytest.mark.parametrize("n,D,world,rank", [(256, 512, 2, 1), (36, 64, 3, 0), (128, 512, 8, 5), (64, 512, 1, 0)])
@@ -478,9 +526,11 @@ def test_slot_addressed_backward_and_reduce_finish(n, D, world, rank):
     pad[16 + rank] = 0
     flag = _ptr_table([others[p].data_ptr() + 4 * (16 + rank) for p in range(world)])
     out = torch.empty(n, 2 * D, device=DEV)
+    pad[48] = 11                         # this rank's ring slot was held for the backward that ends here
     rc = L.load().b200clip_p2p_reduce_finish(recv[rank].data_ptr(), out.data_ptr(), S, flag.data_ptr(), pad.data_ptr() + 64, world,
-                                             world + 2, epoch, L.stream_ptr())
+                                             world + 2, epoch, pad.data_ptr() + 4 * 48, L.stream_ptr())
     L.check(rc, "b200clip_p2p_reduce_finish")
     torch.cuda.synchronize()
+    assert int(pad[48]) == 0             # ... and is released
     assert torch.allclose(out, recv[rank].view(world + 2, n, 2 * D).sum(0), rtol=1e-6, atol=1e-7)
     assert all(int(others[p][16 + rank]) == epoch for p in range(world))

@@ -136,6 +136,37 @@ def test_zero_shot_classifiers_match_reference(tiny):
     assert row_rel(zd.prompt_feat, tiny["openai_di_prompt_feat"]) < 1e-4
 
 
+def test_compute_scores_matches_reference_formula(tiny):
+    """_compute_scores (xclip/zero_shot.py:62-67): softmax(clip.logit_scale * logits) over the class axis; the golden logits
+    are the reference's, logit_scale is the wrapper's exp().clamp(0, 100) (xclip/open_clip/model.py:25-27)."""
+    clip = OpenCLIP(tiny_model(tiny))
+    z = zs.ZeroShotClassifier(clip, FakeTokenizer(300), tiny["zs_names"], prompt_fn=lambda c: f"a photo of a {c}.")
+    feat = z._compute_img_feat(tiny["image"].to(DEV))
+    scores = z._compute_scores(feat)
+    scale = float(tiny["state_dict"]["logit_scale"].exp().clamp(0, 100))
+    want = torch.softmax(scale * tiny["zs_logits"].double().flatten(1), dim=1).reshape_as(tiny["zs_logits"])
+    assert scores.shape == tiny["zs_logits"].shape
+    assert float((scores.double().cpu() - want).abs().max()) < 1e-5
+    assert float((scores.sum(dim=1) - 1).abs().max()) < 1e-5
+    assert torch.equal(scores.argmax(dim=1).cpu(), tiny["zs_pred"])
+
+
+def test_cliploss_second_backward_is_refused():
+    """The fused backward consumes its saved logits in place: a second backward through the same node must raise, not
+    return gradients computed from gradients."""
+    g = torch.load(GOLD / "cliploss.pt", weights_only=False)
+    img = g["img"].to(DEV).requires_grad_(True)
+    txt = g["txt"].to(DEV).requires_grad_(True)
+    scale = torch.tensor(g["scale"], device=DEV, requires_grad=True)
+    loss = open_clip.ClipLoss()(img, txt, scale)
+    loss.backward(retain_graph=True)
+    first = img.grad.clone()
+    assert rel(first, g["w1"]["d_img"]) < 1e-4
+    with pytest.raises(RuntimeError, match="already run"):
+        loss.backward()
+    assert torch.equal(img.grad, first)                  # nothing was accumulated by the refused call
+
+
 def test_cliploss_matches_reference_world1():
     g = torch.load(GOLD / "cliploss.pt", weights_only=False)
     img = g["img"].to(DEV).requires_grad_(True)
@@ -263,6 +294,75 @@ def test_vit_b_32_bf16_against_reference_bf16_and_fp32(vitb32_fp32):
     assert ours_vs_fp32 >= ref16_vs_fp32 - 0.1
 
 
+def prediction_parity_b1024(model_bf16, dev=DEV):
+    """ours-bf16 against the reference's fp32 AND bf16 runs on the same 1024 seeded images (tests/golden/vitb32_seed0_b1024.pt,
+    oracle/make_golden_b1024.py).  Returns the figures SURVEY §7 (hard part 1) asks for; also used by bench.py's `parity` block.
+
+    band = max |logit_ref-bf16 - logit_ref-fp32| over the batch: the reference's OWN bf16 noise on these inputs.  A prediction of
+    ours that differs from the fp32 reference is `explained` when the fp32 logits of the two candidates are closer than
+    2 * band (either rounding could have flipped them); margin-aware agreement = agree or explained."""
+    g = torch.load(GOLD / "vitb32_seed0_b1024.pt", weights_only=False)
+    base = torch.load(GOLD / "vitb32_seed0.pt", weights_only=False)
+    image = torch.randn(g["batch"], 3, 224, 224, generator=torch.Generator().manual_seed(g["seed_images"])).bfloat16().to(dev)
+    feat = model_bf16.encode_image(image, normalize=True)
+    logits, idx, _ = ops.zeroshot(feat, base["prompt_feat"].bfloat16().to(dev), 5, normalize_img=False)
+    logits, idx = logits.float().cpu(), idx.cpu()
+    l32, l16 = g["logits_fp32"], g["logits_bf16"].float()
+    p32, p16 = l32.argmax(1), l16.argmax(1)
+    t32, t16 = l32.topk(5, 1)[1], l16.topk(5, 1)[1]
+
+    def same_set(a, b):
+        return (a.sort(1)[0] == b.sort(1)[0]).all(1)
+
+    band = float((l16 - l32).abs().max())
+    ours1 = idx[:, 0]
+    rows = torch.arange(l32.shape[0])
+    gap1 = l32[rows, p32] - l32[rows, ours1]                        # fp32 margin between the reference's and our top-1
+    ok1 = (ours1 == p32) | (gap1 <= 2 * band)
+    # top-5 set: the classes we swap in / out must sit within the band of the fp32 rank-5 / rank-6 boundary
+    kth = l32.sort(1, descending=True)[0]
+    lo = torch.gather(l32, 1, idx).min(1)[0]                        # weakest fp32 logit among our five
+    ok5 = same_set(idx, t32) | (kth[:, 4] - lo <= 2 * band)
+    return {
+        "batch": int(l32.shape[0]),
+        "embedding_rel_l2_vs_ref_fp32": row_rel(feat, g["image_features_fp32"]),
+        "embedding_rel_l2_vs_ref_bf16": row_rel(feat, g["image_features_bf16"]),
+        "ref_bf16_vs_ref_fp32_embedding_rel_l2": row_rel(g["image_features_bf16"], g["image_features_fp32"]),
+        "top1_ours_vs_ref_bf16": float((ours1 == p16).float().mean()),
+        "top1_ours_vs_ref_fp32": float((ours1 == p32).float().mean()),
+        "top1_ref_bf16_vs_ref_fp32": float((p16 == p32).float().mean()),
+        "top5_ours_vs_ref_bf16": float(same_set(idx, t16).float().mean()),
+        "top5_ours_vs_ref_fp32": float(same_set(idx, t32).float().mean()),
+        "top5_ref_bf16_vs_ref_fp32": float(same_set(t16, t32).float().mean()),
+        "ref_bf16_logit_noise_band": band,
+        "ours_max_logit_err_vs_ref_fp32": float((logits - l32).abs().max()),
+        "top1_margin_aware_vs_ref_fp32": float(ok1.float().mean()),
+        "top5_margin_aware_vs_ref_fp32": float(ok5.float().mean()),
+    }
+
+
+def test_vit_b_32_bf16_prediction_parity_b1024(record_property):
+    """north_star's prediction gate at BASELINE config 2's batch, in numbers: ours-bf16 must agree with the fp32 reference at
+    least as often as the reference's own bf16 run does (minus 1 point of sampling slack), and every disagreement must lie
+    inside the reference's own bf16 noise band (margin-aware agreement >= 99.9 %)."""
+    if not (GOLD / "vitb32_seed0_b1024.pt").exists():
+        pytest.skip("vitb32_seed0_b1024.pt not generated")
+    torch.manual_seed(0)
+    m = open_clip.create_model("ViT-B-32", precision="bf16", device="cpu").to(DEV).eval()
+    r = prediction_parity_b1024(m)
+    for k, v in r.items():
+        record_property(k, v)
+    print("bf16 prediction parity at B=1024: " + json.dumps(r))
+    (Path(__file__).resolve().parent.parent / "gpurun_out").mkdir(exist_ok=True)
+    (Path(__file__).resolve().parent.parent / "gpurun_out" / "parity_b1024.json").write_text(json.dumps(r, indent=1))
+    assert r["embedding_rel_l2_vs_ref_fp32"] < 2e-2 and r["embedding_rel_l2_vs_ref_bf16"] < 2e-2
+    assert r["ours_max_logit_err_vs_ref_fp32"] <= 2.0 * r["ref_bf16_logit_noise_band"]
+    assert r["top1_ours_vs_ref_fp32"] >= r["top1_ref_bf16_vs_ref_fp32"] - 0.01
+    assert r["top5_ours_vs_ref_fp32"] >= r["top5_ref_bf16_vs_ref_fp32"] - 0.02
+    assert r["top1_margin_aware_vs_ref_fp32"] >= 0.999
+    assert r["top5_margin_aware_vs_ref_fp32"] >= 0.999
+
+
 # ------------------------------------------------------------------ (2) oracle on seeded inputs -------
 @pytest.mark.parametrize("name,B,T", [("ViT-B-32", 8, 12), ("ViT-B-16", 2, 4)])
 def test_towers_match_oracle_fp32(name, B, T):
@@ -286,6 +386,72 @@ def test_vit_l_14_bf16_matches_oracle():
     assert row_rel(m.encode_image(image.to(DEV)), O.vit_forward(sd, image.float())) < 2e-2      # K=588 padded patch GEMM
     tokens, _, _ = _domainnet_tokens()
     assert row_rel(m.encode_text(tokens[:3].to(DEV)), O.text_forward(sd, tokens[:3])) < 2e-2
+
+
+@pytest.mark.parametrize("precision,dtype", [("bf16", torch.bfloat16), ("fp16", torch.float16)])
+def test_vit_b_16_low_precision_matches_oracle(precision, dtype):
+    """ViT-B/16 in the 16-bit modes: L = 197 runs the tcgen05 attention kernel (attention_tc_kernel), which the fp32 case
+    above never reaches."""
+    torch.manual_seed(8)
+    m = open_clip.create_model("ViT-B-16", precision=precision, device="cpu")
+    sd = {k: v.float() for k, v in m.state_dict().items()}
+    m = m.to(DEV).eval()
+    image = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(9)).to(dtype)
+    assert row_rel(m.encode_image(image.to(DEV)), O.vit_forward(sd, image.float())) < 2e-2
+    tokens, _, _ = _domainnet_tokens()
+    assert row_rel(m.encode_text(tokens[5:9].to(DEV)), O.text_forward(sd, tokens[5:9])) < 2e-2
+
+
+def test_vit_b_32_fp16_full_size_matches_oracle_sample():
+    """fp16 is the precision the reference's evaluation scripts default to (xclip/open_clip/model.py:35).  Full-size batch
+    (1024 images) on the GPU; the oracle checks a 12-image sample of it, the rest through batch independence."""
+    torch.manual_seed(0)
+    m = open_clip.create_model("ViT-B-32", precision="fp16", device="cpu")
+    sd = {k: v.float() for k, v in m.state_dict().items()}
+    m = m.to(DEV).eval()
+    g = torch.Generator().manual_seed(12)
+    image = torch.randn(1024, 3, 224, 224, generator=g).half()
+    feat = m.encode_image(image.to(DEV))
+    assert torch.isfinite(feat.float()).all()
+    pick = torch.tensor([0, 1, 100, 101, 511, 512, 513, 777, 900, 1021, 1022, 1023])
+    assert row_rel(feat[pick.to(DEV)], O.vit_forward(sd, image[pick].float())) < 2e-2
+    assert torch.equal(m.encode_image(image[pick].to(DEV)), feat[pick.to(DEV)])
+
+
+@pytest.mark.parametrize("name", open_clip.list_models())
+def test_every_registered_config_runs_in_fp32(name):
+    """create_model's default precision on every registered architecture (P = 14 gives K = 588 for the patch
+    GEMM, which needs padding to 16-byte rows in fp32 as well)."""
+    torch.manual_seed(1)
+    m = open_clip.create_model(name, precision="fp32", device="cpu")
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.to(DEV).eval()
+    S = m.visual.image_size[0]
+    image = torch.randn(1, 3, S, S, generator=torch.Generator().manual_seed(2))
+    got = m.encode_image(image.to(DEV))
+    assert got.shape == (1, m.visual.output_dim) and torch.isfinite(got).all()
+    if name in ("ViT-L-14", "ViT-B-32-256", "ViT-L-14-336"):         # the geometries no other test covers in fp32
+        assert row_rel(got, O.vit_forward(sd, image, quick_gelu="quickgelu" in name)) < 1e-4
+
+
+def test_engine_rebuilds_when_public_switches_change():
+    """fold_layernorm / quick_gelu are public attributes baked into the cached weight structs and graphs."""
+    torch.manual_seed(3)
+    m = open_clip.create_model("ViT-B-32", precision="bf16", device=DEV,
+                               vision_cfg={"image_size": 224, "layers": 2, "width": 768, "patch_size": 32}).eval()
+    image = torch.randn(4, 3, 224, 224, device=DEV).bfloat16()
+    a = m.encode_image(image).clone()
+    a2 = m.encode_image(image).clone()            # second call: graph replay
+    assert torch.equal(a, a2)
+    m.visual.fold_layernorm = False
+    b = m.encode_image(image).clone()
+    assert not torch.equal(a, b) and row_rel(b, a) < 2e-2      # a different (unfolded) path ran, same function
+    m.visual.quick_gelu = True
+    c = m.encode_image(image).clone()
+    assert row_rel(c, b) > 1e-3                    # a different activation ran
+    m.visual.quick_gelu = False
+    m.visual.fold_layernorm = True
+    assert torch.equal(m.encode_image(image), a)
 
 
 # ------------------------------------------------------------------ (3) properties at full size -------

@@ -240,10 +240,13 @@ int b200clip_cliploss_packed_backward(const float* gathered, const float* logit_
     return cliploss_packed_backward(gathered, logit_scale, rank, n, N, D, grad_out, d_gathered, d_scale, workspace, S(stream));
 }
 
+int b200clip_p2p_configure(double timeout_seconds, uint32_t* error_word) { return p2p_configure(timeout_seconds, error_word); }
+
 int b200clip_p2p_allgather(int dtype, const void* img, const void* txt, int n, int D, float* const* peer_dst,
                            uint32_t* const* peer_flag, const uint32_t* my_flags, uint32_t* counters, int world, uint32_t epoch,
-                           void* stream) {
-    return p2p_allgather(dtype, img, txt, n, D, peer_dst, peer_flag, my_flags, counters, world, epoch, S(stream));
+                           uint32_t* const* peer_busy, uint32_t* my_busy, int hold, void* stream) {
+    return p2p_allgather(dtype, img, txt, n, D, peer_dst, peer_flag, my_flags, counters, world, epoch, peer_busy, my_busy, hold,
+                         S(stream));
 }
 
 int b200clip_cliploss_packed_backward_p2p(const float* gathered, const float* logit_scale, int rank, int n, int N, int D,
@@ -253,8 +256,8 @@ int b200clip_cliploss_packed_backward_p2p(const float* gathered, const float* lo
 }
 
 int b200clip_p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag, const uint32_t* my_flags,
-                               int world, int slots, uint32_t epoch, void* stream) {
-    return p2p_reduce_finish(recv, out, elems, peer_flag, my_flags, world, slots, epoch, S(stream));
+                               int world, int slots, uint32_t epoch, uint32_t* my_busy, void* stream) {
+    return p2p_reduce_finish(recv, out, elems, peer_flag, my_flags, world, slots, epoch, my_busy, S(stream));
 }
 
 // not part of the public header: timeline capture of the tcgen05 attention kernel (tools/attn_timeline.py)

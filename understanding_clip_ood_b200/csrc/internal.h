@@ -82,10 +82,12 @@ int cliploss_packed_backward_p2p(const float* gathered, const float* logit_scale
                                  float* const* d_slots, float* d_scale, float* workspace, cudaStream_t stream);
 
 // peer-memory exchange of the distributed ClipLoss (p2p.cu)
+int p2p_configure(double timeout_seconds, uint32_t* error_word);
 int p2p_allgather(int dtype, const void* img, const void* txt, int n, int D, float* const* peer_dst, uint32_t* const* peer_flag,
-                  const uint32_t* my_flags, uint32_t* counters, int world, uint32_t epoch, cudaStream_t stream);
+                  const uint32_t* my_flags, uint32_t* counters, int world, uint32_t epoch, uint32_t* const* peer_busy, uint32_t* my_busy,
+                  int hold, cudaStream_t stream);
 int p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag, const uint32_t* my_flags, int world,
-                      int slots, uint32_t epoch, cudaStream_t stream);
+                      int slots, uint32_t epoch, uint32_t* my_busy, cudaStream_t stream);
 
 inline int dtype_size(int dtype) { return dtype == 0 ? 4 : 2; }
 

@@ -85,6 +85,16 @@ def gather_features(image_features, text_features, local_loss=False, gather_with
     return gathered[:, :D], gathered[:, D:]
 
 
+def _consume(ctx) -> None:
+    """The backward kernels turn the saved raw logits into s * dL/dlogits IN PLACE (csrc/cliploss.cu, ce_backward_kernel), and
+    the peer variant hands its ring slot back: a second backward through the same node (retain_graph=True, two losses sharing
+    the node) would silently compute gradients from gradients.  Make that a loud error instead."""
+    if getattr(ctx, "b200clip_consumed", False):
+        raise RuntimeError("b200clip ClipLoss: backward was already run through this loss node — the fused kernels consume the "
+                           "saved logits in place, so retain_graph / a second backward is not supported; call the loss again")
+    ctx.b200clip_consumed = True
+
+
 def _f32c(t: torch.Tensor) -> torch.Tensor:
     t = t.detach()
     if t.dtype != torch.float32:
@@ -113,6 +123,7 @@ class _FusedClipLoss(torch.autograd.Function):
         needs = list(ctx.needs_input_grad[:5])
         if not any(needs):
             return (None,) * 6
+        _consume(ctx)
         grads = ops.cliploss_backward(*ops_f32, scale, ctx.rank, ws, _f32c(g).reshape(()), needs)
         out = []
         for i, (gr, dt) in enumerate(zip(grads, ctx.dtypes)):
@@ -147,6 +158,7 @@ class _DistLocalClipLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        _consume(ctx)
         gathered, scale, ws = ctx.saved_tensors
         rank, n, D, group, dt_i, dt_t, dt_s, s_shape = ctx.meta
         d_g, d_s = ops.cliploss_packed_backward(gathered, scale, rank, n, ws, _f32c(g).reshape(()), ctx.needs_input_grad[2])
@@ -172,17 +184,19 @@ class _PeerLocalClipLoss(torch.autograd.Function):
             img = img.float()
         if txt.dtype != img.dtype:
             txt = txt.to(img.dtype)
-        gathered, slot = ex.all_gather(img.contiguous(), txt.contiguous())
+        hold = any(ctx.needs_input_grad[:3])
+        gathered, slot = ex.all_gather(img.contiguous(), txt.contiguous(), hold=hold)
         scale = _f32c(logit_scale).reshape(())
         loss, ws = ops.cliploss_packed_forward(gathered, scale, rank, n, ws=ex.ws[slot])
         ctx.meta = (rank, n, D, slot, image_features.dtype, text_features.dtype, logit_scale.dtype, logit_scale.shape)
         ctx.ex = ex
-        ctx.token = peer._SlotToken(ex, slot) if any(ctx.needs_input_grad[:3]) else None
+        ctx.token = peer._SlotToken(ex, slot) if hold else None
         ctx.save_for_backward(scale)
         return loss
 
     @staticmethod
     def backward(ctx, g):
+        _consume(ctx)
         scale, = ctx.saved_tensors
         rank, n, D, slot, dt_i, dt_t, dt_s, s_shape = ctx.meta
         ex = ctx.ex

@@ -174,8 +174,10 @@ class _Engine:
         self.__init__()
 
     @staticmethod
-    def signature(params) -> tuple:
-        return tuple((p.data_ptr(), p._version, p.dtype) for p in params)
+    def signature(params, *switches) -> tuple:
+        """Everything the cached structs / captured graphs depend on: parameter storage, version and dtype, plus the public
+        switches that are baked into TowerCfg and the folded weights (fold_layernorm, quick_gelu, ...)."""
+        return tuple((p.data_ptr(), p._version, p.dtype) for p in params) + tuple(switches)
 
     def workspace(self, nbytes: int, device) -> torch.Tensor:
         if self.ws is None or self.ws.numel() < nbytes or self.ws.device != device:
@@ -329,7 +331,7 @@ class VisionTower(nn.Module):
 
     def _build(self, device) -> _Engine:
         params = list(self.parameters())
-        sig = _Engine.signature(params)
+        sig = _Engine.signature(params, bool(self.fold_layernorm), bool(self.quick_gelu), getattr(self, "preprocess_cfg", None) is not None)
         eng = self._engine
         if eng.sig == sig:
             return eng
@@ -338,7 +340,9 @@ class VisionTower(nn.Module):
         W = self.transformer.width
         P = self.patch_size[0]
         kreal = 3 * P * P
-        kpad = kreal if dt == torch.float32 else (kreal + 63) // 64 * 64
+        # K of the patch GEMM: 16-byte rows in fp32 (P = 14 gives 3*P*P = 588, not a multiple of 8), whole 128-byte swizzle
+        # rows in the 16-bit modes; the extra columns are zero in both operands
+        kpad = (kreal + 7) // 8 * 8 if dt == torch.float32 else (kreal + 63) // 64 * 64
         conv = self.conv1.weight.detach().to(dt).reshape(W, kreal)
         if kpad != kreal:
             padded = torch.zeros((W, kpad), dtype=dt, device=device)
@@ -515,7 +519,7 @@ class CLIP(nn.Module):
     def _build_text(self, device) -> _Engine:
         params = [self.token_embedding.weight, self.positional_embedding, self.ln_final.weight, self.ln_final.bias,
                   self.text_projection, *self.transformer.parameters()]
-        sig = _Engine.signature(params)
+        sig = _Engine.signature(params, bool(self.fold_layernorm), bool(self.quick_gelu))
         eng = self._text_engine
         if eng.sig == sig:
             return eng
@@ -536,6 +540,7 @@ class CLIP(nn.Module):
                          embed_dim=self.text_projection.shape[1], seq_len=self.context_length, quick_gelu=int(self.quick_gelu),
                          image_size=0, patch_size=0, patch_kpad=0, vocab_size=self.vocab_size, fold_ln=int(fold))
         eng.sig, eng.keep, eng.blocks, eng.weights, eng.cfg = sig, keep, blocks, w, cfg
+        eng.graphs.clear()      # captured graphs hold the old weight pointers / switches
         return eng
 
     def encode_text(self, text: torch.Tensor, normalize: bool = False) -> torch.Tensor:
