@@ -279,6 +279,25 @@ int b200clip_text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_wei
                           void* out, int batch, int seq_len, int normalize, void* workspace,
                           int64_t workspace_bytes, void* stream);
 
+/* The same two forwards split at the points where caller-owned buffers are touched, so that a host can replay the long
+ * middle part as ONE captured CUDA graph that depends on nothing but the workspace, whatever buffers the inputs arrive in and
+ * the outputs go to (a DataLoader loop hands over a fresh tensor per batch, evaluate_domainnet_lso_openai.py:18-36):
+ *   B200CLIP_STAGE_INPUT   the only kernel that reads `image` / `image_u8` / `text` (im2col resp. embedding gather),
+ *   B200CLIP_STAGE_BODY    patch GEMM, ln_pre, all blocks, ln_post / ln_final on the pooled rows (workspace -> workspace),
+ *   B200CLIP_STAGE_OUTPUT  projection (+ L2 normalisation): the only kernels that write `out`.
+ * `stages` is a bit mask; pointers a selected stage does not use may be NULL.  All three stages in one call, or in three
+ * calls on the same stream and workspace, give bit-identical results to b200clip_vit_forward(_u8) / b200clip_text_forward.
+ * Exactly one of `image` (tower dtype) and `image_u8` (+ mean, std) is used by the vision input stage. */
+#define B200CLIP_STAGE_INPUT 1
+#define B200CLIP_STAGE_BODY 2
+#define B200CLIP_STAGE_OUTPUT 4
+int b200clip_vit_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image,
+                                const uint8_t* image_u8, const float* mean, const float* std, void* out, int batch,
+                                int normalize, void* workspace, int64_t workspace_bytes, int stages, void* stream);
+int b200clip_text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text,
+                                 void* out, int batch, int seq_len, int normalize, void* workspace,
+                                 int64_t workspace_bytes, int stages, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -361,6 +361,8 @@ def test_ctypes_signatures_match_header_prototypes():
             return "i64"
         if re.search(r"\bfloat\b", p):
             return "f32"
+        if re.search(r"\bdouble\b", p):
+            return "f64"
         if re.search(r"\b(int|int32_t|uint32_t)\b", p):
             return "i32"
         raise AssertionError(f"unrecognised parameter {p!r}")
@@ -372,6 +374,8 @@ def test_ctypes_signatures_match_header_prototypes():
             return "i64"
         if t is C.c_float:
             return "f32"
+        if t is C.c_double:
+            return "f64"
         if t in (C.c_int, C.c_int32, C.c_uint32):
             return "i32"
         raise AssertionError(f"unrecognised ctypes type {t}")

@@ -434,6 +434,38 @@ def test_every_registered_config_runs_in_fp32(name):
         assert row_rel(got, O.vit_forward(sd, image, quick_gelu="quickgelu" in name)) < 1e-4
 
 
+def test_graph_replay_is_independent_of_input_and_output_buffers():
+    """The captured graph covers only the workspace-to-workspace body (B200CLIP_STAGE_BODY): a loop that hands over a FRESH
+    tensor per batch — what a DataLoader loop does, evaluate_domainnet_lso_openai.py:18-36 — replays it, results equal the
+    un-graphed path bit for bit, and every call returns its own output tensor (no aliasing of a static buffer)."""
+    from understanding_clip_ood_b200 import _lib as L
+    torch.manual_seed(4)
+    m = open_clip.create_model("ViT-B-32", precision="bf16", device=DEV,
+                               vision_cfg={"image_size": 224, "layers": 3, "width": 768, "patch_size": 32}).eval()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    batches = [torch.randn(32, 3, 224, 224, device=DEV, generator=g).bfloat16() for _ in range(4)]
+    m.visual.use_cuda_graphs = False
+    want = [m.encode_image(b, normalize=True).clone() for b in batches]
+    m.visual.use_cuda_graphs = True
+    outs = [m.encode_image(b.clone(), normalize=True) for b in batches]          # fresh input buffer every call
+    assert len(m.visual._engine.graphs) == 1                                      # captured on the 2nd call, replayed after
+    assert len({o.data_ptr() for o in outs}) == len(outs)
+    for o, w in zip(outs, want):
+        assert torch.equal(o, w)
+    n0 = L.launch_count()
+    m.encode_image(batches[0].clone())
+    assert L.launch_count() - n0 > 20                                             # replayed kernels are counted
+    # text tower: same mechanism, keyed on (batch, sequence length)
+    tokens, _, _ = _domainnet_tokens()
+    m.use_cuda_graphs = False
+    tw = [m.encode_text(tokens[i * 16:(i + 1) * 16].to(DEV)).clone() for i in range(3)]
+    m.use_cuda_graphs = True
+    tg = [m.encode_text(tokens[i * 16:(i + 1) * 16].to(DEV)) for i in range(3)]
+    assert len(m._text_engine.graphs) == 1
+    for o, w in zip(tg, tw):
+        assert torch.equal(o, w)
+
+
 def test_engine_rebuilds_when_public_switches_change():
     """fold_layernorm / quick_gelu are public attributes baked into the cached weight structs and graphs."""
     torch.manual_seed(3)

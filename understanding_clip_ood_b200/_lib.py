@@ -15,6 +15,7 @@ LIB_PATH = _PKG / "libb200clip.so"
 
 F32, BF16, F16 = 0, 1, 2
 EPI_BIAS, EPI_GELU, EPI_QUICKGELU, EPI_RESIDUAL, EPI_PATCH = 0, 1, 2, 3, 4
+STAGE_INPUT, STAGE_BODY, STAGE_OUTPUT = 1, 2, 4
 
 _DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
@@ -83,6 +84,9 @@ SIGNATURES = {
                                           _I, _P, _L, _P]),
     "b200clip_patchify_u8": (C.c_int, [_I, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _I, _I, _I, _I, _P]),
     "b200clip_text_forward": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(TextWeights), _P, _P, _I, _I, _I, _P, _L, _P]),
+    "b200clip_vit_forward_stages": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(VitWeights), _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                              _P, _I, _I, _P, _L, _I, _P]),
+    "b200clip_text_forward_stages": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(TextWeights), _P, _P, _I, _I, _I, _P, _L, _I, _P]),
 }
 # not part of the public header: test hook that forces the GEMM N-tile
 _EXTRA = {

@@ -86,6 +86,11 @@ int vit_forward_u8(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w,
                    const float* std, void* out, int batch, int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s);
 int text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
                  int seq_len, int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s);
+int vit_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, const uint8_t* image_u8,
+                       const float* mean, const float* std, void* out, int batch, int normalize, void* workspace,
+                       int64_t workspace_bytes_, int stages, cudaStream_t s);
+int text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
+                        int seq_len, int normalize, void* workspace, int64_t workspace_bytes_, int stages, cudaStream_t s);
 
 }  // namespace b200clip
 
@@ -276,6 +281,18 @@ int b200clip_vit_forward_u8(const b200clip_tower_cfg* cfg, const b200clip_vit_we
                             const float* std, void* out, int batch, int normalize, void* workspace, int64_t workspace_bytes,
                             void* stream) {
     return vit_forward_u8(cfg, w, image, mean, std, out, batch, normalize, workspace, workspace_bytes, S(stream));
+}
+
+int b200clip_vit_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image,
+                                const uint8_t* image_u8, const float* mean, const float* std, void* out, int batch, int normalize,
+                                void* workspace, int64_t workspace_bytes, int stages, void* stream) {
+    return vit_forward_stages(cfg, w, image, image_u8, mean, std, out, batch, normalize, workspace, workspace_bytes, stages, S(stream));
+}
+
+int b200clip_text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out,
+                                 int batch, int seq_len, int normalize, void* workspace, int64_t workspace_bytes, int stages,
+                                 void* stream) {
+    return text_forward_stages(cfg, w, text, out, batch, seq_len, normalize, workspace, workspace_bytes, stages, S(stream));
 }
 
 int b200clip_patchify_u8(int dtype, const uint8_t* image, const float* mean, const float* std, void* patches, int batch, int image_size,

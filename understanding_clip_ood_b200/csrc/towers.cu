@@ -155,15 +155,18 @@ int64_t workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {
 }
 
 // image_u8 != nullptr: uint8 pixels, ToTensor + Normalize(mean, std) fused into the im2col (`image` is ignored)
+// `stages`: B200CLIP_STAGE_INPUT (im2col: the only kernel that reads `image`) | _BODY (patch GEMM ... ln_post on the pooled rows,
+// workspace -> workspace) | _OUTPUT (projection + optional normalise: the only kernels that write `out`).
 static int vit_forward_impl(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, const uint8_t* image_u8,
                             const float* mean, const float* std, void* out, int batch, int normalize, void* workspace,
-                            int64_t workspace_bytes_, cudaStream_t s) {
+                            int64_t workspace_bytes_, int stages, cudaStream_t s) {
     int rc;
     if ((rc = check_cfg(cfg)) != 0) return rc;
     const b200clip_tower_cfg& c = *cfg;
-    B2C_CHECK_ARG(w != nullptr && (image != nullptr || image_u8 != nullptr) && out != nullptr && workspace != nullptr &&
-                      w->blocks_host != nullptr,
-                  "vit_forward: null pointer");
+    B2C_CHECK_ARG(stages > 0 && stages <= 7, "vit_forward: bad stage mask %d", stages);
+    B2C_CHECK_ARG(w != nullptr && workspace != nullptr && w->blocks_host != nullptr, "vit_forward: null pointer");
+    B2C_CHECK_ARG(!(stages & B200CLIP_STAGE_INPUT) || image != nullptr || image_u8 != nullptr, "vit_forward: null image");
+    B2C_CHECK_ARG(!(stages & B200CLIP_STAGE_OUTPUT) || out != nullptr, "vit_forward: null output");
     B2C_CHECK_ARG(batch > 0, "vit_forward: empty batch");
     B2C_CHECK_ARG(c.patch_size > 0 && c.image_size % c.patch_size == 0, "vit_forward: image %d not divisible by patch %d",
                   c.image_size, c.patch_size);
@@ -180,56 +183,75 @@ static int vit_forward_impl(const b200clip_tower_cfg* cfg, const b200clip_vit_we
     const int W = c.width;
     const int M = batch * L;
 
-    if (dt != B200CLIP_F32 && w->pos_cls != nullptr) {
-        // patch embedding in token layout: im2col with an all-zero row in every class-token slot, then ONE CTA-pair GEMM over
-        // all B*L rows whose epilogue adds the (class + positional) table row of each token
-        rc = image_u8 != nullptr
-                 ? patchify_u8(dt, image_u8, mean, std, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, nullptr, nullptr, nullptr, W, s, 1)
-                 : patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, nullptr, nullptr, nullptr, W, s, 1);
+    const bool token_layout = dt != B200CLIP_F32 && w->pos_cls != nullptr;
+    if (stages & B200CLIP_STAGE_INPUT) {
+        // token layout: im2col with an all-zero row in every class-token slot; otherwise the im2col also writes the class-token
+        // rows of x (class_emb + pos[0])
+        if (token_layout)
+            rc = image_u8 != nullptr
+                     ? patchify_u8(dt, image_u8, mean, std, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, nullptr, nullptr, nullptr, W, s, 1)
+                     : patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, nullptr, nullptr, nullptr, W, s, 1);
+        else
+            rc = image_u8 != nullptr
+                     ? patchify_u8(dt, image_u8, mean, std, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s)
+                     : patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s);
         if (rc != 0) return rc;
-        if ((rc = gemm_pair(dt == B200CLIP_BF16, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, M, W,
-                            c.patch_kpad, B200CLIP_EPI_BIAS, 0, 0, s, nullptr, nullptr, w->pos_cls, L)) != 0)
-            return rc;
-    } else {
-        // im2col -> GEMM whose epilogue scatters to token rows 1..L-1 and adds the positional embedding
-        rc = image_u8 != nullptr
-                 ? patchify_u8(dt, image_u8, mean, std, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s)
-                 : patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s);
-        if (rc != 0) return rc;
-        if ((rc = gemm_any(dt, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, batch * g * g, W,
-                           c.patch_kpad, B200CLIP_EPI_PATCH, w->pos_emb, g * g, L, s)) != 0)
-            return rc;
     }
-    if ((rc = layernorm(dt, ws.x, W, w->ln_pre_g, w->ln_pre_b, ws.x, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
-    if ((rc = run_blocks(c, w->blocks_host, ws, batch, L, 0, s)) != 0) return rc;
-    // pool_type 'tok': ln_post on the class token only (LN is per-row, so pooling first is exact), then @ proj
-    if ((rc = layernorm(dt, ws.x, W, w->ln_post_g, w->ln_post_b, ws.pooled, W, batch, W, 1e-5f, L, nullptr, s)) != 0) return rc;
-    if ((rc = gemm_any(dt, ws.pooled, W, w->proj_t, W, nullptr, nullptr, 0, out, c.embed_dim, batch, c.embed_dim, W,
-                       B200CLIP_EPI_BIAS, nullptr, 0, 0, s)) != 0)
-        return rc;
-    if (normalize && (rc = normalize_rows(dt, out, c.embed_dim, out, c.embed_dim, batch, c.embed_dim, 1e-12f, s)) != 0) return rc;
+    if (stages & B200CLIP_STAGE_BODY) {
+        if (token_layout) {
+            // ONE CTA-pair GEMM over all B*L rows whose epilogue adds the (class + positional) table row of each token
+            if ((rc = gemm_pair(dt == B200CLIP_BF16, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, M, W,
+                                c.patch_kpad, B200CLIP_EPI_BIAS, 0, 0, s, nullptr, nullptr, w->pos_cls, L)) != 0)
+                return rc;
+        } else {
+            // GEMM whose epilogue scatters to token rows 1..L-1 and adds the positional embedding
+            if ((rc = gemm_any(dt, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, batch * g * g, W,
+                               c.patch_kpad, B200CLIP_EPI_PATCH, w->pos_emb, g * g, L, s)) != 0)
+                return rc;
+        }
+        if ((rc = layernorm(dt, ws.x, W, w->ln_pre_g, w->ln_pre_b, ws.x, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
+        if ((rc = run_blocks(c, w->blocks_host, ws, batch, L, 0, s)) != 0) return rc;
+        // pool_type 'tok': ln_post on the class token only (LN is per-row, so pooling first is exact), then @ proj
+        if ((rc = layernorm(dt, ws.x, W, w->ln_post_g, w->ln_post_b, ws.pooled, W, batch, W, 1e-5f, L, nullptr, s)) != 0) return rc;
+    }
+    if (stages & B200CLIP_STAGE_OUTPUT) {
+        if ((rc = gemm_any(dt, ws.pooled, W, w->proj_t, W, nullptr, nullptr, 0, out, c.embed_dim, batch, c.embed_dim, W,
+                           B200CLIP_EPI_BIAS, nullptr, 0, 0, s)) != 0)
+            return rc;
+        if (normalize && (rc = normalize_rows(dt, out, c.embed_dim, out, c.embed_dim, batch, c.embed_dim, 1e-12f, s)) != 0) return rc;
+    }
     return 0;
 }
 
 int vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out, int batch,
                 int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s) {
-    B2C_CHECK_ARG(image != nullptr, "vit_forward: null image");
-    return vit_forward_impl(cfg, w, image, nullptr, nullptr, nullptr, out, batch, normalize, workspace, workspace_bytes_, s);
+    B2C_CHECK_ARG(image != nullptr && out != nullptr, "vit_forward: null image / output");
+    return vit_forward_impl(cfg, w, image, nullptr, nullptr, nullptr, out, batch, normalize, workspace, workspace_bytes_, 7, s);
+}
+
+int vit_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, const uint8_t* image_u8,
+                       const float* mean, const float* std, void* out, int batch, int normalize, void* workspace,
+                       int64_t workspace_bytes_, int stages, cudaStream_t s) {
+    B2C_CHECK_ARG(image_u8 == nullptr || (mean != nullptr && std != nullptr), "vit_forward_stages: uint8 input needs mean / std");
+    return vit_forward_impl(cfg, w, image_u8 != nullptr ? nullptr : image, image_u8, mean, std, out, batch, normalize, workspace,
+                            workspace_bytes_, stages, s);
 }
 
 int vit_forward_u8(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const uint8_t* image, const float* mean,
                    const float* std, void* out, int batch, int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s) {
-    B2C_CHECK_ARG(image != nullptr && mean != nullptr && std != nullptr, "vit_forward_u8: null pointer");
-    return vit_forward_impl(cfg, w, nullptr, image, mean, std, out, batch, normalize, workspace, workspace_bytes_, s);
+    B2C_CHECK_ARG(image != nullptr && mean != nullptr && std != nullptr && out != nullptr, "vit_forward_u8: null pointer");
+    return vit_forward_impl(cfg, w, nullptr, image, mean, std, out, batch, normalize, workspace, workspace_bytes_, 7, s);
 }
 
-int text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
-                 int seq_len, int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s) {
+int text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
+                        int seq_len, int normalize, void* workspace, int64_t workspace_bytes_, int stages, cudaStream_t s) {
     int rc;
     if ((rc = check_cfg(cfg)) != 0) return rc;
     const b200clip_tower_cfg& c = *cfg;
-    B2C_CHECK_ARG(w != nullptr && text != nullptr && out != nullptr && workspace != nullptr && w->blocks_host != nullptr,
-                  "text_forward: null pointer");
+    B2C_CHECK_ARG(stages > 0 && stages <= 7, "text_forward: bad stage mask %d", stages);
+    B2C_CHECK_ARG(w != nullptr && workspace != nullptr && w->blocks_host != nullptr, "text_forward: null pointer");
+    B2C_CHECK_ARG(!(stages & B200CLIP_STAGE_INPUT) || text != nullptr, "text_forward: null token ids");
+    B2C_CHECK_ARG(!(stages & B200CLIP_STAGE_OUTPUT) || out != nullptr, "text_forward: null output");
     B2C_CHECK_ARG(batch > 0, "text_forward: empty batch");
     B2C_CHECK_ARG(seq_len > 0 && seq_len <= c.seq_len, "text_forward: seq_len %d outside (0, %d]", seq_len, c.seq_len);
     B2C_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 256 == 0, "text_forward: workspace must be 256-byte aligned");
@@ -239,17 +261,28 @@ int text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, 
                   (long long)workspace_bytes_, (long long)ws.total);
     const int dt = c.dtype;
     const int W = c.width;
-    if ((rc = text_embed_v(dt, text, c.seq_len, w->tok_emb, w->pos_emb, ws.x, ws.eot, batch, L, W,
+    if ((stages & B200CLIP_STAGE_INPUT) &&
+        (rc = text_embed_v(dt, text, c.seq_len, w->tok_emb, w->pos_emb, ws.x, ws.eot, batch, L, W,
                            c.vocab_size > 0 ? c.vocab_size : 0x7fffffff, s)) != 0)
         return rc;
-    if ((rc = run_blocks(c, w->blocks_host, ws, batch, L, 1, s)) != 0) return rc;
-    // ln_final only on the pooled (EOT) rows: LN is per-row, so this equals pooling after ln_final
-    if ((rc = layernorm(dt, ws.x, W, w->ln_final_g, w->ln_final_b, ws.pooled, W, batch, W, 1e-5f, L, ws.eot, s)) != 0) return rc;
-    if ((rc = gemm_any(dt, ws.pooled, W, w->proj_t, W, nullptr, nullptr, 0, out, c.embed_dim, batch, c.embed_dim, W,
-                       B200CLIP_EPI_BIAS, nullptr, 0, 0, s)) != 0)
-        return rc;
-    if (normalize && (rc = normalize_rows(dt, out, c.embed_dim, out, c.embed_dim, batch, c.embed_dim, 1e-12f, s)) != 0) return rc;
+    if (stages & B200CLIP_STAGE_BODY) {
+        if ((rc = run_blocks(c, w->blocks_host, ws, batch, L, 1, s)) != 0) return rc;
+        // ln_final only on the pooled (EOT) rows: LN is per-row, so this equals pooling after ln_final
+        if ((rc = layernorm(dt, ws.x, W, w->ln_final_g, w->ln_final_b, ws.pooled, W, batch, W, 1e-5f, L, ws.eot, s)) != 0) return rc;
+    }
+    if (stages & B200CLIP_STAGE_OUTPUT) {
+        if ((rc = gemm_any(dt, ws.pooled, W, w->proj_t, W, nullptr, nullptr, 0, out, c.embed_dim, batch, c.embed_dim, W,
+                           B200CLIP_EPI_BIAS, nullptr, 0, 0, s)) != 0)
+            return rc;
+        if (normalize && (rc = normalize_rows(dt, out, c.embed_dim, out, c.embed_dim, batch, c.embed_dim, 1e-12f, s)) != 0) return rc;
+    }
     return 0;
+}
+
+int text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
+                 int seq_len, int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s) {
+    B2C_CHECK_ARG(text != nullptr && out != nullptr, "text_forward: null pointer");
+    return text_forward_stages(cfg, w, text, out, batch, seq_len, normalize, workspace, workspace_bytes_, 7, s);
 }
 
 }  // namespace b200clip

@@ -185,37 +185,43 @@ class _Engine:
             self.graphs.clear()
         return self.ws
 
-    # A tower forward only enqueues kernels on the caller's stream (no allocation, no synchronisation), so the ~90
-    # launches of one call are captured into a CUDA graph the SECOND time the same (input buffer, batch, workspace)
-    # is seen and replayed afterwards: one host call per forward, no launch gaps, and nothing on the host (GIL,
-    # driver locks) can starve the GPU.  Inputs that arrive in ever-changing buffers simply keep the eager path.
+    # A tower forward only enqueues kernels on the caller's stream (no allocation, no synchronisation).  It is issued in
+    # three stages (include/b200clip.h, B200CLIP_STAGE_*): the input stage (the one kernel that reads the caller's batch)
+    # and the output stage (projection + normalise, the kernels that write the result tensor) are launched directly, and
+    # the ~85 launches in between — which touch nothing but the workspace — are captured into a CUDA graph the SECOND
+    # time a (batch, sequence length, workspace) shape is seen and replayed afterwards.  The graph therefore does not
+    # depend on the input or output pointers: a DataLoader loop that hands over a fresh tensor per batch
+    # (scripts/evaluate_domainnet_lso_openai.py:18-36) replays it like a loop over one static buffer does, and the
+    # result lands in a fresh tensor without a copy.
     MAX_GRAPHS = 8
 
-    def run_graphed(self, key, enqueue, out_shape, dtype, device) -> torch.Tensor:
+    def run_staged(self, key, enqueue, out_shape, dtype, device) -> torch.Tensor:
+        """enqueue(stages, out): issue the given stage mask on the current stream.  -> fresh output tensor."""
+        out = torch.empty(out_shape, dtype=dtype, device=device)
         entry = self.graphs.get(key)
         if entry is None:
             if key not in self.seen:
                 if len(self.seen) > 64:
                     self.seen.clear()
                 self.seen.add(key)
-                out = torch.empty(out_shape, dtype=dtype, device=device)
-                enqueue(out)
+                enqueue(L.STAGE_INPUT | L.STAGE_BODY | L.STAGE_OUTPUT, out)
                 return out
             if len(self.graphs) >= self.MAX_GRAPHS:
                 self.graphs.pop(next(iter(self.graphs)))
-            static_out = torch.empty(out_shape, dtype=dtype, device=device)
             graph = torch.cuda.CUDAGraph()
             torch.cuda.synchronize(device)
             n0 = L.launch_count()
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                enqueue(static_out)
-            entry = (graph, static_out, L.launch_count() - n0)    # capture records the kernels without running them
-            L.note_replayed(-entry[2])
+                enqueue(L.STAGE_BODY, None)
+            entry = (graph, L.launch_count() - n0)    # capture records the kernels without running them
+            L.note_replayed(-entry[1])
             self.graphs[key] = entry
-        graph, static_out, n_kernels = entry
+        graph, n_kernels = entry
+        enqueue(L.STAGE_INPUT, None)
         graph.replay()
         L.note_replayed(n_kernels)
-        return static_out.clone()      # the static buffer is overwritten by the next replay
+        enqueue(L.STAGE_OUTPUT, out)
+        return out
 
 
 def _f32(t: torch.Tensor, keep: list) -> int:
@@ -407,20 +413,19 @@ class VisionTower(nn.Module):
                 mean = (C.c_float * 3)(*[float(v) for v in pp.get("mean", OPENAI_DATASET_MEAN)])
                 std = (C.c_float * 3)(*[float(v) for v in pp.get("std", OPENAI_DATASET_STD)])
 
-            def enqueue(dst: torch.Tensor) -> None:
-                if u8:
-                    rc = lib.b200clip_vit_forward_u8(C.byref(eng.cfg), C.byref(eng.weights), image.data_ptr(), mean, std, dst.data_ptr(), B,
-                                                     int(normalize), ws.data_ptr(), ws.numel(), L.stream_ptr())
-                else:
-                    rc = lib.b200clip_vit_forward(C.byref(eng.cfg), C.byref(eng.weights), image.data_ptr(), dst.data_ptr(), B,
-                                                  int(normalize), ws.data_ptr(), ws.numel(), L.stream_ptr())
-                L.check(rc, "b200clip_vit_forward")
+            else:
+                mean = std = None
+
+            def enqueue(stages: int, dst) -> None:
+                rc = lib.b200clip_vit_forward_stages(C.byref(eng.cfg), C.byref(eng.weights), None if u8 else image.data_ptr(),
+                                                     image.data_ptr() if u8 else None, mean, std, L.ptr(dst), B, int(normalize),
+                                                     ws.data_ptr(), ws.numel(), stages, L.stream_ptr())
+                L.check(rc, "b200clip_vit_forward_stages")
 
             if self.use_cuda_graphs and not torch.cuda.is_current_stream_capturing():
-                key = (image.data_ptr(), B, int(normalize), ws.data_ptr(), int(u8), tuple(mean) + tuple(std) if u8 else ())
-                return eng.run_graphed(key, enqueue, (B, self.output_dim), dt, image.device)
+                return eng.run_staged((B, ws.data_ptr()), enqueue, (B, self.output_dim), dt, image.device)
             out = torch.empty((B, self.output_dim), dtype=dt, device=image.device)
-            enqueue(out)
+            enqueue(L.STAGE_INPUT | L.STAGE_BODY | L.STAGE_OUTPUT, out)
         return out
 
 
@@ -488,6 +493,8 @@ class CLIP(nn.Module):
         #: 16-bit modes: fold ln_1 / ln_2 of the text blocks into the QKV / c_fc GEMM epilogues
         self.fold_layernorm = True
         self._text_engine = _Engine()
+        #: replay encode_text's block stack as a CUDA graph per (batch, sequence length) (see _Engine.run_staged)
+        self.use_cuda_graphs = True
 
     def _init_text_parameters(self) -> None:
         """TextTransformer.init_parameters (transformer.py:724-745)."""
@@ -569,10 +576,16 @@ class CLIP(nn.Module):
             eng = self._build_text(text.device)
             nbytes = lib.b200clip_workspace_bytes(C.byref(eng.cfg), T, seq_len)
             ws = eng.workspace(nbytes, text.device)
+
+            def enqueue(stages: int, dst) -> None:
+                rc = lib.b200clip_text_forward_stages(C.byref(eng.cfg), C.byref(eng.weights), text.data_ptr(), L.ptr(dst), T, seq_len,
+                                                      int(normalize), ws.data_ptr(), ws.numel(), stages, L.stream_ptr())
+                L.check(rc, "b200clip_text_forward_stages")
+
+            if self.use_cuda_graphs and not torch.cuda.is_current_stream_capturing():
+                return eng.run_staged((T, seq_len, ws.data_ptr()), enqueue, (T, D), dt, text.device)
             out = torch.empty((T, D), dtype=dt, device=text.device)
-            rc = lib.b200clip_text_forward(C.byref(eng.cfg), C.byref(eng.weights), text.data_ptr(), out.data_ptr(), T, seq_len,
-                                           int(normalize), ws.data_ptr(), ws.numel(), L.stream_ptr())
-        L.check(rc, "b200clip_text_forward")
+            enqueue(L.STAGE_INPUT | L.STAGE_BODY | L.STAGE_OUTPUT, out)
         return out
 
     def get_logits(self, image, text):
