@@ -54,6 +54,16 @@ int b200clip_gemm(int dtype, const void* A, int64_t lda, const void* W, int64_t 
                   const void* residual, int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue,
                   const float* pos, int g_in, int g_out, void* stream);
 
+/* The same GEMM with a caller-provided scratch buffer (b200clip_gemm_workspace_bytes() bytes, 256-byte aligned, device memory):
+ * when the output tiles do not fill whole rounds of the persistent grid (e.g. 75 tiles on 74 SM pairs: the out-proj / c_proj of
+ * a 128-image shard), the ragged part is cut stream-K fashion into equal runs of K-blocks; partial accumulators (fp32) and
+ * flags live in the workspace, the sums are taken in a fixed order (deterministic).  Epilogues BIAS / GELU / QUICKGELU /
+ * RESIDUAL; a RESIDUAL that does not alias C keeps whole tiles.  The tower drivers pass part of their own workspace. */
+int64_t b200clip_gemm_workspace_bytes(void);
+int b200clip_gemm_ws(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias,
+                     const void* residual, int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 /* LayerNorm folded into the following GEMM (16-bit dtypes): C = act(LN(x) W^T + b) computed WITHOUT materialising LN(x):
  *   C[m,n] = act( rstd_m * (x W'^T)[m,n] - rstd_m * mean_m * colsum[n] + bias_f32[n] )
  * with W' = W diag(gamma) in `dtype`, colsum[n] = sum_k W'[n,k] and bias_f32 = b + W beta (both fp32, prepared once by
@@ -62,6 +72,11 @@ int b200clip_gemm(int dtype, const void* A, int64_t lda, const void* W, int64_t 
 int b200clip_gemm_ln(int dtype, const void* x, int64_t ldx, const void* Wf, int64_t ldw, const float* colsum,
                      const float* bias_f32, const float* rowstats, void* C, int64_t ldc, int M, int N, int K, int epilogue,
                      void* stream);
+
+/* b200clip_gemm_ln with the stream-K workspace of b200clip_gemm_ws */
+int b200clip_gemm_ln_ws(int dtype, const void* x, int64_t ldx, const void* Wf, int64_t ldw, const float* colsum,
+                        const float* bias_f32, const float* rowstats, void* C, int64_t ldc, int M, int N, int K,
+                        int epilogue, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* The row statistics can also come out of the GEMM that WROTE the rows (the residual GEMMs of the block, whose output is the
  * input of the next LayerNorm), which removes the separate statistics pass over the residual stream:

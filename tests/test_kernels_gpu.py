@@ -75,6 +75,63 @@ def test_gemm_tc_inplace_residual_and_nobias():
     assert _rel(out, ref) < 3e-3
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K,epi,inplace", [
+    (6400, 768, 3072, L.EPI_RESIDUAL, True),     # c_proj of a 128-image shard: 75 pair tiles on 74 clusters -> stream-K
+    (6400, 768, 768, L.EPI_RESIDUAL, True),      # out-proj of the same shard
+    (6400, 2304, 768, L.EPI_BIAS, False),        # QKV: 3 whole rounds + 3 tiles
+    (6400, 3072, 768, L.EPI_GELU, False),        # c_fc
+    (12800, 768, 3072, L.EPI_RESIDUAL, True),    # 256-image shard: 150 tiles
+    (6300, 768, 3072, L.EPI_RESIDUAL, True),     # ragged last M tile inside the stream-K region
+    (51200, 768, 768, L.EPI_RESIDUAL, True),     # full batch: 600 tiles = 8 rounds + 8
+    (2000, 512, 2048, L.EPI_BIAS, False),        # fewer tiles (16) than clusters: every tile is shared by several clusters
+    (6400, 768, 3072, L.EPI_RESIDUAL, False),    # separate residual: keeps whole tiles (TMA-loaded residual path)
+])
+def test_gemm_stream_k(dtype, M, N, K, epi, inplace):
+    """b200clip_gemm_ws: ragged tile grids are cut into equal runs of K-blocks (fp32 partials through the workspace, fixed
+    summation order).  Same tolerance as the whole-tile kernel, bit-identical when repeated (deterministic), and the flag words
+    of the workspace are zero again afterwards."""
+    g = _gen(3)
+    a = (torch.randn(M, K, device=DEV, generator=g) * 0.5).to(dtype)
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.05).to(dtype)
+    bias = (torch.randn(N, device=DEV, generator=g) * 0.1).to(dtype)
+    res = torch.randn(M, N, device=DEV, generator=g).to(dtype) if epi == L.EPI_RESIDUAL else None
+    lin = (a.float() @ w.float().t() + bias.float()).to(dtype).float()
+    ref = {L.EPI_GELU: lambda: F.gelu(lin), L.EPI_RESIDUAL: lambda: lin + res.float(), L.EPI_BIAS: lambda: lin}[epi]().to(dtype).float()
+    ws = torch.zeros(int(L.load().b200clip_gemm_workspace_bytes()), dtype=torch.uint8, device=DEV)
+    outs = []
+    for _ in range(2):
+        x = res.clone() if inplace else None
+        outs.append(ops.gemm_ws(a, w, bias, epilogue=epi, residual=x if inplace else res, out=x, workspace=ws))
+    torch.cuda.synchronize()
+    ulp = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    assert (outs[0].float() - ref).abs().max().item() <= 2 * ulp * ref.abs().max().item() + 1e-3
+    assert _rel(outs[0], ref) < 3e-3
+    assert torch.equal(outs[0], outs[1])
+    # workspace = one fp32 accumulator slot (2 CTAs x 64 float4 columns x 128 rows x 16 B) per SM pair, then the flag words
+    off = (torch.cuda.get_device_properties(0).multi_processor_count // 2) * 2 * 64 * 128 * 16
+    assert int(ws[off:].view(torch.int32).abs().sum()) == 0
+
+
+def test_gemm_stream_k_with_folded_layernorm():
+    """LN-fold + GELU epilogue on top of a stream-K fix-up (c_fc of a 256-image shard: 600 tiles = 8 rounds + 8)."""
+    g = _gen(4)
+    M, N, K = 12800, 3072, 768
+    x = (torch.randn(M, K, device=DEV, generator=g) * 0.7 + 0.1).bfloat16()
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.04).bfloat16()
+    b = (torch.randn(N, device=DEV, generator=g) * 0.1).bfloat16()
+    gamma = 1 + 0.1 * torch.randn(K, device=DEV, generator=g)
+    beta = 0.1 * torch.randn(K, device=DEV, generator=g)
+    wf, colsum, bf = ops.fold_layernorm(w, b, gamma, beta, torch.bfloat16)
+    stats = ops.row_stats(x)
+    got = ops.gemm_ln_ws(x, wf, colsum, bf, stats, epilogue=L.EPI_GELU)
+    want = ops.gemm_ln(x, wf, colsum, bf, stats, epilogue=L.EPI_GELU)            # whole-tile schedule of the same kernel
+    ln = F.layer_norm(x.float(), (K,), gamma, beta, 1e-5)
+    ref = F.gelu((ln @ w.float().t() + b.float()).bfloat16().float())
+    assert _rel(got, ref) < 8e-3 and _rel(got, want) < 2e-3
+    assert torch.equal(got, ops.gemm_ln_ws(x, wf, colsum, bf, stats, epilogue=L.EPI_GELU))
+
+
 def test_gemm_bad_args_raise():
     a = torch.zeros(8, 12, device=DEV, dtype=torch.bfloat16)   # K % 8 != 0
     w = torch.zeros(16, 12, device=DEV, dtype=torch.bfloat16)

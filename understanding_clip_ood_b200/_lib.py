@@ -55,6 +55,9 @@ SIGNATURES = {
     "b200clip_last_error": (C.c_char_p, []),
     "b200clip_launch_count": (C.c_uint64, []),
     "b200clip_gemm": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "b200clip_gemm_workspace_bytes": (C.c_int64, []),
+    "b200clip_gemm_ws": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _P]),
+    "b200clip_gemm_ln_ws": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _L, _P]),
     "b200clip_gemm_ln": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
     "b200clip_gemm_stats_slots": (C.c_int, [_I, _I]),
     "b200clip_gemm_residual_stats": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _P, _P]),

@@ -63,7 +63,7 @@ static bool force_single_cta_gemm() {
 
 int gemm_any(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
              int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in, int g_out,
-             cudaStream_t stream) {
+             cudaStream_t stream, void* sk_workspace) {
     if (dtype == B200CLIP_F32)
         return gemm_f32(static_cast<const float*>(A), lda, static_cast<const float*>(W), ldw, static_cast<const float*>(bias),
                         static_cast<const float*>(residual), ldr, static_cast<float*>(C), ldc, M, N, K, epilogue, pos, g_in, g_out,
@@ -71,7 +71,8 @@ int gemm_any(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, 
     if (dtype == B200CLIP_BF16 || dtype == B200CLIP_F16) {
         // the patch-embedding epilogue remaps rows (no TMA-store box), it stays on the single-CTA kernel
         if (epilogue != B200CLIP_EPI_PATCH && !force_single_cta_gemm())
-            return gemm_pair(dtype == B200CLIP_BF16, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, 0, 0, stream);
+            return gemm_pair(dtype == B200CLIP_BF16, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, 0, 0, stream, nullptr,
+                             nullptr, nullptr, 0, nullptr, nullptr, 0, 1e-5f, sk_workspace);
         return gemm_tc(dtype == B200CLIP_BF16, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, pos, g_in, g_out, 0,
                        stream);
     }
@@ -112,6 +113,36 @@ int b200clip_gemm(int dtype, const void* A, int64_t lda, const void* W, int64_t 
     B2C_CHECK_ARG(A != nullptr && W != nullptr && C != nullptr, "gemm: null pointer");
     B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 4, "gemm: unknown epilogue %d", epilogue);
     return gemm_any(dtype, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, pos, g_in, g_out, S(stream));
+}
+
+int64_t b200clip_gemm_workspace_bytes(void) { return gemm_pair_sk_workspace_bytes(); }
+
+int b200clip_gemm_ws(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
+                     int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, void* workspace, int64_t workspace_bytes,
+                     void* stream) {
+    B2C_CHECK_ARG(A != nullptr && W != nullptr && C != nullptr, "gemm_ws: null pointer");
+    B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm_ws: epilogue must be BIAS, GELU, QUICKGELU or RESIDUAL");
+    if (dtype == B200CLIP_F32)  // the FFMA parity kernel tiles finely enough: no workspace needed
+        return gemm_any(dtype, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, nullptr, 0, 0, S(stream));
+    B2C_CHECK_ARG(workspace != nullptr && workspace_bytes >= gemm_pair_sk_workspace_bytes(), "gemm_ws: workspace too small (%lld < %lld bytes)",
+                  (long long)workspace_bytes, (long long)gemm_pair_sk_workspace_bytes());
+    int rc;
+    if ((rc = gemm_pair_sk_workspace_reset(workspace, S(stream))) != 0) return rc;
+    return gemm_any(dtype, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, nullptr, 0, 0, S(stream), workspace);
+}
+
+int b200clip_gemm_ln_ws(int dtype, const void* x, int64_t ldx, const void* Wf, int64_t ldw, const float* colsum, const float* bias_f32,
+                        const float* rowstats, void* C, int64_t ldc, int M, int N, int K, int epilogue, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
+    B2C_CHECK_ARG(x && Wf && colsum && bias_f32 && rowstats && C, "gemm_ln_ws: null pointer");
+    B2C_CHECK_ARG(dtype == B200CLIP_BF16 || dtype == B200CLIP_F16, "gemm_ln_ws: 16-bit dtypes only");
+    B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 2, "gemm_ln_ws: epilogue must be BIAS, GELU or QUICKGELU");
+    B2C_CHECK_ARG(workspace != nullptr && workspace_bytes >= gemm_pair_sk_workspace_bytes(), "gemm_ln_ws: workspace too small (%lld < %lld bytes)",
+                  (long long)workspace_bytes, (long long)gemm_pair_sk_workspace_bytes());
+    int rc;
+    if ((rc = gemm_pair_sk_workspace_reset(workspace, S(stream))) != 0) return rc;
+    return gemm_pair(dtype == B200CLIP_BF16, x, ldx, Wf, ldw, bias_f32, nullptr, 0, C, ldc, M, N, K, epilogue, 0, 0, S(stream), colsum,
+                     rowstats, nullptr, 0, nullptr, nullptr, 0, 1e-5f, workspace);
 }
 
 /* test hook: same as b200clip_gemm for 16-bit dtypes but with a forced N tile (128 or 256) */

@@ -11,8 +11,16 @@
 //     both CTAs' TMA loads), TMEM full/empty (MMA <-> both CTAs' epilogues; double-buffered accumulators: the epilogue of
 //     tile i overlaps the MMAs of tile i+1);
 //   * epilogue: tcgen05.ld -> registers -> bias / GELU / residual -> 128B-swizzled shared-memory staging -> TMA store, so
-//     global writes are full 128-byte lines issued by the copy engine instead of per-thread 16-byte scatters.  The residual
-//     operand is TMA-loaded into the same staging buffer ahead of time (prefetched one chunk ahead) and updated in place.
+//     global writes are full 128-byte lines issued by the copy engine instead of per-thread 16-byte scatters.  Every epilogue
+//     warp owns the 32 accumulator rows its TMEM lane quarter can read, its own staging buffers and its own TMA stores
+//     (32 x 64 boxes): the eight warps never synchronise with each other (no block / named barriers in the steady state).
+//     The residual operand is TMA-loaded into the same staging buffer ahead of time (two chunks ahead) and updated in place.
+//   * stream-K for the ragged part of the tile grid: when the tile count does not fill whole rounds of the 74 clusters
+//     (75 tiles for the out-proj / c_proj of a 128-image shard: 2 rounds for 1.01 rounds of work), the last full round plus
+//     the remainder is cut into 74 EQUAL runs of K-blocks.  A cluster whose run starts inside a tile dumps that accumulator as
+//     an fp32 partial into the caller's workspace and raises a flag; the cluster that holds the tile's first K-block adds the
+//     partials (fixed order: deterministic) and runs the normal epilogue.  The dump comes first in a run, the fix-up last, so
+//     nobody ever waits on a cluster that could be waiting itself.
 // Rounding points mirror the reference's bf16/fp16 eager path: (acc + bias) is rounded to the storage type before the
 // activation / residual add, which round again.
 #include "common.cuh"
@@ -35,8 +43,13 @@ constexpr int kAccStride = 256;   // TMEM columns between the two accumulator st
 constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 8;      // two groups of 4 warps (one warp per TMEM lane quarter)
-constexpr int kChunkN = 64;       // epilogue / store granularity: 128 rows x 64 columns (128 B rows)
-constexpr int kChunkBytes = kBM * kChunkN * 2;
+constexpr int kChunkN = 64;       // epilogue / store granularity: 64 columns (128 B rows) ...
+constexpr int kWarpRows = 32;     // ... x the 32 rows of one epilogue warp (one TMEM lane quarter)
+constexpr int kChunkBytes = kWarpRows * kChunkN * 2;   // one warp's staging buffer / TMA store box
+// stream-K workspace (per cluster slot): the pair tile's accumulator as fp32, laid out [CTA half][column / 4][row][4] so that
+// a warp's 32 lanes (= 32 rows) touch 512 contiguous bytes per access, + one flag word per (CTA half, epilogue warp)
+constexpr int kSkSlotFloat4 = 2 * (256 / 4) * kBM;
+constexpr int kSkFlagsPerSlot = 2 * kEpiWarps;
 // EPI values beyond the public ones: 5 = residual that aliases C (x += A W^T + b): the add is done by the L2 through a TMA
 // reduce-add store, so the residual never travels to the SM (no load, no shared-memory pass)
 constexpr int kEpiResidualInPlace = 5;
@@ -70,6 +83,10 @@ struct PairParams {
     int group_m;
     int pf_dist;           // L2 prefetch distance of the A operand, in K-blocks (0 = off)
     int dbg;               // measurement-only switches (B200CLIP_GEMM_DBG): 1 = skip the epilogue, 2 = MMA without operand loads
+    // stream-K: tiles [0, sk_tiles) are cut into equal runs of K-blocks over the clusters, tiles [sk_tiles, ...) stay whole
+    int sk_tiles;
+    float4* sk_partial;    // [clusters][kSkSlotFloat4]
+    uint32_t* sk_flags;    // [clusters][kSkFlagsPerSlot], zero between launches (owners reset what they consume)
 };
 
 // STG_BUFS = staging buffers per epilogue group (3 with a loaded residual: landing / in-place update / store draining)
@@ -79,15 +96,15 @@ template <int BLOCK_N, int STG_BUFS> struct PairCfg {
     static constexpr int kBBytes = (BLOCK_N / 2) * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStgBufs = STG_BUFS;
-    static constexpr int kStagingBytes = 2 * kStgBufs * kChunkBytes;
-    static constexpr int kBarBytes = 256;
+    static constexpr int kStagingBytes = kEpiWarps * kStgBufs * kChunkBytes;
+    static constexpr int kBarBytes = 512;
     static constexpr int kBudget = 227 * 1024 - 1024 - kStagingBytes - kBarBytes;
     static constexpr int kStagesFit = kBudget / kStageBytes;
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;
     static constexpr int kChunks = BLOCK_N / kChunkN;
     static_assert(kStages >= 3, "not enough shared memory for the operand ring");
-    static_assert((2 * kStages + 2 * kAccStages + 2 * kStgBufs) * 8 + 8 <= kBarBytes, "barrier block too small");
+    static_assert((2 * kStages + 2 * kAccStages + kEpiWarps * kStgBufs) * 8 + 8 <= kBarBytes, "barrier block too small");
 };
 
 __device__ __forceinline__ void pair_tile_coords(int t, const PairParams& p, int& mt, int& nt) {
@@ -100,8 +117,62 @@ __device__ __forceinline__ void pair_tile_coords(int t, const PairParams& p, int
     mt = m0 + (r - nt * gm);
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+// Work list of one cluster, generated identically by its producer, MMA and epilogue warps: first its run of the stream-K
+// region (units = K-blocks of tiles [0, sk_tiles), run c = [c U / C, (c + 1) U / C)), then whole tiles round-robin.
+struct Piece {
+    int tile, kb0, kb1;
+};
+struct PieceIter {
+    int64_t u, end;
+    int t_dp, num_tiles, num_kb, stride;
+    __device__ __forceinline__ static int64_t sk_begin(int c, int64_t units, int clusters) { return static_cast<int64_t>(c) * units / clusters; }
+    __device__ __forceinline__ PieceIter(const PairParams& p, int num_kb_, int cluster_id, int num_clusters) {
+        const int64_t units = static_cast<int64_t>(p.sk_tiles) * num_kb_;
+        u = sk_begin(cluster_id, units, num_clusters);
+        end = sk_begin(cluster_id + 1, units, num_clusters);
+        t_dp = p.sk_tiles + cluster_id;
+        num_tiles = p.m_tiles * p.n_tiles;
+        num_kb = num_kb_;
+        stride = num_clusters;
+    }
+    __device__ __forceinline__ bool next(Piece& pc) {
+        if (u < end) {
+            pc.tile = static_cast<int>(u / num_kb);
+            pc.kb0 = static_cast<int>(u - static_cast<int64_t>(pc.tile) * num_kb);
+            const int64_t len = min(static_cast<int64_t>(num_kb - pc.kb0), end - u);
+            pc.kb1 = pc.kb0 + static_cast<int>(len);
+            u += len;
+            return true;
+        }
+        if (t_dp < num_tiles) {
+            pc.tile = t_dp;
+            pc.kb0 = 0;
+            pc.kb1 = num_kb;
+            t_dp += stride;
+            return true;
+        }
+        return false;
+    }
+};
+
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// bounded like mbar_wait: a protocol bug becomes a trap the host reports, not a hung GPU
+__device__ __forceinline__ void sk_wait_flag(const uint32_t* flag) {
+    if (ld_acquire_gpu(flag) != 0u) return;
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(flag) == 0u) {
+        if (clock64() - t0 > (1ll << 31)) {
+            printf("b200clip: stream-K partial never arrived (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
@@ -198,8 +269,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             const int row_in_cluster = static_cast<int>(pair) * kPairM + static_cast<int>(half) * kBM;
-            // L2 prefetch cursor: runs p.pf_dist K-blocks ahead of the shared-memory ring (across tile boundaries), so the
-            // ring only has to cover L2 latency, not the DRAM latency of the streamed activations
+            // L2 prefetch cursor (whole-tile schedules only): runs p.pf_dist K-blocks ahead of the shared-memory ring (across tile
+            // boundaries), so the ring only has to cover L2 latency, not the DRAM latency of the streamed activations
+            const int pf_dist = p.sk_tiles == 0 ? p.pf_dist : 0;
             int pf_t = cluster_id, pf_kb = 0, pf_row = 0;
             auto prefetch_next = [&]() {
                 if (pf_t >= num_tiles) return;
@@ -214,14 +286,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     pf_t += num_clusters;
                 }
             };
-            for (int i = 0; i < p.pf_dist; ++i) prefetch_next();
-            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+            for (int i = 0; i < pf_dist; ++i) prefetch_next();
+            PieceIter pieces(p, num_kb, cluster_id, num_clusters);
+            Piece pc;
+            while (pieces.next(pc)) {
                 int mt, nt;
-                pair_tile_coords(t, p, mt, nt);
+                pair_tile_coords(pc.tile, p, mt, nt);
                 const int row_a = mt * kClusterM + row_in_cluster;
                 const int row_w = nt * BLOCK_N + static_cast<int>(half) * (BLOCK_N / 2);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    if (p.pf_dist > 0) prefetch_next();
+                for (int kb = pc.kb0; kb < pc.kb1; ++kb) {
+                    if (pf_dist > 0) prefetch_next();
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
                     else mbar_arrive_remote(&full_bar[stage], leader_rank);
@@ -252,23 +326,25 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+            PieceIter pieces(p, num_kb, cluster_id, num_clusters);
+            Piece pc;
+            for (; pieces.next(pc); ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * kAccStride;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = pc.kb0; kb < pc.kb1; ++kb) {
                     if (!(p.dbg & 2)) mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint64_t desc_a = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
                     const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k)
-                        umma_f16_pair(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, (kb | k) != 0);
+                        umma_f16_pair(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, ((kb - pc.kb0) | k) != 0);
                     // frees the slot in EVERY CTA of the cluster (each of them writes into some of the buffers just read)
                     if (!(p.dbg & 2)) umma_commit_pair(&empty_bar[stage], kAllCtas);
-                    if (kb == num_kb - 1) umma_commit_pair(&tmem_full_bar[acc], pair_mask);
+                    if (kb == pc.kb1 - 1) umma_commit_pair(&tmem_full_bar[acc], pair_mask);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -287,24 +363,26 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         __syncwarp();
     } else if (warp >= kEpiWarp0) {
-        // ===================== epilogue (every CTA) =====================
+        // ===================== epilogue (every CTA; eight independent warps) =====================
         const int e = warp - kEpiWarp0;
-        const int q = warp & 3;   // TMEM lane quarter this warp may access
-        const int grp = e >> 2;   // epilogue group: handles column chunks grp, grp+2, ...
-        const bool grp_leader = (e & 3) == 0 && lane == 0;
-        const int bar_id = 1 + grp;
+        const int q = warp & 3;   // TMEM lane quarter this warp may access = rows [32 q, 32 q + 32) of this CTA's 128
+        const int grp = e >> 2;   // handles column chunks grp, grp+2, ...
         const int r = q * 32 + lane;  // row inside this CTA's 128-row half
-        uint8_t* stg_ptr = staging + grp * kStgBufs * kChunkBytes;
+        uint8_t* stg_ptr = staging + e * kStgBufs * kChunkBytes;
         const uint32_t stg_base = smem_u32(stg_ptr);
-        uint64_t* my_res_bar = res_bar + grp * kStgBufs;
-        const uint32_t row_off = static_cast<uint32_t>(r) * 128;
-        const uint32_t rx = static_cast<uint32_t>(r & 7);
+        uint64_t* my_res_bar = res_bar + e * kStgBufs;
+        const uint32_t row_off = static_cast<uint32_t>(lane) * 128;
+        const uint32_t rx = static_cast<uint32_t>(lane & 7);
         const int row_in_cluster = static_cast<int>(pair) * kPairM + static_cast<int>(half) * kBM;
         const T* bias = static_cast<const T*>(p.bias);
         const float* bias_f32 = static_cast<const float*>(p.bias);
-        uint32_t bufc = 0;  // chunks processed by this group so far (buffer = bufc % kStgBufs)
+        uint32_t bufc = 0;  // chunks stored by this warp so far (buffer = bufc % kStgBufs)
+        // stream-K bookkeeping of this warp: its part of every cluster slot, its flag in every slot
+        const int64_t sk_units = static_cast<int64_t>(p.sk_tiles) * num_kb;
+        const int sk_lane_off = static_cast<int>(half) * (BLOCK_N / 4) * kBM + r;       // + col4 * kBM, in float4
+        const int sk_flag_off = static_cast<int>(half) * kEpiWarps + e;
 
-        // (tile, chunk) -> the next chunk this group processes
+        // (tile, chunk) -> the next chunk this warp processes (whole-tile schedules; the residual prefetch runs ahead on it)
         auto advance = [&](int& tile, int& chunk) {
             chunk += 2;
             if (chunk >= Cfg::kChunks) {
@@ -312,32 +390,79 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 tile += num_clusters;
             }
         };
-        auto issue_residual = [&](int tile, int chunk, uint32_t use) {  // group leader only
+        auto issue_residual = [&](int tile, int chunk, uint32_t use) {  // lane 0 only
             int mt2, nt2;
             pair_tile_coords(tile, p, mt2, nt2);
             const uint32_t b = use % kStgBufs;
             mbar_arrive_expect_tx(&my_res_bar[b], kChunkBytes);
             tma_load_2d(&tmap_r, &my_res_bar[b], stg_ptr + b * kChunkBytes, nt2 * BLOCK_N + chunk * kChunkN,
-                        mt2 * kClusterM + row_in_cluster, kCacheHintEvictFirst);
+                        mt2 * kClusterM + row_in_cluster + q * kWarpRows, kCacheHintEvictFirst);
         };
-        // residual prefetch, two chunks ahead: the first two chunks of this group
+        // residual prefetch, two chunks ahead: the first two chunks of this warp
         if constexpr (kRes) {
-            if (grp_leader && !(p.dbg & 1)) {
-                int pt = cluster_id, pc = grp;
-                if (pt < num_tiles) issue_residual(pt, pc, 0);
-                advance(pt, pc);
-                if (pt < num_tiles) issue_residual(pt, pc, 1);
+            if (lane == 0 && !(p.dbg & 1)) {
+                int pt = cluster_id, pcn = grp;
+                if (pt < num_tiles) issue_residual(pt, pcn, 0);
+                advance(pt, pcn);
+                if (pt < num_tiles) issue_residual(pt, pcn, 1);
             }
             __syncwarp();
         }
 
         int it = 0;
-        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        PieceIter pieces(p, num_kb, cluster_id, num_clusters);
+        Piece pc;
+        for (; pieces.next(pc); ++it) {
+            const int t = pc.tile;
             int mt, nt;
             pair_tile_coords(t, p, mt, nt);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int row0 = mt * kClusterM + row_in_cluster;
+            const bool dump = pc.kb0 != 0;                                // run starts inside the tile: accumulator -> fp32 partial
+            const bool fixup = pc.kb0 == 0 && pc.kb1 < num_kb;           // tile's first K-block, but not its last: add the others' partials
+
+            if (dump) {
+                mbar_wait(&tmem_full_bar[acc], acc_phase);
+                tc_fence_after();
+                float4* slot = p.sk_partial + static_cast<int64_t>(cluster_id) * kSkSlotFloat4 + sk_lane_off;
+                if (!(p.dbg & 1)) {
+#pragma unroll 1
+                    for (int c = grp; c < Cfg::kChunks; c += 2) {
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            uint32_t v[32];
+                            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride + c * kChunkN + hf * 32, v);
+                            tmem_ld_wait();
+                            float4* dst = slot + (c * (kChunkN / 4) + hf * 8) * kBM;
+#pragma unroll
+                            for (int g = 0; g < 8; ++g)
+                                __stcg(dst + g * kBM, make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                                                  __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
+                        }
+                    }
+                }
+                tc_fence_before();
+                __threadfence();      // every lane's partial rows are visible device-wide before the flag goes up
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive_remote(&tmem_empty_bar[acc], leader_rank);
+                    st_release_gpu(p.sk_flags + cluster_id * kSkFlagsPerSlot + sk_flag_off, 1u);
+                }
+                __syncwarp();
+                continue;
+            }
+
+            // clusters (cluster_id, peer_end) hold the rest of this tile's K range, one partial each
+            int peer_end = cluster_id + 1;
+            if (fixup) {
+                const int64_t tile_end = static_cast<int64_t>(t + 1) * num_kb;
+                while (peer_end < num_clusters && PieceIter::sk_begin(peer_end, sk_units, num_clusters) < tile_end) ++peer_end;
+                if (lane == 0 && !(p.dbg & 1))
+                    for (int pc2 = cluster_id + 1; pc2 < peer_end; ++pc2) sk_wait_flag(p.sk_flags + pc2 * kSkFlagsPerSlot + sk_flag_off);
+                __syncwarp();
+            }
+
             const float* pos_row = nullptr;
             if constexpr (kPos) pos_row = p.pos + static_cast<int64_t>((row0 + r) % p.pos_period) * p.N;
             float ln_rstd = 0.f, ln_nmr = 0.f;
@@ -366,14 +491,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             float st_s = 0.f, st_q = 0.f;   // epilogue 10: this thread's share of sum x / sum x^2 of its output row
             if constexpr (kRes) {
-                // pull the residual tiles this group will need two tiles from now into L2
-                if (grp_leader && p.pf_dist > 0) {
+                // pull the residual boxes this warp will need two tiles from now into L2
+                if (lane == 0 && p.pf_dist > 0) {
                     const int ft = t + 2 * num_clusters;
                     if (ft < num_tiles) {
                         int fm, fn;
                         pair_tile_coords(ft, p, fm, fn);
                         for (int c = grp; c < Cfg::kChunks; c += 2)
-                            tma_prefetch_l2_2d(&tmap_r, fn * BLOCK_N + c * kChunkN, fm * kClusterM + row_in_cluster);
+                            tma_prefetch_l2_2d(&tmap_r, fn * BLOCK_N + c * kChunkN, fm * kClusterM + row_in_cluster + q * kWarpRows);
                     }
                 }
                 __syncwarp();
@@ -392,17 +517,34 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const bool last_of_tile = c + 2 >= Cfg::kChunks;
                 const uint32_t buf = bufc % kStgBufs;
                 const uint32_t stg = stg_base + buf * kChunkBytes;
-                // Staging buffer `buf` is free here: the group leader drains its outstanding TMA store before it joins the
-                // barrier that ends each chunk (below), so the store issued kStgBufs chunks ago finished reading long ago.
-                if constexpr (kRes) mbar_wait(&my_res_bar[buf], (bufc / kStgBufs) & 1);
+                if constexpr (kRes) {
+                    mbar_wait(&my_res_bar[buf], (bufc / kStgBufs) & 1);
+                } else {
+                    // staging buffer `buf` is free once the store issued kStgBufs chunks ago has read it (at most the
+                    // previous chunk's store may still be in flight)
+                    if (lane == 0) tma_store_wait_read<kStgBufs - 1>();
+                    __syncwarp();
+                }
                 const int col0 = nt * BLOCK_N + c * kChunkN;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t v[32];
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride + c * kChunkN + hf * 32;
                     tmem_ld_32x32(taddr, v);
+                    // per-column operands of these 32 columns (the same for every lane: broadcast loads), issued under the TMEM load
+                    // (LN-fold: the first 16 columns' colsum / bias here, the other 16 while those are being used)
                     uint4 bvec[4];
-                    if constexpr (!kLn) {
+                    float4 cvec[4], fvec[4];
+                    auto load_ln = [&](int i, float4& c4, float4& f4) {   // i = 4-column group of this half-chunk
+                        const int col = col0 + hf * 32 + i * 4;
+                        const bool ok = col < p.N;
+                        c4 = ok ? __ldg(reinterpret_cast<const float4*>(p.colsum + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        f4 = ok ? __ldg(reinterpret_cast<const float4*>(bias_f32 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    };
+                    if constexpr (kLn) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) load_ln(i, cvec[i], fvec[i]);
+                    } else if constexpr (!kPos) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             const int col = col0 + hf * 32 + g * 8;
@@ -417,10 +559,28 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         __syncwarp();
                         if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], leader_rank);
                     }
+                    if (fixup) {
+                        // + the partial sums of the tile's remaining K range, in cluster order (deterministic)
+                        for (int pc2 = cluster_id + 1; pc2 < peer_end; ++pc2) {
+                            const float4* src = p.sk_partial + static_cast<int64_t>(pc2) * kSkSlotFloat4 + sk_lane_off +
+                                                (c * (kChunkN / 4) + hf * 8) * kBM;
+#pragma unroll 2
+                            for (int g = 0; g < 8; ++g) {
+                                const float4 pv = __ldcg(src + g * kBM);
+                                v[4 * g + 0] = __float_as_uint(__uint_as_float(v[4 * g + 0]) + pv.x);
+                                v[4 * g + 1] = __float_as_uint(__uint_as_float(v[4 * g + 1]) + pv.y);
+                                v[4 * g + 2] = __float_as_uint(__uint_as_float(v[4 * g + 2]) + pv.z);
+                                v[4 * g + 3] = __float_as_uint(__uint_as_float(v[4 * g + 3]) + pv.w);
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const uint32_t saddr = stg + row_off + (((static_cast<uint32_t>(hf * 4 + g)) ^ rx) << 4);
-                        const uint32_t bw[4] = {bvec[g].x, bvec[g].y, bvec[g].z, bvec[g].w};
+                        uint32_t bw[4] = {0, 0, 0, 0};
+                        if constexpr (!kLn && !kPos) {
+                            bw[0] = bvec[g].x; bw[1] = bvec[g].y; bw[2] = bvec[g].z; bw[3] = bvec[g].w;
+                        }
                         uint32_t rw[4] = {0, 0, 0, 0};
                         if constexpr (kRes) {
                             const uint4 rv = lds128(saddr);
@@ -438,12 +598,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             }
                         }
                         if constexpr (kLn) {
-                            const int col = col0 + hf * 32 + g * 8;
-                            const bool ok = col < p.N;
 #pragma unroll
                             for (int q4 = 0; q4 < 2; ++q4) {
-                                const float4 c4 = ok ? __ldg(reinterpret_cast<const float4*>(p.colsum + col) + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                const float4 b4 = ok ? __ldg(reinterpret_cast<const float4*>(bias_f32 + col) + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                float4 c4, b4;
+                                if (g < 2) {
+                                    c4 = cvec[g * 2 + q4];
+                                    b4 = fvec[g * 2 + q4];
+                                } else {
+                                    load_ln(g * 2 + q4, c4, b4);
+                                }
                                 cf[q4 * 4 + 0] = c4.x; cf[q4 * 4 + 1] = c4.y; cf[q4 * 4 + 2] = c4.z; cf[q4 * 4 + 3] = c4.w;
                                 bf[q4 * 4 + 0] = b4.x; bf[q4 * 4 + 1] = b4.y; bf[q4 * 4 + 2] = b4.z; bf[q4 * 4 + 3] = b4.w;
                             }
@@ -453,9 +616,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             float x0, x1;
                             if constexpr (kLn) {
                                 // rstd * acc + (b' - rstd * mean * c): two packed FMAs per pair
-                                const uint64_t t = fma_f2(pack_f2(ln_nmr, ln_nmr), pack_f2(cf[2 * j], cf[2 * j + 1]), pack_f2(bf[2 * j], bf[2 * j + 1]));
+                                const uint64_t tt = fma_f2(pack_f2(ln_nmr, ln_nmr), pack_f2(cf[2 * j], cf[2 * j + 1]), pack_f2(bf[2 * j], bf[2 * j + 1]));
                                 unpack_f2(fma_f2(pack_f2(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])),
-                                                 pack_f2(ln_rstd, ln_rstd), t), x0, x1);
+                                                 pack_f2(ln_rstd, ln_rstd), tt), x0, x1);
                             } else if constexpr (kPos) {
                                 // conv output and table entry are each rounded to the storage type before the add
                                 const float2 a2 = H::unpack(H::pack(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])));
@@ -493,38 +656,39 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
                 fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
-                if constexpr (!kRes) {
-                    // every store but (at most) the previous chunk's has long completed; waiting for that one too BEFORE the
-                    // barrier tells the whole group that the other staging buffer is free for the next chunk
-                    if (grp_leader) tma_store_wait_read<0>();
-                    __syncwarp();
-                }
-                named_bar_sync(bar_id, 128);
-                if (grp_leader) {
-                    if constexpr (EPI == kEpiResidualInPlace) tma_reduce_add_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, row0);
-                    else tma_store_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, row0);
+                __syncwarp();
+                if (lane == 0) {
+                    const int srow = row0 + q * kWarpRows;
+                    if constexpr (EPI == kEpiResidualInPlace) tma_reduce_add_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, srow);
+                    else tma_store_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, srow);
                     tma_store_commit();
                     if constexpr (kRes) {
                         // prefetch the residual of the chunk two steps ahead into the buffer whose store was committed one
                         // step ago (everything but the store just committed must have released its buffer)
-                        int pt = t, pc = c;
-                        advance(pt, pc);
-                        advance(pt, pc);
+                        int pt = t, pcn = c;
+                        advance(pt, pcn);
+                        advance(pt, pcn);
                         if (pt < num_tiles) {
                             tma_store_wait_read<1>();
-                            issue_residual(pt, pc, bufc + 2);
+                            issue_residual(pt, pcn, bufc + 2);
                         }
                     }
                 }
                 __syncwarp();
                 ++bufc;
             }
+            if (fixup) {
+                // this warp has consumed its part of every peer's partial: the flags are zero again for the next launch
+                __syncwarp();
+                if (lane == 0)
+                    for (int pc2 = cluster_id + 1; pc2 < peer_end; ++pc2) p.sk_flags[pc2 * kSkFlagsPerSlot + sk_flag_off] = 0u;
+            }
             if constexpr (kStats) {
                 if (row0 + r < p.M)
                     p.stats_out[static_cast<int64_t>(row0 + r) * p.stats_slots + nt * 2 + grp] = make_float2(st_s, st_q);
             }
         }
-        if (grp_leader) tma_store_wait_all<0>();  // global writes complete before the CTA retires
+        if (lane == 0) tma_store_wait_all<0>();  // global writes complete before the CTA retires
         __syncwarp();
     }
 
@@ -535,6 +699,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tmem_dealloc_pair(tmem_base, 512);
     }
 }
+
+// clusters the stream-K schedule is planned for = one per SM pair of the device (the persistent grid of a busy GEMM)
+int sk_clusters_planned() { return num_sms() / 2; }
 
 template <typename T, int BLOCK_N, int EPI, int PAIRS>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr, const PairParams& p,
@@ -569,7 +736,13 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "gemm_pair: kernel attribute / cluster occupancy query");
     B2C_CHECK_ARG(max_clusters > 0, "gemm_pair: the device cannot co-schedule a cluster of %d CTAs", 2 * PAIRS);
     const int tiles = p.m_tiles * p.n_tiles;
-    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    int clusters = tiles < max_clusters ? tiles : max_clusters;
+    if (p.sk_tiles > 0) {
+        // the stream-K split was planned for `sk_clusters` clusters: all of them must be co-resident (flag waits)
+        B2C_CHECK_ARG(PAIRS == 1 && sk_clusters_planned() <= max_clusters, "gemm_pair: stream-K needs %d co-resident clusters, device holds %d",
+                      sk_clusters_planned(), max_clusters);
+        clusters = sk_clusters_planned();
+    }
     cfg.gridDim = dim3(2 * PAIRS * clusters);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tw, tc, tr, p);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_pair_kernel)");
@@ -652,7 +825,7 @@ int l2_prefetch_distance() {
 
 // Tile-shape choice: the persistent grid runs ceil(tiles / clusters) rounds; pick the N tile that minimises
 // rounds x tile cost (a 256-wide tile is the most efficient per MAC, narrower ones waste less of the last round).
-int pick_pair_block_n(int M, int N, int pairs) {
+int pick_pair_block_n(int M, int N, int pairs, bool stream_k = false) {
     const int clusters = pairs == 2 ? 33 : num_sms() / 2;
     const long mt = (M + pairs * kPairM - 1) / (pairs * kPairM);
     double best_cost = 1e30;
@@ -665,8 +838,10 @@ int pick_pair_block_n(int M, int N, int pairs) {
         const int bn = cands[i];
         const long nt = (N + bn - 1) / bn;
         const long tiles = mt * nt;
-        const long rounds = (tiles + clusters - 1) / clusters;
-        const double cost = static_cast<double>(rounds) * bn * eff[i];
+        // whole rounds, or — with stream-K evening out the ragged part — the exact share of work per cluster
+        double rounds = static_cast<double>((tiles + clusters - 1) / clusters);
+        if (stream_k && tiles > clusters) rounds = static_cast<double>(tiles) / clusters;
+        const double cost = rounds * bn * eff[i];
         if (cost < best_cost) {
             best_cost = cost;
             best = bn;
@@ -678,11 +853,47 @@ int pick_pair_block_n(int M, int N, int pairs) {
 // Partial-sum slots per row that an epilogue-10 GEMM of this shape writes (2 per N tile); the consumer passes it back.
 int gemm_pair_stats_slots(int M, int N) { return 2 * ((N + pick_pair_block_n(M, N, 1) - 1) / pick_pair_block_n(M, N, 1)); }
 
+// Stream-K workspace: one fp32 accumulator slot + flag words per cluster.  Fixed size (independent of the problem).
+int64_t gemm_pair_sk_workspace_bytes() {
+    const int64_t clusters = sk_clusters_planned();
+    return clusters * kSkSlotFloat4 * 16 + ((clusters * kSkFlagsPerSlot * 4 + 255) / 256) * 256;
+}
+static uint32_t* sk_flags_of(void* ws) {
+    return reinterpret_cast<uint32_t*>(static_cast<char*>(ws) + static_cast<int64_t>(sk_clusters_planned()) * kSkSlotFloat4 * 16);
+}
+// flags must be zero before the first stream-K GEMM on a workspace (afterwards the kernels leave them at zero)
+int gemm_pair_sk_workspace_reset(void* ws, cudaStream_t stream) {
+    B2C_CHECK_ARG(ws != nullptr, "gemm: null stream-K workspace");
+    B2C_CUDA(cudaMemsetAsync(sk_flags_of(ws), 0, static_cast<size_t>(sk_clusters_planned()) * kSkFlagsPerSlot * 4, stream));
+    return 0;
+}
+
+// How many tiles (from the front of the tile order) go through stream-K: none when whole rounds fit (or nearly: >= 94 % of
+// the last round busy), otherwise the remainder plus — when there is one — one full round, so that every cluster gets
+// between one and two tiles' worth of K-blocks and no tile is cut into more than two or three pieces.
+// B200CLIP_STREAMK=0 disables it, =1 forces it whenever there is a remainder (A/B measurements).
+static int plan_stream_k(int tiles, int num_kb, int clusters) {
+    static const int mode = [] {
+        const char* e = getenv("B200CLIP_STREAMK");
+        return e != nullptr ? atoi(e) : -1;
+    }();
+    if (mode == 0 || clusters <= 1) return 0;
+    const int rem = tiles % clusters;
+    if (rem == 0) return 0;
+    const int full = tiles / clusters;
+    const double eff = static_cast<double>(tiles) / (static_cast<double>(full + 1) * clusters);
+    if (mode != 1 && eff >= 0.94) return 0;
+    const int sk = rem + (full >= 1 ? clusters : 0);
+    // every cluster must get a run of at least 4 K-blocks (pieces shorter than the operand ring are all fill and drain)
+    if (static_cast<int64_t>(sk) * num_kb < static_cast<int64_t>(clusters) * 4) return 0;
+    return sk;
+}
+
 // pairs: 1 = clusters of 2 CTAs, 2 = clusters of 4 with W multicast, 0 = choose
 int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
               int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs,
               cudaStream_t stream, const float* ln_colsum, const float* ln_rowstats, const float* pos_table, int pos_period,
-              float* stats_out, const float* stats_part, int stats_slots, float ln_eps) {
+              float* stats_out, const float* stats_part, int stats_slots, float ln_eps, void* sk_workspace) {
     B2C_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm_pair: unsupported epilogue %d", epilogue);
     const bool ln = ln_colsum != nullptr || ln_rowstats != nullptr || stats_part != nullptr;
@@ -711,20 +922,24 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     B2C_CHECK_ARG(pairs >= 0 && pairs <= 2, "gemm_pair: pairs must be 0, 1 or 2");
     if (pairs == 0) pairs = default_gemm_pairs(M);
     if (stats_out != nullptr) pairs = 1;
-    const int bn = force_block_n > 0 ? force_block_n : pick_pair_block_n(M, N, pairs);
+    // stream-K needs the caller's workspace, single pairs, and an epilogue without the TMA-loaded residual (whose prefetch runs
+    // ahead on the whole-tile order): the in-place residual form (TMA reduce-add store) qualifies, a separate residual does not
+    const bool res_in_place = epilogue == 3 && residual == C && ldr == ldc && !no_reduce_store();
+    const bool sk_ok = sk_workspace != nullptr && pairs == 1 && stats_out == nullptr && (epilogue != 3 || res_in_place);
+    const int bn = force_block_n > 0 ? force_block_n : pick_pair_block_n(M, N, pairs, sk_ok);
 
     CUtensorMap ta, tw, tc, tr;
     if (make_tmap_2d(&ta, is_bf16, A, M, K, lda, kBM, kBK) != 0) return -1;
     if (make_tmap_2d(&tw, is_bf16, W, N, K, ldw, pairs == 2 ? bn / 4 : bn / 2, kBK) != 0) return -1;
-    if (make_tmap_2d(&tc, is_bf16, C, M, N, ldc, kBM, kChunkN) != 0) return -1;
+    if (make_tmap_2d(&tc, is_bf16, C, M, N, ldc, kWarpRows, kChunkN) != 0) return -1;
     if (stats_out != nullptr) {
-        if (make_tmap_2d(&tr, is_bf16, residual, M, N, ldr, kBM, kChunkN) != 0) return -1;
+        if (make_tmap_2d(&tr, is_bf16, residual, M, N, ldr, kWarpRows, kChunkN) != 0) return -1;
         epilogue = kEpiResidualStats;
     } else if (epilogue == 3 && residual == C && ldr == ldc && !no_reduce_store()) {
         epilogue = kEpiResidualInPlace;
         tr = tc;
     } else if (epilogue == 3) {
-        if (make_tmap_2d(&tr, is_bf16, residual, M, N, ldr, kBM, kChunkN) != 0) return -1;
+        if (make_tmap_2d(&tr, is_bf16, residual, M, N, ldr, kWarpRows, kChunkN) != 0) return -1;
     } else {
         tr = tc;
     }
@@ -753,6 +968,15 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     p.group_m = pairs == 2 ? 4 : 8;
     p.pf_dist = l2_prefetch_distance();
     p.dbg = gemm_debug_switches();
+    p.sk_tiles = 0;
+    p.sk_partial = nullptr;
+    p.sk_flags = nullptr;
+    if (sk_ok && epilogue != 3 && epilogue != kEpiResidualStats) {
+        B2C_CHECK_ARG(reinterpret_cast<uintptr_t>(sk_workspace) % 16 == 0, "gemm: stream-K workspace must be 16-byte aligned");
+        p.sk_tiles = plan_stream_k(p.m_tiles * p.n_tiles, (K + kBK - 1) / kBK, sk_clusters_planned());
+        p.sk_partial = static_cast<float4*>(sk_workspace);
+        p.sk_flags = sk_flags_of(sk_workspace);
+    }
     if (pairs == 2)
         return is_bf16 ? launch_pair_bn<__nv_bfloat16, 2>(bn, epilogue, ta, tw, tc, tr, p, stream)
                        : launch_pair_bn<__half, 2>(bn, epilogue, ta, tw, tc, tr, p, stream);

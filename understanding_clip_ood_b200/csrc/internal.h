@@ -15,7 +15,13 @@ int gemm_tc(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw
 int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
               int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs, cudaStream_t stream,
               const float* ln_colsum = nullptr, const float* ln_rowstats = nullptr, const float* pos_table = nullptr, int pos_period = 0,
-              float* stats_out = nullptr, const float* stats_part = nullptr, int stats_slots = 0, float ln_eps = 1e-5f);
+              float* stats_out = nullptr, const float* stats_part = nullptr, int stats_slots = 0, float ln_eps = 1e-5f,
+              void* sk_workspace = nullptr);
+// Stream-K (gemm_pair.cu): `sk_workspace` of gemm_pair_sk_workspace_bytes() bytes lets a GEMM whose tile count does not fill
+// whole rounds of the persistent grid cut its ragged part into equal runs of K-blocks (fp32 partials + flags live there).
+// The flag words must be zero before the first use (gemm_pair_sk_workspace_reset); the kernels leave them at zero.
+int64_t gemm_pair_sk_workspace_bytes();
+int gemm_pair_sk_workspace_reset(void* ws, cudaStream_t stream);
 // LayerNorm statistics fused into the residual GEMMs: `stats_out` ([M][gemm_pair_stats_slots(M, N)] float2 partial (sum x,
 // sum x^2) of the output rows) is written by a residual-epilogue GEMM and read back through `stats_part` / `stats_slots` by
 // the LN-fold GEMM that consumes those rows, instead of (mean, rstd) from row_stats.
@@ -31,7 +37,7 @@ int gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const flo
 // dtype-dispatching GEMM used by the tower drivers
 int gemm_any(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
              int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in, int g_out,
-             cudaStream_t stream);
+             cudaStream_t stream, void* sk_workspace = nullptr);
 
 int layernorm(int dtype, const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy, int rows,
               int width, float eps, int row_stride_rows, const int32_t* row_idx, cudaStream_t stream);

@@ -36,6 +36,7 @@ struct Workspace {
     int32_t* eot;
     float* stats;   // [rows, 2] (mean, rstd) for the LN-fold GEMM of the first layer
     float* part[2]; // [rows, slots, 2] partial (sum x, sum x^2) written by the residual GEMMs (after attention / after the MLP)
+    void* sk;       // stream-K partial accumulators + flags of the CTA-pair GEMM (16-bit modes)
     int64_t total;
 };
 
@@ -62,6 +63,7 @@ Workspace carve(const b200clip_tower_cfg& c, int batch, int seq_len, void* base)
     const int64_t max_slots = c.width / 64 + 2;   // >= 2 * ceil(width / 128), the narrowest N tile
     w.part[0] = reinterpret_cast<float*>(take(rows * max_slots * 8));
     w.part[1] = reinterpret_cast<float*>(take(rows * max_slots * 8));
+    w.sk = c.dtype != B200CLIP_F32 ? take(gemm_pair_sk_workspace_bytes()) : nullptr;
     w.total = off;
     return w;
 }
@@ -108,12 +110,12 @@ int run_blocks(const b200clip_tower_cfg& c, const b200clip_block_weights* blocks
             if (!have && (rc = row_stats(dt, ws.x, W, ws.stats, M, W, 1e-5f, s)) != 0) return rc;
             if ((rc = gemm_pair(bf, ws.x, W, bw.in_proj_wf, W, bw.in_proj_bf, nullptr, 0, ws.qkv, 3 * W, M, 3 * W, W, B200CLIP_EPI_BIAS, 0,
                                 0, s, bw.in_proj_c, have ? nullptr : ws.stats, nullptr, 0, nullptr, have ? ws.part[1] : nullptr, slots,
-                                1e-5f)) != 0)
+                                1e-5f, ws.sk)) != 0)
                 return rc;
         } else {
             if ((rc = layernorm(dt, ws.x, W, bw.ln1_g, bw.ln1_b, ws.h, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
             if ((rc = gemm_any(dt, ws.h, W, bw.in_proj_w, W, bw.in_proj_b, nullptr, 0, ws.qkv, 3 * W, M, 3 * W, W, B200CLIP_EPI_BIAS,
-                               nullptr, 0, 0, s)) != 0) return rc;
+                               nullptr, 0, 0, s, ws.sk)) != 0) return rc;
         }
         if ((rc = attention(dt, ws.qkv, ws.h, batch, L, c.heads, causal, s)) != 0) return rc;
         if (fold && fused_stats) {
@@ -121,26 +123,26 @@ int run_blocks(const b200clip_tower_cfg& c, const b200clip_block_weights* blocks
                                 nullptr, nullptr, nullptr, 0, ws.part[0])) != 0)
                 return rc;
         } else if ((rc = gemm_any(dt, ws.h, W, bw.out_proj_w, W, bw.out_proj_b, ws.x, W, ws.x, W, M, W, W, B200CLIP_EPI_RESIDUAL, nullptr,
-                                  0, 0, s)) != 0) {
+                                  0, 0, s, ws.sk)) != 0) {
             return rc;
         }
         if (fold) {
             if (!fused_stats && (rc = row_stats(dt, ws.x, W, ws.stats, M, W, 1e-5f, s)) != 0) return rc;
             if ((rc = gemm_pair(bf, ws.x, W, bw.fc_wf, W, bw.fc_bf, nullptr, 0, ws.mlp, c.mlp_width, M, c.mlp_width, W, act, 0, 0, s, bw.fc_c,
                                 fused_stats ? nullptr : ws.stats, nullptr, 0, nullptr, fused_stats ? ws.part[0] : nullptr, slots,
-                                1e-5f)) != 0)
+                                1e-5f, ws.sk)) != 0)
                 return rc;
         } else {
             if ((rc = layernorm(dt, ws.x, W, bw.ln2_g, bw.ln2_b, ws.h, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
             if ((rc = gemm_any(dt, ws.h, W, bw.fc_w, W, bw.fc_b, nullptr, 0, ws.mlp, c.mlp_width, M, c.mlp_width, W, act, nullptr, 0, 0,
-                               s)) != 0) return rc;
+                               s, ws.sk)) != 0) return rc;
         }
         if (fold && fused_stats && l + 1 < c.layers) {
             if ((rc = gemm_pair(bf, ws.mlp, c.mlp_width, bw.proj_w, c.mlp_width, bw.proj_b, ws.x, W, ws.x, W, M, W, c.mlp_width,
                                 B200CLIP_EPI_RESIDUAL, 0, 0, s, nullptr, nullptr, nullptr, 0, ws.part[1])) != 0)
                 return rc;
         } else if ((rc = gemm_any(dt, ws.mlp, c.mlp_width, bw.proj_w, c.mlp_width, bw.proj_b, ws.x, W, ws.x, W, M, W, c.mlp_width,
-                                  B200CLIP_EPI_RESIDUAL, nullptr, 0, 0, s)) != 0) {
+                                  B200CLIP_EPI_RESIDUAL, nullptr, 0, 0, s, ws.sk)) != 0) {
             return rc;
         }
     }
@@ -198,10 +200,13 @@ static int vit_forward_impl(const b200clip_tower_cfg* cfg, const b200clip_vit_we
         if (rc != 0) return rc;
     }
     if (stages & B200CLIP_STAGE_BODY) {
+        // stream-K flag words start at zero (the kernels leave them at zero; this also heals a workspace a failed launch left dirty)
+        if (ws.sk != nullptr && (rc = gemm_pair_sk_workspace_reset(ws.sk, s)) != 0) return rc;
         if (token_layout) {
             // ONE CTA-pair GEMM over all B*L rows whose epilogue adds the (class + positional) table row of each token
             if ((rc = gemm_pair(dt == B200CLIP_BF16, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, M, W,
-                                c.patch_kpad, B200CLIP_EPI_BIAS, 0, 0, s, nullptr, nullptr, w->pos_cls, L)) != 0)
+                                c.patch_kpad, B200CLIP_EPI_BIAS, 0, 0, s, nullptr, nullptr, w->pos_cls, L, nullptr, nullptr, 0, 1e-5f,
+                                ws.sk)) != 0)
                 return rc;
         } else {
             // GEMM whose epilogue scatters to token rows 1..L-1 and adds the positional embedding
@@ -266,6 +271,7 @@ int text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_text_weigh
                            c.vocab_size > 0 ? c.vocab_size : 0x7fffffff, s)) != 0)
         return rc;
     if (stages & B200CLIP_STAGE_BODY) {
+        if (ws.sk != nullptr && (rc = gemm_pair_sk_workspace_reset(ws.sk, s)) != 0) return rc;
         if ((rc = run_blocks(c, w->blocks_host, ws, batch, L, 1, s)) != 0) return rc;
         // ln_final only on the pooled (EOT) rows: LN is per-row, so this equals pooling after ln_final
         if ((rc = layernorm(dt, ws.x, W, w->ln_final_g, w->ln_final_b, ws.pooled, W, batch, W, 1e-5f, L, ws.eot, s)) != 0) return rc;

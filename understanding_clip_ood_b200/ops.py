@@ -40,6 +40,53 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, 
     return out
 
 
+_gemm_ws: dict = {}
+
+
+def gemm_workspace(device) -> torch.Tensor:
+    """Per-device scratch buffer of the stream-K GEMMs (`b200clip_gemm_workspace_bytes`), allocated once."""
+    dev = torch.device(device)
+    ws = _gemm_ws.get(dev)
+    if ws is None:
+        ws = torch.zeros(int(L.load().b200clip_gemm_workspace_bytes()), dtype=torch.uint8, device=dev)
+        _gemm_ws[dev] = ws
+    return ws
+
+
+def gemm_ws(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, *, epilogue: int = L.EPI_BIAS,
+            residual: torch.Tensor | None = None, out: torch.Tensor | None = None, workspace: torch.Tensor | None = None) -> torch.Tensor:
+    """`gemm` with the stream-K workspace (ragged tile grids are cut into equal runs of K-blocks); see b200clip_gemm_ws."""
+    L.require_cuda(a, w, bias, residual, out)
+    a, w = _c(a), _c(w)
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    ws = workspace if workspace is not None else gemm_workspace(a.device)
+    rc = L.load().b200clip_gemm_ws(L.dtype_code(a.dtype), a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), L.ptr(bias), L.ptr(residual),
+                                   residual.stride(0) if residual is not None else 0, out.data_ptr(), out.stride(0), M, N, K, epilogue,
+                                   ws.data_ptr(), ws.numel(), L.stream_ptr())
+    L.check(rc, "b200clip_gemm_ws")
+    return out
+
+
+def gemm_ln_ws(x: torch.Tensor, wf: torch.Tensor, colsum: torch.Tensor, bias_f32: torch.Tensor, stats: torch.Tensor, *,
+               epilogue: int = L.EPI_BIAS, out: torch.Tensor | None = None, workspace: torch.Tensor | None = None) -> torch.Tensor:
+    """`gemm_ln` with the stream-K workspace; see b200clip_gemm_ln_ws."""
+    L.require_cuda(x, wf, colsum, bias_f32, stats, out)
+    x, wf = _c(x), _c(wf)
+    M, K = x.shape
+    N = wf.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    ws = workspace if workspace is not None else gemm_workspace(x.device)
+    rc = L.load().b200clip_gemm_ln_ws(L.dtype_code(x.dtype), x.data_ptr(), x.stride(0), wf.data_ptr(), wf.stride(0), colsum.data_ptr(),
+                                      bias_f32.data_ptr(), stats.data_ptr(), out.data_ptr(), out.stride(0), M, N, K, epilogue,
+                                      ws.data_ptr(), ws.numel(), L.stream_ptr())
+    L.check(rc, "b200clip_gemm_ln_ws")
+    return out
+
+
 def row_stats(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     """-> [rows, 2] fp32 (mean, rstd) per row; see b200clip_row_stats."""
     L.require_cuda(x)
