@@ -51,7 +51,9 @@ def test_workspace_bytes_formula():
     rows = 128 * 50
     expect = rows * 768 * 2 * 2 + rows * 2304 * 2 + rows * 3072 * 2 + 128 * 768 * 2 + 128 * 4 + rows * 2 * 4   # + LN-fold row stats
     expect += 2 * rows * (768 // 64 + 2) * 8                 # + partial-sum slots of the two residual GEMMs (fused statistics)
-    assert expect <= n <= expect + 9 * 256
+    expect += lib.b200clip_gemm_workspace_bytes()             # + stream-K partial accumulators and flags of the CTA-pair GEMM
+    assert lib.b200clip_gemm_workspace_bytes() == 74 * 2 * 64 * 128 * 16 + ((74 * 16 * 4 + 255) // 256) * 256   # 148 SMs assumed off-GPU
+    assert expect <= n <= expect + 10 * 256
 
 
 # ------------------------------------------------------------------ module surface ------------------

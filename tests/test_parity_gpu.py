@@ -428,6 +428,17 @@ def test_every_registered_config_runs_in_fp32(name):
     m = m.to(DEV).eval()
     S = m.visual.image_size[0]
     image = torch.randn(1, 3, S, S, generator=torch.Generator().manual_seed(2))
+    if name == "ViT-L-14-336":
+        # 577 tokens: the fp32 parity kernel keeps K and V of a whole (image, head) in shared memory (<= 435 tokens) and says
+        # so; the 16-bit modes (the ones that configuration is run in) take the streaming attention kernel
+        from understanding_clip_ood_b200 import _lib as L
+        with pytest.raises(L.B200ClipError, match="too long for the shared-memory path"):
+            m.encode_image(image.to(DEV))
+        mb = open_clip.create_model(name, precision="bf16", device="cpu")
+        mb.load_state_dict(sd)
+        got = mb.to(DEV).eval().encode_image(image.bfloat16().to(DEV))
+        assert row_rel(got, O.vit_forward(sd, image)) < 2e-2
+        return
     got = m.encode_image(image.to(DEV))
     assert got.shape == (1, m.visual.output_dim) and torch.isfinite(got).all()
     if name in ("ViT-L-14", "ViT-B-32-256", "ViT-L-14-336"):         # the geometries no other test covers in fp32

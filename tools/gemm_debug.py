@@ -79,8 +79,10 @@ def check():
     return allok
 
 
-VARIANTS = tuple(int(v) for v in os.environ.get('GEMM_VARIANTS', '256,1256,1192,2256,2192').split(','))
-BATCHES = tuple(int(v) for v in os.environ.get('GEMM_BATCHES', '128,1024').split(','))
+# 1000 + N tile: CTA-pair kernel with whole tiles; -1: the same kernel with the stream-K workspace (b200clip_gemm_ws, tile picked
+# by the library); 0: b200clip_gemm as the towers call it without a workspace
+VARIANTS = tuple(int(v) for v in os.environ.get('GEMM_VARIANTS', '0,-1,1256,1192').split(','))
+BATCHES = tuple(int(v) for v in os.environ.get('GEMM_BATCHES', '128,256,512,1024').split(','))
 
 
 def sm_clock():
@@ -122,11 +124,42 @@ def bench():
 
             label = name + f" M={M} N={N} K={K}"
             for bn in VARIANTS:
-                us = timeit(lambda: ops.gemm(a, w, b, epilogue=epi, residual=res, out=out, block_n=bn))
+                if bn == -1:
+                    if epi == 3 and not inplace:
+                        continue
+                    us = timeit(lambda: ops.gemm_ws(a, w, b, epilogue=epi, residual=res, out=out))
+                else:
+                    us = timeit(lambda: ops.gemm(a, w, b, epilogue=epi, residual=res, out=out, block_n=bn))
                 print(f"{label:>34} {bn:>10} {us:9.1f} {2.0 * M * N * K / us / 1e6:9.1f}", flush=True)
             if not inplace and os.environ.get("GEMM_CUBLAS", "1") == "1":
                 us = timeit(lambda: torch.nn.functional.linear(a, w, b))
                 print(f"{label:>34} {'cublas':>10} {us:9.1f} {2.0 * M * N * K / us / 1e6:9.1f}   (F.linear + bias only, no act/residual)", flush=True)
+
+
+def bench_ln():
+    """c_fc exactly as the tower runs it: LayerNorm folded into the epilogue (+bias +GELU), whole tiles vs stream-K."""
+    for batch in BATCHES:
+        M, N, K = batch * 50, 3072, 768
+        g = torch.Generator(device="cuda").manual_seed(7)
+        x = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+        w = (torch.randn(N, K, device="cuda", generator=g) * 0.04).bfloat16()
+        b = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
+        wf, colsum, bf = ops.fold_layernorm(w, b, torch.ones(K, device="cuda"), torch.zeros(K, device="cuda"), torch.bfloat16)
+        stats = ops.row_stats(x)
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        for name, fn in (("ln+gelu", lambda: ops.gemm_ln(x, wf, colsum, bf, stats, epilogue=L.EPI_GELU, out=out)),
+                         ("ln+gelu ws", lambda: ops.gemm_ln_ws(x, wf, colsum, bf, stats, epilogue=L.EPI_GELU, out=out))):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(40):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 40 * 1e3
+            print(f"{'c_fc M=%d N=%d K=%d' % (M, N, K):>34} {name:>10} {us:9.1f} {2.0 * M * N * K / us / 1e6:9.1f}", flush=True)
 
 
 if __name__ == "__main__":
@@ -137,4 +170,5 @@ if __name__ == "__main__":
         ok = check()
     if "bench" in what:
         bench()
+        bench_ln()
     sys.exit(0 if ok else 1)

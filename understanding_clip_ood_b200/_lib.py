@@ -10,8 +10,11 @@ from pathlib import Path
 
 import torch
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libb200clip.so"
+# B200CLIP_LIB=<path>: load another build of the same ABI (A/B measurements of kernel variants only)
+LIB_PATH = Path(os.environ["B200CLIP_LIB"]).resolve() if os.environ.get("B200CLIP_LIB") else _PKG / "libb200clip.so"
 
 F32, BF16, F16 = 0, 1, 2
 EPI_BIAS, EPI_GELU, EPI_QUICKGELU, EPI_RESIDUAL, EPI_PATCH = 0, 1, 2, 3, 4

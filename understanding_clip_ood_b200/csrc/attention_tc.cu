@@ -60,7 +60,7 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+__device__ __forceinline__ void attn_tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
         :
@@ -68,7 +68,6 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v
           "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // tcgen05.wait::ld + a register dependency on the loaded values: nothing may be scheduled on `v` before the wait.
 __device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&v)[32]) {
@@ -372,7 +371,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                             pk[j] = H::pack(p0, p1);
                         }
                     }
-                    tmem_st_32x16(tm + ch * 16, pk);
+                    attn_tmem_st_32x16(tm + ch * 16, pk);
                 };
                 {
                     uint32_t va[32];

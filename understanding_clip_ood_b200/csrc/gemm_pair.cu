@@ -11,10 +11,11 @@
 //     both CTAs' TMA loads), TMEM full/empty (MMA <-> both CTAs' epilogues; double-buffered accumulators: the epilogue of
 //     tile i overlaps the MMAs of tile i+1);
 //   * epilogue: tcgen05.ld -> registers -> bias / GELU / residual -> 128B-swizzled shared-memory staging -> TMA store, so
-//     global writes are full 128-byte lines issued by the copy engine instead of per-thread 16-byte scatters.  Every epilogue
-//     warp owns the 32 accumulator rows its TMEM lane quarter can read, its own staging buffers and its own TMA stores
-//     (32 x 64 boxes): the eight warps never synchronise with each other (no block / named barriers in the steady state).
-//     The residual operand is TMA-loaded into the same staging buffer ahead of time (two chunks ahead) and updated in place.
+//     global writes are full 128-byte lines issued by the copy engine instead of per-thread 16-byte scatters.  The residual
+//     operand is TMA-loaded into the same staging buffer ahead of time (two chunks ahead) and updated in place.
+//     (Measured and rejected in round 2: one 32 x 64 TMA store per epilogue WARP with private staging and no named barrier —
+//     20-25 % slower on every tower shape, profiles/r2_gemm_epilogue_ab.txt: four times as many TMA store instructions
+//     compete with the operand loads for the one TMA unit of the SM.)
 //   * stream-K for the ragged part of the tile grid: when the tile count does not fill whole rounds of the 74 clusters
 //     (75 tiles for the out-proj / c_proj of a 128-image shard: 2 rounds for 1.01 rounds of work), the last full round plus
 //     the remainder is cut into 74 EQUAL runs of K-blocks.  A cluster whose run starts inside a tile dumps that accumulator as
@@ -43,9 +44,8 @@ constexpr int kAccStride = 256;   // TMEM columns between the two accumulator st
 constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 8;      // two groups of 4 warps (one warp per TMEM lane quarter)
-constexpr int kChunkN = 64;       // epilogue / store granularity: 64 columns (128 B rows) ...
-constexpr int kWarpRows = 32;     // ... x the 32 rows of one epilogue warp (one TMEM lane quarter)
-constexpr int kChunkBytes = kWarpRows * kChunkN * 2;   // one warp's staging buffer / TMA store box
+constexpr int kChunkN = 64;       // epilogue / store granularity: 128 rows x 64 columns (128 B rows)
+constexpr int kChunkBytes = kBM * kChunkN * 2;
 // stream-K workspace (per cluster slot): the pair tile's accumulator as fp32, laid out [CTA half][column / 4][row][4] so that
 // a warp's 32 lanes (= 32 rows) touch 512 contiguous bytes per access, + one flag word per (CTA half, epilogue warp)
 constexpr int kSkSlotFloat4 = 2 * (256 / 4) * kBM;
@@ -96,15 +96,15 @@ template <int BLOCK_N, int STG_BUFS> struct PairCfg {
     static constexpr int kBBytes = (BLOCK_N / 2) * kBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStgBufs = STG_BUFS;
-    static constexpr int kStagingBytes = kEpiWarps * kStgBufs * kChunkBytes;
-    static constexpr int kBarBytes = 512;
+    static constexpr int kStagingBytes = 2 * kStgBufs * kChunkBytes;
+    static constexpr int kBarBytes = 256;
     static constexpr int kBudget = 227 * 1024 - 1024 - kStagingBytes - kBarBytes;
     static constexpr int kStagesFit = kBudget / kStageBytes;
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;
     static constexpr int kChunks = BLOCK_N / kChunkN;
     static_assert(kStages >= 3, "not enough shared memory for the operand ring");
-    static_assert((2 * kStages + 2 * kAccStages + kEpiWarps * kStgBufs) * 8 + 8 <= kBarBytes, "barrier block too small");
+    static_assert((2 * kStages + 2 * kAccStages + 2 * kStgBufs) * 8 + 8 <= kBarBytes, "barrier block too small");
 };
 
 __device__ __forceinline__ void pair_tile_coords(int t, const PairParams& p, int& mt, int& nt) {
@@ -122,10 +122,26 @@ __device__ __forceinline__ void pair_tile_coords(int t, const PairParams& p, int
 struct Piece {
     int tile, kb0, kb1;
 };
-struct PieceIter {
+__device__ __forceinline__ int64_t sk_begin(int c, int64_t units, int clusters) { return static_cast<int64_t>(c) * units / clusters; }
+// SK == false: the plain persistent tile walk t = cluster, cluster + stride, ... (what the kernel ran before stream-K existed;
+// instantiated separately so that whole-tile GEMMs carry none of the stream-K code)
+template <bool SK> struct PieceIter;
+template <> struct PieceIter<false> {
+    int t_dp, num_tiles, num_kb, stride;
+    __device__ __forceinline__ PieceIter(const PairParams& p, int num_kb_, int cluster_id, int num_clusters)
+        : t_dp(cluster_id), num_tiles(p.m_tiles * p.n_tiles), num_kb(num_kb_), stride(num_clusters) {}
+    __device__ __forceinline__ bool next(Piece& pc) {
+        if (t_dp >= num_tiles) return false;
+        pc.tile = t_dp;
+        pc.kb0 = 0;
+        pc.kb1 = num_kb;
+        t_dp += stride;
+        return true;
+    }
+};
+template <> struct PieceIter<true> {
     int64_t u, end;
     int t_dp, num_tiles, num_kb, stride;
-    __device__ __forceinline__ static int64_t sk_begin(int c, int64_t units, int clusters) { return static_cast<int64_t>(c) * units / clusters; }
     __device__ __forceinline__ PieceIter(const PairParams& p, int num_kb_, int cluster_id, int num_clusters) {
         const int64_t units = static_cast<int64_t>(p.sk_tiles) * num_kb_;
         u = sk_begin(cluster_id, units, num_clusters);
@@ -155,6 +171,9 @@ struct PieceIter {
     }
 };
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -183,11 +202,81 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :
+        : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
+// The two rare stream-K paths are kept out of line (and narrow: 16 columns per step) so that they cannot raise the register
+// allocation or disturb the scheduling of the epilogue's hot loop.  `tmem_row` = this warp's lane quarter of the accumulator
+// stage, `slot` = this lane's row of the partial slot(s) (layout: kSkSlotFloat4 above).
+__device__ __noinline__ void sk_dump_accumulator(uint32_t tmem_row, float4* slot, int grp, int chunks) {
+    for (int c = grp; c < chunks; c += 2) {
+#pragma unroll 1
+        for (int s16 = 0; s16 < kChunkN / 16; ++s16) {
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_row + c * kChunkN + s16 * 16, v);
+            tmem_ld_wait();
+            float4* dst = slot + (c * (kChunkN / 4) + s16 * 4) * kBM;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                __stcg(dst + g * kBM, make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
+                                                  __uint_as_float(v[4 * g + 3])));
+        }
+    }
+}
+// TMEM[this warp's slice] += partial slots [peer_begin, peer_end), in that order
+__device__ __noinline__ void sk_add_partials(uint32_t tmem_row, const float4* slots_lane, int peer_begin, int peer_end, int grp, int chunks) {
+    for (int c = grp; c < chunks; c += 2) {
+#pragma unroll 1
+        for (int s16 = 0; s16 < kChunkN / 16; ++s16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_row + c * kChunkN + s16 * 16;
+            tmem_ld_32x16(taddr, v);
+            const int off = (c * (kChunkN / 4) + s16 * 4) * kBM;
+            float4 pv[4];
+            {
+                const float4* src = slots_lane + static_cast<int64_t>(peer_begin) * kSkSlotFloat4 + off;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) pv[g] = __ldcg(src + g * kBM);
+            }
+            tmem_ld_wait();
+            for (int pc2 = peer_begin;;) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    v[4 * g + 0] = __float_as_uint(__uint_as_float(v[4 * g + 0]) + pv[g].x);
+                    v[4 * g + 1] = __float_as_uint(__uint_as_float(v[4 * g + 1]) + pv[g].y);
+                    v[4 * g + 2] = __float_as_uint(__uint_as_float(v[4 * g + 2]) + pv[g].z);
+                    v[4 * g + 3] = __float_as_uint(__uint_as_float(v[4 * g + 3]) + pv[g].w);
+                }
+                if (++pc2 >= peer_end) break;
+                const float4* src = slots_lane + static_cast<int64_t>(pc2) * kSkSlotFloat4 + off;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) pv[g] = __ldcg(src + g * kBM);
+            }
+            tmem_st_32x16(taddr, v);
+        }
+    }
+    tmem_st_wait();
+}
+
 // PAIRS = CTA pairs per cluster (cluster size = 2 * PAIRS).  PAIRS == 2: the two pairs own vertically adjacent 256-row
 // tiles of the same BLOCK_N columns; every CTA fetches one QUARTER of the W tile and TMA-multicasts it to the CTA of the
 // other pair that needs the same half, so the cluster reads each W byte from L2 once instead of twice (the single-pair
 // kernel is bound by the ~10 TB/s L2 -> SM read bandwidth, not by the tensor pipe: profiles/r1_gemm_pair_v1_ncu.md).
-template <typename T, int BLOCK_N, int EPI, int PAIRS>
+template <typename T, int BLOCK_N, int EPI, int PAIRS, bool SK>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, const PairParams p) {
@@ -271,7 +360,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int row_in_cluster = static_cast<int>(pair) * kPairM + static_cast<int>(half) * kBM;
             // L2 prefetch cursor (whole-tile schedules only): runs p.pf_dist K-blocks ahead of the shared-memory ring (across tile
             // boundaries), so the ring only has to cover L2 latency, not the DRAM latency of the streamed activations
-            const int pf_dist = p.sk_tiles == 0 ? p.pf_dist : 0;
+            const int pf_dist = SK ? 0 : p.pf_dist;
             int pf_t = cluster_id, pf_kb = 0, pf_row = 0;
             auto prefetch_next = [&]() {
                 if (pf_t >= num_tiles) return;
@@ -287,7 +376,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             };
             for (int i = 0; i < pf_dist; ++i) prefetch_next();
-            PieceIter pieces(p, num_kb, cluster_id, num_clusters);
+            PieceIter<SK> pieces(p, num_kb, cluster_id, num_clusters);
             Piece pc;
             while (pieces.next(pc)) {
                 int mt, nt;
@@ -326,7 +415,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            PieceIter pieces(p, num_kb, cluster_id, num_clusters);
+            PieceIter<SK> pieces(p, num_kb, cluster_id, num_clusters);
             Piece pc;
             for (; pieces.next(pc); ++it) {
                 const int acc = it & 1;
@@ -363,26 +452,28 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         __syncwarp();
     } else if (warp >= kEpiWarp0) {
-        // ===================== epilogue (every CTA; eight independent warps) =====================
+        // ===================== epilogue (every CTA) =====================
         const int e = warp - kEpiWarp0;
-        const int q = warp & 3;   // TMEM lane quarter this warp may access = rows [32 q, 32 q + 32) of this CTA's 128
-        const int grp = e >> 2;   // handles column chunks grp, grp+2, ...
+        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        const int grp = e >> 2;   // epilogue group: handles column chunks grp, grp+2, ...
+        const bool grp_leader = (e & 3) == 0 && lane == 0;
+        const int bar_id = 1 + grp;
         const int r = q * 32 + lane;  // row inside this CTA's 128-row half
-        uint8_t* stg_ptr = staging + e * kStgBufs * kChunkBytes;
+        uint8_t* stg_ptr = staging + grp * kStgBufs * kChunkBytes;
         const uint32_t stg_base = smem_u32(stg_ptr);
-        uint64_t* my_res_bar = res_bar + e * kStgBufs;
-        const uint32_t row_off = static_cast<uint32_t>(lane) * 128;
-        const uint32_t rx = static_cast<uint32_t>(lane & 7);
+        uint64_t* my_res_bar = res_bar + grp * kStgBufs;
+        const uint32_t row_off = static_cast<uint32_t>(r) * 128;
+        const uint32_t rx = static_cast<uint32_t>(r & 7);
         const int row_in_cluster = static_cast<int>(pair) * kPairM + static_cast<int>(half) * kBM;
         const T* bias = static_cast<const T*>(p.bias);
         const float* bias_f32 = static_cast<const float*>(p.bias);
-        uint32_t bufc = 0;  // chunks stored by this warp so far (buffer = bufc % kStgBufs)
+        uint32_t bufc = 0;  // chunks processed by this group so far (buffer = bufc % kStgBufs)
         // stream-K bookkeeping of this warp: its part of every cluster slot, its flag in every slot
         const int64_t sk_units = static_cast<int64_t>(p.sk_tiles) * num_kb;
         const int sk_lane_off = static_cast<int>(half) * (BLOCK_N / 4) * kBM + r;       // + col4 * kBM, in float4
         const int sk_flag_off = static_cast<int>(half) * kEpiWarps + e;
 
-        // (tile, chunk) -> the next chunk this warp processes (whole-tile schedules; the residual prefetch runs ahead on it)
+        // (tile, chunk) -> the next chunk this group processes (whole-tile schedules; the residual prefetch runs ahead on it)
         auto advance = [&](int& tile, int& chunk) {
             chunk += 2;
             if (chunk >= Cfg::kChunks) {
@@ -390,17 +481,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 tile += num_clusters;
             }
         };
-        auto issue_residual = [&](int tile, int chunk, uint32_t use) {  // lane 0 only
+        auto issue_residual = [&](int tile, int chunk, uint32_t use) {  // group leader only
             int mt2, nt2;
             pair_tile_coords(tile, p, mt2, nt2);
             const uint32_t b = use % kStgBufs;
             mbar_arrive_expect_tx(&my_res_bar[b], kChunkBytes);
             tma_load_2d(&tmap_r, &my_res_bar[b], stg_ptr + b * kChunkBytes, nt2 * BLOCK_N + chunk * kChunkN,
-                        mt2 * kClusterM + row_in_cluster + q * kWarpRows, kCacheHintEvictFirst);
+                        mt2 * kClusterM + row_in_cluster, kCacheHintEvictFirst);
         };
-        // residual prefetch, two chunks ahead: the first two chunks of this warp
+        // residual prefetch, two chunks ahead: the first two chunks of this group
         if constexpr (kRes) {
-            if (lane == 0 && !(p.dbg & 1)) {
+            if (grp_leader && !(p.dbg & 1)) {
                 int pt = cluster_id, pcn = grp;
                 if (pt < num_tiles) issue_residual(pt, pcn, 0);
                 advance(pt, pcn);
@@ -410,7 +501,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
 
         int it = 0;
-        PieceIter pieces(p, num_kb, cluster_id, num_clusters);
+        PieceIter<SK> pieces(p, num_kb, cluster_id, num_clusters);
         Piece pc;
         for (; pieces.next(pc); ++it) {
             const int t = pc.tile;
@@ -419,29 +510,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int row0 = mt * kClusterM + row_in_cluster;
-            const bool dump = pc.kb0 != 0;                                // run starts inside the tile: accumulator -> fp32 partial
-            const bool fixup = pc.kb0 == 0 && pc.kb1 < num_kb;           // tile's first K-block, but not its last: add the others' partials
+            const bool dump = SK && pc.kb0 != 0;                          // run starts inside the tile: accumulator -> fp32 partial
+            const bool fixup = SK && pc.kb0 == 0 && pc.kb1 < num_kb;     // tile's first K-block, but not its last: add the others' partials
 
-            if (dump) {
+            if (SK && dump) {
                 mbar_wait(&tmem_full_bar[acc], acc_phase);
                 tc_fence_after();
-                float4* slot = p.sk_partial + static_cast<int64_t>(cluster_id) * kSkSlotFloat4 + sk_lane_off;
-                if (!(p.dbg & 1)) {
-#pragma unroll 1
-                    for (int c = grp; c < Cfg::kChunks; c += 2) {
-#pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            uint32_t v[32];
-                            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride + c * kChunkN + hf * 32, v);
-                            tmem_ld_wait();
-                            float4* dst = slot + (c * (kChunkN / 4) + hf * 8) * kBM;
-#pragma unroll
-                            for (int g = 0; g < 8; ++g)
-                                __stcg(dst + g * kBM, make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                                                                  __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
-                        }
-                    }
-                }
+                if (!(p.dbg & 1))
+                    sk_dump_accumulator(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride,
+                                        p.sk_partial + static_cast<int64_t>(cluster_id) * kSkSlotFloat4 + sk_lane_off, grp, Cfg::kChunks);
                 tc_fence_before();
                 __threadfence();      // every lane's partial rows are visible device-wide before the flag goes up
                 __syncwarp();
@@ -457,7 +534,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int peer_end = cluster_id + 1;
             if (fixup) {
                 const int64_t tile_end = static_cast<int64_t>(t + 1) * num_kb;
-                while (peer_end < num_clusters && PieceIter::sk_begin(peer_end, sk_units, num_clusters) < tile_end) ++peer_end;
+                while (peer_end < num_clusters && sk_begin(peer_end, sk_units, num_clusters) < tile_end) ++peer_end;
                 if (lane == 0 && !(p.dbg & 1))
                     for (int pc2 = cluster_id + 1; pc2 < peer_end; ++pc2) sk_wait_flag(p.sk_flags + pc2 * kSkFlagsPerSlot + sk_flag_off);
                 __syncwarp();
@@ -491,14 +568,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             float st_s = 0.f, st_q = 0.f;   // epilogue 10: this thread's share of sum x / sum x^2 of its output row
             if constexpr (kRes) {
-                // pull the residual boxes this warp will need two tiles from now into L2
-                if (lane == 0 && p.pf_dist > 0) {
+                // pull the residual tiles this group will need two tiles from now into L2
+                if (grp_leader && p.pf_dist > 0) {
                     const int ft = t + 2 * num_clusters;
                     if (ft < num_tiles) {
                         int fm, fn;
                         pair_tile_coords(ft, p, fm, fn);
                         for (int c = grp; c < Cfg::kChunks; c += 2)
-                            tma_prefetch_l2_2d(&tmap_r, fn * BLOCK_N + c * kChunkN, fm * kClusterM + row_in_cluster + q * kWarpRows);
+                            tma_prefetch_l2_2d(&tmap_r, fn * BLOCK_N + c * kChunkN, fm * kClusterM + row_in_cluster);
                     }
                 }
                 __syncwarp();
@@ -511,40 +588,35 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], leader_rank);
                 continue;
             }
+            if (fixup) {
+                // Stream-K fix-up as a separate pass over this warp's slice of the accumulator: TMEM += the partial sums of
+                // the tile's remaining K range, in cluster order (deterministic).  The ordinary epilogue below then runs
+                // unchanged (its loop is the hot path of every GEMM: nothing of the fix-up lives in it).
+                sk_add_partials(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride, p.sk_partial + sk_lane_off,
+                                cluster_id + 1, peer_end, grp, Cfg::kChunks);
+                // this warp has consumed its part of every peer's partial: the flags are zero again for the next launch
+                __syncwarp();
+                if (lane == 0)
+                    for (int pc2 = cluster_id + 1; pc2 < peer_end; ++pc2) p.sk_flags[pc2 * kSkFlagsPerSlot + sk_flag_off] = 0u;
+                __syncwarp();
+            }
 
 #pragma unroll 1
             for (int c = grp; c < Cfg::kChunks; c += 2) {
                 const bool last_of_tile = c + 2 >= Cfg::kChunks;
                 const uint32_t buf = bufc % kStgBufs;
                 const uint32_t stg = stg_base + buf * kChunkBytes;
-                if constexpr (kRes) {
-                    mbar_wait(&my_res_bar[buf], (bufc / kStgBufs) & 1);
-                } else {
-                    // staging buffer `buf` is free once the store issued kStgBufs chunks ago has read it (at most the
-                    // previous chunk's store may still be in flight)
-                    if (lane == 0) tma_store_wait_read<kStgBufs - 1>();
-                    __syncwarp();
-                }
+                // Staging buffer `buf` is free here: the group leader drains its outstanding TMA store before it joins the
+                // barrier that ends each chunk (below), so the store issued kStgBufs chunks ago finished reading long ago.
+                if constexpr (kRes) mbar_wait(&my_res_bar[buf], (bufc / kStgBufs) & 1);
                 const int col0 = nt * BLOCK_N + c * kChunkN;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t v[32];
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride + c * kChunkN + hf * 32;
                     tmem_ld_32x32(taddr, v);
-                    // per-column operands of these 32 columns (the same for every lane: broadcast loads), issued under the TMEM load
-                    // (LN-fold: the first 16 columns' colsum / bias here, the other 16 while those are being used)
                     uint4 bvec[4];
-                    float4 cvec[4], fvec[4];
-                    auto load_ln = [&](int i, float4& c4, float4& f4) {   // i = 4-column group of this half-chunk
-                        const int col = col0 + hf * 32 + i * 4;
-                        const bool ok = col < p.N;
-                        c4 = ok ? __ldg(reinterpret_cast<const float4*>(p.colsum + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        f4 = ok ? __ldg(reinterpret_cast<const float4*>(bias_f32 + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    };
-                    if constexpr (kLn) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) load_ln(i, cvec[i], fvec[i]);
-                    } else if constexpr (!kPos) {
+                    if constexpr (!kLn) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             const int col = col0 + hf * 32 + g * 8;
@@ -559,28 +631,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         __syncwarp();
                         if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], leader_rank);
                     }
-                    if (fixup) {
-                        // + the partial sums of the tile's remaining K range, in cluster order (deterministic)
-                        for (int pc2 = cluster_id + 1; pc2 < peer_end; ++pc2) {
-                            const float4* src = p.sk_partial + static_cast<int64_t>(pc2) * kSkSlotFloat4 + sk_lane_off +
-                                                (c * (kChunkN / 4) + hf * 8) * kBM;
-#pragma unroll 2
-                            for (int g = 0; g < 8; ++g) {
-                                const float4 pv = __ldcg(src + g * kBM);
-                                v[4 * g + 0] = __float_as_uint(__uint_as_float(v[4 * g + 0]) + pv.x);
-                                v[4 * g + 1] = __float_as_uint(__uint_as_float(v[4 * g + 1]) + pv.y);
-                                v[4 * g + 2] = __float_as_uint(__uint_as_float(v[4 * g + 2]) + pv.z);
-                                v[4 * g + 3] = __float_as_uint(__uint_as_float(v[4 * g + 3]) + pv.w);
-                            }
-                        }
-                    }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const uint32_t saddr = stg + row_off + (((static_cast<uint32_t>(hf * 4 + g)) ^ rx) << 4);
-                        uint32_t bw[4] = {0, 0, 0, 0};
-                        if constexpr (!kLn && !kPos) {
-                            bw[0] = bvec[g].x; bw[1] = bvec[g].y; bw[2] = bvec[g].z; bw[3] = bvec[g].w;
-                        }
+                        const uint32_t bw[4] = {bvec[g].x, bvec[g].y, bvec[g].z, bvec[g].w};
                         uint32_t rw[4] = {0, 0, 0, 0};
                         if constexpr (kRes) {
                             const uint4 rv = lds128(saddr);
@@ -598,15 +652,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             }
                         }
                         if constexpr (kLn) {
+                            const int col = col0 + hf * 32 + g * 8;
+                            const bool ok = col < p.N;
 #pragma unroll
                             for (int q4 = 0; q4 < 2; ++q4) {
-                                float4 c4, b4;
-                                if (g < 2) {
-                                    c4 = cvec[g * 2 + q4];
-                                    b4 = fvec[g * 2 + q4];
-                                } else {
-                                    load_ln(g * 2 + q4, c4, b4);
-                                }
+                                const float4 c4 = ok ? __ldg(reinterpret_cast<const float4*>(p.colsum + col) + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float4 b4 = ok ? __ldg(reinterpret_cast<const float4*>(bias_f32 + col) + q4) : make_float4(0.f, 0.f, 0.f, 0.f);
                                 cf[q4 * 4 + 0] = c4.x; cf[q4 * 4 + 1] = c4.y; cf[q4 * 4 + 2] = c4.z; cf[q4 * 4 + 3] = c4.w;
                                 bf[q4 * 4 + 0] = b4.x; bf[q4 * 4 + 1] = b4.y; bf[q4 * 4 + 2] = b4.z; bf[q4 * 4 + 3] = b4.w;
                             }
@@ -616,9 +667,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             float x0, x1;
                             if constexpr (kLn) {
                                 // rstd * acc + (b' - rstd * mean * c): two packed FMAs per pair
-                                const uint64_t tt = fma_f2(pack_f2(ln_nmr, ln_nmr), pack_f2(cf[2 * j], cf[2 * j + 1]), pack_f2(bf[2 * j], bf[2 * j + 1]));
+                                const uint64_t t = fma_f2(pack_f2(ln_nmr, ln_nmr), pack_f2(cf[2 * j], cf[2 * j + 1]), pack_f2(bf[2 * j], bf[2 * j + 1]));
                                 unpack_f2(fma_f2(pack_f2(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])),
-                                                 pack_f2(ln_rstd, ln_rstd), tt), x0, x1);
+                                                 pack_f2(ln_rstd, ln_rstd), t), x0, x1);
                             } else if constexpr (kPos) {
                                 // conv output and table entry are each rounded to the storage type before the add
                                 const float2 a2 = H::unpack(H::pack(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])));
@@ -656,11 +707,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
                 fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
-                __syncwarp();
-                if (lane == 0) {
-                    const int srow = row0 + q * kWarpRows;
-                    if constexpr (EPI == kEpiResidualInPlace) tma_reduce_add_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, srow);
-                    else tma_store_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, srow);
+                if constexpr (!kRes) {
+                    // every store but (at most) the previous chunk's has long completed; waiting for that one too BEFORE the
+                    // barrier tells the whole group that the other staging buffer is free for the next chunk
+                    if (grp_leader) tma_store_wait_read<0>();
+                    __syncwarp();
+                }
+                named_bar_sync(bar_id, 128);
+                if (grp_leader) {
+                    if constexpr (EPI == kEpiResidualInPlace) tma_reduce_add_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, row0);
+                    else tma_store_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, row0);
                     tma_store_commit();
                     if constexpr (kRes) {
                         // prefetch the residual of the chunk two steps ahead into the buffer whose store was committed one
@@ -677,18 +733,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 __syncwarp();
                 ++bufc;
             }
-            if (fixup) {
-                // this warp has consumed its part of every peer's partial: the flags are zero again for the next launch
-                __syncwarp();
-                if (lane == 0)
-                    for (int pc2 = cluster_id + 1; pc2 < peer_end; ++pc2) p.sk_flags[pc2 * kSkFlagsPerSlot + sk_flag_off] = 0u;
-            }
             if constexpr (kStats) {
                 if (row0 + r < p.M)
                     p.stats_out[static_cast<int64_t>(row0 + r) * p.stats_slots + nt * 2 + grp] = make_float2(st_s, st_q);
             }
         }
-        if (lane == 0) tma_store_wait_all<0>();  // global writes complete before the CTA retires
+        if (grp_leader) tma_store_wait_all<0>();  // global writes complete before the CTA retires
         __syncwarp();
     }
 
@@ -703,11 +753,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // clusters the stream-K schedule is planned for = one per SM pair of the device (the persistent grid of a busy GEMM)
 int sk_clusters_planned() { return num_sms() / 2; }
 
-template <typename T, int BLOCK_N, int EPI, int PAIRS>
-int launch_pair(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr, const PairParams& p,
-                cudaStream_t stream) {
+template <typename T, int BLOCK_N, int EPI, int PAIRS, bool SK>
+int launch_pair_sk(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr, const PairParams& p,
+                   cudaStream_t stream) {
     using Cfg = PairCfg<BLOCK_N, (EPI == 3 || EPI == kEpiResidualStats) ? 3 : 2>;
-    auto kern = gemm_pair_kernel<T, BLOCK_N, EPI, PAIRS>;
+    auto kern = gemm_pair_kernel<T, BLOCK_N, EPI, PAIRS, SK>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     static int max_clusters = 0;
@@ -737,9 +787,9 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
     B2C_CHECK_ARG(max_clusters > 0, "gemm_pair: the device cannot co-schedule a cluster of %d CTAs", 2 * PAIRS);
     const int tiles = p.m_tiles * p.n_tiles;
     int clusters = tiles < max_clusters ? tiles : max_clusters;
-    if (p.sk_tiles > 0) {
+    if constexpr (SK) {
         // the stream-K split was planned for `sk_clusters` clusters: all of them must be co-resident (flag waits)
-        B2C_CHECK_ARG(PAIRS == 1 && sk_clusters_planned() <= max_clusters, "gemm_pair: stream-K needs %d co-resident clusters, device holds %d",
+        B2C_CHECK_ARG(sk_clusters_planned() <= max_clusters, "gemm_pair: stream-K needs %d co-resident clusters, device holds %d",
                       sk_clusters_planned(), max_clusters);
         clusters = sk_clusters_planned();
     }
@@ -748,6 +798,18 @@ int launch_pair(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap&
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(gemm_pair_kernel)");
     B2C_LAUNCH_CHECK("gemm_pair_kernel");
     return 0;
+}
+
+// whole-tile GEMMs run the kernel instantiated without any stream-K code; the stream-K instantiation exists for single pairs and
+// the epilogues without a TMA-loaded residual
+template <typename T, int BLOCK_N, int EPI, int PAIRS>
+int launch_pair(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr, const PairParams& p,
+                cudaStream_t stream) {
+    if constexpr (PAIRS == 1 && EPI != 3 && EPI != kEpiResidualStats) {
+        if (p.sk_tiles > 0) return launch_pair_sk<T, BLOCK_N, EPI, PAIRS, true>(ta, tw, tc, tr, p, stream);
+    }
+    B2C_CHECK_ARG(p.sk_tiles == 0, "gemm_pair: stream-K is not available for this kernel variant");
+    return launch_pair_sk<T, BLOCK_N, EPI, PAIRS, false>(ta, tw, tc, tr, p, stream);
 }
 
 template <typename T, int BLOCK_N, int PAIRS>
@@ -878,6 +940,9 @@ static int plan_stream_k(int tiles, int num_kb, int clusters) {
         return e != nullptr ? atoi(e) : -1;
     }();
     if (mode == 0 || clusters <= 1) return 0;
+    // the dump + fix-up of a split tile cost about as much as 8 K-blocks of tensor work: worth it only for long K
+    // (c_proj, K = 4 W: 48 K-blocks), not for the K = W GEMMs (12) -- profiles/r2_gemm_stream_k.txt
+    if (mode != 1 && num_kb < 32) return 0;
     const int rem = tiles % clusters;
     if (rem == 0) return 0;
     const int full = tiles / clusters;
@@ -931,15 +996,15 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     CUtensorMap ta, tw, tc, tr;
     if (make_tmap_2d(&ta, is_bf16, A, M, K, lda, kBM, kBK) != 0) return -1;
     if (make_tmap_2d(&tw, is_bf16, W, N, K, ldw, pairs == 2 ? bn / 4 : bn / 2, kBK) != 0) return -1;
-    if (make_tmap_2d(&tc, is_bf16, C, M, N, ldc, kWarpRows, kChunkN) != 0) return -1;
+    if (make_tmap_2d(&tc, is_bf16, C, M, N, ldc, kBM, kChunkN) != 0) return -1;
     if (stats_out != nullptr) {
-        if (make_tmap_2d(&tr, is_bf16, residual, M, N, ldr, kWarpRows, kChunkN) != 0) return -1;
+        if (make_tmap_2d(&tr, is_bf16, residual, M, N, ldr, kBM, kChunkN) != 0) return -1;
         epilogue = kEpiResidualStats;
     } else if (epilogue == 3 && residual == C && ldr == ldc && !no_reduce_store()) {
         epilogue = kEpiResidualInPlace;
         tr = tc;
     } else if (epilogue == 3) {
-        if (make_tmap_2d(&tr, is_bf16, residual, M, N, ldr, kWarpRows, kChunkN) != 0) return -1;
+        if (make_tmap_2d(&tr, is_bf16, residual, M, N, ldr, kBM, kChunkN) != 0) return -1;
     } else {
         tr = tc;
     }
