@@ -1,15 +1,22 @@
 #!/usr/bin/env python
-"""Benchmark of the CLIP zero-shot hot path (BASELINE.json configs[1]): ViT-B-32 bf16, synthetic 224x224 images,
-345 DomainNet-shaped class prompts, 1024 images per GPU per step.
+"""Benchmark of the CLIP hot path.  Default = BASELINE.json configs[1]: ViT-B-32 bf16 zero-shot evaluation, synthetic 224x224
+images, 345 DomainNet-shaped class prompts, 1024 images per GPU per step.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA path through the drop-in API / C ABI)
-    python bench.py --impl reference --steps K --warmup W    # reference arm: the CPU oracle port on the host cores
+    python bench.py --impl reference --steps K --warmup W    # reference arm: the reference's own code on the host cores
+    python bench.py --config 3|4|5 ...                       # the other BASELINE configs (driver-runnable, same JSON contract)
 
 A step = one pass of the hot path over one batch: image tower -> L2-normalise -> image x class-prompt logits -> top-5.
 The class-prompt features are built once before the timed region (they are per checkpoint, not per batch).
-N > 1 (torchrun, one process per GPU, NCCL): every rank processes its own 1024-image batches (weak scaling, no
-data-path collective); the only collective is the final all-reduce of [top-1 hits, top-5 hits, n].
+N > 1 (torchrun, one process per GPU, NCCL): `value` is WEAK scaling — every rank processes its own 1024-image batches, no
+data-path collective, the only collective is the final all-reduce of [top-1 hits, top-5 hits, n].  The same line carries
+`strong`: BASELINE config 2 as written, ONE 1024-image batch sharded 1024/N per GPU.
 Prints ONE JSON line on rank 0.
+
+Reference arm / baselines: `baseline/_ref` holds the UNMODIFIED vendored OpenCLIP of the reference (baseline/install_ref.sh);
+when it is present `--impl reference` and `cpu_baseline` time THAT code on the host cores (kind "reference") and
+`gpu_eager_baseline` times it on the B200 itself through its stock eager path; otherwise the CPU oracle port is timed
+(kind "port").
 """
 from __future__ import annotations
 
@@ -20,6 +27,7 @@ import statistics
 import sys
 import threading
 import time
+import types
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
@@ -28,14 +36,15 @@ sys.path.insert(0, str(ROOT))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-MODEL = "ViT-B-32"
 BATCH = 1024
 CLASSES, TEMPLATES = 345, 86
 TOPK = 5
 METRIC = "zero_shot_images_per_sec"
 UNIT = "images/s"
-# algorithmic FLOPs per image of the ViT-B/32 tower (= docs/model_profile.csv:8) + logits
-FLOPS_PER_IMAGE = 8.818e9 + 2 * 512 * CLASSES
+# algorithmic FLOPs per image (= docs/model_profile.csv:8,26,49) and tokens per image
+MODELS = {"ViT-B-32": {"flops": 8.818e9, "tokens": 50, "dim": 512, "width": 768}, "ViT-B-16": {"flops": 35.127e9, "tokens": 197, "dim": 512, "width": 768},
+          "ViT-L-14": {"flops": 162.026e9, "tokens": 257, "dim": 768, "width": 1024}}
+TEXT_FLOPS = {"ViT-B-32": 5.960e9, "ViT-B-16": 5.960e9, "ViT-L-14": 13.300e9}
 
 
 def measured_peaks():
@@ -116,86 +125,124 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port on the host cores (cpu_baseline of our line; the whole `--impl reference` line)
+# The reference's own code (baseline/_ref = the vendored OpenCLIP 2.24.0, unmodified) and the CPU oracle port
 # ------------------------------------------------------------------------------------------------------------------
-def cpu_hot_path(sd, image, prompt_feat):
-    from oracle import clip_oracle as O
-    feat = O.vit_forward(sd, image)
-    logits = O.zero_shot_logits(feat, prompt_feat)
-    return O.topk(logits, TOPK)
+def load_reference_open_clip():
+    """-> the reference's `open_clip` module from baseline/_ref, or None when it was not installed (baseline/install_ref.sh).
+    `ftfy` (hard import of open_clip/tokenizer.py:14, not in the image) is stubbed with the identity, as in oracle/ref_loader.py."""
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "open_clip" / "model.py").exists():
+        return None
+    if "ftfy" not in sys.modules:
+        try:
+            import ftfy  # noqa: F401
+        except ImportError:
+            stub = types.ModuleType("ftfy")
+            stub.fix_text = lambda s: s
+            sys.modules["ftfy"] = stub
+    if str(ref) not in sys.path:
+        sys.path.insert(0, str(ref))
+    import importlib
+    mod = importlib.import_module("open_clip")
+    if Path(mod.__file__).resolve().parent.parent != ref.resolve():
+        return None          # something else named open_clip is first on the path: do not pass it off as the reference
+    return mod
 
 
-def cpu_setup(sample_images: int):
-    from understanding_clip_ood_b200 import open_clip
+def reference_zero_shot_step(model, image, prompt_feat):
+    """The reference's hot path on whatever device `model` lives on: encode_image (open_clip/model.py:265-267) and the three
+    similarity lines of xclip/zero_shot.py (:42-52 normalise, :54-60 tensordot, training/zero_shot.py:11-14 top-k)."""
+    with torch.no_grad():
+        feat = torch.nn.functional.normalize(model.encode_image(image), dim=-1)
+        logits = torch.tensordot(feat, prompt_feat.movedim(-1, 0), dims=1)
+        return logits.topk(TOPK, 1, True, True)[1]
+
+
+def cpu_setup(model_name: str, sample_images: int):
+    """-> (step(image) callable, image, kind, description).  Reference code when baseline/_ref exists, else the oracle port."""
     torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(0)
-    model = open_clip.create_model(MODEL, precision="fp32", device="cpu")     # parameter container only; never called on CPU
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     image = torch.randn(sample_images, 3, 224, 224, generator=torch.Generator().manual_seed(1))
-    prompt = torch.nn.functional.normalize(torch.randn(CLASSES, 512, generator=torch.Generator().manual_seed(2)), dim=-1)
-    return sd, image, prompt
+    dim = MODELS[model_name]["dim"]
+    prompt = torch.nn.functional.normalize(torch.randn(CLASSES, dim, generator=torch.Generator().manual_seed(2)), dim=-1)
+    ref = load_reference_open_clip()
+    if ref is not None:
+        torch.manual_seed(0)
+        model = ref.create_model(model_name, precision="fp32", device="cpu").eval()
+        return (lambda img: reference_zero_shot_step(model, img, prompt)), image, "reference", \
+            "unmodified vendored OpenCLIP 2.24.0 of the reference (baseline/_ref) in fp32 on the host cores: encode_image + normalize + tensordot + top-5"
+    from oracle import clip_oracle as O
+    from understanding_clip_ood_b200 import open_clip
+    torch.manual_seed(0)
+    model = open_clip.create_model(model_name, precision="fp32", device="cpu")     # parameter container only; never called on CPU
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    def step(img):
+        return O.topk(O.zero_shot_logits(O.vit_forward(sd, img), prompt), TOPK)
+
+    return step, image, "port", "fp32 oracle port of the same hot path (baseline/_ref not installed)"
 
 
-def run_cpu_baseline(target_s: float = 12.0, chunk: int = 32, max_images: int = 4096) -> dict:
-    """Oracle port on the host cores over a bounded sample of the workload: one calibration chunk, then as many chunks of
-    the same 1024-image batch shape as fit in about `target_s` seconds."""
-    sd, image, prompt = cpu_setup(chunk)
-    cpu_hot_path(sd, image[:2], prompt)                                            # warm-up (thread pool, allocator)
+def run_cpu_baseline(model_name: str, target_s: float = 12.0, chunk: int = 32, max_images: int = 4096) -> dict:
+    """The CPU arm on the host cores over a bounded sample of the workload: one calibration chunk, then as many chunks of
+    the same batch shape as fit in about `target_s` seconds."""
+    step, image, kind, what = cpu_setup(model_name, chunk)
+    step(image[:2])                                                                # warm-up (thread pool, allocator)
     t0 = time.perf_counter()
-    cpu_hot_path(sd, image, prompt)
+    step(image)
     cal = time.perf_counter() - t0
     reps = max(1, min(int(target_s / max(cal, 1e-3)), max_images // chunk))
     t0 = time.perf_counter()
     for _ in range(reps):
-        cpu_hot_path(sd, image, prompt)
+        step(image)
     dt = time.perf_counter() - t0
-    return {"value": chunk * reps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{reps} x {chunk} images, fp32 oracle port of the same hot path (ViT-B-32 tower + logits + top-5), "
-                      f"{dt:.1f} s of CPU work on {torch.get_num_threads()} threads"}
+    return {"value": chunk * reps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{reps} x {chunk} images, {what}, {dt:.1f} s of CPU work on {torch.get_num_threads()} threads"}
 
 
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = int(os.environ.get("B200CLIP_REF_SAMPLE", "64"))      # images per step (a bounded sample of the 1024-image batch)
-    sd, image, prompt = cpu_setup(sample)
+    model_name = CONFIG_MODEL[args.config]
+    sample = int(os.environ.get("B200CLIP_REF_SAMPLE", "64" if model_name == "ViT-B-32" else "16"))   # images per step
+    step, image, kind, what = cpu_setup(model_name, sample)
     for _ in range(max(args.warmup, 1)):
-        cpu_hot_path(sd, image[:4], prompt)
+        step(image[:4])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_hot_path(sd, image, prompt)
+        step(image)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus, extra={"cpu_sample_images_per_step": sample}),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps x {sample} images (bounded sample of the 1024-image batch), fp32 oracle "
-                                       "port of the reference algorithm; /root/reference is pure Python + PyTorch and does not exist on "
-                                       "the GPU box"},
+            "config": workload_config(model_name, BATCH_PER_GPU[args.config], args.gpus, extra={"cpu_sample_images_per_step": sample}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{args.steps} steps x {sample} images (bounded sample of the batch), {what}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def workload_config(n_gpus: int, extra: dict | None = None) -> dict:
-    cfg = {"workload": f"{MODEL} zero-shot DomainNet-shaped eval: synthetic 224x224, {CLASSES} class prompts x {TEMPLATES} templates, "
-                       f"batch {BATCH} per GPU, image tower -> normalize -> logits -> top-{TOPK}",
-           "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "classes": CLASSES, "topk": TOPK, "precision": "bf16",
+CONFIG_MODEL = {2: "ViT-B-32", 3: "ViT-B-16", 4: "ViT-B-32", 5: "ViT-L-14"}
+BATCH_PER_GPU = {2: BATCH, 3: 1024, 4: 128, 5: 256}
+
+
+def workload_config(model_name: str, batch: int, n_gpus: int, extra: dict | None = None) -> dict:
+    act_mb = batch * MODELS[model_name]["tokens"] * MODELS[model_name]["width"] * 2 * 9 / 1e6    # x, h, qkv (3), mlp (4) in bf16
+    cfg = {"workload": f"{model_name} zero-shot DomainNet-shaped eval: synthetic 224x224, {CLASSES} class prompts x {TEMPLATES} templates, "
+                       f"batch {batch} per GPU, image tower -> normalize -> logits -> top-{TOPK}",
+           "batch_per_gpu": batch, "global_batch": batch * n_gpus, "classes": CLASSES, "topk": TOPK, "precision": "bf16",
            "parallelism": f"dp{n_gpus} (independent shards, final accuracy all-reduce only)",
-           "l2_policy": "inputs_larger_than_l2 (308 MB image batch + >300 MB activations per step vs 126 MB L2)",
+           "l2_policy": f"inputs_larger_than_l2 ({batch * 3 * 224 * 224 * 2 / 1e6:.0f} MB image batch + ~{act_mb:.0f} MB activations per layer vs 126 MB L2)",
            "weights": "random init, torch.manual_seed(0)"}
     if extra:
         cfg.update(extra)
     return cfg
 
 
-def bind_to_gpu_numa_node(local_rank: int):
-    """Multi-rank runs: keep this process (and with it the pinned host batches it allocates, first-touch) on the NUMA node
-    the GPU's PCIe root hangs off, so that the per-step H2D copy of every rank does not cross the socket interconnect.
-    Best effort: returns the node or None and never raises."""
+def gpu_numa_node(local_rank: int):
+    """-> (numa node of the GPU's PCIe root or None, reason string)."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -208,9 +255,25 @@ def bind_to_gpu_numa_node(local_rank: int):
         bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
         bus = bus.decode() if isinstance(bus, bytes) else bus
         dom, rest = bus.split(":", 1)
-        node = int((Path("/sys/bus/pci/devices") / f"{dom[-4:]}:{rest}".lower() / "numa_node").read_text())
+        path = Path("/sys/bus/pci/devices") / f"{dom[-4:]}:{rest}".lower() / "numa_node"
+        if not path.exists():
+            return None, f"{path} does not exist (no sysfs PCI view in this container)"
+        node = int(path.read_text())
         if node < 0:
-            return None
+            return None, "the GPU's PCI device reports numa_node = -1 (single NUMA domain / virtualised topology)"
+        return node, "ok"
+    except Exception as e:  # noqa: BLE001
+        return None, f"{type(e).__name__}: {e}"
+
+
+def bind_to_gpu_numa_node(local_rank: int):
+    """Multi-rank runs: keep this process (and with it the pinned host batches it allocates, first-touch) on the NUMA node
+    the GPU's PCIe root hangs off, so that the per-step H2D copy of every rank does not cross the socket interconnect.
+    Best effort: returns (node or None, reason) and never raises."""
+    node, why = gpu_numa_node(local_rank)
+    if node is None:
+        return None, why
+    try:
         cpus = set()
         for part in (Path("/sys/devices/system/node") / f"node{node}" / "cpulist").read_text().strip().split(","):
             lo, _, hi = part.partition("-")
@@ -218,20 +281,20 @@ def bind_to_gpu_numa_node(local_rank: int):
         allowed = os.sched_getaffinity(0) & cpus
         if len(allowed) >= 2:
             os.sched_setaffinity(0, allowed)
-            return node
-    except Exception:  # noqa: BLE001
-        pass
-    return None
+            return node, f"bound to {len(allowed)} cpus of node {node}"
+        return None, f"node {node} has fewer than 2 cpus in this process's affinity mask"
+    except Exception as e:  # noqa: BLE001
+        return None, f"{type(e).__name__}: {e}"
 
 
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
-def time_gemm_roofline(ops, L, peaks) -> dict:
+def time_gemm_roofline(ops, L, peaks, M: int, K: int = 768) -> dict:
     """Dominant kernel timed alone with CUDA events on the launching stream: the c_fc GEMM of one layer at the benchmark's
-    token count (M = 1024*50) exactly as the tower runs it — LayerNorm folded into the epilogue (+bias +GELU), fed by the
-    un-normalised residual stream.  Operands (78 MB in, 314 MB out) exceed the L2."""
-    M, N, K = BATCH * 50, 3072, 768
+    token count exactly as the tower runs it — LayerNorm folded into the epilogue (+bias +GELU), fed by the un-normalised
+    residual stream.  Operands exceed the L2."""
+    N = 4 * K
     g = torch.Generator(device="cuda").manual_seed(7)
     x = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
     w = (torch.randn(N, K, device="cuda", generator=g) * 0.04).bfloat16()
@@ -252,14 +315,123 @@ def time_gemm_roofline(ops, L, peaks) -> dict:
     ms = e0.elapsed_time(e1) / iters
     flops = 2.0 * M * N * K
     achieved = flops / (ms * 1e-3) / 1e12
-    traffic = None
+    traffic, traffic_source = None, None
     tp = ROOT / "profiles" / "roofline_traffic.json"
-    if tp.exists():
-        traffic = json.loads(tp.read_text()).get("gemm_pair_cfc_bytes_per_launch")
+    if tp.exists() and M == 51200 and K == 768:
+        tj = json.loads(tp.read_text())
+        traffic = tj.get("gemm_pair_cfc_bytes_per_launch")
+        traffic_source = tj.get("source", "ncu --set full capture of this kernel at this shape (profiles/), dram__bytes_read.sum + dram__bytes_write.sum per launch; "
+                                          "not re-measured inside this run (ncu cannot run inside the timed process)")
     return {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
-            "kernel": f"gemm_pair_kernel<bf16, 256, LN-fold+GELU> M={M} N={N} K={K} (ln_2 + mlp.c_fc + GELU of one layer at batch {BATCH})",
+            "frac": achieved / peaks["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_source,
+            "algorithmic_bytes": float(M * K * 2 + N * K * 2 + M * N * 2),
+            "kernel": f"gemm_pair_kernel<bf16, 256, LN-fold+GELU> M={M} N={N} K={K} (ln_2 + mlp.c_fc + GELU of one layer)",
             "ms_per_launch": ms, "flops_per_launch": flops, "peak_source": f"{peaks['source']} burst bf16 GEMM (MEASURED_PEAKS.json)"}
+
+
+def cliploss_block(open_clip, ops, dist, dev, rank: int, world: int) -> dict:
+    """ClipLoss step (BASELINE config 4 shape: 256 local rows per rank = batch 128 x accum 2) and, at N > 1, a parity check of
+    the peer-memory path against the NCCL form and the float64 closed form of the oracle (driver-side proof for SCALE)."""
+    n_loc = 256
+    gl = torch.Generator(device=dev).manual_seed(100 + rank)
+    fi = ops.normalize(torch.randn(n_loc, 512, device=dev, generator=gl)).requires_grad_(True)
+    ft = ops.normalize(torch.randn(n_loc, 512, device=dev, generator=gl)).requires_grad_(True)
+    ls = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
+    loss_fn = open_clip.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+
+    def loss_step():
+        fi.grad = ft.grad = ls.grad = None
+        loss = loss_fn(fi, ft, ls)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(5):
+        loss_step()
+    barrier()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0.record()
+    loss_iters = 50
+    for _ in range(loss_iters):
+        loss_step()
+    l1.record()
+    barrier()
+    t = torch.tensor([l0.elapsed_time(l1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t) / loss_iters
+    flops = 12.0 * n_loc * (n_loc * world) * 512
+    out = {"steps_per_s": 1e3 / ms, "us_per_step": ms * 1e3, "local_rows": n_loc, "gathered_rows": n_loc * world, "dim": 512,
+           "algorithmic_gflop_per_step": flops / 1e9, "achieved_tflops": flops / (ms * 1e-3) / 1e12,
+           "bound": "launch / exchange latency (3.2 GFLOP at N = 2048: microseconds of tensor work)",
+           "what": "ClipLoss(local_loss, gather_with_grad) fwd+bwd incl. feature all-gather / reduce-scatter, fp32"}
+    if dist is None:
+        return out
+    # ---- parity at N > 1: one step of the path that was just timed vs (a) the NCCL form of the same node, (b) the oracle ----
+    from understanding_clip_ood_b200.open_clip import loss as loss_mod
+    loss = loss_step()
+    path = type(loss.grad_fn).__name__
+    g_i, g_t, g_s = fi.grad.clone(), ft.grad.clone(), ls.grad.clone()
+    fi2, ft2, ls2 = [x.detach().clone().requires_grad_(True) for x in (fi, ft, ls)]
+    loss2 = loss_mod._DistLocalClipLoss.apply(fi2, ft2, ls2, rank, world, None)
+    loss2.backward()
+    nccl_loss_rel = abs(float(loss2) - float(loss)) / abs(float(loss2))
+    nccl_grad_rel = float((g_i - fi2.grad).norm() / fi2.grad.norm())
+    both = torch.cat([fi.detach(), ft.detach()], dim=1).contiguous()
+    gathered = torch.empty((world * n_loc, 1024), device=dev)
+    dist.all_gather_into_tensor(gathered, both)
+    stats = torch.zeros(3, device=dev, dtype=torch.float64)
+    if rank == 0:
+        from oracle import clip_oracle as O      # the checker (float64 closed form), rank 0 only
+        ai, at = gathered[:, :512].cpu(), gathered[:, 512:].cpu()
+        want_loss = float(O.clip_loss_local(ai[:n_loc], at[:n_loc], ai, at, float(ls), 0))
+        d_img = torch.zeros(n_loc, 512, dtype=torch.float64)
+        for q in range(world):
+            sl = slice(q * n_loc, (q + 1) * n_loc)
+            gi, _, gai, _, _ = O.clip_loss_local_grads(ai[sl], at[sl], ai, at, float(ls), q)
+            d_img += gai[:n_loc]
+            if q == 0:
+                d_img += gi
+        stats[0] = abs(float(loss) - want_loss) / abs(want_loss)
+        stats[1] = float((g_i.double().cpu() - d_img).norm() / d_img.norm())
+    stats[2] = max(nccl_loss_rel, nccl_grad_rel)
+    dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    out["parity"] = {"path": path, "loss_rel_vs_oracle_f64_rank0": float(stats[0]), "grad_rel_vs_oracle_f64_rank0": float(stats[1]),
+                     "max_rel_vs_nccl_form_all_ranks": float(stats[2]), "gates": {"loss_rel": 1e-3, "grad_rel": 1e-4},
+                     "ok": bool(stats[0] < 1e-3 and stats[1] < 1e-4 and stats[2] < 1e-4)}
+    return out
+
+
+def gpu_eager_baseline(model_name: str, batch: int, dev, steps: int) -> dict | None:
+    """The reference's own eager path on this GPU (SURVEY §8d "the real bar"): the unmodified vendored OpenCLIP from
+    baseline/_ref, precision='bf16', stock torch ops (cuBLAS F.linear, nn.MultiheadAttention / SDPA, F.layer_norm, nn.GELU)."""
+    ref = load_reference_open_clip()
+    if ref is None:
+        return None
+    torch.manual_seed(0)
+    model = ref.create_model(model_name, precision="bf16", device="cpu").to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(1)
+    image = torch.randn(batch, 3, 224, 224, device=dev, generator=g).bfloat16()
+    prompt = torch.nn.functional.normalize(torch.randn(CLASSES, MODELS[model_name]["dim"], device=dev, generator=g), dim=-1).bfloat16()
+    for _ in range(3):
+        reference_zero_shot_step(model, image, prompt)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        reference_zero_shot_step(model, image, prompt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model
+    torch.cuda.empty_cache()
+    return {"value": batch / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "steps": steps, "batch": batch,
+            "what": "unmodified vendored OpenCLIP 2.24.0 of the reference (baseline/_ref), precision='bf16', eager PyTorch on the same B200: "
+                    "encode_image + normalize + tensordot + top-5, device-resident inputs, CUDA events"}
 
 
 def run_ours(args) -> None:
@@ -275,7 +447,7 @@ def run_ours(args) -> None:
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    numa_node, numa_why = bind_to_gpu_numa_node(local_rank) if world > 1 else gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -284,10 +456,13 @@ def run_ours(args) -> None:
         dist.init_process_group("nccl", device_id=dev)
     L.load()
     peaks = measured_peaks()
+    model_name = CONFIG_MODEL[args.config]
+    batch = BATCH_PER_GPU[args.config]
+    flops_per_image = MODELS[model_name]["flops"] + 2 * MODELS[model_name]["dim"] * CLASSES
 
     # ---- model + class-prompt features (outside the timed region) -------------------------------------------------
     torch.manual_seed(0)
-    model = open_clip.create_model(MODEL, precision="bf16", device="cpu").to(dev).eval()
+    model = open_clip.create_model(model_name, precision="bf16", device="cpu").to(dev).eval()
     model.truncate_text_at_eot = True
     clip = OpenCLIP(model)
     tokens = domainnet_tokens()
@@ -302,12 +477,12 @@ def run_ours(args) -> None:
 
     # ---- synthetic inputs -----------------------------------------------------------------------------------------
     g = torch.Generator(device=dev).manual_seed(1 + rank)
-    image = torch.randn(BATCH, 3, 224, 224, device=dev, generator=g).bfloat16()
-    labels = torch.randint(0, CLASSES, (BATCH,), device=dev, generator=g)
+    image = torch.randn(batch, 3, 224, 224, device=dev, generator=g).bfloat16()
+    labels = torch.randint(0, CLASSES, (batch,), device=dev, generator=g)
     hits = torch.zeros(3, dtype=torch.int64, device=dev)
 
-    def step_device():
-        feat = model.encode_image(image, normalize=True)
+    def step_device(img):
+        feat = model.encode_image(img, normalize=True)
         _, idx, _ = ops.zeroshot(feat, prompt, TOPK, normalize_img=False, want_logits=False)
         return idx
 
@@ -316,51 +491,82 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def count_hits(idx, lab):
+        hits[0] += (idx[:, 0] == lab).sum()
+        hits[1] += (idx == lab[:, None]).any(dim=1).sum()
+        hits[2] += idx.shape[0]
+
+    def timed_steps(img, lab, steps, final_reduce=True):
+        """K steps bracketed by barrier + synchronize on both sides, CUDA events, max over ranks -> total ms."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            count_hits(step_device(img), lab)
+        if dist is not None and final_reduce:
+            dist.all_reduce(hits)                                   # the only collective: final accuracy reduction
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
     sampler = ClockSampler(local_rank, period_s=float(os.environ.get("B200CLIP_CLOCK_PERIOD_S", "0.02")))
     if rank == 0:
         sampler.start()
-    def count_hits(idx):
-        hits[0] += (idx[:, 0] == labels).sum()
-        hits[1] += (idx == labels[:, None]).any(dim=1).sum()
-        hits[2] += BATCH
-
-    for _ in range(max(args.warmup, 3)):
-        count_hits(step_device())     # the accuracy bookkeeping is warmed too (its torch kernels load lazily on first use)
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        count_hits(step_device(image), labels)     # the accuracy bookkeeping is warmed too (its torch kernels load lazily on first use)
     hits.zero_()
-    barrier()
     launches0 = L.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
     sampler.begin()
     profile_region = os.environ.get("B200CLIP_PROFILE_REGION") == "1"   # `ncu --profile-from-start off` captures only the timed steps
     if profile_region:
         torch.cuda.profiler.start()
-    e0.record()
-    for _ in range(args.steps):
-        count_hits(step_device())
-    if dist is not None:
-        dist.all_reduce(hits)                                   # the only collective: final accuracy reduction
-    e1.record()
-    barrier()
+    ms_total = timed_steps(image, labels, args.steps)
     if profile_region:
         torch.cuda.profiler.stop()
     launches = L.launch_count() - launches0
-    ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t)
-    value = BATCH * world * args.steps / (ms_total * 1e-3)
+    accuracy = {"top1_hits": int(hits[0]), "top5_hits": int(hits[1]), "n": int(hits[2])}
+    value = batch * world * args.steps / (ms_total * 1e-3)
+
+    # ---- BASELINE config 2 as written (strong scaling): ONE `batch`-image batch sharded batch/N per GPU ------------------
+    strong = None
+    if args.config == 2:
+        shard = batch // world
+        s_img, s_lab = image[:shard], labels[:shard]
+        for _ in range(3):
+            count_hits(step_device(s_img), s_lab)
+        ms_strong = timed_steps(s_img, s_lab, args.steps)
+        strong_value = shard * world * args.steps / (ms_strong * 1e-3)
+        strong = {"scaling": "strong", "global_batch": shard * world, "batch_per_gpu": shard, "value": strong_value, "unit": UNIT,
+                  "ms_per_step": ms_strong / args.steps,
+                  "per_gpu_rate_vs_full_batch": (strong_value / world) / (value / world),
+                  "what": f"BASELINE config 2 as written: one {shard * world}-image batch per step sharded over {world} GPU(s); "
+                          "speed-up over one GPU = n_gpus x per_gpu_rate_vs_full_batch (the N = 1 line's value is the denominator)"}
+        if world == 1:
+            # projection for the N = 2 / 4 / 8 shard sizes on this GPU (the multi-GPU lines measure it for real)
+            proj = {}
+            for n in (2, 4, 8):
+                sh = batch // n
+                for _ in range(3):
+                    step_device(image[:sh])
+                ms_sh = timed_steps(image[:sh], labels[:sh], max(args.steps // 2, 5), final_reduce=False)
+                rate = sh * max(args.steps // 2, 5) / (ms_sh * 1e-3)
+                proj[str(n)] = {"batch_per_gpu": sh, "images_per_s_per_gpu": rate, "projected_speedup": n * rate / value}
+            strong["single_gpu_projection"] = proj
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region ---------
     copy_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-    half = BATCH // 2
+    half = batch // 2
 
     def e2e_measure(host_img):
         """predict() on pinned host batches: H2D (two halves on two copy streams, double-buffered) + D2H of the predictions
         inside the timed region.  -> images/s over all ranks (max wall time over ranks)."""
-        host_pred = torch.empty((BATCH,), dtype=torch.int64).pin_memory()
+        host_pred = torch.empty((batch,), dtype=torch.int64).pin_memory()
         dev_img = [torch.empty_like(host_img[0], device=dev), torch.empty_like(host_img[0], device=dev)]
         ready = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(2)]
         consumed = [torch.cuda.Event(), torch.cuda.Event()]
@@ -395,63 +601,56 @@ def run_ours(args) -> None:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return BATCH * world * args.steps / float(t)
+        return batch * world * args.steps / float(t)
 
-    # (a) the reference's input contract: images already preprocessed on the host and cast to the tower dtype (16 bit)
-    e2e_value = e2e_measure([torch.randn(BATCH, 3, 224, 224, generator=torch.Generator().manual_seed(11 + i)).bfloat16().pin_memory()
-                             for i in range(2)])
-    # (b) uint8 pixel batches: ToTensor + Normalize fused into the im2col kernel, half the H2D bytes
-    e2e_u8_value = e2e_measure([torch.randint(0, 256, (BATCH, 3, 224, 224), generator=torch.Generator().manual_seed(21 + i),
+    # (a) uint8 pixel batches (what a decode -> resize -> crop pipeline produces): ToTensor + Normalize fused into the im2col
+    #     kernel, 1 byte per pixel over the host link.  This is the headline `e2e`.
+    e2e_u8_value = e2e_measure([torch.randint(0, 256, (batch, 3, 224, 224), generator=torch.Generator().manual_seed(21 + i),
                                               dtype=torch.uint8).pin_memory() for i in range(2)])
+    # (b) the reference scripts' input contract: images preprocessed on the host and cast to the tower dtype (2 bytes per pixel)
+    e2e_bf16_value = e2e_measure([torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(11 + i)).bfloat16().pin_memory()
+                                  for i in range(2)])
 
-    # ---- ClipLoss step (BASELINE config 4 shape: 256 local rows per rank), reported next to the headline ---------
-    n_loc = 256
-    gl = torch.Generator(device=dev).manual_seed(100 + rank)
-    fi = ops.normalize(torch.randn(n_loc, 512, device=dev, generator=gl)).requires_grad_(True)
-    ft = ops.normalize(torch.randn(n_loc, 512, device=dev, generator=gl)).requires_grad_(True)
-    ls = torch.tensor(1 / 0.07, device=dev, requires_grad=True)
-    loss_fn = open_clip.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
-
-    def loss_step():
-        fi.grad = ft.grad = ls.grad = None
-        loss_fn(fi, ft, ls).backward()
-
-    for _ in range(5):
-        loss_step()
-    barrier()
-    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0.record()
-    loss_iters = 50
-    for _ in range(loss_iters):
-        loss_step()
-    l1.record()
-    barrier()
-    t = torch.tensor([l0.elapsed_time(l1)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    cliploss = {"steps_per_s": loss_iters / (float(t) * 1e-3), "local_rows": n_loc, "gathered_rows": n_loc * world, "dim": 512,
-                "what": "ClipLoss(local_loss, gather_with_grad) fwd+bwd incl. feature all-gather / reduce-scatter, fp32"}
+    cliploss = cliploss_block(open_clip, ops, dist, dev, rank, world) if args.config in (2, 4) else None
 
     if rank == 0:
-        roof = time_gemm_roofline(ops, L, peaks)
-        cpu = run_cpu_baseline() if world == 1 else {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
-                                                     "sample": "not run at N > 1 (reported by the N = 1 line and by --impl reference)"}
-        tower_tflops = FLOPS_PER_IMAGE * value / world / 1e12
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        roof = time_gemm_roofline(ops, L, peaks, batch * MODELS[model_name]["tokens"], 1024 if model_name == "ViT-L-14" else 768)
+        parity = None
+        cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "n/a", "sample": "not run at N > 1 (reported by the N = 1 line and by --impl reference)"}
+        eager = None
+        if world == 1:
+            from tests import parity_metrics
+            if args.config == 2 and parity_metrics.available():
+                parity = parity_metrics.prediction_parity_b1024(model, dev)
+                parity["fixture"] = "tests/golden/vitb32_seed0_b1024.pt: unmodified reference, fp32 and bf16, same seeded 1024 images (oracle/make_golden_b1024.py)"
+                parity["gates"] = {"embedding_rel_l2": 2e-2, "top1_vs_ref_fp32": ">= reference bf16's own agreement - 0.01",
+                                   "margin_aware_top1_top5": 0.999}
+                parity["ok"] = bool(parity["embedding_rel_l2_vs_ref_fp32"] < 2e-2 and
+                                    parity["top1_ours_vs_ref_fp32"] >= parity["top1_ref_bf16_vs_ref_fp32"] - 0.01 and
+                                    parity["top1_margin_aware_vs_ref_fp32"] >= 0.999 and parity["top5_margin_aware_vs_ref_fp32"] >= 0.999)
+            eager = gpu_eager_baseline(model_name, batch, dev, max(args.steps // 2, 5))
+            if eager is not None:
+                eager["ours_over_eager"] = value / eager["value"]
+            cpu = run_cpu_baseline(model_name)
+        tower_tflops = flops_per_image * value / world / 1e12
+        h2d_u8 = batch * 3 * 224 * 224
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 224 * 224 * 2, "d2h_bytes_per_step": BATCH * 8,
-                        "what": "ZeroShotClassifier.predict(images) from pinned host bf16 batches, H2D double-buffered on two copy streams, "
-                                "int64 predictions copied back to pinned host memory", "numa_node_rank0": numa_node},
-                "e2e_uint8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * 224 * 224, "d2h_bytes_per_step": BATCH * 8,
-                              "what": "same call with uint8 pixel batches (resized / cropped on the host): ToTensor + Normalize run "
-                                      "inside the im2col kernel (b200clip_vit_forward_u8)"},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "dtype": "bf16", "data": "synthetic", "config": workload_config(model_name, batch, world, {"baseline_config": args.config}),
+                "e2e": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": batch * 8,
+                        "what": "ZeroShotClassifier.predict(images) from pinned host uint8 pixel batches (resized / cropped on the host): "
+                                "H2D double-buffered on two copy streams, ToTensor + Normalize inside the im2col kernel "
+                                "(b200clip_vit_forward_stages, uint8 input), int64 predictions copied back to pinned host memory",
+                        "numa_node_rank0": numa_node, "numa_binding": numa_why},
+                "e2e_bf16_host": {"value": e2e_bf16_value, "unit": UNIT, "h2d_bytes_per_step": 2 * h2d_u8, "d2h_bytes_per_step": batch * 8,
+                                  "what": "same call with batches preprocessed on the host and cast to bf16 (the reference scripts' input contract)"},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": eager,
                 "per_gpu": {"images_per_s": value / world, "algorithmic_tflops": tower_tflops,
                             "frac_of_bf16_peak_burst": tower_tflops / peaks["bf16_tflops"],
                             "frac_of_bf16_peak_sustained": tower_tflops / peaks["bf16_tflops_sustained"] if peaks["bf16_tflops_sustained"] else None},
+                "strong": strong, "parity": parity,
                 "classifier_build_s": classifier_build_s, "classifier_prompts": int(tokens.shape[0]), "cliploss": cliploss,
-                "accuracy_reduction": {"top1_hits": int(hits[0]), "top5_hits": int(hits[1]), "n": int(hits[2])}}
+                "accuracy_reduction": accuracy}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -464,6 +663,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 2 ViT-B-32 zero-shot (default), 3 ViT-B-16 feature extraction, 4 ViT-B-32 contrastive "
+                         "training shapes (128 images per GPU), 5 ViT-L-14 zero-shot (256 per GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 
 from oracle import clip_oracle as O  # noqa: E402  (the checker)
 from oracle.make_golden import FakeTokenizer  # noqa: E402
+from tests.parity_metrics import prediction_parity_b1024  # noqa: E402
 from understanding_clip_ood_b200 import open_clip, ops  # noqa: E402
 from understanding_clip_ood_b200.xclip import zero_shot as zs  # noqa: E402
 from understanding_clip_ood_b200.xclip.open_clip import OpenCLIP  # noqa: E402
@@ -292,53 +293,6 @@ def test_vit_b_32_bf16_against_reference_bf16_and_fp32(vitb32_fp32):
     print(f"top-1 agreement: ours-bf16 vs ref-fp32 {ours_vs_fp32:.3f}; ref-bf16 vs ref-fp32 {ref16_vs_fp32:.3f}; "
           f"ours-bf16 vs ref-bf16 {ours_vs_ref16:.3f}")
     assert ours_vs_fp32 >= ref16_vs_fp32 - 0.1
-
-
-def prediction_parity_b1024(model_bf16, dev=DEV):
-    """ours-bf16 against the reference's fp32 AND bf16 runs on the same 1024 seeded images (tests/golden/vitb32_seed0_b1024.pt,
-    oracle/make_golden_b1024.py).  Returns the figures SURVEY §7 (hard part 1) asks for; also used by bench.py's `parity` block.
-
-    band = max |logit_ref-bf16 - logit_ref-fp32| over the batch: the reference's OWN bf16 noise on these inputs.  A prediction of
-    ours that differs from the fp32 reference is `explained` when the fp32 logits of the two candidates are closer than
-    2 * band (either rounding could have flipped them); margin-aware agreement = agree or explained."""
-    g = torch.load(GOLD / "vitb32_seed0_b1024.pt", weights_only=False)
-    base = torch.load(GOLD / "vitb32_seed0.pt", weights_only=False)
-    image = torch.randn(g["batch"], 3, 224, 224, generator=torch.Generator().manual_seed(g["seed_images"])).bfloat16().to(dev)
-    feat = model_bf16.encode_image(image, normalize=True)
-    logits, idx, _ = ops.zeroshot(feat, base["prompt_feat"].bfloat16().to(dev), 5, normalize_img=False)
-    logits, idx = logits.float().cpu(), idx.cpu()
-    l32, l16 = g["logits_fp32"], g["logits_bf16"].float()
-    p32, p16 = l32.argmax(1), l16.argmax(1)
-    t32, t16 = l32.topk(5, 1)[1], l16.topk(5, 1)[1]
-
-    def same_set(a, b):
-        return (a.sort(1)[0] == b.sort(1)[0]).all(1)
-
-    band = float((l16 - l32).abs().max())
-    ours1 = idx[:, 0]
-    rows = torch.arange(l32.shape[0])
-    gap1 = l32[rows, p32] - l32[rows, ours1]                        # fp32 margin between the reference's and our top-1
-    ok1 = (ours1 == p32) | (gap1 <= 2 * band)
-    # top-5 set: the classes we swap in / out must sit within the band of the fp32 rank-5 / rank-6 boundary
-    kth = l32.sort(1, descending=True)[0]
-    lo = torch.gather(l32, 1, idx).min(1)[0]                        # weakest fp32 logit among our five
-    ok5 = same_set(idx, t32) | (kth[:, 4] - lo <= 2 * band)
-    return {
-        "batch": int(l32.shape[0]),
-        "embedding_rel_l2_vs_ref_fp32": row_rel(feat, g["image_features_fp32"]),
-        "embedding_rel_l2_vs_ref_bf16": row_rel(feat, g["image_features_bf16"]),
-        "ref_bf16_vs_ref_fp32_embedding_rel_l2": row_rel(g["image_features_bf16"], g["image_features_fp32"]),
-        "top1_ours_vs_ref_bf16": float((ours1 == p16).float().mean()),
-        "top1_ours_vs_ref_fp32": float((ours1 == p32).float().mean()),
-        "top1_ref_bf16_vs_ref_fp32": float((p16 == p32).float().mean()),
-        "top5_ours_vs_ref_bf16": float(same_set(idx, t16).float().mean()),
-        "top5_ours_vs_ref_fp32": float(same_set(idx, t32).float().mean()),
-        "top5_ref_bf16_vs_ref_fp32": float(same_set(t16, t32).float().mean()),
-        "ref_bf16_logit_noise_band": band,
-        "ours_max_logit_err_vs_ref_fp32": float((logits - l32).abs().max()),
-        "top1_margin_aware_vs_ref_fp32": float(ok1.float().mean()),
-        "top5_margin_aware_vs_ref_fp32": float(ok5.float().mean()),
-    }
 
 
 def test_vit_b_32_bf16_prediction_parity_b1024(record_property):
