@@ -313,6 +313,73 @@ int b200clip_text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_t
                                  void* out, int batch, int seq_len, int normalize, void* workspace,
                                  int64_t workspace_bytes, int stages, void* stream);
 
+/* ----- training path: tower backward + fused optimizer -------------------------------------------------------
+ * What autograd does for the reference's training step (deps/open_clip/src/training/train.py:115-183) through
+ * CLIP.encode_image / encode_text with --grad-checkpointing (transformer.py:353-355): the training forward keeps only the
+ * residual stream at every block boundary (`saved`, b200clip_train_saved_bytes bytes), the backward recomputes each block
+ * and produces the gradient of every parameter.  Gradient buffers are OVERWRITTEN (the caller accumulates); layouts and
+ * dtypes mirror the weight structs: matrices / biases in `cfg.dtype`, LayerNorm parameters and embedding tables fp32. */
+typedef struct b200clip_block_grads {
+    float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    void *in_proj_w, *in_proj_b;   /* [3W,W], [3W] */
+    void *out_proj_w, *out_proj_b; /* [W,W],  [W]  */
+    void *fc_w, *fc_b;             /* [4W,W], [4W] */
+    void *proj_w, *proj_b;         /* [W,4W], [W]  */
+} b200clip_block_grads;
+
+typedef struct b200clip_vit_grads {
+    void* conv1_w;       /* [W, patch_kpad] (the padding columns are don't-care) */
+    float* class_emb;    /* [W] */
+    float* pos_emb;      /* [L, W] */
+    float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
+    void* proj;          /* [W, D]: gradient of visual.proj in ITS layout (not transposed) */
+    const b200clip_block_grads* blocks_host; /* HOST array of `layers` entries */
+} b200clip_vit_grads;
+
+typedef struct b200clip_text_grads {
+    float* tok_emb;      /* [vocab, W] (zeroed, then scatter-added) */
+    float* pos_emb;      /* [ctx, W] */
+    float *ln_final_g, *ln_final_b;
+    void* proj;          /* [W, D]: gradient of text_projection */
+    const b200clip_block_grads* blocks_host;
+} b200clip_text_grads;
+
+int64_t b200clip_train_saved_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len);
+int64_t b200clip_backward_workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len);
+/* forward of b200clip_vit_forward / b200clip_text_forward that also fills `saved` */
+int b200clip_vit_forward_train(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out,
+                               int batch, int normalize, void* saved, int64_t saved_bytes, void* workspace,
+                               int64_t workspace_bytes, void* stream);
+int b200clip_text_forward_train(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text,
+                                void* out, int batch, int seq_len, int normalize, void* saved, int64_t saved_bytes,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+/* d_out [batch, D] = gradient of the features the training forward returned (normalised when `normalize` != 0; same flag as
+ * in the forward).  `workspace`: b200clip_backward_workspace_bytes bytes, 256-byte aligned.  The weights must not have
+ * changed since the forward.  cfg.fold_ln is ignored (the recompute runs the LayerNorms as kernels). */
+int b200clip_vit_backward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, const void* d_out,
+                          int batch, int normalize, const void* saved, const b200clip_vit_grads* grads, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+int b200clip_text_backward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text,
+                           const void* d_out, int batch, int seq_len, int normalize, const void* saved,
+                           const b200clip_text_grads* grads, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Fused multi-tensor AdamW (torch.optim.AdamW semantics; training/main.py:299-326): `items` = DEVICE table of `n` tensors,
+ * `chunk_item` / `chunk_off` = DEVICE lists of `chunks` work items (tensor index, element offset; 4096 elements each,
+ * b200clip_adamw_chunk()).  grad is read as grad * grad_scale (loss-scaling / accumulation averaging); `step` >= 1. */
+typedef struct b200clip_adamw_tensor {
+    void* param;
+    const void* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t count;
+    int32_t param_dtype; /* B200CLIP_* */
+    int32_t grad_dtype;
+} b200clip_adamw_tensor;
+int b200clip_adamw_chunk(void);
+int b200clip_adamw_step(const b200clip_adamw_tensor* items, const int32_t* chunk_item, const int64_t* chunk_off, int chunks,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,7 +101,15 @@ def test_configs_and_errors():
     with pytest.raises(RuntimeError):
         open_clip.create_model("RN50")
     with pytest.raises(RuntimeError):
-        open_clip.create_model("ViT-B-32", precision="amp")
+        open_clip.create_model("ViT-B-32", precision="amp_fp8")
+    tiny_kw = dict(vision_cfg={"image_size": 64, "layers": 1, "width": 64, "patch_size": 32},
+                   text_cfg={"context_length": 77, "vocab_size": 64, "width": 64, "heads": 1, "layers": 1}, embed_dim=64)
+    for prec, want in (("amp", torch.float16), ("amp_bf16", torch.bfloat16), ("amp_bfloat16", torch.bfloat16)):
+        m = open_clip.create_model("ViT-B-32", precision=prec, **tiny_kw)      # fp32 master parameters, 16-bit kernels
+        assert all(p.dtype == torch.float32 for p in m.parameters())
+        assert m.visual._compute_dtype() == want and m._text_compute_dtype() == want
+    m = open_clip.create_model("ViT-B-32", precision="fp32", **tiny_kw)
+    assert m.visual._compute_dtype() == torch.float32
     with pytest.raises(RuntimeError):
         open_clip.create_model("ViT-B-32", pretrained="laion2b_s34b_b79k")
     m = open_clip.create_model("ViT-B-32-quickgelu", vision_cfg={"image_size": 64, "layers": 1, "width": 64, "patch_size": 32},
@@ -323,27 +331,18 @@ def test_built_library_is_blackwell_native_sass():
     assert per["p2p_reduce_finish_kernel"]["STG.E.STRONG.SYS"] > 0 and per["p2p_reduce_finish_kernel"]["LDG.E.STRONG.SYS"] > 0
 
 
-def test_training_mode_forward_warns_that_the_towers_are_forward_only():
-    """A training loop calling the towers with autograd on would silently train nothing: the first such call warns."""
-    import warnings as W
+def test_training_mode_takes_the_training_path_and_still_refuses_cpu_tensors():
+    """In training mode with autograd on the towers go through their autograd nodes (open_clip/train.py); CPU tensors still get
+    the loud no-fallback error, in training as in evaluation mode."""
     from understanding_clip_ood_b200 import _lib, open_clip
-    from understanding_clip_ood_b200.open_clip import model as M
     m = open_clip.create_model("ViT-B-32", vision_cfg={"image_size": 64, "layers": 1, "width": 64, "patch_size": 32},
                                text_cfg={"context_length": 77, "vocab_size": 64, "width": 64, "heads": 1, "layers": 1}, embed_dim=32)
-    m.train()
-    M._warned_no_backward = False
-    with W.catch_warnings(record=True) as rec:
-        W.simplefilter("always")
-        with pytest.raises(_lib.B200ClipError):          # CPU tensors: still the loud no-fallback error afterwards
-            m.encode_image(torch.zeros(1, 3, 64, 64))
-    assert any("forward-only" in str(w.message) for w in rec)
-    m.eval()
-    M._warned_no_backward = False
-    with W.catch_warnings(record=True) as rec:
-        W.simplefilter("always")
+    for mode in (m.train, m.eval):
+        mode()
         with pytest.raises(_lib.B200ClipError):
             m.encode_image(torch.zeros(1, 3, 64, 64))
-    assert not any("forward-only" in str(w.message) for w in rec)
+        with pytest.raises(_lib.B200ClipError):
+            m.encode_text(torch.zeros(1, 77, dtype=torch.long))
 
 
 def test_ctypes_signatures_match_header_prototypes():

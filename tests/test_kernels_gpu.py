@@ -427,7 +427,7 @@ def test_class_mean(dtype):
 
 
 # ------------------------------------------------------------------ ClipLoss -------------------------
-@pytest.mark.parametrize("n,world,rank,D", [(256, 1, 0, 512), (128, 4, 2, 512), (256, 8, 7, 512), (12, 2, 1, 64)])
+@pytest.mark.parametrize("n,world,rank,D", [(256, 1, 0, 512), (128, 4, 2, 512), (256, 8, 7, 512), (12, 2, 1, 64), (6, 1, 0, 64), (7, 3, 1, 30)])
 def test_cliploss_fwd_bwd(n, world, rank, D):
     g = _gen(12)
     N = n * world

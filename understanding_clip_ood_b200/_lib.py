@@ -50,6 +50,25 @@ class TextWeights(C.Structure):
         "tok_emb", "pos_emb", "ln_final_g", "ln_final_b", "proj_t", "blocks_host")]
 
 
+class BlockGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "fc_w", "fc_b", "proj_w", "proj_b")]
+
+
+class VitGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "conv1_w", "class_emb", "pos_emb", "ln_pre_g", "ln_pre_b", "ln_post_g", "ln_post_b", "proj", "blocks_host")]
+
+
+class TextGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("tok_emb", "pos_emb", "ln_final_g", "ln_final_b", "proj", "blocks_host")]
+
+
+class AdamWTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("count", C.c_int64),
+                ("param_dtype", C.c_int32), ("grad_dtype", C.c_int32)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); must list every symbol include/b200clip.h declares (tests check this)
@@ -93,6 +112,14 @@ SIGNATURES = {
     "b200clip_vit_forward_stages": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(VitWeights), _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                               _P, _I, _I, _P, _L, _I, _P]),
     "b200clip_text_forward_stages": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(TextWeights), _P, _P, _I, _I, _I, _P, _L, _I, _P]),
+    "b200clip_train_saved_bytes": (C.c_int64, [C.POINTER(TowerCfg), _I, _I]),
+    "b200clip_backward_workspace_bytes": (C.c_int64, [C.POINTER(TowerCfg), _I, _I]),
+    "b200clip_vit_forward_train": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(VitWeights), _P, _P, _I, _I, _P, _L, _P, _L, _P]),
+    "b200clip_text_forward_train": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(TextWeights), _P, _P, _I, _I, _I, _P, _L, _P, _L, _P]),
+    "b200clip_vit_backward": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(VitWeights), _P, _P, _I, _I, _P, C.POINTER(VitGrads), _P, _L, _P]),
+    "b200clip_text_backward": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(TextWeights), _P, _P, _I, _I, _I, _P, C.POINTER(TextGrads), _P, _L, _P]),
+    "b200clip_adamw_chunk": (C.c_int, []),
+    "b200clip_adamw_step": (C.c_int, [_P, _P, _P, _I, _F, _F, _F, _F, _F, _I, _F, _P]),
 }
 # not part of the public header: test hook that forces the GEMM N-tile
 _EXTRA = {

@@ -87,6 +87,16 @@ int vit_forward_u8(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w,
                    const float* std, void* out, int batch, int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s);
 int text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
                  int seq_len, int normalize, void* workspace, int64_t workspace_bytes_, cudaStream_t s);
+int64_t train_saved_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len);
+int64_t backward_workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len);
+int vit_forward_train(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out, int batch, int normalize,
+                      void* saved, int64_t saved_bytes, void* workspace, int64_t workspace_bytes_, cudaStream_t s);
+int text_forward_train(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch, int seq_len,
+                       int normalize, void* saved, int64_t saved_bytes, void* workspace, int64_t workspace_bytes_, cudaStream_t s);
+int vit_backward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, const void* d_out, int batch, int normalize,
+                 const void* saved, const b200clip_vit_grads* g, void* workspace, int64_t workspace_bytes_, cudaStream_t s);
+int text_backward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, const void* d_out, int batch, int seq_len,
+                  int normalize, const void* saved, const b200clip_text_grads* g, void* workspace, int64_t workspace_bytes_, cudaStream_t s);
 int vit_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, const uint8_t* image_u8,
                        const float* mean, const float* std, void* out, int batch, int normalize, void* workspace,
                        int64_t workspace_bytes_, int stages, cudaStream_t s);
@@ -324,6 +334,35 @@ int b200clip_text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_t
                                  int batch, int seq_len, int normalize, void* workspace, int64_t workspace_bytes, int stages,
                                  void* stream) {
     return text_forward_stages(cfg, w, text, out, batch, seq_len, normalize, workspace, workspace_bytes, stages, S(stream));
+}
+
+int64_t b200clip_train_saved_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) { return train_saved_bytes(cfg, batch, seq_len); }
+int64_t b200clip_backward_workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {
+    return backward_workspace_bytes(cfg, batch, seq_len);
+}
+int b200clip_vit_forward_train(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out, int batch,
+                               int normalize, void* saved, int64_t saved_bytes, void* workspace, int64_t workspace_bytes, void* stream) {
+    return vit_forward_train(cfg, w, image, out, batch, normalize, saved, saved_bytes, workspace, workspace_bytes, S(stream));
+}
+int b200clip_text_forward_train(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
+                                int seq_len, int normalize, void* saved, int64_t saved_bytes, void* workspace, int64_t workspace_bytes,
+                                void* stream) {
+    return text_forward_train(cfg, w, text, out, batch, seq_len, normalize, saved, saved_bytes, workspace, workspace_bytes, S(stream));
+}
+int b200clip_vit_backward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, const void* d_out, int batch,
+                          int normalize, const void* saved, const b200clip_vit_grads* grads, void* workspace, int64_t workspace_bytes,
+                          void* stream) {
+    return vit_backward(cfg, w, image, d_out, batch, normalize, saved, grads, workspace, workspace_bytes, S(stream));
+}
+int b200clip_text_backward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, const void* d_out, int batch,
+                           int seq_len, int normalize, const void* saved, const b200clip_text_grads* grads, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+    return text_backward(cfg, w, text, d_out, batch, seq_len, normalize, saved, grads, workspace, workspace_bytes, S(stream));
+}
+int b200clip_adamw_chunk(void) { return 4096; }
+int b200clip_adamw_step(const b200clip_adamw_tensor* items, const int32_t* chunk_item, const int64_t* chunk_off, int chunks, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+    return adamw_step(items, chunk_item, chunk_off, chunks, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));
 }
 
 int b200clip_patchify_u8(int dtype, const uint8_t* image, const float* mean, const float* std, void* patches, int batch, int image_size,

@@ -49,7 +49,17 @@ __device__ __forceinline__ float4 load_kc(const float* base, int64_t ld, int r0,
     const int r = tid >> 2;
     const int lk = (tid & 3) * 4;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r0 + r < rows && k0 + lk < K) a = *reinterpret_cast<const float4*>(base + static_cast<int64_t>(r0 + r) * ld + k0 + lk);
+    if (r0 + r < rows && k0 + lk < K) {
+        const float* src = base + static_cast<int64_t>(r0 + r) * ld + k0 + lk;
+        if (k0 + lk + 3 < K && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            a = *reinterpret_cast<const float4*>(src);
+        } else {   // ragged K or an unaligned row: element by element
+            a.x = src[0];
+            if (k0 + lk + 1 < K) a.y = src[1];
+            if (k0 + lk + 2 < K) a.z = src[2];
+            if (k0 + lk + 3 < K) a.w = src[3];
+        }
+    }
     return a;
 }
 __device__ __forceinline__ void store_kc(float (*S)[kT + 4], float4 a, int tid) {
@@ -62,7 +72,17 @@ __device__ __forceinline__ float4 load_mc(const float* base, int64_t ld, int r0,
     const int k = tid >> 4;
     const int r = (tid & 15) * 4;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k0 + k < K && r0 + r < rows) a = *reinterpret_cast<const float4*>(base + static_cast<int64_t>(k0 + k) * ld + r0 + r);
+    if (k0 + k < K && r0 + r < rows) {
+        const float* src = base + static_cast<int64_t>(k0 + k) * ld + r0 + r;
+        if (r0 + r + 3 < rows && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            a = *reinterpret_cast<const float4*>(src);
+        } else {   // ragged row count or an unaligned row: element by element
+            a.x = src[0];
+            if (r0 + r + 1 < rows) a.y = src[1];
+            if (r0 + r + 2 < rows) a.z = src[2];
+            if (r0 + r + 3 < rows) a.w = src[3];
+        }
+    }
     return a;
 }
 __device__ __forceinline__ void store_mc(float (*S)[kT + 4], float4 a, int tid) {
@@ -110,21 +130,28 @@ __device__ __forceinline__ void tile_gemm(const GemmProb& p, int m0, int n0, flo
     for (int i = 0; i < 4; ++i) {
         const int row = m0 + ty * 4 + i;
         const int col = n0 + tx * 4;
-        if (row < p.M && col < p.N) {  // N % 4 == 0 is checked on the host
-            float4* dst;
+        if (row < p.M && col < p.N) {
+            float* dstf;
             if (p.slots != nullptr) {
                 const int gr = p.slot_row0 + row;
                 const int sl = gr / p.slot_rows;
-                dst = reinterpret_cast<float4*>(p.slots[sl] + static_cast<int64_t>(gr - sl * p.slot_rows) * p.ldc + p.slot_col0 + col);
+                dstf = p.slots[sl] + static_cast<int64_t>(gr - sl * p.slot_rows) * p.ldc + p.slot_col0 + col;
             } else {
-                dst = reinterpret_cast<float4*>(p.C + static_cast<int64_t>(row) * p.ldc + col);
+                dstf = p.C + static_cast<int64_t>(row) * p.ldc + col;
             }
-            float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-            if (p.accumulate) {
-                const float4 c = *dst;
-                o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+            if (col + 3 < p.N && (reinterpret_cast<uintptr_t>(dstf) & 15) == 0) {
+                float4* dst = reinterpret_cast<float4*>(dstf);
+                float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                if (p.accumulate) {
+                    const float4 c = *dst;
+                    o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+                }
+                *dst = o;
+            } else {   // ragged N or an unaligned row
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (col + j < p.N) dstf[j] = p.accumulate ? dstf[j] + acc[i][j] : acc[i][j];
             }
-            *dst = o;
         }
     }
 }
@@ -174,6 +201,22 @@ GemmProb to_slots(GemmProb p, float* const* slots, int slot_rows, int row0, int 
     p.slots = slots; p.slot_rows = slot_rows; p.slot_row0 = row0; p.slot_col0 = col0;
     return p;
 }
+
+}  // namespace
+
+// General fp32 GEMM with optional operand transposes, the kernel of the loss step reused by the fp32 (parity-mode) tower
+// backward: C[M,N] (+)= op(A) op(B)^T-free form  C = A' B' with A' = ta ? A^T : A (A stored [K,M] when ta) and
+// B' = tb ? B : B^T (B stored [K,N] when tb, [N,K] otherwise).  Any shape (16-byte vector accesses where a row allows them).
+int gemm_f32_general(const float* A, int64_t lda, bool ta, const float* B, int64_t ldb, bool tb, float* C, int64_t ldc, int M, int N, int K,
+                     bool accumulate, cudaStream_t stream) {
+    B2C_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "gemm_f32_general: bad arguments");
+    GemmBatch b;
+    b.count = 1;
+    b.prob[0] = make_prob(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, accumulate);
+    return launch_batch(b, stream);
+}
+
+namespace {
 
 __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -277,8 +320,7 @@ ce_backward_kernel(float* __restrict__ x, const float* __restrict__ logit_scale,
 int check_shapes(int rank, int n, int N, int D) {
     B2C_CHECK_ARG(n > 0 && N >= n && D > 0 && N % n == 0, "cliploss: bad shape n=%d N=%d D=%d", n, N, D);
     B2C_CHECK_ARG(rank >= 0 && (rank + 1) * n <= N, "cliploss: rank %d out of range for n=%d N=%d", rank, n, N);
-    B2C_CHECK_ARG(n % 4 == 0 && D % 4 == 0, "cliploss: n and D must be multiples of 4");
-    return 0;
+    return 0;   // any n, D: the GEMM tiles fall back to scalar accesses on ragged / unaligned rows
 }
 
 // Operand views with explicit row pitches: the contiguous API passes pitch D everywhere, the packed (img | txt) API of the

@@ -95,6 +95,30 @@ int p2p_allgather(int dtype, const void* img, const void* txt, int n, int D, flo
 int p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag, const uint32_t* my_flags, int world,
                       int slots, uint32_t epoch, uint32_t* my_busy, cudaStream_t stream);
 
+// ---- training path (backward.cu, towers_bwd.cu, optim.cu) ----
+int gemm_f32_general(const float* A, int64_t lda, bool ta, const float* B, int64_t ldb, bool tb, float* C, int64_t ldc, int M, int N, int K,
+                     bool accumulate, cudaStream_t stream);
+int transpose16(int dtype, const void* in, int64_t ldi, void* out, int64_t ldo, int R, int C, int Rpad, cudaStream_t stream);
+int64_t col_sum_scratch_floats(int rows, int cols);
+int col_sum(int dtype, const void* g, int64_t ld, int rows, int cols, void* out, int out_f32, int accumulate, float* scratch, cudaStream_t stream);
+int64_t ln_backward_scratch_floats(int rows, int width);
+int ln_backward(int dtype, const void* g, int64_t ldg, const void* x, int64_t ldx, const float* gamma, const void* dres, int64_t ldr, void* dx,
+                int64_t ldd, float* d_gamma, float* d_beta, int rows, int width, float eps, int row_stride, const int32_t* row_idx, int accumulate,
+                float* scratch, cudaStream_t stream);
+int act_backward(int dtype, const void* da, const void* z, void* dz, int64_t n, int quick, cudaStream_t stream);
+int act_forward(int dtype, const void* z, void* a, int64_t n, int quick, cudaStream_t stream);
+int attention_backward(int dtype, const void* qkv, const void* d_out, void* d_qkv, int batch, int seq_len, int heads, int causal, cudaStream_t stream);
+int normalize_backward(int dtype, const void* x, const void* g, void* dx, int rows, int dim, float eps, cudaStream_t stream);
+int period_sum(int dtype, const void* dx, int64_t ld, int groups, int L, int width, float* out, int64_t ldo, int accumulate, cudaStream_t stream);
+int token_scatter(int dtype, const void* dx, int64_t ld, const int64_t* text, int ctx, int T_, int L, int width, int vocab, float* d_tok, cudaStream_t stream);
+int convert(int dtype_in, const void* in, int dtype_out, void* out, int64_t n, cudaStream_t stream);
+
 inline int dtype_size(int dtype) { return dtype == 0 ? 4 : 2; }
+
+}  // namespace b200clip
+struct b200clip_adamw_tensor;
+namespace b200clip {
+int adamw_step(const b200clip_adamw_tensor* items, const int32_t* chunk_item, const int64_t* chunk_off, int chunks, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream);
 
 }  // namespace b200clip

@@ -79,8 +79,21 @@ int check_cfg(const b200clip_tower_cfg* c) {
     return 0;
 }
 
+// Training forward: the input of every block (slot 1 + l) and the final residual stream (slot layers + 1) are copied into
+// `saved` (slot 0 = the vision tower's token matrix before ln_pre); the backward recomputes everything else per block, the
+// way --grad-checkpointing does in the reference (transformer.py:353-355).
+inline int64_t saved_slot_bytes(const b200clip_tower_cfg& c, int batch, int L) {
+    return align_up(static_cast<int64_t>(batch) * L * c.width * dtype_size(c.dtype), 256);
+}
+inline int save_slot(void* saved, int slot, const void* x, const b200clip_tower_cfg& c, int batch, int L, cudaStream_t s) {
+    if (saved == nullptr) return 0;
+    const int64_t bytes = static_cast<int64_t>(batch) * L * c.width * dtype_size(c.dtype);
+    B2C_CUDA(cudaMemcpyAsync(static_cast<char*>(saved) + slot * saved_slot_bytes(c, batch, L), x, bytes, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
 int run_blocks(const b200clip_tower_cfg& c, const b200clip_block_weights* blocks, const Workspace& ws, int batch, int L,
-               int causal, cudaStream_t s) {
+               int causal, cudaStream_t s, void* saved = nullptr) {
     const int dt = c.dtype;
     const int M = batch * L;
     const int W = c.width;
@@ -101,6 +114,7 @@ int run_blocks(const b200clip_tower_cfg& c, const b200clip_block_weights* blocks
     B2C_CHECK_ARG(slots <= W / 64 + 2, "tower: statistics slot count %d exceeds the workspace carve-up", slots);
     for (int l = 0; l < c.layers; ++l) {
         const b200clip_block_weights& bw = blocks[l];
+        if ((rc = save_slot(saved, 1 + l, ws.x, c, batch, L, s)) != 0) return rc;
         if (fold) {
             // LN-fold: the GEMM reads x itself; per-row statistics come from row_stats (first layer) or from the epilogue of the
             // c_proj GEMM of the previous layer
@@ -146,7 +160,7 @@ int run_blocks(const b200clip_tower_cfg& c, const b200clip_block_weights* blocks
             return rc;
         }
     }
-    return 0;
+    return save_slot(saved, 1 + c.layers, ws.x, c, batch, L, s);
 }
 
 }  // namespace
@@ -161,7 +175,7 @@ int64_t workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {
 // workspace -> workspace) | _OUTPUT (projection + optional normalise: the only kernels that write `out`).
 static int vit_forward_impl(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, const uint8_t* image_u8,
                             const float* mean, const float* std, void* out, int batch, int normalize, void* workspace,
-                            int64_t workspace_bytes_, int stages, cudaStream_t s) {
+                            int64_t workspace_bytes_, int stages, cudaStream_t s, void* saved = nullptr) {
     int rc;
     if ((rc = check_cfg(cfg)) != 0) return rc;
     const b200clip_tower_cfg& c = *cfg;
@@ -214,8 +228,9 @@ static int vit_forward_impl(const b200clip_tower_cfg* cfg, const b200clip_vit_we
                                c.patch_kpad, B200CLIP_EPI_PATCH, w->pos_emb, g * g, L, s)) != 0)
                 return rc;
         }
+        if ((rc = save_slot(saved, 0, ws.x, c, batch, L, s)) != 0) return rc;
         if ((rc = layernorm(dt, ws.x, W, w->ln_pre_g, w->ln_pre_b, ws.x, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
-        if ((rc = run_blocks(c, w->blocks_host, ws, batch, L, 0, s)) != 0) return rc;
+        if ((rc = run_blocks(c, w->blocks_host, ws, batch, L, 0, s, saved)) != 0) return rc;
         // pool_type 'tok': ln_post on the class token only (LN is per-row, so pooling first is exact), then @ proj
         if ((rc = layernorm(dt, ws.x, W, w->ln_post_g, w->ln_post_b, ws.pooled, W, batch, W, 1e-5f, L, nullptr, s)) != 0) return rc;
     }
@@ -248,8 +263,8 @@ int vit_forward_u8(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w,
     return vit_forward_impl(cfg, w, nullptr, image, mean, std, out, batch, normalize, workspace, workspace_bytes_, 7, s);
 }
 
-int text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
-                        int seq_len, int normalize, void* workspace, int64_t workspace_bytes_, int stages, cudaStream_t s) {
+static int text_forward_impl(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
+                             int seq_len, int normalize, void* workspace, int64_t workspace_bytes_, int stages, cudaStream_t s, void* saved) {
     int rc;
     if ((rc = check_cfg(cfg)) != 0) return rc;
     const b200clip_tower_cfg& c = *cfg;
@@ -272,7 +287,7 @@ int text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_text_weigh
         return rc;
     if (stages & B200CLIP_STAGE_BODY) {
         if (ws.sk != nullptr && (rc = gemm_pair_sk_workspace_reset(ws.sk, s)) != 0) return rc;
-        if ((rc = run_blocks(c, w->blocks_host, ws, batch, L, 1, s)) != 0) return rc;
+        if ((rc = run_blocks(c, w->blocks_host, ws, batch, L, 1, s, saved)) != 0) return rc;
         // ln_final only on the pooled (EOT) rows: LN is per-row, so this equals pooling after ln_final
         if ((rc = layernorm(dt, ws.x, W, w->ln_final_g, w->ln_final_b, ws.pooled, W, batch, W, 1e-5f, L, ws.eot, s)) != 0) return rc;
     }
@@ -283,6 +298,33 @@ int text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_text_weigh
         if (normalize && (rc = normalize_rows(dt, out, c.embed_dim, out, c.embed_dim, batch, c.embed_dim, 1e-12f, s)) != 0) return rc;
     }
     return 0;
+}
+
+int text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
+                        int seq_len, int normalize, void* workspace, int64_t workspace_bytes_, int stages, cudaStream_t s) {
+    return text_forward_impl(cfg, w, text, out, batch, seq_len, normalize, workspace, workspace_bytes_, stages, s, nullptr);
+}
+
+// ---- training forwards: the same kernels, plus the copies of the residual stream the backward starts from -----------------
+int64_t train_saved_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {
+    if (cfg == nullptr || batch <= 0 || seq_len <= 0) return -1;
+    return (cfg->layers + 2) * saved_slot_bytes(*cfg, batch, seq_len);
+}
+
+int vit_forward_train(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out, int batch, int normalize,
+                      void* saved, int64_t saved_bytes, void* workspace, int64_t workspace_bytes_, cudaStream_t s) {
+    B2C_CHECK_ARG(cfg && image && out && saved, "vit_forward_train: null pointer");
+    B2C_CHECK_ARG(saved_bytes >= train_saved_bytes(cfg, batch, cfg->seq_len) && reinterpret_cast<uintptr_t>(saved) % 256 == 0,
+                  "vit_forward_train: activation buffer too small or misaligned");
+    return vit_forward_impl(cfg, w, image, nullptr, nullptr, nullptr, out, batch, normalize, workspace, workspace_bytes_, 7, s, saved);
+}
+
+int text_forward_train(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch, int seq_len,
+                       int normalize, void* saved, int64_t saved_bytes, void* workspace, int64_t workspace_bytes_, cudaStream_t s) {
+    B2C_CHECK_ARG(cfg && text && out && saved, "text_forward_train: null pointer");
+    B2C_CHECK_ARG(saved_bytes >= train_saved_bytes(cfg, batch, seq_len) && reinterpret_cast<uintptr_t>(saved) % 256 == 0,
+                  "text_forward_train: activation buffer too small or misaligned");
+    return text_forward_impl(cfg, w, text, out, batch, seq_len, normalize, workspace, workspace_bytes_, 7, s, saved);
 }
 
 int text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,

@@ -3,6 +3,7 @@
 from .factory import (OPENAI_DATASET_MEAN, OPENAI_DATASET_STD, create_loss, create_model, create_model_and_transforms,
                       create_model_from_pretrained, get_tokenizer, image_transform, load_checkpoint, load_state_dict)
 from .loss import ClipLoss, gather_features
+from .optim import AdamW
 from .model import CLIP, VisionTower, convert_weights_to_fp16, convert_weights_to_lp, get_cast_dtype, get_input_dtype
 from .model_configs import get_model_config, list_models
 from .tokenizer import SimpleTokenizer, tokenize

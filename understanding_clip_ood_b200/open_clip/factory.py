@@ -76,10 +76,8 @@ def create_model(
         model_cfg["vision_cfg"]["image_size"] = force_image_size
     if isinstance(device, str):
         device = torch.device(device)
-    if precision in ("amp", "amp_bf16", "amp_bfloat16"):
-        raise RuntimeError(f"precision={precision!r} relies on torch.autocast through eager modules; use 'bf16', 'fp16', "
-                           "'pure_bf16', 'pure_fp16' or 'fp32' with the B200-native model")
-    if precision not in ("fp32", "bf16", "fp16", "pure_bf16", "pure_fp16"):
+    amp_dtype = {"amp": torch.float16, "amp_bf16": torch.bfloat16, "amp_bfloat16": torch.bfloat16}.get(precision)
+    if amp_dtype is None and precision not in ("fp32", "bf16", "fp16", "pure_bf16", "pure_fp16"):
         raise RuntimeError(f"unknown precision {precision!r}")
 
     cast_dtype = get_cast_dtype(precision)
@@ -93,6 +91,13 @@ def create_model(
         model.to(device=device, dtype=torch.float16 if "fp16" in precision else torch.bfloat16)
     else:
         model.to(device=device)
+    if amp_dtype is not None:
+        # The reference's training default (training/params.py:201-206): fp32 master parameters, 16-bit arithmetic.  There
+        # the model is plain fp32 and the train loop opens torch.autocast (training/precision.py:5-12); here the towers run
+        # their kernels in the autocast dtype on 16-bit copies of the parameters — under an autocast context, or always when
+        # the model was created with an `amp*` precision — and hand fp32 gradients to the master parameters.
+        model.visual.compute_dtype = amp_dtype
+        model.compute_dtype = amp_dtype
 
     pretrained_loaded = False
     if pretrained:

@@ -5,9 +5,10 @@ reference's `open_clip.model.CLIP` (deps/open_clip/src/open_clip/model.py:220-31
 contains no PyTorch arithmetic and there is no CPU / eager fallback: calling an encoder with CPU tensors or
 without the built library raises.
 
-Scope notes: inference forward only — outputs carry no autograd graph (tower backward is the
-"next" row §8(f)1); precision modes fp32 / bf16 / fp16 / pure_bf16 / pure_fp16 (the `amp*` modes need autocast
-through eager modules and are rejected by `create_model`).
+Training: a tower called in training mode with autograd enabled returns features that carry an autograd
+node (`open_clip/train.py`) whose backward is ONE call into the library (`b200clip_vit_backward` / `b200clip_text_backward`,
+block recompute as with --grad-checkpointing).  Precision modes fp32 / bf16 / fp16 / pure_bf16 / pure_fp16, and the
+mixed-precision `amp` / `amp_bf16` / `amp_bfloat16` modes as fp32 master parameters with 16-bit compute (`compute_dtype`).
 """
 from __future__ import annotations
 
@@ -262,21 +263,20 @@ def _pack_blocks(stack: _Stack, dtype: torch.dtype, keep: list, fold_ln: bool = 
     return arr
 
 
-_warned_no_backward = False
+def _resolve_compute_dtype(override, param_dtype: torch.dtype) -> torch.dtype:
+    """Kernel dtype of a tower: an explicit `compute_dtype` (models created with an `amp*` precision), else the autocast dtype
+    when fp32 parameters are called inside a torch.autocast context (what the reference's train loop opens), else the
+    parameter dtype."""
+    if override is not None:
+        return override
+    if param_dtype == torch.float32 and torch.is_autocast_enabled():
+        return torch.get_autocast_gpu_dtype()
+    return param_dtype
 
 
-def _note_forward_only(module: nn.Module, what: str) -> None:
-    """The towers are forward kernels: their outputs carry no autograd graph.  A caller in training mode with gradients
-    enabled (the reference's train loop, training/train.py:115-183) would otherwise train nothing but logit_scale without
-    noticing — say so once, loudly.  (The tower backward is the next row of SURVEY §8f; ClipLoss itself has its backward.)"""
-    global _warned_no_backward
-    if _warned_no_backward or not module.training or not torch.is_grad_enabled():
-        return
-    if any(p.requires_grad for p in module.parameters()):
-        _warned_no_backward = True
-        warnings.warn(f"b200clip: {what} was called in training mode with autograd enabled, but the B200 towers are forward-only: "
-                      "the returned features do not propagate gradients to the tower parameters (use model.eval() / torch.no_grad() "
-                      "for inference; the tower backward is not implemented yet)", RuntimeWarning, stacklevel=3)
+def _wants_grad(module: nn.Module, params) -> bool:
+    """Training path: the module is in training mode, autograd is recording and some parameter wants a gradient."""
+    return module.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
 
 
 def _check_device(t: torch.Tensor, what: str) -> None:
@@ -323,25 +323,29 @@ class VisionTower(nn.Module):
         self.use_cuda_graphs = True
         #: 16-bit modes: fold ln_1 / ln_2 into the QKV / c_fc GEMM epilogues (no normalised activations in HBM)
         self.fold_layernorm = True
+        #: mixed precision (`amp*`): fp32 master parameters, kernels run in this dtype on 16-bit copies (None = parameter dtype)
+        self.compute_dtype = None
 
     # -- reference API surface ---------------------------------------------------------------
     def set_grad_checkpointing(self, enable: bool = True):
-        self.transformer.grad_checkpointing = enable
+        self.transformer.grad_checkpointing = enable      # the training path always recomputes per block (train.py)
 
     def lock(self, unlocked_groups: int = 0, freeze_bn_stats: bool = False):
         for p in self.parameters():
             p.requires_grad = False
 
     def _compute_dtype(self) -> torch.dtype:
-        return self.transformer.get_cast_dtype()
+        return _resolve_compute_dtype(self.compute_dtype, self.transformer.get_cast_dtype())
 
-    def _build(self, device) -> _Engine:
+    def _build(self, device, for_training: bool = False) -> _Engine:
         params = list(self.parameters())
-        sig = _Engine.signature(params, bool(self.fold_layernorm), bool(self.quick_gelu), getattr(self, "preprocess_cfg", None) is not None)
+        dt = self._compute_dtype()
+        # training path: no LayerNorm folding (the folded weights would have to be re-derived after every optimizer step)
+        fold = bool(self.fold_layernorm) and dt != torch.float32 and not for_training
+        sig = _Engine.signature(params, fold, bool(self.quick_gelu), dt)
         eng = self._engine
         if eng.sig == sig:
             return eng
-        dt = self._compute_dtype()
         keep: list = []
         W = self.transformer.width
         P = self.patch_size[0]
@@ -350,6 +354,8 @@ class VisionTower(nn.Module):
         # rows in the 16-bit modes; the extra columns are zero in both operands
         kpad = (kreal + 7) // 8 * 8 if dt == torch.float32 else (kreal + 63) // 64 * 64
         conv = self.conv1.weight.detach().to(dt).reshape(W, kreal)
+        if conv.data_ptr() == self.conv1.weight.data_ptr() and kpad == kreal:
+            conv = conv.clone()
         if kpad != kreal:
             padded = torch.zeros((W, kpad), dtype=dt, device=device)
             padded[:, :kreal] = conv
@@ -358,7 +364,6 @@ class VisionTower(nn.Module):
         keep.append(conv)
         proj_t = self.proj.detach().to(dt).t().contiguous()
         keep.append(proj_t)
-        fold = bool(self.fold_layernorm) and dt != torch.float32
         blocks = _pack_blocks(self.transformer, dt, keep, fold)
         w = L.VitWeights()
         w.conv1_w = conv.data_ptr()
@@ -386,11 +391,12 @@ class VisionTower(nn.Module):
 
     def forward(self, image: torch.Tensor, normalize: bool = False) -> torch.Tensor:
         """[B,3,S,S] -> [B,D] (transformer.py:601-643); `normalize` fuses CLIP.encode_image's F.normalize."""
-        _note_forward_only(self, "encode_image")
         _check_device(image, "encode_image")
         _check_device(self.proj, "encode_image (model weights)")
         dt = self._compute_dtype()
         u8 = image.dtype == torch.uint8
+        if image.dtype == torch.float32 and dt != torch.float32 and self.transformer.get_cast_dtype() == torch.float32:
+            image = image.to(dt)          # autocast's input cast (mixed-precision modes take fp32 batches, precision.py:5-12)
         if not u8 and image.dtype != dt:
             raise RuntimeError(f"Input type ({image.dtype}) and weight type ({dt}) should be the same "
                                f"(cast the batch with get_input_dtype(precision), as the reference requires; uint8 pixel "
@@ -401,6 +407,13 @@ class VisionTower(nn.Module):
         B = image.shape[0]
         if B == 0:
             return torch.empty((0, self.output_dim), dtype=dt, device=image.device)
+        params = list(self.parameters())
+        if _wants_grad(self, params):
+            if u8:
+                raise RuntimeError("the training path takes batches in the tower dtype (uint8 pixel batches are an inference input)")
+            from .train import VitTrainFn
+            names = [n for n, _ in self.named_parameters()]
+            return VitTrainFn.apply(self, image, bool(normalize), names, *params)
         lib = L.load()
         with torch.cuda.device(image.device):
             eng = self._build(image.device)
@@ -495,6 +508,8 @@ class CLIP(nn.Module):
         self._text_engine = _Engine()
         #: replay encode_text's block stack as a CUDA graph per (batch, sequence length) (see _Engine.run_staged)
         self.use_cuda_graphs = True
+        #: mixed precision (`amp*`): compute dtype of the text tower on fp32 master parameters (None = parameter dtype)
+        self.compute_dtype = None
 
     def _init_text_parameters(self) -> None:
         """TextTransformer.init_parameters (transformer.py:724-745)."""
@@ -523,18 +538,26 @@ class CLIP(nn.Module):
     def encode_image(self, image: torch.Tensor, normalize: bool = False) -> torch.Tensor:
         return self.visual(image, normalize=normalize)
 
-    def _build_text(self, device) -> _Engine:
-        params = [self.token_embedding.weight, self.positional_embedding, self.ln_final.weight, self.ln_final.bias,
-                  self.text_projection, *self.transformer.parameters()]
-        sig = _Engine.signature(params, bool(self.fold_layernorm), bool(self.quick_gelu))
+    def _text_compute_dtype(self) -> torch.dtype:
+        return _resolve_compute_dtype(self.compute_dtype, self.transformer.get_cast_dtype())
+
+    def _text_named_parameters(self):
+        """(name, parameter) of everything encode_text reads, names as in the CLIP state_dict."""
+        return [("token_embedding.weight", self.token_embedding.weight), ("positional_embedding", self.positional_embedding),
+                ("ln_final.weight", self.ln_final.weight), ("ln_final.bias", self.ln_final.bias), ("text_projection", self.text_projection),
+                *[("transformer." + n, p) for n, p in self.transformer.named_parameters()]]
+
+    def _build_text(self, device, for_training: bool = False) -> _Engine:
+        params = [p for _, p in self._text_named_parameters()]
+        dt = self._text_compute_dtype()
+        fold = bool(self.fold_layernorm) and dt != torch.float32 and not for_training
+        sig = _Engine.signature(params, fold, bool(self.quick_gelu), dt)
         eng = self._text_engine
         if eng.sig == sig:
             return eng
-        dt = self.transformer.get_cast_dtype()
         keep: list = []
         proj_t = self.text_projection.detach().to(dt).t().contiguous()
         keep.append(proj_t)
-        fold = bool(self.fold_layernorm) and dt != torch.float32
         blocks = _pack_blocks(self.transformer, dt, keep, fold)
         w = L.TextWeights()
         w.tok_emb = _f32(self.token_embedding.weight, keep)
@@ -552,7 +575,6 @@ class CLIP(nn.Module):
 
     def encode_text(self, text: torch.Tensor, normalize: bool = False) -> torch.Tensor:
         """[T, context_length] int64 -> [T, D] (model.py:269-284)."""
-        _note_forward_only(self, "encode_text")
         _check_device(text, "encode_text")
         _check_device(self.text_projection, "encode_text (model weights)")
         if text.ndim != 2 or text.shape[1] != self.context_length:
@@ -561,7 +583,7 @@ class CLIP(nn.Module):
             text = text.long()
         text = text.contiguous()
         T = text.shape[0]
-        dt = self.transformer.get_cast_dtype()
+        dt = self._text_compute_dtype()
         D = self.text_projection.shape[1]
         if T == 0:
             return torch.empty((0, D), dtype=dt, device=text.device)
@@ -573,6 +595,10 @@ class CLIP(nn.Module):
                 L.check(lib.b200clip_eot_argmax(text.data_ptr(), self.context_length, eot.data_ptr(), T, L.stream_ptr()),
                         "b200clip_eot_argmax")
                 seq_len = int(np.max(eot.cpu().numpy())) + 1
+            named = self._text_named_parameters()
+            if _wants_grad(self, [p for _, p in named]):
+                from .train import TextTrainFn
+                return TextTrainFn.apply(self, text, seq_len, bool(normalize), [n for n, _ in named], *[p for _, p in named])
             eng = self._build_text(text.device)
             nbytes = lib.b200clip_workspace_bytes(C.byref(eng.cfg), T, seq_len)
             ws = eng.workspace(nbytes, text.device)
