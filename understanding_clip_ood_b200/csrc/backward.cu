@@ -37,7 +37,8 @@ template <> __device__ __forceinline__ __half from_f<__half>(float v) { return _
 // transpose (16-bit): 64 x 64 tiles through shared memory, 2-element vector accesses on both sides
 // ------------------------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, int64_t ldi, T* __restrict__ out, int64_t ldo, int R, int C, int Rpad) {
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, int64_t ldi, T* __restrict__ out, int64_t ldo, int R, int C, int Rpad,
+                                                        int act) {
     __shared__ T tile[64][72];
     const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
     const bool vec_in = sizeof(T) == 2 && (ldi % 8 == 0) && (reinterpret_cast<uintptr_t>(in) % 16 == 0) && c0 + 64 <= C;
@@ -57,6 +58,15 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in
         }
     }
     __syncthreads();
+    if (act != 0) {
+        // out = act(in)^T: the activation of the MLP is applied on the way through (the recompute keeps only the pre-activation)
+        for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+            const int rr = i >> 6, cc = i & 63;
+            const float v = to_f<T>(tile[rr][cc]);
+            tile[rr][cc] = from_f<T>(act == 2 ? quick_gelu(v) : gelu_erf(v));
+        }
+        __syncthreads();
+    }
     const bool vec_out = sizeof(T) == 2 && (ldo % 8 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) && r0 + 64 <= Rpad;
     if (vec_out) {
         // output row c (64 of them) x 8 vectors of 8 consecutive r
@@ -115,14 +125,24 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
         }
     }
 }
+// out[c] (+)= sum over chunks of part[chunk][c]: 32 columns x 8 chunk lanes per block (fixed summation order)
 template <typename TO>
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int chunks, int cols, TO* __restrict__ out, int accumulate) {
-    const int c = blockIdx.x * 256 + threadIdx.x;
-    if (c >= cols) return;
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
     float s = 0.f;
-    for (int k = 0; k < chunks; ++k) s += part[static_cast<int64_t>(k) * cols + c];
-    if (accumulate) s += to_f<TO>(out[c]);
-    out[c] = from_f<TO>(s);
+    if (c < cols)
+        for (int k = ty; k < chunks; k += 8) s += part[static_cast<int64_t>(k) * cols + c];
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][tx];
+        if (accumulate) t += to_f<TO>(out[c]);
+        out[c] = from_f<TO>(t);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -196,6 +216,144 @@ ln_backward_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict__ x
         dgamma_part[static_cast<int64_t>(blockIdx.x) * width + j] = tg;
         dbeta_part[static_cast<int64_t>(blockIdx.x) * width + j] = tb;
     }
+}
+
+// Vectorised form for widths that are a multiple of 32 lanes x 16 bytes: every lane keeps its VPL vectors of the row in
+// registers (ONE read of g, x and dres), and its d(gamma) / d(beta) contributions for its own columns across all rows of the
+// warp; the warps of the block are combined through shared memory at the end.
+template <typename T> struct VecOf { static constexpr int n = 16 / sizeof(T); };
+template <typename T> __device__ __forceinline__ void load16(const T* p, float* f) {
+    if constexpr (sizeof(T) == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    } else {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 t = Half16<T>::unpack(w[i]);
+            f[2 * i] = t.x;
+            f[2 * i + 1] = t.y;
+        }
+    }
+}
+template <typename T> __device__ __forceinline__ void store16(T* p, const float* f) {
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    } else {
+        using H = Half16<T>;
+        *reinterpret_cast<uint4*>(p) = make_uint4(H::pack(f[0], f[1]), H::pack(f[2], f[3]), H::pack(f[4], f[5]), H::pack(f[6], f[7]));
+    }
+}
+
+template <typename T, int VPL>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_backward_vec_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict__ x, int64_t ldx, const float* __restrict__ gamma,
+                       const T* __restrict__ dres, int64_t ldr, T* __restrict__ dx, int64_t ldd, float* __restrict__ dgamma_part,
+                       float* __restrict__ dbeta_part, int rows, int width, float eps, int row_stride, const int32_t* __restrict__ row_idx) {
+    constexpr int V = VecOf<T>::n;
+    extern __shared__ float sm[];   // [2][kLnWarps][width]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float gam[VPL * V], ag[VPL * V], ab[VPL * V];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            gam[k * V + i] = gamma[(k * 32 + lane) * V + i];
+            ag[k * V + i] = 0.f;
+            ab[k * V + i] = 0.f;
+        }
+    const int row_begin = blockIdx.x * kLnRowsPerBlock;
+    const int row_end = min(rows, row_begin + kLnRowsPerBlock);
+    const float inv_w = 1.0f / static_cast<float>(width);
+    for (int r = row_begin + warp; r < row_end; r += kLnWarps) {
+        const int64_t pr = static_cast<int64_t>(r) * row_stride + (row_idx != nullptr ? row_idx[r] : 0);
+        float xv[VPL * V], gv[VPL * V];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            load16<T>(x + pr * ldx + (k * 32 + lane) * V, xv + k * V);
+            load16<T>(g + static_cast<int64_t>(r) * ldg + (k * 32 + lane) * V, gv + k * V);
+#pragma unroll
+            for (int i = 0; i < V; ++i) s += xv[k * V + i];
+        }
+        const float mean = warp_sum(s) * inv_w;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL * V; ++i) {
+            xv[i] -= mean;
+            q = fmaf(xv[i], xv[i], q);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * inv_w + eps);
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < VPL * V; ++i) {
+            xv[i] *= rstd;                       // xhat
+            const float gy = gv[i] * gam[i];
+            a += gy;
+            b = fmaf(gy, xv[i], b);
+            ag[i] = fmaf(gv[i], xv[i], ag[i]);
+            ab[i] += gv[i];
+        }
+        a = warp_sum(a) * inv_w;
+        b = warp_sum(b) * inv_w;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+            float o[V];
+            if (dres != nullptr) load16<T>(dres + pr * ldr + (k * 32 + lane) * V, o);
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const float v = rstd * (gv[k * V + i] * gam[k * V + i] - a - xv[k * V + i] * b);
+                o[i] = dres != nullptr ? o[i] + v : v;
+            }
+            store16<T>(dx + pr * ldd + (k * 32 + lane) * V, o);
+        }
+    }
+    float* sg = sm;
+    float* sb = sm + kLnWarps * width;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k)
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+            sg[warp * width + (k * 32 + lane) * V + i] = ag[k * V + i];
+            sb[warp * width + (k * 32 + lane) * V + i] = ab[k * V + i];
+        }
+    __syncthreads();
+    for (int j = threadIdx.x; j < width; j += kLnWarps * 32) {
+        float tg = 0.f, tb = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnWarps; ++w) {
+            tg += sg[w * width + j];
+            tb += sb[w * width + j];
+        }
+        dgamma_part[static_cast<int64_t>(blockIdx.x) * width + j] = tg;
+        dbeta_part[static_cast<int64_t>(blockIdx.x) * width + j] = tb;
+    }
+}
+
+template <typename T>
+bool launch_ln_backward_vec(const T* g, int64_t ldg, const T* x, int64_t ldx, const float* gamma, const T* dres, int64_t ldr, T* dx, int64_t ldd,
+                            float* pg, float* pb, int rows, int width, float eps, int row_stride, const int32_t* row_idx, int blocks, size_t smem,
+                            cudaStream_t stream) {
+    constexpr int V = VecOf<T>::n;
+    if (width % (32 * V) != 0 || ldg % V != 0 || ldx % V != 0 || ldd % V != 0 || (dres != nullptr && ldr % V != 0)) return false;
+    if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dres) |
+         reinterpret_cast<uintptr_t>(gamma)) % 16 != 0)
+        return false;
+    const int vpl = width / (32 * V);
+#define B2C_LN_VEC(N)                                                                                                                       \
+    case N:                                                                                                                                 \
+        ln_backward_vec_kernel<T, N><<<blocks, kLnWarps * 32, smem, stream>>>(g, ldg, x, ldx, gamma, dres, ldr, dx, ldd, pg, pb, rows, width, eps, \
+                                                                              row_stride, row_idx);                                         \
+        return true;
+    switch (vpl) {
+        B2C_LN_VEC(1)
+        B2C_LN_VEC(2)
+        B2C_LN_VEC(3)
+        B2C_LN_VEC(4)
+    }   // wider rows (fp32 at W >= 768: the parity mode) keep the scalar kernel
+#undef B2C_LN_VEC
+    return false;
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -574,21 +732,22 @@ inline int grid_for(int64_t n, int per_block = 256, int max_blocks = 148 * 16) {
     return static_cast<int>(b);
 }
 
-#define B2C_DISPATCH_T(dtype, CALL)                                          \
+#define B2C_DISPATCH_T(dtype, ...)                                           \
     do {                                                                     \
-        if ((dtype) == 0) { using T = float; CALL; }                         \
-        else if ((dtype) == 1) { using T = __nv_bfloat16; CALL; }            \
-        else if ((dtype) == 2) { using T = __half; CALL; }                   \
+        if ((dtype) == 0) { using T = float; __VA_ARGS__; }                  \
+        else if ((dtype) == 1) { using T = __nv_bfloat16; __VA_ARGS__; }     \
+        else if ((dtype) == 2) { using T = __half; __VA_ARGS__; }            \
         else { B2C_CHECK_ARG(false, "unknown dtype %d", (dtype)); }          \
     } while (0)
 
 }  // namespace
 
 // out[c][r] = in[r][c] for r < R, 0 for R <= r < Rpad (Rpad <= ldo: zero padding of the contraction dimension of a GEMM operand)
-int transpose16(int dtype, const void* in, int64_t ldi, void* out, int64_t ldo, int R, int C, int Rpad, cudaStream_t stream) {
-    B2C_CHECK_ARG(in && out && R > 0 && C > 0 && Rpad >= R && Rpad <= ldo, "transpose: bad arguments");
+// act: 0 = plain transpose, 1 = erf GELU, 2 = QuickGELU applied to every element on the way
+int transpose16(int dtype, const void* in, int64_t ldi, void* out, int64_t ldo, int R, int C, int Rpad, cudaStream_t stream, int act) {
+    B2C_CHECK_ARG(in && out && R > 0 && C > 0 && Rpad >= R && Rpad <= ldo && act >= 0 && act <= 2, "transpose: bad arguments");
     dim3 grid((C + 63) / 64, (Rpad + 63) / 64);
-    B2C_DISPATCH_T(dtype, (transpose_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(in), ldi, static_cast<T*>(out), ldo, R, C, Rpad)));
+    B2C_DISPATCH_T(dtype, (transpose_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(in), ldi, static_cast<T*>(out), ldo, R, C, Rpad, act)));
     B2C_LAUNCH_CHECK("transpose_kernel");
     return 0;
 }
@@ -603,9 +762,9 @@ int col_sum(int dtype, const void* g, int64_t ld, int rows, int cols, void* out,
     B2C_DISPATCH_T(dtype, (colsum_partial_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(g), ld, rows, cols, scratch)));
     B2C_LAUNCH_CHECK("colsum_partial_kernel");
     if (out_f32 || dtype == 0) {
-        colsum_final_kernel<float><<<(cols + 255) / 256, 256, 0, stream>>>(scratch, chunks, cols, static_cast<float*>(out), accumulate);
+        colsum_final_kernel<float><<<(cols + 31) / 32, 256, 0, stream>>>(scratch, chunks, cols, static_cast<float*>(out), accumulate);
     } else {
-        B2C_DISPATCH_T(dtype, (colsum_final_kernel<T><<<(cols + 255) / 256, 256, 0, stream>>>(scratch, chunks, cols, static_cast<T*>(out), accumulate)));
+        B2C_DISPATCH_T(dtype, (colsum_final_kernel<T><<<(cols + 31) / 32, 256, 0, stream>>>(scratch, chunks, cols, static_cast<T*>(out), accumulate)));
     }
     B2C_LAUNCH_CHECK("colsum_final_kernel");
     return 0;
@@ -623,13 +782,18 @@ int ln_backward(int dtype, const void* g, int64_t ldg, const void* x, int64_t ld
     B2C_CHECK_ARG(smem <= 48 * 1024, "ln_backward: width %d too large", width);
     float* pg = scratch;
     float* pb = scratch + static_cast<int64_t>(blocks) * width;
-    B2C_DISPATCH_T(dtype, (ln_backward_kernel<T><<<blocks, kLnWarps * 32, smem, stream>>>(
-                              static_cast<const T*>(g), ldg, static_cast<const T*>(x), ldx, gamma, static_cast<const T*>(dres), ldr,
-                              static_cast<T*>(dx), ldd, pg, pb, rows, width, eps, row_stride > 0 ? row_stride : 1, row_idx)));
+    const int rs = row_stride > 0 ? row_stride : 1;
+    B2C_DISPATCH_T(dtype, {
+        if (!launch_ln_backward_vec<T>(static_cast<const T*>(g), ldg, static_cast<const T*>(x), ldx, gamma, static_cast<const T*>(dres), ldr,
+                                       static_cast<T*>(dx), ldd, pg, pb, rows, width, eps, rs, row_idx, blocks, smem, stream))
+            ln_backward_kernel<T><<<blocks, kLnWarps * 32, smem, stream>>>(static_cast<const T*>(g), ldg, static_cast<const T*>(x), ldx, gamma,
+                                                                           static_cast<const T*>(dres), ldr, static_cast<T*>(dx), ldd, pg, pb, rows,
+                                                                           width, eps, rs, row_idx);
+    });
     B2C_LAUNCH_CHECK("ln_backward_kernel");
-    colsum_final_kernel<float><<<(width + 255) / 256, 256, 0, stream>>>(pg, blocks, width, d_gamma, accumulate);
+    colsum_final_kernel<float><<<(width + 31) / 32, 256, 0, stream>>>(pg, blocks, width, d_gamma, accumulate);
     B2C_LAUNCH_CHECK("colsum_final_kernel");
-    colsum_final_kernel<float><<<(width + 255) / 256, 256, 0, stream>>>(pb, blocks, width, d_beta, accumulate);
+    colsum_final_kernel<float><<<(width + 31) / 32, 256, 0, stream>>>(pb, blocks, width, d_beta, accumulate);
     B2C_LAUNCH_CHECK("colsum_final_kernel");
     return 0;
 }

@@ -98,7 +98,7 @@ int p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* co
 // ---- training path (backward.cu, towers_bwd.cu, optim.cu) ----
 int gemm_f32_general(const float* A, int64_t lda, bool ta, const float* B, int64_t ldb, bool tb, float* C, int64_t ldc, int M, int N, int K,
                      bool accumulate, cudaStream_t stream);
-int transpose16(int dtype, const void* in, int64_t ldi, void* out, int64_t ldo, int R, int C, int Rpad, cudaStream_t stream);
+int transpose16(int dtype, const void* in, int64_t ldi, void* out, int64_t ldo, int R, int C, int Rpad, cudaStream_t stream, int act = 0);
 int64_t col_sum_scratch_floats(int rows, int cols);
 int col_sum(int dtype, const void* g, int64_t ld, int rows, int cols, void* out, int out_f32, int accumulate, float* scratch, cudaStream_t stream);
 int64_t ln_backward_scratch_floats(int rows, int width);

@@ -102,8 +102,9 @@ int dgrad(const Ctx& c, const void* G, int64_t ldg, const void* Wt, int64_t ldw,
                      nullptr, 0, nullptr, nullptr, 0, 1e-5f, c.ws->sk);
 }
 
-// dW[N, K] = G[M, N]^T X[M, K]  (+ optional bias gradient db[N] = column sums of G)
-int wgrad(const Ctx& c, const void* G, int64_t ldg, const void* X, int64_t ldx, void* dW, int64_t ldw, void* db, int M, int N, int K) {
+// dW[N, K] = G[M, N]^T X[M, K]  (+ optional bias gradient db[N] = column sums of G).  x_act != 0 (16-bit modes only): X is given
+// as the pre-activation and the activation (1 = GELU, 2 = QuickGELU) is applied inside the operand transpose.
+int wgrad(const Ctx& c, const void* G, int64_t ldg, const void* X, int64_t ldx, void* dW, int64_t ldw, void* db, int M, int N, int K, int x_act = 0) {
     int rc;
     if (db != nullptr && (rc = col_sum(c.dt, G, ldg, M, N, db, 0, 0, c.ws->scratch, c.s)) != 0) return rc;
     if (c.dt == B200CLIP_F32)
@@ -111,7 +112,7 @@ int wgrad(const Ctx& c, const void* G, int64_t ldg, const void* X, int64_t ldx, 
                                 false, c.s);
     const int64_t ldt = c.ws->ldt;
     if ((rc = transpose16(c.dt, G, ldg, c.ws->tA, ldt, M, N, static_cast<int>(ldt), c.s)) != 0) return rc;     // [M, N] -> [N, Mpad]
-    if ((rc = transpose16(c.dt, X, ldx, c.ws->tB, ldt, M, K, static_cast<int>(ldt), c.s)) != 0) return rc;     // [M, K] -> [K, Mpad]
+    if ((rc = transpose16(c.dt, X, ldx, c.ws->tB, ldt, M, K, static_cast<int>(ldt), c.s, x_act)) != 0) return rc;   // [M, K] -> [K, Mpad]
     return gemm_pair(c.dt == B200CLIP_BF16, c.ws->tA, ldt, c.ws->tB, ldt, nullptr, nullptr, 0, dW, ldw, N, K, static_cast<int>(ldt), B200CLIP_EPI_BIAS, 0,
                      0, c.s, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0, 1e-5f, c.ws->sk);
 }
@@ -134,9 +135,11 @@ int block_backward(const b200clip_tower_cfg& c, const b200clip_block_weights& bw
     if ((rc = gemm_any(dt, ws.att, W, bw.out_proj_w, W, bw.out_proj_b, x_in, W, ws.xmid, W, M, W, W, B200CLIP_EPI_RESIDUAL, nullptr, 0, 0, s, ws.sk)) != 0) return rc;
     if ((rc = layernorm(dt, ws.xmid, W, bw.ln2_g, bw.ln2_b, ws.h2, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
     if ((rc = gemm_any(dt, ws.h2, W, bw.fc_w, W, bw.fc_b, nullptr, 0, ws.z, H, M, H, W, B200CLIP_EPI_BIAS, nullptr, 0, 0, s, ws.sk)) != 0) return rc;
-    if ((rc = act_forward(dt, ws.z, ws.a, static_cast<int64_t>(M) * H, c.quick_gelu, s)) != 0) return rc;
+    // a = act(z) is an operand of dWproj only: the 16-bit path applies the activation inside that operand's transpose
+    const bool lp = dt != B200CLIP_F32;
+    if (!lp && (rc = act_forward(dt, ws.z, ws.a, static_cast<int64_t>(M) * H, c.quick_gelu, s)) != 0) return rc;
     // ---- MLP branch ----
-    if ((rc = wgrad(cx, ws.gA, W, ws.a, H, bg.proj_w, H, bg.proj_b, M, W, H)) != 0) return rc;                       // dWproj [W, H], dbproj
+    if ((rc = wgrad(cx, ws.gA, W, lp ? ws.z : ws.a, H, bg.proj_w, H, bg.proj_b, M, W, H, lp ? (c.quick_gelu ? 2 : 1) : 0)) != 0) return rc;   // dWproj, dbproj
     if ((rc = dgrad(cx, ws.gA, W, bw.proj_w, H, ws.big, H, M, W, H)) != 0) return rc;                                // d_a [M, H]
     if ((rc = act_backward(dt, ws.big, ws.z, ws.big, static_cast<int64_t>(M) * H, c.quick_gelu, s)) != 0) return rc;  // d_z in place
     if ((rc = wgrad(cx, ws.big, H, ws.h2, W, bg.fc_w, W, bg.fc_b, M, H, W)) != 0) return rc;                          // dWfc [H, W], dbfc

@@ -157,6 +157,7 @@ class _Engine:
 
     def __init__(self):
         self.sig = None
+        self.static_sig = None  # the part of the signature that does not change with an optimizer step
         self.keep = []          # tensors whose storage the structs point into
         self.blocks = None
         self.weights = None
@@ -179,6 +180,21 @@ class _Engine:
         """Everything the cached structs / captured graphs depend on: parameter storage, version and dtype, plus the public
         switches that are baked into TowerCfg and the folded weights (fold_layernorm, quick_gelu, ...)."""
         return tuple((p.data_ptr(), p._version, p.dtype) for p in params) + tuple(switches)
+
+    def try_refresh(self, params, static_sig: tuple) -> bool:
+        """Same storages, dtypes and switches as at build time, only newer values (an optimizer step): update the converted
+        copies and the derived operands in place — the structs, and any captured graph, stay valid.  Not for folded
+        LayerNorms (their operands are re-derived by a full rebuild)."""
+        keep = self.keep
+        if self.static_sig != static_sig or not isinstance(keep, _Keep) or getattr(self.cfg, "fold_ln", 0):
+            return False
+        with torch.no_grad():
+            if keep.pairs:
+                torch._foreach_copy_([d for d, _ in keep.pairs], [s_.detach() for _, s_ in keep.pairs])
+            for fn in keep.refresh:
+                fn()
+        self.sig = self.signature(params) + static_sig
+        return True
 
     def workspace(self, nbytes: int, device) -> torch.Tensor:
         if self.ws is None or self.ws.numel() < nbytes or self.ws.device != device:
@@ -225,9 +241,23 @@ class _Engine:
         return out
 
 
+class _Keep(list):
+    """Tensors the ctypes structs point into.  `pairs` = (copy, source parameter) for every parameter that had to be converted,
+    `refresh` = callables that recompute derived operands in place: after an optimizer step (same storages, new values) the
+    engine re-fills the copies with one multi-tensor copy instead of rebuilding everything (see _Engine.try_refresh)."""
+
+    def __init__(self):
+        super().__init__()
+        self.pairs: list = []
+        self.refresh: list = []
+
+
 def _f32(t: torch.Tensor, keep: list) -> int:
     if t.dtype != torch.float32 or not t.is_contiguous():
+        src = t
         t = t.detach().to(torch.float32).contiguous()
+        if isinstance(keep, _Keep):
+            keep.pairs.append((t, src))
     keep.append(t)
     return t.data_ptr()
 
@@ -236,7 +266,10 @@ def _as(t: Optional[torch.Tensor], dtype: torch.dtype, keep: list) -> Optional[i
     if t is None:
         return None
     if t.dtype != dtype or not t.is_contiguous():
+        src = t
         t = t.detach().to(dtype).contiguous()
+        if isinstance(keep, _Keep):
+            keep.pairs.append((t, src))
     keep.append(t)
     return t.data_ptr()
 
@@ -342,28 +375,29 @@ class VisionTower(nn.Module):
         dt = self._compute_dtype()
         # training path: no LayerNorm folding (the folded weights would have to be re-derived after every optimizer step)
         fold = bool(self.fold_layernorm) and dt != torch.float32 and not for_training
-        sig = _Engine.signature(params, fold, bool(self.quick_gelu), dt)
+        static_sig = (tuple((p.data_ptr(), p.dtype) for p in params), fold, bool(self.quick_gelu), dt)
+        sig = _Engine.signature(params) + static_sig
         eng = self._engine
         if eng.sig == sig:
             return eng
-        keep: list = []
+        if eng.try_refresh(params, static_sig):
+            return eng
+        keep = _Keep()
         W = self.transformer.width
         P = self.patch_size[0]
         kreal = 3 * P * P
         # K of the patch GEMM: 16-byte rows in fp32 (P = 14 gives 3*P*P = 588, not a multiple of 8), whole 128-byte swizzle
         # rows in the 16-bit modes; the extra columns are zero in both operands
         kpad = (kreal + 7) // 8 * 8 if dt == torch.float32 else (kreal + 63) // 64 * 64
-        conv = self.conv1.weight.detach().to(dt).reshape(W, kreal)
-        if conv.data_ptr() == self.conv1.weight.data_ptr() and kpad == kreal:
-            conv = conv.clone()
-        if kpad != kreal:
-            padded = torch.zeros((W, kpad), dtype=dt, device=device)
-            padded[:, :kreal] = conv
-            conv = padded
-        conv = conv.contiguous()
-        keep.append(conv)
-        proj_t = self.proj.detach().to(dt).t().contiguous()
-        keep.append(proj_t)
+        conv = torch.zeros((W, kpad), dtype=dt, device=device)
+        proj_t = torch.empty((self.output_dim, W), dtype=dt, device=device)
+
+        def refresh_conv_proj():
+            conv[:, :kreal].copy_(self.conv1.weight.detach().reshape(W, kreal))
+            proj_t.copy_(self.proj.detach().t())
+
+        keep.refresh.append(refresh_conv_proj)
+        keep.extend((conv, proj_t))
         blocks = _pack_blocks(self.transformer, dt, keep, fold)
         w = L.VitWeights()
         w.conv1_w = conv.data_ptr()
@@ -376,16 +410,23 @@ class VisionTower(nn.Module):
         if dt != torch.float32:
             # token-layout patch embedding: the class-token row of the additive table holds dtype(class_emb) + dtype(pos[0])
             # (an exact fp32 sum of two 16-bit values), the other rows are the fp32 positional embedding
-            pos_cls = self.positional_embedding.detach().float().clone()
-            pos_cls[0] = self.class_embedding.detach().to(dt).float() + self.positional_embedding.detach()[0].to(dt).float()
-            pos_cls = pos_cls.contiguous()
+            pos_cls = torch.empty_like(self.positional_embedding, dtype=torch.float32, device=device)
+
+            def refresh_pos_cls():
+                pos_cls.copy_(self.positional_embedding.detach())
+                pos_cls[0] = self.class_embedding.detach().to(dt).float() + self.positional_embedding.detach()[0].to(dt).float()
+
+            keep.refresh.append(refresh_pos_cls)
             keep.append(pos_cls)
             w.pos_cls = pos_cls.data_ptr()
+        with torch.no_grad():
+            for fn in keep.refresh:
+                fn()
         cfg = L.TowerCfg(dtype=L.dtype_code(dt), width=W, layers=self.transformer.layers, heads=self.transformer.heads,
                          mlp_width=self.transformer.mlp_width, embed_dim=self.output_dim,
                          seq_len=self.grid_size[0] * self.grid_size[1] + 1, quick_gelu=int(self.quick_gelu),
                          image_size=self.image_size[0], patch_size=P, patch_kpad=kpad, vocab_size=0, fold_ln=int(fold))
-        eng.sig, eng.keep, eng.blocks, eng.weights, eng.cfg = sig, keep, blocks, w, cfg
+        eng.sig, eng.static_sig, eng.keep, eng.blocks, eng.weights, eng.cfg = sig, static_sig, keep, blocks, w, cfg
         eng.graphs.clear()      # captured graphs hold the old weight pointers
         return eng
 
@@ -551,12 +592,20 @@ class CLIP(nn.Module):
         params = [p for _, p in self._text_named_parameters()]
         dt = self._text_compute_dtype()
         fold = bool(self.fold_layernorm) and dt != torch.float32 and not for_training
-        sig = _Engine.signature(params, fold, bool(self.quick_gelu), dt)
+        static_sig = (tuple((p.data_ptr(), p.dtype) for p in params), fold, bool(self.quick_gelu), dt)
+        sig = _Engine.signature(params) + static_sig
         eng = self._text_engine
         if eng.sig == sig:
             return eng
-        keep: list = []
-        proj_t = self.text_projection.detach().to(dt).t().contiguous()
+        if eng.try_refresh(params, static_sig):
+            return eng
+        keep = _Keep()
+        proj_t = torch.empty((self.text_projection.shape[1], self.transformer.width), dtype=dt, device=device)
+
+        def refresh_proj():
+            proj_t.copy_(self.text_projection.detach().t())
+
+        keep.refresh.append(refresh_proj)
         keep.append(proj_t)
         blocks = _pack_blocks(self.transformer, dt, keep, fold)
         w = L.TextWeights()
@@ -565,11 +614,13 @@ class CLIP(nn.Module):
         w.ln_final_g, w.ln_final_b = _f32(self.ln_final.weight, keep), _f32(self.ln_final.bias, keep)
         w.proj_t = proj_t.data_ptr()
         w.blocks_host = C.cast(blocks, C.c_void_p)
+        with torch.no_grad():
+            refresh_proj()
         st = self.transformer
         cfg = L.TowerCfg(dtype=L.dtype_code(dt), width=st.width, layers=st.layers, heads=st.heads, mlp_width=st.mlp_width,
                          embed_dim=self.text_projection.shape[1], seq_len=self.context_length, quick_gelu=int(self.quick_gelu),
                          image_size=0, patch_size=0, patch_kpad=0, vocab_size=self.vocab_size, fold_ln=int(fold))
-        eng.sig, eng.keep, eng.blocks, eng.weights, eng.cfg = sig, keep, blocks, w, cfg
+        eng.sig, eng.static_sig, eng.keep, eng.blocks, eng.weights, eng.cfg = sig, static_sig, keep, blocks, w, cfg
         eng.graphs.clear()      # captured graphs hold the old weight pointers / switches
         return eng
 

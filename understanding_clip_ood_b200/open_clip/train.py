@@ -23,16 +23,66 @@ _BLOCK_FIELDS = (("ln_1.weight", "ln1_g"), ("ln_1.bias", "ln1_b"), ("ln_2.weight
 _F32_FIELDS = {"ln1_g", "ln1_b", "ln2_g", "ln2_b"}
 
 
-def _block_grads(stack, prefix: str, dt: torch.dtype, device, out: dict):
-    """-> ctypes array of BlockGrads whose buffers are registered in `out` under the parameters' qualified names."""
-    arr = (L.BlockGrads * stack.layers)()
+class _Arena:
+    """Gradient buffers of one backward as TWO allocations (one per dtype) carved into views: ~150 tensors per tower would
+    otherwise cost one allocator call each, and — in the mixed-precision modes — one up-cast launch each."""
+
+    def __init__(self, device, dt: torch.dtype):
+        self.device, self.dt = device, dt
+        self.plan: list = []          # (name, shape, is_f32, offset)
+        self.n16 = self.n32 = 0
+
+    def add(self, name: str, shape, f32: bool) -> None:
+        n = 1
+        for d in shape:
+            n *= d
+        n_al = (n + 63) // 64 * 64    # 256-byte aligned in either dtype
+        if f32 or self.dt == torch.float32:
+            self.plan.append((name, tuple(shape), True, self.n32))
+            self.n32 += n_al
+        else:
+            self.plan.append((name, tuple(shape), False, self.n16))
+            self.n16 += n_al
+
+    def allocate(self) -> dict:
+        self.flat32 = torch.empty(max(self.n32, 1), dtype=torch.float32, device=self.device)
+        self.flat16 = torch.empty(max(self.n16, 1), dtype=self.dt, device=self.device) if self.dt != torch.float32 else None
+        out = {}
+        for name, shape, f32, off in self.plan:
+            n = 1
+            for d in shape:
+                n *= d
+            out[name] = (self.flat32 if f32 else self.flat16)[off:off + n].view(shape)
+        return out
+
+    def upcast(self, grads: dict) -> dict:
+        """All 16-bit gradients as fp32 views of ONE converted buffer (fp32 master parameters of the `amp*` modes)."""
+        if self.flat16 is None:
+            return grads
+        wide = self.flat16.float()
+        out = dict(grads)
+        for name, shape, f32, off in self.plan:
+            if not f32:
+                n = 1
+                for d in shape:
+                    n *= d
+                out[name] = wide[off:off + n].view(shape)
+        return out
+
+
+def _plan_blocks(arena: _Arena, stack, prefix: str) -> None:
     named = dict(stack.named_parameters())
     for i in range(stack.layers):
         for pname, field in _BLOCK_FIELDS:
-            p = named[f"resblocks.{i}.{pname}"]
-            g = torch.empty(p.shape, dtype=torch.float32 if field in _F32_FIELDS else dt, device=device)
-            out[f"{prefix}resblocks.{i}.{pname}"] = g
-            setattr(arr[i], field, g.data_ptr())
+            arena.add(f"{prefix}resblocks.{i}.{pname}", named[f"resblocks.{i}.{pname}"].shape, field in _F32_FIELDS)
+
+
+def _block_grads(stack, prefix: str, grads: dict):
+    """-> ctypes array of BlockGrads pointing at the arena's views."""
+    arr = (L.BlockGrads * stack.layers)()
+    for i in range(stack.layers):
+        for pname, field in _BLOCK_FIELDS:
+            setattr(arr[i], field, grads[f"{prefix}resblocks.{i}.{pname}"].data_ptr())
     return arr
 
 
@@ -104,16 +154,19 @@ class VitTrainFn(torch.autograd.Function):
             eng, cfg, weights = _captured_engine(ctx, "vision tower")
             dt = ctx.dt
             B, Lq, W = image.shape[0], cfg.seq_len, cfg.width
-            grads: dict = {}
-            blocks = _block_grads(tower.transformer, "transformer.", dt, dev, grads)
-            g = L.VitGrads()
-            conv = torch.empty((W, cfg.patch_kpad), dtype=dt, device=dev)
-            f32 = dict(dtype=torch.float32, device=dev)
-            grads["class_embedding"] = torch.empty(W, **f32)
-            grads["positional_embedding"] = torch.empty((Lq, W), **f32)
+            arena = _Arena(dev, dt)
+            _plan_blocks(arena, tower.transformer, "transformer.")
+            arena.add("conv1.padded", (W, cfg.patch_kpad), False)
+            arena.add("class_embedding", (W,), True)
+            arena.add("positional_embedding", (Lq, W), True)
             for n in ("ln_pre", "ln_post"):
-                grads[f"{n}.weight"], grads[f"{n}.bias"] = torch.empty(W, **f32), torch.empty(W, **f32)
-            grads["proj"] = torch.empty((W, tower.output_dim), dtype=dt, device=dev)
+                arena.add(f"{n}.weight", (W,), True)
+                arena.add(f"{n}.bias", (W,), True)
+            arena.add("proj", (W, tower.output_dim), False)
+            grads = arena.allocate()
+            blocks = _block_grads(tower.transformer, "transformer.", grads)
+            g = L.VitGrads()
+            conv = grads["conv1.padded"]
             g.conv1_w, g.class_emb, g.pos_emb = conv.data_ptr(), grads["class_embedding"].data_ptr(), grads["positional_embedding"].data_ptr()
             g.ln_pre_g, g.ln_pre_b = grads["ln_pre.weight"].data_ptr(), grads["ln_pre.bias"].data_ptr()
             g.ln_post_g, g.ln_post_b = grads["ln_post.weight"].data_ptr(), grads["ln_post.bias"].data_ptr()
@@ -125,7 +178,9 @@ class VitTrainFn(torch.autograd.Function):
                                               ctx.saved.data_ptr(), C.byref(g), bws.data_ptr(), bws.numel(), L.stream_ptr()),
                     "b200clip_vit_backward")
             P = tower.patch_size[0]
-            grads["conv1.weight"] = conv[:, :3 * P * P].reshape(W, 3, P, P)
+            if any(p.dtype == torch.float32 for p in ctx.params) and dt != torch.float32:
+                grads = arena.upcast(grads)
+            grads["conv1.weight"] = grads["conv1.padded"][:, :3 * P * P].reshape(W, 3, P, P)
         ctx.saved = None
         return (None, None, None, None, *_hand_over(grads, ctx.names, ctx.params))
 
@@ -163,13 +218,15 @@ class TextTrainFn(torch.autograd.Function):
             eng, cfg, weights = _captured_engine(ctx, "text tower")
             dt = ctx.dt
             T, W, D = text.shape[0], cfg.width, model.text_projection.shape[1]
-            grads: dict = {}
-            blocks = _block_grads(model.transformer, "transformer.", dt, dev, grads)
-            f32 = dict(dtype=torch.float32, device=dev)
-            grads["token_embedding.weight"] = torch.empty((model.vocab_size, W), **f32)
-            grads["positional_embedding"] = torch.empty((model.context_length, W), **f32)
-            grads["ln_final.weight"], grads["ln_final.bias"] = torch.empty(W, **f32), torch.empty(W, **f32)
-            grads["text_projection"] = torch.empty((W, D), dtype=dt, device=dev)
+            arena = _Arena(dev, dt)
+            _plan_blocks(arena, model.transformer, "transformer.")
+            arena.add("token_embedding.weight", (model.vocab_size, W), True)
+            arena.add("positional_embedding", (model.context_length, W), True)
+            arena.add("ln_final.weight", (W,), True)
+            arena.add("ln_final.bias", (W,), True)
+            arena.add("text_projection", (W, D), False)
+            grads = arena.allocate()
+            blocks = _block_grads(model.transformer, "transformer.", grads)
             g = L.TextGrads()
             g.tok_emb, g.pos_emb = grads["token_embedding.weight"].data_ptr(), grads["positional_embedding"].data_ptr()
             g.ln_final_g, g.ln_final_b = grads["ln_final.weight"].data_ptr(), grads["ln_final.bias"].data_ptr()
@@ -180,5 +237,7 @@ class TextTrainFn(torch.autograd.Function):
             L.check(lib.b200clip_text_backward(C.byref(cfg), C.byref(weights), text.data_ptr(), d_out.data_ptr(), T, ctx.seq_len,
                                                int(ctx.normalize), ctx.saved.data_ptr(), C.byref(g), bws.data_ptr(), bws.numel(), L.stream_ptr()),
                     "b200clip_text_backward")
+            if any(p.dtype == torch.float32 for p in ctx.params) and dt != torch.float32:
+                grads = arena.upcast(grads)
         ctx.saved = None
         return (None, None, None, None, None, *_hand_over(grads, ctx.names, ctx.params))
