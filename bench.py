@@ -434,6 +434,229 @@ def gpu_eager_baseline(model_name: str, batch: int, dev, steps: int) -> dict | N
                     "encode_image + normalize + tensordot + top-5, device-resident inputs, CUDA events"}
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE config 4: contrastive training step (ViT-B-32, 128 pairs per GPU, ClipLoss --local-loss --gather-with-grad)
+# ------------------------------------------------------------------------------------------------------------------
+TRAIN_METRIC = "contrastive_train_pairs_per_sec"
+TRAIN_UNIT = "pairs/s"
+TRAIN_BATCH = 128
+# executed FLOPs per pair: (image 8.818 + text 5.960 GFLOP forward) x (forward + block recompute + 2 x backward)
+TRAIN_FLOPS_PER_PAIR = (8.818e9 + 5.960e9) * 4
+
+
+def synthetic_pairs(batch: int, seed: int, device=None):
+    g = torch.Generator(device=device).manual_seed(seed) if device is not None else torch.Generator().manual_seed(seed)
+    image = torch.randn(batch, 3, 224, 224, generator=g, device=device)
+    text = torch.zeros(batch, 77, dtype=torch.long, device=device)
+    text[:, 0] = 49406
+    text[:, 1:9] = torch.randint(1000, 40000, (batch, 8), generator=g, device=device)
+    text[:, 9] = 49407
+    return image, text
+
+
+def reference_train_step_factory(ref, device, batch: int, amp: bool):
+    """The reference's own training step (training/train.py:115-183 with --grad-checkpointing --precision amp_bf16 on the GPU,
+    fp32 on the CPU): its CLIP, its ClipLoss, torch.optim.AdamW (training/main.py:299-326)."""
+    torch.manual_seed(0)
+    model = ref.create_model("ViT-B-32", precision="fp32", device="cpu").to(device).train()
+    model.set_grad_checkpointing(True)
+    import importlib
+    loss_fn = importlib.import_module("open_clip.loss").ClipLoss()
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2)
+    image, text = synthetic_pairs(batch, 1, device)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            fi, ft, scale = model(image, text)
+            loss = loss_fn(fi, ft, scale)
+        loss.backward()
+        opt.step()
+        return loss
+
+    return step
+
+
+def run_train_reference_arm(args) -> None:
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    ref = load_reference_open_clip()
+    sample = int(os.environ.get("B200CLIP_REF_SAMPLE", "8"))
+    torch.set_num_threads(os.cpu_count() or 1)
+    if ref is None:
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref (the reference's vendored OpenCLIP) is not installed: no CPU training step to time"}))
+        return
+    step = reference_train_step_factory(ref, torch.device("cpu"), sample, amp=False)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    what = (f"{args.steps} steps x {sample} pairs (bounded sample of the 128-pair batch): the reference's CLIP + ClipLoss + torch AdamW with "
+            "--grad-checkpointing, fp32, on the host cores (baseline/_ref)")
+    print(json.dumps({"impl": "reference", "metric": TRAIN_METRIC, "value": value, "unit": TRAIN_UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic", "config": train_config(args.gpus, {"cpu_sample_pairs_per_step": sample}),
+                      "cpu_baseline": {"value": value, "unit": TRAIN_UNIT, "cores": torch.get_num_threads(), "kind": "reference", "sample": what},
+                      "e2e": {"value": value, "unit": TRAIN_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def train_config(n_gpus: int, extra: dict | None = None) -> dict:
+    cfg = {"workload": f"ViT-B-32 contrastive training step (BASELINE config 4 shapes): {TRAIN_BATCH} image-text pairs per GPU, both towers forward, "
+                       "ClipLoss --local-loss --gather-with-grad, tower backward with per-block recompute (--grad-checkpointing), fused AdamW; "
+                       "accum-freq 1 (the reference's accum 2 runs this step's forward twice more under no_grad)",
+           "batch_per_gpu": TRAIN_BATCH, "global_batch": TRAIN_BATCH * n_gpus, "precision": "amp_bf16 (fp32 master weights, bf16 kernels)",
+           "parallelism": f"dp{n_gpus}: feature exchange over peer memory inside ClipLoss, gradient all-reduce by torch DistributedDataParallel (NCCL)",
+           "l2_policy": "activations + gradients of a step (>1 GB) exceed the 126 MB L2", "weights": "random init, torch.manual_seed(0)",
+           "baseline_config": 4}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def run_train(args) -> None:
+    from understanding_clip_ood_b200 import _lib as L
+    from understanding_clip_ood_b200 import open_clip, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+    peaks = measured_peaks()
+    torch.manual_seed(0)
+    model = open_clip.create_model("ViT-B-32", precision="amp_bf16", device="cpu").to(dev).train()
+    net = model
+    if dist is not None:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True)   # as training/main.py:311-326
+    opt = open_clip.AdamW(model.parameters(), lr=5e-4, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2)
+    loss_fn = open_clip.ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+    image, text = synthetic_pairs(TRAIN_BATCH, 1 + rank, dev)
+
+    def step(img, txt):
+        opt.zero_grad(set_to_none=True)
+        fi, ft, scale = net(img, txt)
+        loss = loss_fn(fi, ft, scale)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank, period_s=float(os.environ.get("B200CLIP_CLOCK_PERIOD_S", "0.02")))
+    if rank == 0:
+        sampler.start()
+    warmup = max(args.warmup, 3)
+    first = None
+    for i in range(warmup):
+        loss = step(image, text)
+        if i == 0:
+            first = float(loss.detach())
+    barrier()
+    launches0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.begin()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(image, text)
+    e1.record()
+    barrier()
+    launches = L.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t)
+    value = TRAIN_BATCH * world * args.steps / (ms_total * 1e-3)
+    last = float(loss.detach())
+
+    # ---- end to end: the batch arrives in pinned host memory every step (fp32 images as the reference's DataLoader delivers them) --
+    host = [(img.pin_memory(), txt.pin_memory()) for img, txt in (synthetic_pairs(TRAIN_BATCH, 50 + i) for i in range(2))]
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_run(steps):
+        for i in range(steps):
+            img, txt = host[i % 2]
+            host_loss.copy_(step(img.to(dev, non_blocking=True), txt.to(dev, non_blocking=True)).detach(), non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_run(2)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(args.steps)
+    t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = TRAIN_BATCH * world * args.steps / float(t)
+
+    if rank == 0:
+        roof = time_gemm_roofline(ops, L, peaks, TRAIN_BATCH * 50)
+        cpu = {"value": None, "unit": TRAIN_UNIT, "cores": 0, "kind": "n/a", "sample": "not run at N > 1"}
+        eager = None
+        if world == 1:
+            ref = load_reference_open_clip()
+            if ref is not None:
+                del net, opt
+                torch.cuda.empty_cache()
+                rstep = reference_train_step_factory(ref, dev, TRAIN_BATCH, amp=True)
+                for _ in range(3):
+                    rstep()
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                r0.record()
+                n = max(args.steps // 2, 5)
+                for _ in range(n):
+                    rstep()
+                r1.record()
+                torch.cuda.synchronize()
+                rms = r0.elapsed_time(r1) / n
+                eager = {"value": TRAIN_BATCH / rms * 1e3, "unit": TRAIN_UNIT, "ms_per_step": rms, "ours_over_eager": value / (TRAIN_BATCH / rms * 1e3),
+                         "what": "unmodified vendored OpenCLIP of the reference (baseline/_ref) on the same B200: torch.autocast(bf16), "
+                                 "--grad-checkpointing, its ClipLoss, torch.optim.AdamW, eager PyTorch"}
+                rstep = None
+                torch.cuda.empty_cache()
+                cstep = reference_train_step_factory(ref, torch.device("cpu"), 8, amp=False)
+                torch.set_num_threads(os.cpu_count() or 1)
+                cstep()
+                t0 = time.perf_counter()
+                reps = 0
+                while time.perf_counter() - t0 < 12.0 or reps < 1:
+                    cstep()
+                    reps += 1
+                cdt = time.perf_counter() - t0
+                cpu = {"value": 8 * reps / cdt, "unit": TRAIN_UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+                       "sample": f"{reps} steps x 8 pairs, the reference's CLIP + ClipLoss + torch AdamW with --grad-checkpointing in fp32 on the host cores, {cdt:.1f} s"}
+        tflops = TRAIN_FLOPS_PER_PAIR * value / world / 1e12
+        img_bytes = TRAIN_BATCH * 3 * 224 * 224 * 4 + TRAIN_BATCH * 77 * 8
+        line = {"metric": TRAIN_METRIC, "value": value, "unit": TRAIN_UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic", "config": train_config(world),
+                "e2e": {"value": e2e_value, "unit": TRAIN_UNIT, "h2d_bytes_per_step": img_bytes, "d2h_bytes_per_step": 4,
+                        "what": "the same step with the batch (fp32 images + int64 tokens) copied from pinned host memory every step and the loss read back"},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": eager,
+                "per_gpu": {"pairs_per_s": value / world, "executed_tflops": tflops, "frac_of_bf16_peak_burst": tflops / peaks["bf16_tflops"]},
+                "loss_first_step": first, "loss_last_step": last}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_ours(args) -> None:
     from understanding_clip_ood_b200 import _lib as L
     from understanding_clip_ood_b200 import open_clip, ops
@@ -666,8 +889,15 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 2 ViT-B-32 zero-shot (default), 3 ViT-B-16 feature extraction, 4 ViT-B-32 contrastive "
                          "training shapes (128 images per GPU), 5 ViT-L-14 zero-shot (256 per GPU)")
+    ap.add_argument("--train", action="store_true",
+                    help="BASELINE config 4 as a full training step (both towers forward + ClipLoss + backward + fused AdamW) instead of the "
+                         "zero-shot step; metric contrastive_train_pairs_per_sec")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.config == 4:
+        args.train = True
+    if args.train:
+        (run_train_reference_arm if args.impl == "reference" else run_train)(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)
