@@ -429,3 +429,18 @@ def test_statistics_slot_count_fits_the_workspace_carve_up():
             assert slots >= 2 and slots % 2 == 0 and slots <= W // 64 + 2, (W, rows, slots)
     assert lib.b200clip_gemm_stats_slots(51200, 768) == 6          # three 256-wide N tiles, two epilogue groups each
     assert lib.b200clip_gemm_stats_slots(0, 768) < 0               # invalid argument -> error code, no crash
+
+
+def test_eval_driver_shards_batches_round_robin():
+    """xclip/evaluate.py: rank r takes batches r, r + world, ...; together the ranks cover every batch exactly once."""
+    from understanding_clip_ood_b200.xclip.evaluate import shard_batches
+    batches = list(range(11))
+    seen = []
+    for r in range(4):
+        mine = list(shard_batches(batches, r, 4))
+        assert mine == batches[r::4]
+        seen += mine
+    assert sorted(seen) == batches
+    assert list(shard_batches(batches)) == batches
+    with pytest.raises(ValueError):
+        list(shard_batches(batches, 4, 4))

@@ -137,6 +137,35 @@ def test_zero_shot_classifiers_match_reference(tiny):
     assert row_rel(zd.prompt_feat, tiny["openai_di_prompt_feat"]) < 1e-4
 
 
+def test_multi_checkpoint_eval_driver(tiny, tmp_path):
+    """xclip/evaluate.py: several checkpoints x datasets through ONE model instance; accuracies equal those of a
+    fresh model + classifier per checkpoint (the reference loop, scripts/evaluate_domainnet_lso_openai.py:214-228)."""
+    from torch.utils.data import TensorDataset
+    from understanding_clip_ood_b200.xclip.evaluate import evaluate_checkpoints
+    tok = FakeTokenizer(300)
+    names = tiny["zs_names"]
+    g = torch.Generator().manual_seed(31)
+    ds = {"a": TensorDataset(torch.randn(37, 3, 64, 64, generator=g), torch.randint(0, len(names), (37,), generator=g)),
+          "b": TensorDataset(torch.randint(0, 256, (20, 3, 64, 64), generator=g, dtype=torch.uint8), torch.randint(0, len(names), (20,), generator=g))}
+    ckpts = []
+    for i in range(3):
+        torch.manual_seed(40 + i)
+        m = open_clip.create_model("ViT-B-32", precision="fp32", device="cpu", **tiny["cfg"])
+        path = tmp_path / f"epoch_{i}.pt"
+        torch.save({"state_dict": m.state_dict(), "epoch": i}, path)
+        ckpts.append(str(path))
+    res = evaluate_checkpoints("ViT-B-32", ckpts, ds, {"a": names, "b": names}, tokenizer=tok, precision="fp32", batch_size=8, **tiny["cfg"])
+    for i, path in enumerate(ckpts):
+        m = open_clip.create_model("ViT-B-32", precision="fp32", device=DEV, pretrained=path, **tiny["cfg"]).eval()
+        z = zs.OpenAIZeroShotClassifier(OpenCLIP(m), tok, names)
+        for name, d in ds.items():
+            img, lab = d.tensors
+            pred = z.predict(img.to(DEV))["pred"].cpu()
+            assert res[name][path]["num-samples"] == len(lab)
+            assert res[name][path]["top1"] == pytest.approx(float((pred == lab).float().mean()), abs=1e-9)
+            assert res[name][path]["top5"] >= res[name][path]["top1"]
+
+
 def test_compute_scores_matches_reference_formula(tiny):
     """_compute_scores (xclip/zero_shot.py:62-67): softmax(clip.logit_scale * logits) over the class axis; the golden logits
     are the reference's, logit_scale is the wrapper's exp().clamp(0, 100) (xclip/open_clip/model.py:25-27)."""
