@@ -283,6 +283,19 @@ int b200clip_vit_forward_u8(const b200clip_tower_cfg* cfg, const b200clip_vit_we
 int b200clip_patchify_u8(int dtype, const uint8_t* image, const float* mean, const float* std, void* patches, int batch,
                          int image_size, int patch, int kpad, void* stream);
 
+/* Bicubic resize + centre crop in front of the uint8 entry: a decoded image `src_hwc` [H, W, 3] uint8 (row pitch `row_stride`
+ * bytes) -> `dst_chw` [3, out_h, out_w] uint8 = the crop window of torchvision's Resize(S, BICUBIC) + CenterCrop(S) on a PIL
+ * image (deps/open_clip/src/open_clip/transform.py:372-392), BIT-IDENTICAL to Pillow's ImagingResample: two integer passes
+ * (horizontal, then vertical) with Pillow's anti-aliasing bicubic coefficients in 22-bit fixed point and an 8-bit intermediate.
+ * The host computes the tables the way Pillow does (open_clip/gpu_transform.py) for the crop window only:
+ *   h_bounds [out_w][2] = (first source column, taps), h_coeffs [out_w][h_ksize] int32; v_bounds / v_coeffs likewise for the
+ *   out_h output rows (source ROW indices); [y0, y0 + rows) = the source rows the vertical windows touch;
+ *   tmp: rows * out_w * 3 bytes of scratch (the horizontally resampled rows). */
+int b200clip_resize_crop_u8(const uint8_t* src_hwc, int H, int W, int64_t row_stride, const int32_t* h_bounds,
+                            const int32_t* h_coeffs, int h_ksize, const int32_t* v_bounds, const int32_t* v_coeffs,
+                            int v_ksize, int y0, int rows, uint8_t* tmp, uint8_t* dst_chw, int out_h, int out_w,
+                            void* stream);
+
 /* VisionTransformer.forward (transformer.py:601-643): image [B,3,S,S] dtype -> out [B,D] dtype
  * (L2-normalised when `normalize` != 0, CLIP.encode_image model.py:265-267). */
 int b200clip_vit_forward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, void* out,

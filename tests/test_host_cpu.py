@@ -6,6 +6,7 @@ import os
 import re
 from pathlib import Path
 
+import numpy as np
 import pytest
 import torch
 
@@ -444,3 +445,20 @@ def test_eval_driver_shards_batches_round_robin():
     assert list(shard_batches(batches)) == batches
     with pytest.raises(ValueError):
         list(shard_batches(batches, 4, 4))
+
+
+@pytest.mark.parametrize("h,w,S", [(300, 400, 224), (500, 333, 224), (224, 224, 224), (231, 517, 224), (100, 150, 224), (768, 512, 336), (64, 96, 32)])
+def test_resize_crop_tables_reproduce_pillow_bit_for_bit(h, w, S):
+    """open_clip/gpu_transform.py restates how Pillow derives its fixed-point bicubic tables; the two integer passes evaluated in
+    numpy must equal torchvision Resize(S, BICUBIC) + CenterCrop(S) on the PIL image — the eval preprocessing the reference builds
+    (deps/open_clip/src/open_clip/transform.py:372-392) — bit for bit, for down- and up-scaling, both orientations."""
+    from PIL import Image
+    from torchvision import transforms as T
+    from torchvision.transforms import InterpolationMode
+    from understanding_clip_ood_b200.open_clip import gpu_transform as G
+    rng = np.random.default_rng(h * 1000 + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    img[: h // 2] = (np.linspace(0, 255, w)[None, :, None] * np.ones((h // 2, 1, 3))).astype(np.uint8)     # a smooth half as well
+    ref = np.asarray(T.Compose([T.Resize(S, interpolation=InterpolationMode.BICUBIC), T.CenterCrop(S)])(Image.fromarray(img))).transpose(2, 0, 1)
+    assert np.array_equal(G.emulate_numpy(img, S), ref)
+    assert G.resized_size(h, w, S) == tuple(T.Resize(S)(Image.fromarray(img)).size[::-1])

@@ -591,3 +591,25 @@ def test_slot_addressed_backward_and_reduce_finish(n, D, world, rank):
     assert int(pad[48]) == 0             # ... and is released
     assert torch.allclose(out, recv[rank].view(world + 2, n, 2 * D).sum(0), rtol=1e-6, atol=1e-7)
     assert all(int(others[p][16 + rank]) == epoch for p in range(world))
+
+
+# ------------------------------------------------------------------ bicubic resize + centre crop (csrc/preprocess.cu) -------
+@pytest.mark.parametrize("h,w,S", [(300, 400, 224), (500, 333, 224), (224, 224, 224), (1080, 1920, 224), (100, 150, 224), (768, 512, 336)])
+def test_resize_center_crop_is_pillow_bicubic_bit_for_bit(h, w, S):
+    """The GPU preprocessing front end against the PIL pipeline of the reference's eval transform (torchvision Resize(S, BICUBIC) +
+    CenterCrop(S), transform.py:372-392): integer arithmetic, so byte-identical."""
+    import numpy as np
+    from PIL import Image
+    from torchvision import transforms as T
+    from torchvision.transforms import InterpolationMode
+    from understanding_clip_ood_b200.open_clip import gpu_transform as G
+    rng = np.random.default_rng(h + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ref = np.asarray(T.Compose([T.Resize(S, interpolation=InterpolationMode.BICUBIC), T.CenterCrop(S)])(Image.fromarray(img))).transpose(2, 0, 1)
+    got = G.resize_center_crop(torch.from_numpy(img).to(DEV), S)
+    assert got.dtype == torch.uint8 and tuple(got.shape) == (3, S, S)
+    assert np.array_equal(got.cpu().numpy(), ref)
+    tf = G.GpuEvalTransform(S)
+    assert torch.equal(tf(Image.fromarray(img)), got)                      # PIL image / numpy array inputs take the same route
+    view = torch.from_numpy(np.concatenate([img, img], axis=1)).to(DEV)[:, :w]   # a strided view (row pitch 2 W)
+    assert torch.equal(G.resize_center_crop(view, S), got)

@@ -112,6 +112,7 @@ SIGNATURES = {
     "b200clip_vit_forward_stages": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(VitWeights), _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                               _P, _I, _I, _P, _L, _I, _P]),
     "b200clip_text_forward_stages": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(TextWeights), _P, _P, _I, _I, _I, _P, _L, _I, _P]),
+    "b200clip_resize_crop_u8": (C.c_int, [_P, _I, _I, _L, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P]),
     "b200clip_train_saved_bytes": (C.c_int64, [C.POINTER(TowerCfg), _I, _I]),
     "b200clip_backward_workspace_bytes": (C.c_int64, [C.POINTER(TowerCfg), _I, _I]),
     "b200clip_vit_forward_train": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(VitWeights), _P, _P, _I, _I, _P, _L, _P, _L, _P]),

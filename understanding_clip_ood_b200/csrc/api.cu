@@ -336,6 +336,13 @@ int b200clip_text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_t
     return text_forward_stages(cfg, w, text, out, batch, seq_len, normalize, workspace, workspace_bytes, stages, S(stream));
 }
 
+int b200clip_resize_crop_u8(const uint8_t* src_hwc, int H, int W, int64_t row_stride, const int32_t* h_bounds, const int32_t* h_coeffs,
+                            int h_ksize, const int32_t* v_bounds, const int32_t* v_coeffs, int v_ksize, int y0, int rows, uint8_t* tmp,
+                            uint8_t* dst_chw, int out_h, int out_w, void* stream) {
+    return resize_crop_u8(src_hwc, H, W, row_stride, h_bounds, h_coeffs, h_ksize, v_bounds, v_coeffs, v_ksize, y0, rows, tmp, dst_chw, out_h, out_w,
+                          S(stream));
+}
+
 int64_t b200clip_train_saved_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) { return train_saved_bytes(cfg, batch, seq_len); }
 int64_t b200clip_backward_workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {
     return backward_workspace_bytes(cfg, batch, seq_len);

@@ -95,6 +95,11 @@ int p2p_allgather(int dtype, const void* img, const void* txt, int n, int D, flo
 int p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag, const uint32_t* my_flags, int world,
                       int slots, uint32_t epoch, uint32_t* my_busy, cudaStream_t stream);
 
+// bicubic resize + centre crop of a decoded uint8 HWC image (preprocess.cu); tables from the host (Pillow's fixed-point coefficients)
+int resize_crop_u8(const uint8_t* src_hwc, int H, int W, int64_t row_stride, const int32_t* h_bounds, const int32_t* h_coeffs, int h_ksize,
+                   const int32_t* v_bounds, const int32_t* v_coeffs, int v_ksize, int y0, int rows, uint8_t* tmp, uint8_t* dst_chw, int out_h,
+                   int out_w, cudaStream_t stream);
+
 // ---- training path (backward.cu, towers_bwd.cu, optim.cu) ----
 int gemm_f32_general(const float* A, int64_t lda, bool ta, const float* B, int64_t ldb, bool tb, float* C, int64_t ldc, int M, int N, int K,
                      bool accumulate, cudaStream_t stream);
