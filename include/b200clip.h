@@ -38,6 +38,8 @@ extern "C" {
 #define B200CLIP_EPI_QUICKGELU 2 /* C = x*sigmoid(1.702x)             (QuickGELU, transformer.py:33-36)                  */
 #define B200CLIP_EPI_RESIDUAL 3  /* C = R + (A W^T + b)               (out_proj / c_proj + residual, transformer.py:262-263) */
 #define B200CLIP_EPI_PATCH 4     /* patch-embedding: row remap + positional add (transformer.py:602-609)                 */
+#define B200CLIP_EPI_RELU 5      /* C = relu(A W^T + b)               (conv + folded BatchNorm + ReLU, modified_resnet.py:42-45) */
+#define B200CLIP_EPI_RESIDUAL_RELU 6 /* C = relu(R + (A W^T + b))     (bn3(conv3) + identity + ReLU, modified_resnet.py:46-55)   */
 
 int b200clip_version(void);
 const char* b200clip_last_error(void);

@@ -17,7 +17,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["B200CLIP_LIB"]).resolve() if os.environ.get("B200CLIP_LIB") else _PKG / "libb200clip.so"
 
 F32, BF16, F16 = 0, 1, 2
-EPI_BIAS, EPI_GELU, EPI_QUICKGELU, EPI_RESIDUAL, EPI_PATCH = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_GELU, EPI_QUICKGELU, EPI_RESIDUAL, EPI_PATCH, EPI_RELU, EPI_RESIDUAL_RELU = 0, 1, 2, 3, 4, 5, 6
 STAGE_INPUT, STAGE_BODY, STAGE_OUTPUT = 1, 2, 4
 
 _DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}

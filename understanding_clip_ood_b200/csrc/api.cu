@@ -70,7 +70,7 @@ int gemm_any(int dtype, const void* A, int64_t lda, const void* W, int64_t ldw, 
                         stream);
     if (dtype == B200CLIP_BF16 || dtype == B200CLIP_F16) {
         // the patch-embedding epilogue remaps rows (no TMA-store box), it stays on the single-CTA kernel
-        if (epilogue != B200CLIP_EPI_PATCH && !force_single_cta_gemm())
+        if (epilogue != B200CLIP_EPI_PATCH && (!force_single_cta_gemm() || epilogue >= B200CLIP_EPI_RELU))
             return gemm_pair(dtype == B200CLIP_BF16, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, 0, 0, stream, nullptr,
                              nullptr, nullptr, 0, nullptr, nullptr, 0, 1e-5f, sk_workspace);
         return gemm_tc(dtype == B200CLIP_BF16, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, pos, g_in, g_out, 0,
@@ -121,7 +121,7 @@ int b200clip_gemm(int dtype, const void* A, int64_t lda, const void* W, int64_t 
                   int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in, int g_out,
                   void* stream) {
     B2C_CHECK_ARG(A != nullptr && W != nullptr && C != nullptr, "gemm: null pointer");
-    B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 4, "gemm: unknown epilogue %d", epilogue);
+    B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 6, "gemm: unknown epilogue %d", epilogue);
     return gemm_any(dtype, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, pos, g_in, g_out, S(stream));
 }
 

@@ -114,8 +114,9 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const F32Params p) {
                 if (p.bias != nullptr) x += p.bias[col + j];
                 if constexpr (EPI == 1) x = gelu_erf(x);
                 else if constexpr (EPI == 2) x = x / (1.0f + expf(-1.702f * x));
-                else if constexpr (EPI == 3) x += p.residual[(int64_t)row * p.ldr + col + j];
+                else if constexpr (EPI == 3 || EPI == 6) x += p.residual[(int64_t)row * p.ldr + col + j];
                 else if constexpr (EPI == 4) x += pos_row[col + j];
+                if constexpr (EPI == 5 || EPI == 6) x = fmaxf(x, 0.f);
                 o[j] = x;
             }
             *reinterpret_cast<float4*>(p.C + out_row * p.ldc + col) = make_float4(o[0], o[1], o[2], o[3]);
@@ -133,7 +134,7 @@ int gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const flo
                   "gemm_f32: N, K and leading dimensions must be multiples of 4");
     B2C_CHECK_ARG((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) % 16 == 0,
                   "gemm_f32: A, W, C must be 16-byte aligned");
-    if (epilogue == 3) B2C_CHECK_ARG(residual != nullptr, "gemm_f32: residual epilogue needs a residual pointer");
+    if (epilogue == 3 || epilogue == 6) B2C_CHECK_ARG(residual != nullptr, "gemm_f32: residual epilogue needs a residual pointer");
     if (epilogue == 4) B2C_CHECK_ARG(pos != nullptr && g_in > 0 && g_out == g_in + 1, "gemm_f32: bad patch epilogue arguments");
     F32Params p{A, W, bias, residual, pos, C, M, N, K, lda, ldw, ldc, ldr, g_in, g_out};
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
@@ -143,6 +144,8 @@ int gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const flo
         case 2: gemm_f32_kernel<2, false, false><<<grid, 256, 0, stream>>>(p); break;
         case 3: gemm_f32_kernel<3, false, false><<<grid, 256, 0, stream>>>(p); break;
         case 4: gemm_f32_kernel<4, false, false><<<grid, 256, 0, stream>>>(p); break;
+        case 5: gemm_f32_kernel<5, false, false><<<grid, 256, 0, stream>>>(p); break;
+        case 6: gemm_f32_kernel<6, false, false><<<grid, 256, 0, stream>>>(p); break;
         default: set_last_error("gemm_f32: unknown epilogue %d", epilogue); return -1;
     }
     B2C_LAUNCH_CHECK("gemm_f32_kernel");

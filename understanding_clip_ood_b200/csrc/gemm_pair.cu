@@ -67,6 +67,11 @@ constexpr int kEpiPosAdd = 9;
 // the separate row-statistics pass over the residual stream (one more read of x per LayerNorm) disappears.  Deterministic:
 // fixed slots, fixed summation order, no atomics.
 constexpr int kEpiResidualStats = 10;
+// 11 = bias + ReLU, 12 = residual (TMA-loaded) + ReLU: conv + folded BatchNorm (+ identity) + ReLU of the ModifiedResNet
+// bottlenecks (deps/open_clip/src/open_clip/modified_resnet.py:42-55), the convolutions being GEMMs over NHWC rows
+constexpr int kEpiRelu = 11;
+constexpr int kEpiResidualRelu = 12;
+constexpr bool epi_loads_residual(int epi) { return epi == 3 || epi == kEpiResidualStats || epi == kEpiResidualRelu; }
 
 struct PairParams {
     const void* bias;      // storage-type bias [N]; LN-fold epilogues: fp32 b'[N]
@@ -280,7 +285,8 @@ template <typename T, int BLOCK_N, int EPI, int PAIRS, bool SK>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, const PairParams p) {
-    constexpr bool kRes = EPI == 3 || EPI == kEpiResidualStats;   // residual operand TMA-loaded into the staging ring
+    constexpr bool kRes = epi_loads_residual(EPI);   // residual operand TMA-loaded into the staging ring
+    constexpr bool kRelu = EPI == kEpiRelu || EPI == kEpiResidualRelu;
     constexpr bool kStats = EPI == kEpiResidualStats;
     using Cfg = PairCfg<BLOCK_N, kRes ? 3 : 2>;
     using H = Half16<T>;
@@ -696,6 +702,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 x0 += r2.x;
                                 x1 += r2.y;
                             }
+                            if constexpr (kRelu) {
+                                x0 = fmaxf(x0, 0.f);
+                                x1 = fmaxf(x1, 0.f);
+                            }
                             ow[j] = H::pack(x0, x1);
                             if constexpr (kStats) {
                                 const float2 rr = H::unpack(ow[j]);   // the values the next GEMM will read
@@ -756,7 +766,7 @@ int sk_clusters_planned() { return num_sms() / 2; }
 template <typename T, int BLOCK_N, int EPI, int PAIRS, bool SK>
 int launch_pair_sk(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr, const PairParams& p,
                    cudaStream_t stream) {
-    using Cfg = PairCfg<BLOCK_N, (EPI == 3 || EPI == kEpiResidualStats) ? 3 : 2>;
+    using Cfg = PairCfg<BLOCK_N, epi_loads_residual(EPI) ? 3 : 2>;
     auto kern = gemm_pair_kernel<T, BLOCK_N, EPI, PAIRS, SK>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -805,7 +815,7 @@ int launch_pair_sk(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorM
 template <typename T, int BLOCK_N, int EPI, int PAIRS>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr, const PairParams& p,
                 cudaStream_t stream) {
-    if constexpr (PAIRS == 1 && EPI != 3 && EPI != kEpiResidualStats) {
+    if constexpr (PAIRS == 1 && !epi_loads_residual(EPI)) {
         if (p.sk_tiles > 0) return launch_pair_sk<T, BLOCK_N, EPI, PAIRS, true>(ta, tw, tc, tr, p, stream);
     }
     B2C_CHECK_ARG(p.sk_tiles == 0, "gemm_pair: stream-K is not available for this kernel variant");
@@ -827,6 +837,12 @@ int launch_pair_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tw, const
         case kEpiPosAdd: return launch_pair<T, BLOCK_N, kEpiPosAdd, PAIRS>(ta, tw, tc, tr, p, s);
         case kEpiResidualStats:
             if constexpr (PAIRS == 1) return launch_pair<T, BLOCK_N, kEpiResidualStats, 1>(ta, tw, tc, tr, p, s);
+            break;
+        case kEpiRelu:
+            if constexpr (PAIRS == 1) return launch_pair<T, BLOCK_N, kEpiRelu, 1>(ta, tw, tc, tr, p, s);
+            break;
+        case kEpiResidualRelu:
+            if constexpr (PAIRS == 1) return launch_pair<T, BLOCK_N, kEpiResidualRelu, 1>(ta, tw, tc, tr, p, s);
             break;
     }
     set_last_error("gemm_pair: unsupported epilogue %d", epi);
@@ -960,7 +976,10 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
               cudaStream_t stream, const float* ln_colsum, const float* ln_rowstats, const float* pos_table, int pos_period,
               float* stats_out, const float* stats_part, int stats_slots, float ln_eps, void* sk_workspace) {
     B2C_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-    B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm_pair: unsupported epilogue %d", epilogue);
+    B2C_CHECK_ARG((epilogue >= 0 && epilogue <= 3) || epilogue == 5 || epilogue == 6, "gemm_pair: unsupported epilogue %d", epilogue);
+    const bool relu = epilogue == 5 || epilogue == 6;          // B200CLIP_EPI_RELU / B200CLIP_EPI_RESIDUAL_RELU
+    if (epilogue == 5) epilogue = 0;
+    if (epilogue == 6) epilogue = 3;
     const bool ln = ln_colsum != nullptr || ln_rowstats != nullptr || stats_part != nullptr;
     if (ln) {
         B2C_CHECK_ARG(ln_colsum != nullptr && (ln_rowstats != nullptr) != (stats_part != nullptr) && bias != nullptr && epilogue <= 2,
@@ -989,7 +1008,8 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     if (stats_out != nullptr) pairs = 1;
     // stream-K needs the caller's workspace, single pairs, and an epilogue without the TMA-loaded residual (whose prefetch runs
     // ahead on the whole-tile order): the in-place residual form (TMA reduce-add store) qualifies, a separate residual does not
-    const bool res_in_place = epilogue == 3 && residual == C && ldr == ldc && !no_reduce_store();
+    const bool res_in_place = epilogue == 3 && !relu && residual == C && ldr == ldc && !no_reduce_store();
+    if (relu) pairs = 1;
     const bool sk_ok = sk_workspace != nullptr && pairs == 1 && stats_out == nullptr && (epilogue != 3 || res_in_place);
     const int bn = force_block_n > 0 ? force_block_n : pick_pair_block_n(M, N, pairs, sk_ok);
 
@@ -1000,7 +1020,7 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     if (stats_out != nullptr) {
         if (make_tmap_2d(&tr, is_bf16, residual, M, N, ldr, kBM, kChunkN) != 0) return -1;
         epilogue = kEpiResidualStats;
-    } else if (epilogue == 3 && residual == C && ldr == ldc && !no_reduce_store()) {
+    } else if (res_in_place) {
         epilogue = kEpiResidualInPlace;
         tr = tc;
     } else if (epilogue == 3) {
@@ -1009,6 +1029,10 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
         tr = tc;
     }
 
+    if (relu) {
+        B2C_CHECK_ARG(!ln && pos_table == nullptr && stats_out == nullptr, "gemm_pair: the ReLU epilogues take a plain bias (+ residual)");
+        epilogue = epilogue == 3 ? kEpiResidualRelu : kEpiRelu;
+    }
     if (ln) epilogue += kEpiLnFold;
     if (pos_table != nullptr) {
         B2C_CHECK_ARG(!ln && epilogue == 0 && bias == nullptr && pos_period > 0 && reinterpret_cast<uintptr_t>(pos_table) % 16 == 0,
