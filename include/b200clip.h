@@ -328,6 +328,61 @@ int b200clip_text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_t
                                  void* out, int batch, int seq_len, int normalize, void* workspace,
                                  int64_t workspace_bytes, int stages, void* stream);
 
+/* ----- ModifiedResNet image tower (RN50 family) ----------------------------------------------------------------
+ * ModifiedResNet.forward in eval mode (deps/open_clip/src/open_clip/modified_resnet.py:95-181): activations are NHWC rows
+ * [B*H*W, C]; every convolution is a GEMM over those rows (3x3: over an im2col of them, K order (ky, kx, cin)) with
+ * BatchNorm's inference statistics folded into the weight rows and a per-channel shift by the caller:
+ *   w' = w * gamma / sqrt(running_var + eps),  b' = beta - running_mean * gamma / sqrt(running_var + eps).
+ * Weights are [cout, K] in the tower dtype (K contiguous), shifts [cout] in the tower dtype. */
+typedef struct b200clip_resnet_cfg {
+    int32_t dtype;       /* B200CLIP_F32 / BF16 / F16 */
+    int32_t image_size;  /* square input, multiple of 32 */
+    int32_t width;       /* stem output channels (64 for RN50); the stage widths are width * (1, 2, 4, 8) */
+    int32_t embed_dim;   /* attention-pool output dimension (CLIP embed_dim) */
+    int32_t heads;       /* attention-pool heads = width * 32 / 64 */
+    int32_t n_blocks;    /* bottlenecks over all four stages */
+    int32_t stem_kpad;   /* K of the stem conv1 GEMM: 27 taps zero-padded to whole 16-byte vectors */
+} b200clip_resnet_cfg;
+
+/* One Bottleneck (modified_resnet.py:10-56): conv1 1x1 [planes, cin], conv2 3x3 [planes, 9*planes], conv3 1x1
+ * [4*planes, planes]; `stride` 2 = AvgPool2d(2) after conv2 and in front of the downsample convolution;
+ * down_w [4*planes, cin] (NULL when the block has no downsample branch: stride 1 and cin == 4*planes). */
+typedef struct b200clip_resnet_block {
+    const void *conv1_w, *conv1_b, *conv2_w, *conv2_b, *conv3_w, *conv3_b, *down_w, *down_b;
+    int32_t cin, planes, stride, reserved;
+} b200clip_resnet_block;
+
+typedef struct b200clip_resnet_weights {
+    const void* stem_w[3];   /* [width/2, stem_kpad], [width/2, 9*width/2], [width, 9*width/2] */
+    const void* stem_b[3];
+    const b200clip_resnet_block* blocks_host;  /* HOST array of n_blocks entries (pointers inside are device pointers) */
+    const float* pos;        /* attnpool.positional_embedding [HW + 1, 32*width] fp32 */
+    const void* qkv_w;       /* [3*E, E] = q_proj | k_proj | v_proj weights stacked (E = 32*width), tower dtype */
+    const void* qkv_b;       /* [3*E] */
+    const void* c_proj_w;    /* [embed_dim, E] */
+    const void* c_proj_b;    /* [embed_dim] */
+} b200clip_resnet_weights;
+
+int64_t b200clip_resnet_workspace_bytes(const b200clip_resnet_cfg* cfg, const b200clip_resnet_weights* w, int batch);
+/* image [B,3,S,S] tower dtype -> out [B, embed_dim] (L2-normalised when `normalize` != 0); `stages` as for the ViT:
+ * INPUT = the stem im2col (the only kernel that reads `image`), BODY = stem GEMMs ... attention pool (workspace only),
+ * OUTPUT = attnpool.c_proj of the pooled token (+ normalise), the only kernels that write `out`. */
+int b200clip_resnet_forward_stages(const b200clip_resnet_cfg* cfg, const b200clip_resnet_weights* w, const void* image,
+                                   void* out, int batch, int normalize, void* workspace, int64_t workspace_bytes,
+                                   int stages, void* stream);
+
+/* The tower's data-movement operators on NHWC rows, also callable on their own:
+ *   stem_im2col      image [B,3,S,S] -> [B*(S/2)^2, kpad], conv1's 3x3 / stride 2 / padding 1 windows, K = (ky*3+kx)*3 + c
+ *                    (modified_resnet.py:107), columns 27.. zero;
+ *   im2col3x3        [B*H*W, C] -> [B*H*W, 9*C], 3x3 / stride 1 / padding 1 windows (modified_resnet.py:21,110,113);
+ *   avgpool2         nn.AvgPool2d(2) on [B,H,W,C] -> [B,H/2,W/2,C] (modified_resnet.py:25,36,116), fp32 sum, one rounding;
+ *   attnpool_tokens  [B*HW, C] -> [B*(HW+1), C]: the mean token in front, positional embedding added
+ *                    (AttentionPool2d.forward, modified_resnet.py:70-72). */
+int b200clip_stem_im2col(int dtype, const void* image, void* out, int batch, int image_size, int kpad, void* stream);
+int b200clip_im2col3x3(int dtype, const void* in, void* out, int batch, int H, int W, int C, void* stream);
+int b200clip_avgpool2(int dtype, const void* in, void* out, int batch, int H, int W, int C, void* stream);
+int b200clip_attnpool_tokens(int dtype, const void* x, const float* pos, void* tok, int batch, int HW, int C, void* stream);
+
 /* ----- training path: tower backward + fused optimizer -------------------------------------------------------
  * What autograd does for the reference's training step (deps/open_clip/src/training/train.py:115-183) through
  * CLIP.encode_image / encode_text with --grad-checkpointing (transformer.py:353-355): the training forward keeps only the

@@ -21,6 +21,9 @@ lives in the third-party dependency PyTorch (pinned torch==2.4.1 in /root/refere
   predict / topk     predict_from_features / accuracy  xclip/zero_shot.py:103-109 ; training/zero_shot.py:11-14
   class_prompt_feat  OpenAIZeroShotClassifier.__init__ xclip/zero_shot.py:223-240
   clip_loss_local    ClipLoss(local_loss, gather_with_grad)  deps/open_clip/src/open_clip/loss.py:89-131
+  resnet_forward     ModifiedResNet.forward (eval)   deps/open_clip/src/open_clip/modified_resnet.py:95-181 (Bottleneck :42-56,
+                     AttentionPool2d :69-92; torch nn.Conv2d = unfold + matmul, nn.BatchNorm2d on running statistics,
+                     nn.AvgPool2d(2) = mean of 2x2 windows, F.multi_head_attention_forward with separate q/k/v weights)
 
 PINNING: the reference ships no golden tensors for this path (tests/data is absent), so the
 oracle is pinned against outputs of the reference itself, generated in the build container by
@@ -35,7 +38,7 @@ import torch
 
 __all__ = [
     "vit_forward", "text_forward", "normalize", "zero_shot_logits", "predict", "topk", "class_prompt_feat",
-    "clip_loss_local", "clip_loss_local_grads", "cfg_from_state_dict", "preprocess_u8", "train_step_grads",
+    "clip_loss_local", "clip_loss_local_grads", "cfg_from_state_dict", "preprocess_u8", "train_step_grads", "resnet_forward", "randomize_batchnorm_", "test_images",
 ]
 
 
@@ -145,6 +148,90 @@ def _text(sd: dict, text: torch.Tensor, heads: int | None, quick_gelu: bool, seq
     x = _layer_norm(x, sd["ln_final.weight"], sd["ln_final.bias"])
     pooled = x[torch.arange(x.shape[0]), eot]
     return pooled @ sd["text_projection"]
+
+
+def randomize_batchnorm_(visual: torch.nn.Module, seed: int = 5, branch_gain: float = 0.25) -> None:
+    """Test helper: give every BatchNorm2d of a ModifiedResNet tower (the reference's or this repo's: same module order)
+    seeded non-trivial affine parameters.  At initialisation bn3.weight is zero (modified_resnet.py:143-146), which would
+    make every bottleneck's main branch vanish and the parity check blind."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, m in visual.named_modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                n = m.weight.shape
+                m.weight.copy_(torch.rand(n, generator=g) * 0.8 + 0.6)
+                m.bias.copy_(torch.randn(n, generator=g) * 0.1)
+                if name.startswith("layer") and name.endswith(".bn3"):
+                    m.weight.mul_(branch_gain)      # residual branches weaker than the identity path, as in a trained tower
+
+
+def test_images(n: int, size: int, seed: int) -> torch.Tensor:
+    """Seeded images with low-frequency structure (a random 7 x 7 field upsampled, plus pixel noise): unlike white noise they
+    survive the tower's average pools, so the embeddings of different images differ."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.nn.functional.interpolate(torch.randn(n, 3, 7, 7, generator=g), size=size, mode="bilinear", align_corners=False)
+    return 2.0 * low + 0.5 * torch.randn(n, 3, size, size, generator=g)
+
+
+def _conv_bn(x: torch.Tensor, sd: dict, conv: str, bn: str, *, stride: int = 1, relu: bool = True) -> torch.Tensor:
+    """nn.Conv2d (no bias, padding = k // 2) as unfold + matmul, then eval-mode nn.BatchNorm2d (eps 1e-5) and ReLU."""
+    w = sd[conv + ".weight"]
+    cout, cin, k, _ = w.shape
+    B, _, H, W = x.shape
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    cols = torch.nn.functional.unfold(x, k, padding=pad, stride=stride)            # [B, cin*k*k, Ho*Wo], K order (c, ky, kx)
+    y = (w.reshape(cout, cin * k * k) @ cols).reshape(B, cout, Ho, Wo)
+    g, b, m, v = (sd[f"{bn}.{n}"].reshape(1, cout, 1, 1) for n in ("weight", "bias", "running_mean", "running_var"))
+    y = (y - m) / torch.sqrt(v + 1e-5) * g + b
+    return y.clamp_min(0) if relu else y
+
+
+def _avgpool2(x: torch.Tensor) -> torch.Tensor:
+    B, C, H, W = x.shape
+    return x.reshape(B, C, H // 2, 2, W // 2, 2).mean(dim=(3, 5))
+
+
+def resnet_forward(sd: dict, image: torch.Tensor, *, heads: int | None = None) -> torch.Tensor:
+    """image [B,3,S,S] -> [B,D]: ModifiedResNet.forward in eval mode (modified_resnet.py:163-181)."""
+    sd = _f32(sd)
+    x = image.detach().to(torch.float32).cpu()
+    v = "visual."
+    x = _conv_bn(x, sd, v + "conv1", v + "bn1", stride=2)
+    x = _conv_bn(x, sd, v + "conv2", v + "bn2")
+    x = _conv_bn(x, sd, v + "conv3", v + "bn3")
+    x = _avgpool2(x)
+    for li in range(1, 5):
+        bi = 0
+        while f"{v}layer{li}.{bi}.conv1.weight" in sd:
+            p = f"{v}layer{li}.{bi}."
+            stride = 2 if (li > 1 and bi == 0) else 1
+            out = _conv_bn(x, sd, p + "conv1", p + "bn1")
+            out = _conv_bn(out, sd, p + "conv2", p + "bn2")
+            if stride > 1:
+                out = _avgpool2(out)
+            out = _conv_bn(out, sd, p + "conv3", p + "bn3", relu=False)
+            identity = x
+            if p + "downsample.0.weight" in sd:
+                identity = _conv_bn(_avgpool2(x) if stride > 1 else x, sd, p + "downsample.0", p + "downsample.1", relu=False)
+            x = (out + identity).clamp_min(0)
+            bi += 1
+    # AttentionPool2d (modified_resnet.py:69-92): the mean token queries all HW + 1 tokens
+    a = v + "attnpool."
+    B, E, H, W = x.shape
+    heads = heads or E // 64
+    t = x.reshape(B, E, H * W).permute(0, 2, 1)                                    # [B, HW, E]
+    t = torch.cat([t.mean(dim=1, keepdim=True), t], dim=1) + sd[a + "positional_embedding"]
+    q = t[:, :1] @ sd[a + "q_proj.weight"].t() + sd[a + "q_proj.bias"]
+    k = t @ sd[a + "k_proj.weight"].t() + sd[a + "k_proj.bias"]
+    val = t @ sd[a + "v_proj.weight"].t() + sd[a + "v_proj.bias"]
+    hd = E // heads
+    q = q.reshape(B, 1, heads, hd).transpose(1, 2) * hd ** -0.5
+    k = k.reshape(B, -1, heads, hd).transpose(1, 2)
+    val = val.reshape(B, -1, heads, hd).transpose(1, 2)
+    att = torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ val                     # [B, heads, 1, hd]
+    att = att.transpose(1, 2).reshape(B, E)
+    return att @ sd[a + "c_proj.weight"].t() + sd[a + "c_proj.bias"]
 
 
 def normalize(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:

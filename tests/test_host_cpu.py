@@ -99,8 +99,9 @@ def test_configs_and_errors():
     from understanding_clip_ood_b200 import open_clip
     assert {"ViT-B-32", "ViT-B-16", "ViT-L-14", "ViT-B-32-quickgelu"} <= set(open_clip.list_models())
     assert open_clip.get_model_config("ViT-L-14")["vision_cfg"]["width"] == 1024
+    assert {"RN50", "RN101", "RN50x4", "RN50x16", "RN50x64", "RN50-quickgelu"} <= set(open_clip.list_models())
     with pytest.raises(RuntimeError):
-        open_clip.create_model("RN50")
+        open_clip.create_model("convnext_base")
     with pytest.raises(RuntimeError):
         open_clip.create_model("ViT-B-32", precision="amp_fp8")
     tiny_kw = dict(vision_cfg={"image_size": 64, "layers": 1, "width": 64, "patch_size": 32},
@@ -194,6 +195,51 @@ def test_seeded_init_equals_reference_full_vit_b_32():
     torch.manual_seed(0)
     m = mine.create_model("ViT-B-32").state_dict()
     assert all(torch.equal(r[k], m[k]) for k in r) and list(r) == list(m)
+
+
+@pytest.mark.parametrize("name,precision", [("RN50", "fp32"), ("RN50", "bf16"), ("RN50x4", "fp16")])
+def test_seeded_init_equals_reference_modified_resnet(name, precision):
+    """ModifiedResNet towers: same state_dict keys, order, dtypes (BatchNorm and the positional table stay fp32) and seed-0 values."""
+    ref_oc, _, _ = _ref()
+    from understanding_clip_ood_b200 import open_clip as mine
+    torch.manual_seed(0)
+    r = ref_oc.create_model(name, precision=precision).state_dict()
+    torch.manual_seed(0)
+    m = mine.create_model(name, precision=precision).state_dict()
+    assert list(r) == list(m)
+    for k in r:
+        assert r[k].dtype == m[k].dtype and torch.equal(r[k], m[k]), k
+
+
+def test_modified_resnet_host_logic():
+    """Folding BatchNorm into the convolution operands (resnet.py:_fold) against the reference's conv -> bn on the CPU, the
+    state_dict layout, and the no-CPU-fallback rule."""
+    from understanding_clip_ood_b200 import open_clip
+    from understanding_clip_ood_b200._lib import B200ClipError
+    from understanding_clip_ood_b200.open_clip.resnet import _fold
+    from oracle import clip_oracle as O
+    kw = dict(embed_dim=128, vision_cfg={"image_size": 64, "layers": [1, 2, 1, 1], "width": 32, "patch_size": None},
+              text_cfg={"context_length": 77, "vocab_size": 100, "width": 64, "heads": 1, "layers": 1})
+    torch.manual_seed(0)
+    m = open_clip.create_model("RN50", **kw).eval()
+    keys = list(m.state_dict())
+    assert "visual.layer2.0.downsample.1.running_var" in keys and "visual.attnpool.positional_embedding" in keys
+    assert "visual.layer2.1.downsample.0.weight" not in keys and m.visual.attnpool.num_heads == 16
+    assert all(float(b.bn3.weight.abs().max()) == 0 for b in m.visual.bottlenecks())      # modified_resnet.py:143-146
+    O.randomize_batchnorm_(m.visual, 5)
+    blk = m.visual.layer2[0]
+    blk.bn2.running_mean.normal_(generator=torch.Generator().manual_seed(1))
+    blk.bn2.running_var.uniform_(0.5, 2.0, generator=torch.Generator().manual_seed(2))
+    x = torch.randn(2, blk.conv2.in_channels, 6, 6, generator=torch.Generator().manual_seed(3))
+    want = blk.bn2(blk.conv2(x))                                                          # eval-mode BatchNorm
+    w, b = _fold(blk.conv2, blk.bn2)
+    cols = torch.nn.functional.unfold(x, 3, padding=1).reshape(2, x.shape[1], 9, 36).permute(0, 3, 2, 1).reshape(72, -1)   # K = (tap, c)
+    got = (cols @ w.t() + b).reshape(2, 36, -1).permute(0, 2, 1).reshape(want.shape)
+    assert float((got - want).abs().max()) < 1e-5
+    w0, _ = _fold(m.visual.conv1, m.visual.bn1, kpad=32)
+    assert w0.shape == (16, 32) and float(w0[:, 27:].abs().max()) == 0
+    with pytest.raises(B200ClipError):
+        m.encode_image(torch.zeros(1, 3, 64, 64))                                         # CPU tensors: no fallback
 
 
 def test_tokenizer_equals_reference():

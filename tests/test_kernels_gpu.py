@@ -613,3 +613,84 @@ def test_resize_center_crop_is_pillow_bicubic_bit_for_bit(h, w, S):
     assert torch.equal(tf(Image.fromarray(img)), got)                      # PIL image / numpy array inputs take the same route
     view = torch.from_numpy(np.concatenate([img, img], axis=1)).to(DEV)[:, :w]   # a strided view (row pitch 2 W)
     assert torch.equal(G.resize_center_crop(view, S), got)
+
+
+# ------------------------------------------------------------------ ModifiedResNet operators (csrc/resnet.cu) ---------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("M,N,K,epi", [
+    (3 * 56 * 56, 64, 256, L.EPI_RELU),              # layer1 conv1 (1x1): narrow N
+    (2 * 112 * 112, 32, 288, L.EPI_RELU),            # stem conv2 as im2col GEMM: N = 32, K = 4.5 K-blocks
+    (2 * 112 * 112, 32, 32, L.EPI_RELU),             # stem conv1: K = 32 (27 taps padded)
+    (3 * 56 * 56, 256, 64, L.EPI_RESIDUAL_RELU),     # layer1 conv3 + identity + ReLU
+    (5 * 49, 2048, 512, L.EPI_RESIDUAL_RELU),        # layer4 conv3, ragged M
+    (1000, 264, 72, L.EPI_RESIDUAL_RELU),            # ragged M, N and K tails
+    (6400, 1024, 2304, L.EPI_RELU),                  # long K (stream-K when the workspace is given)
+])
+def test_gemm_relu_epilogues(dtype, M, N, K, epi):
+    """conv + folded BatchNorm (+ identity) + ReLU as GEMM epilogues (modified_resnet.py:42-56), vs fp32 torch."""
+    g = _gen(3)
+    a = (torch.randn(M, K, device=DEV, generator=g) * 0.5).to(dtype)
+    w = (torch.randn(N, K, device=DEV, generator=g) * 0.05).to(dtype)
+    bias = (torch.randn(N, device=DEV, generator=g) * 0.1).to(dtype)
+    res = torch.randn(M, N, device=DEV, generator=g).to(dtype) if epi == L.EPI_RESIDUAL_RELU else None
+    lin = a.float() @ w.float().t() + bias.float()
+    if dtype != torch.float32:
+        lin = lin.to(dtype).float()
+    ref = (lin + res.float() if res is not None else lin).clamp_min(0).to(dtype).float()
+    ulp = {torch.bfloat16: 2 ** -8, torch.float16: 2 ** -11, torch.float32: 2 ** -22}[dtype]
+    tol = 2 * ulp * ref.abs().max().item() + (1e-3 if dtype != torch.float32 else 1e-5)
+    outs = [ops.gemm(a, w, bias, epilogue=epi, residual=res)]
+    if dtype != torch.float32:
+        outs.append(ops.gemm_ws(a, w, bias, epilogue=epi, residual=res))
+    for out in outs:
+        assert (out.float() - ref).abs().max().item() <= tol
+        assert (out >= 0).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("B,H,W,C", [(2, 56, 56, 64), (3, 7, 7, 512), (1, 14, 10, 8), (2, 112, 112, 32)])
+def test_im2col3x3_is_unfold(dtype, B, H, W, C):
+    x = torch.randn(B, H, W, C, device=DEV, generator=_gen(4)).to(dtype)
+    out = torch.empty(B * H * W, 9 * C, dtype=dtype, device=DEV)
+    L.check(L.load().b200clip_im2col3x3(L.dtype_code(dtype), x.data_ptr(), out.data_ptr(), B, H, W, C, L.stream_ptr()), "im2col3x3")
+    cols = F.unfold(x.permute(0, 3, 1, 2).float(), 3, padding=1)                    # [B, C*9, H*W], K order (c, ky, kx)
+    ref = cols.reshape(B, C, 9, H * W).permute(0, 3, 2, 1).reshape(B * H * W, 9 * C)  # -> (tap, c)
+    assert torch.equal(out.float(), ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("B,S,kpad", [(2, 224, 32), (1, 64, 32), (3, 32, 64)])
+def test_stem_im2col_is_strided_unfold(dtype, B, S, kpad):
+    img = torch.randn(B, 3, S, S, device=DEV, generator=_gen(5)).to(dtype)
+    Ho = S // 2
+    out = torch.full((B * Ho * Ho, kpad), float("nan"), dtype=dtype, device=DEV)
+    L.check(L.load().b200clip_stem_im2col(L.dtype_code(dtype), img.data_ptr(), out.data_ptr(), B, S, kpad, L.stream_ptr()), "stem_im2col")
+    cols = F.unfold(img.float(), 3, padding=1, stride=2)                            # [B, 3*9, Ho*Ho], K order (c, tap)
+    ref = cols.reshape(B, 3, 9, Ho * Ho).permute(0, 3, 2, 1).reshape(B * Ho * Ho, 27)
+    assert torch.equal(out[:, :27].float(), ref)
+    assert (out[:, 27:] == 0).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("B,H,W,C", [(2, 56, 56, 256), (3, 14, 14, 8), (1, 112, 112, 64)])
+def test_avgpool2_nhwc(dtype, B, H, W, C):
+    x = torch.randn(B, H, W, C, device=DEV, generator=_gen(6)).to(dtype)
+    out = torch.empty(B, H // 2, W // 2, C, dtype=dtype, device=DEV)
+    L.check(L.load().b200clip_avgpool2(L.dtype_code(dtype), x.data_ptr(), out.data_ptr(), B, H, W, C, L.stream_ptr()), "avgpool2")
+    ref = F.avg_pool2d(x.permute(0, 3, 1, 2).float(), 2).permute(0, 2, 3, 1).to(dtype)
+    assert (out.float() - ref.float()).abs().max().item() <= (1e-6 if dtype == torch.float32 else 2 ** -8 * ref.float().abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("B,HW,C", [(4, 49, 2048), (2, 4, 1024), (3, 81, 2560)])
+def test_attnpool_tokens(dtype, B, HW, C):
+    g = _gen(7)
+    x = torch.randn(B, HW, C, device=DEV, generator=g).to(dtype)
+    pos = torch.randn(HW + 1, C, device=DEV, generator=g) * 0.05
+    tok = torch.empty(B, HW + 1, C, dtype=dtype, device=DEV)
+    L.check(L.load().b200clip_attnpool_tokens(L.dtype_code(dtype), x.data_ptr(), pos.data_ptr(), tok.data_ptr(), B, HW, C, L.stream_ptr()),
+            "attnpool_tokens")
+    # the reference's ops on `dtype` tensors (modified_resnet.py:70-72): mean, cat, + pos.to(dtype), one rounding each
+    ref = torch.cat([x.float().mean(dim=1, keepdim=True).to(dtype), x], dim=1) + pos.to(dtype)
+    ulp = {torch.bfloat16: 2 ** -8, torch.float16: 2 ** -11, torch.float32: 2 ** -22}[dtype]
+    assert (tok.float() - ref.float()).abs().max().item() <= ulp * ref.float().abs().max().item()

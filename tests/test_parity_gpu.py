@@ -536,3 +536,86 @@ def test_cliploss_full_size_properties():
     assert abs(sum(losses) / world - float(full)) / float(full) < 1e-5
     ref = float(O.clip_loss_local(all_img[:n], all_txt[:n], all_img, all_txt, float(scale), 0))
     assert abs(losses[0] - ref) / ref < 1e-3
+
+
+# ------------------------------------------------------------------ ModifiedResNet tower
+@pytest.fixture(scope="module")
+def rn_gold():
+    return torch.load(GOLD / "rn_seed0.pt", weights_only=False)
+
+
+def rn_model(gold, which, precision):
+    """Seed-0 weights (bit-identical to the reference's, tests/test_host_cpu.py), the fixture's BatchNorm recipe + statistics."""
+    torch.manual_seed(gold["seed_weights"])
+    kw = gold["tiny_cfg"] if which == "tiny" else {}
+    m = open_clip.create_model("RN50", precision=precision, device="cpu", **kw)
+    O.randomize_batchnorm_(m.visual, gold["seed_bn"])
+    missing, unexpected = m.load_state_dict({"visual." + k: v for k, v in gold[which + "_bn"].items()}, strict=False)
+    assert not unexpected
+    return m.to(DEV).eval()
+
+
+def centered_rel(a, b):
+    """relative error of the image-dependent part (features minus their batch mean)"""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float(((a - a.mean(0)) - (b - b.mean(0))).norm() / (b - b.mean(0)).norm())
+
+
+@pytest.mark.parametrize("which,size,n", [("tiny", 64, 6), ("rn50", 224, 8)])
+def test_resnet_fp32_matches_reference_golden(rn_gold, which, size, n):
+    m = rn_model(rn_gold, which, "fp32")
+    img = O.test_images(n, size, rn_gold["seed_images"])
+    want = rn_gold[which + "_fp32"]
+    got = m.encode_image(img.to(DEV))
+    assert row_rel(got, want) < 1e-4 and centered_rel(got, want) < 1e-4
+    got2 = m.encode_image(img.to(DEV).clone())        # second sighting of the shape: CUDA-graph replay, fresh input tensor
+    assert torch.equal(got2, got)
+    assert row_rel(O.resnet_forward(m.state_dict(), img), want) < 1e-4      # the oracle on the same weights
+    nrm = m.encode_image(img.to(DEV), normalize=True)
+    assert row_rel(nrm, torch.nn.functional.normalize(want, dim=-1)) < 1e-4
+    if which == "tiny":
+        from oracle.make_golden_rn import tiny_text
+        assert row_rel(m.encode_text(tiny_text().to(DEV)), rn_gold["tiny_text"]) < 1e-4
+
+
+@pytest.mark.parametrize("precision,dtype", [("bf16", torch.bfloat16), ("fp16", torch.float16)])
+def test_resnet_16bit_matches_reference(rn_gold, precision, dtype):
+    """RN50 in the 16-bit modes vs the reference's fp32 golden (gate 2e-2, north_star) — the reference's own bf16 run is the
+    yardstick for what 16-bit arithmetic costs on this tower (fixture rn50_bf16)."""
+    m = rn_model(rn_gold, "rn50", precision)
+    img = O.test_images(8, 224, rn_gold["seed_images"])
+    want = rn_gold["rn50_fp32"]
+    got = m.encode_image(img.to(dtype).to(DEV))
+    assert got.dtype == dtype
+    ref16 = row_rel(rn_gold["rn50_bf16"].float(), want)
+    ours = row_rel(got.float(), want)
+    print(f"RN50 {precision}: ours vs ref-fp32 {ours:.3e}, ref-bf16 vs ref-fp32 {ref16:.3e}, centered {centered_rel(got.float(), want):.3e}")
+    assert ours < 2e-2
+    assert centered_rel(got.float(), want) < 4e-2
+
+
+def test_resnet_large_batch_is_batch_invariant_and_classifies(rn_gold):
+    """Full-size property checks (no oracle at this size): a 256-image bf16 batch reproduces the rows of its 8-image prefix run
+    alone up to the batch-dependent fp32 summation order of the stream-K GEMMs, and the zero-shot stage runs on the tower."""
+    m = rn_model(rn_gold, "rn50", "bf16")
+    img = O.test_images(256, 224, 11).bfloat16().to(DEV)
+    big = m.encode_image(img, normalize=True)
+    small = m.encode_image(img[:8].contiguous(), normalize=True)
+    assert torch.isfinite(big.float()).all()
+    assert row_rel(big[:8].float(), small.float()) < 1e-2
+    clf = zs.ZeroShotClassifier(OpenCLIP(m), FakeTokenizer(300), [f"class {i}" for i in range(7)])
+    out = clf.predict(img[:32].contiguous())
+    assert out["pred"].shape == (32,)
+
+
+def test_resnet_rejects_what_is_not_on_the_path(rn_gold):
+    m = rn_model(rn_gold, "tiny", "fp32")
+    img = O.test_images(2, 64, 1).to(DEV)
+    m.train()
+    with pytest.raises(RuntimeError, match="BatchNorm"):
+        m.encode_image(img)
+    m.visual.lock(freeze_bn_stats=True)               # frozen statistics + no gradients: the eval path again
+    assert m.encode_image(img).shape == (2, 128)
+    m.eval()
+    with pytest.raises(RuntimeError, match="expected images"):
+        m.encode_image(img[:, :, :32, :32])

@@ -50,6 +50,20 @@ class TextWeights(C.Structure):
         "tok_emb", "pos_emb", "ln_final_g", "ln_final_b", "proj_t", "blocks_host")]
 
 
+class ResnetCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("dtype", "image_size", "width", "embed_dim", "heads", "n_blocks", "stem_kpad")]
+
+
+class ResnetBlock(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("conv1_w", "conv1_b", "conv2_w", "conv2_b", "conv3_w", "conv3_b", "down_w", "down_b")] + \
+               [(n, C.c_int32) for n in ("cin", "planes", "stride", "reserved")]
+
+
+class ResnetWeights(C.Structure):
+    _fields_ = [("stem_w", C.c_void_p * 3), ("stem_b", C.c_void_p * 3), ("blocks_host", C.c_void_p), ("pos", C.c_void_p),
+                ("qkv_w", C.c_void_p), ("qkv_b", C.c_void_p), ("c_proj_w", C.c_void_p), ("c_proj_b", C.c_void_p)]
+
+
 class BlockGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "ln1_g", "ln1_b", "ln2_g", "ln2_b", "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "fc_w", "fc_b", "proj_w", "proj_b")]
@@ -112,6 +126,12 @@ SIGNATURES = {
     "b200clip_vit_forward_stages": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(VitWeights), _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                               _P, _I, _I, _P, _L, _I, _P]),
     "b200clip_text_forward_stages": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(TextWeights), _P, _P, _I, _I, _I, _P, _L, _I, _P]),
+    "b200clip_resnet_workspace_bytes": (C.c_int64, [C.POINTER(ResnetCfg), C.POINTER(ResnetWeights), _I]),
+    "b200clip_resnet_forward_stages": (C.c_int, [C.POINTER(ResnetCfg), C.POINTER(ResnetWeights), _P, _P, _I, _I, _P, _L, _I, _P]),
+    "b200clip_stem_im2col": (C.c_int, [_I, _P, _P, _I, _I, _I, _P]),
+    "b200clip_im2col3x3": (C.c_int, [_I, _P, _P, _I, _I, _I, _I, _P]),
+    "b200clip_avgpool2": (C.c_int, [_I, _P, _P, _I, _I, _I, _I, _P]),
+    "b200clip_attnpool_tokens": (C.c_int, [_I, _P, _P, _P, _I, _I, _I, _P]),
     "b200clip_resize_crop_u8": (C.c_int, [_P, _I, _I, _L, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P]),
     "b200clip_train_saved_bytes": (C.c_int64, [C.POINTER(TowerCfg), _I, _I]),
     "b200clip_backward_workspace_bytes": (C.c_int64, [C.POINTER(TowerCfg), _I, _I]),

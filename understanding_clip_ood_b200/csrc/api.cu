@@ -103,6 +103,14 @@ int vit_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_vit_weights
 int text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w, const int64_t* text, void* out, int batch,
                         int seq_len, int normalize, void* workspace, int64_t workspace_bytes_, int stages, cudaStream_t s);
 
+int64_t resnet_workspace_bytes(const b200clip_resnet_cfg* cfg, const b200clip_resnet_weights* w, int batch);
+int resnet_forward_stages(const b200clip_resnet_cfg* cfg, const b200clip_resnet_weights* w, const void* image, void* out, int batch,
+                          int normalize, void* workspace, int64_t workspace_bytes_, int stages, cudaStream_t s);
+int stem_im2col(int dtype, const void* image, void* out, int batch, int image_size, int kpad, cudaStream_t s);
+int im2col3x3(int dtype, const void* in, void* out, int batch, int H, int W, int C, cudaStream_t s);
+int avgpool2(int dtype, const void* in, void* out, int batch, int H, int W, int C, cudaStream_t s);
+int attnpool_tokens(int dtype, const void* x, const float* pos, void* tok, int batch, int HW, int C, cudaStream_t s);
+
 }  // namespace b200clip
 
 using namespace b200clip;
@@ -131,7 +139,8 @@ int b200clip_gemm_ws(int dtype, const void* A, int64_t lda, const void* W, int64
                      int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, void* workspace, int64_t workspace_bytes,
                      void* stream) {
     B2C_CHECK_ARG(A != nullptr && W != nullptr && C != nullptr, "gemm_ws: null pointer");
-    B2C_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm_ws: epilogue must be BIAS, GELU, QUICKGELU or RESIDUAL");
+    B2C_CHECK_ARG((epilogue >= 0 && epilogue <= 3) || epilogue == B200CLIP_EPI_RELU || epilogue == B200CLIP_EPI_RESIDUAL_RELU,
+                  "gemm_ws: epilogue must be BIAS, GELU, QUICKGELU, RESIDUAL, RELU or RESIDUAL_RELU");
     if (dtype == B200CLIP_F32)  // the FFMA parity kernel tiles finely enough: no workspace needed
         return gemm_any(dtype, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, nullptr, 0, 0, S(stream));
     B2C_CHECK_ARG(workspace != nullptr && workspace_bytes >= gemm_pair_sk_workspace_bytes(), "gemm_ws: workspace too small (%lld < %lld bytes)",
@@ -334,6 +343,31 @@ int b200clip_text_forward_stages(const b200clip_tower_cfg* cfg, const b200clip_t
                                  int batch, int seq_len, int normalize, void* workspace, int64_t workspace_bytes, int stages,
                                  void* stream) {
     return text_forward_stages(cfg, w, text, out, batch, seq_len, normalize, workspace, workspace_bytes, stages, S(stream));
+}
+
+int64_t b200clip_resnet_workspace_bytes(const b200clip_resnet_cfg* cfg, const b200clip_resnet_weights* w, int batch) {
+    return resnet_workspace_bytes(cfg, w, batch);
+}
+
+int b200clip_resnet_forward_stages(const b200clip_resnet_cfg* cfg, const b200clip_resnet_weights* w, const void* image, void* out,
+                                   int batch, int normalize, void* workspace, int64_t workspace_bytes, int stages, void* stream) {
+    return resnet_forward_stages(cfg, w, image, out, batch, normalize, workspace, workspace_bytes, stages, S(stream));
+}
+
+int b200clip_stem_im2col(int dtype, const void* image, void* out, int batch, int image_size, int kpad, void* stream) {
+    return stem_im2col(dtype, image, out, batch, image_size, kpad, S(stream));
+}
+
+int b200clip_im2col3x3(int dtype, const void* in, void* out, int batch, int H, int W, int C, void* stream) {
+    return im2col3x3(dtype, in, out, batch, H, W, C, S(stream));
+}
+
+int b200clip_avgpool2(int dtype, const void* in, void* out, int batch, int H, int W, int C, void* stream) {
+    return avgpool2(dtype, in, out, batch, H, W, C, S(stream));
+}
+
+int b200clip_attnpool_tokens(int dtype, const void* x, const float* pos, void* tok, int batch, int HW, int C, void* stream) {
+    return attnpool_tokens(dtype, x, pos, tok, batch, HW, C, S(stream));
 }
 
 int b200clip_resize_crop_u8(const uint8_t* src_hwc, int H, int W, int64_t row_stride, const int32_t* h_bounds, const int32_t* h_coeffs,

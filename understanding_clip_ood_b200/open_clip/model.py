@@ -496,13 +496,14 @@ class CLIP(nn.Module):
         from .model_configs import TEXT_DEFAULTS, VISION_DEFAULTS
         v = {**VISION_DEFAULTS, **(vision_cfg if isinstance(vision_cfg, dict) else vars(vision_cfg))}
         t = {**TEXT_DEFAULTS, **(text_cfg if isinstance(text_cfg, dict) else vars(text_cfg))}
-        if isinstance(v["layers"], (tuple, list)) or v.get("timm_model_name") or t.get("hf_model_name"):
-            raise RuntimeError("only ViT image towers with the native text transformer are on this hot path "
-                               "(ModifiedResNet / timm / HF towers: SURVEY.md §8(f))")
+        if v.get("timm_model_name") or t.get("hf_model_name"):
+            raise RuntimeError("only the native ViT / ModifiedResNet image towers with the native text transformer are on this hot "
+                               "path (timm / HF towers: SURVEY.md §8(f))")
+        resnet = isinstance(v["layers"], (tuple, list))
         for k in ("attentional_pool", "no_ln_pre", "final_ln_after_pool", "output_tokens"):
             if v.get(k):
                 raise RuntimeError(f"vision_cfg.{k} is not supported on this hot path")
-        if v.get("pool_type", "tok") != "tok" or v.get("pos_embed_type", "learnable") != "learnable":
+        if not resnet and (v.get("pool_type", "tok") != "tok" or v.get("pos_embed_type", "learnable") != "learnable"):
             raise RuntimeError("only pool_type='tok' with learnable positional embeddings is supported")
         if v.get("ls_init_value") is not None or t.get("ls_init_value") is not None:
             raise RuntimeError("LayerScale (ls_init_value) is not supported on this hot path")
@@ -514,8 +515,13 @@ class CLIP(nn.Module):
         self.output_dict = output_dict
         self.quick_gelu = bool(quick_gelu)
 
-        self.visual = VisionTower(v["image_size"], v["patch_size"], v["width"], v["layers"], v["width"] // v["head_width"],
-                                  v["mlp_ratio"], embed_dim, quick_gelu)
+        if resnet:
+            # ModifiedResNet (model.py:131-139): heads = width * 32 / head_width; quick_gelu does not reach this tower
+            from .resnet import ResNetTower
+            self.visual = ResNetTower(v["layers"], embed_dim, v["width"] * 32 // v["head_width"], v["image_size"], v["width"])
+        else:
+            self.visual = VisionTower(v["image_size"], v["patch_size"], v["width"], v["layers"], v["width"] // v["head_width"],
+                                      v["mlp_ratio"], embed_dim, quick_gelu)
 
         # text tower; parameters are re-exported on the CLIP module like the reference does (model.py:239-248)
         Wt = t["width"]
@@ -709,7 +715,7 @@ def convert_weights_to_lp(model: nn.Module, dtype=torch.float16):
     parameters, embeddings, positional tables and logit_scale stay fp32 — same split as model.py:396-423."""
 
     def _convert(m):
-        if isinstance(m, (_Dense, _PatchConv)):
+        if isinstance(m, (_Dense, _PatchConv, nn.Conv2d, nn.Linear)):     # nn.Conv2d / nn.Linear: the ModifiedResNet tower
             m.weight.data = m.weight.data.to(dtype)
             if getattr(m, "bias", None) is not None:
                 m.bias.data = m.bias.data.to(dtype)

@@ -1,4 +1,4 @@
-"""Architecture registry for the ViT CLIP family on the hot path.
+"""Architecture registry for the ViT and ModifiedResNet CLIP families on the hot path.
 
 Same schema as the reference's JSON configs (deps/open_clip/src/open_clip/model_configs/ViT-B-32.json etc.:
 `embed_dim`, `vision_cfg`, `text_cfg`, optional `quick_gelu`).  Only the ViT towers this framework
@@ -33,6 +33,28 @@ _MODEL_CONFIGS = {
     "ViT-L-14-336": _vit(768, 336, 24, 1024, 14, 768, 12),
     "ViT-L-16": _vit(768, 224, 24, 1024, 16, 768, 12),
 }
+
+def _rn(embed_dim, image_size, v_layers, v_width, t_width, t_heads, quick_gelu=False):
+    cfg = {
+        "embed_dim": embed_dim,
+        "vision_cfg": {"image_size": image_size, "layers": list(v_layers), "width": v_width, "patch_size": None},
+        "text_cfg": {"context_length": 77, "vocab_size": 49408, "width": t_width, "heads": t_heads, "layers": 12},
+    }
+    if quick_gelu:
+        cfg["quick_gelu"] = True
+    return cfg
+
+
+# ModifiedResNet towers (model_configs/RN50.json ...): the model the paper trains (slurm/train-clip.sh:114)
+_MODEL_CONFIGS.update({
+    "RN50": _rn(1024, 224, (3, 4, 6, 3), 64, 512, 8),
+    "RN50-quickgelu": _rn(1024, 224, (3, 4, 6, 3), 64, 512, 8, quick_gelu=True),
+    "RN101": _rn(512, 224, (3, 4, 23, 3), 64, 512, 8),
+    "RN101-quickgelu": _rn(512, 224, (3, 4, 23, 3), 64, 512, 8, quick_gelu=True),
+    "RN50x4": _rn(640, 288, (4, 6, 10, 6), 80, 640, 10),
+    "RN50x16": _rn(768, 384, (6, 8, 18, 8), 96, 768, 12),
+    "RN50x64": _rn(1024, 448, (3, 15, 36, 10), 128, 1024, 16),
+})
 
 VISION_DEFAULTS = {"layers": 12, "width": 768, "head_width": 64, "mlp_ratio": 4.0, "patch_size": 16, "image_size": 224}
 TEXT_DEFAULTS = {"context_length": 77, "vocab_size": 49408, "width": 512, "heads": 8, "layers": 12, "mlp_ratio": 4.0}
