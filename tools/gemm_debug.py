@@ -101,6 +101,8 @@ def bench():
         M = batch * 50
         for (name, N, K, epi, inplace) in [("qkv", 2304, 768, 0, False), ("out_proj", 768, 768, 3, False), ("out_proj_inplace", 768, 768, 3, True),
                                            ("c_fc", 3072, 768, 1, False), ("c_proj", 768, 3072, 3, False), ("c_proj_inplace", 768, 3072, 3, True)]:
+            if os.environ.get("GEMM_SHAPES") and name not in os.environ["GEMM_SHAPES"].split(","):
+                continue
             g = torch.Generator(device="cuda").manual_seed(1)
             a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
             w = (torch.randn(N, K, device="cuda", generator=g) * 0.04).bfloat16()

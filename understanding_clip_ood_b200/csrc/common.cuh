@@ -157,9 +157,9 @@ __device__ __forceinline__ void gelu_pair_fast(float& x0, float& x1) {
     q = fma_f2(q, s, pack_f2(1.59565838e+00f * kL, 1.59565838e+00f * kL));
     float u0, u1;
     unpack_f2(mul_f2(q, x), u0, u1);
-    const float r0 = rcp_fast(1.0f + ex2_fast(u0));
-    const float r1 = rcp_fast(1.0f + ex2_fast(u1));
-    unpack_f2(mul_f2(x, pack_f2(r0, r1)), x0, x1);
+    float d0, d1;
+    unpack_f2(add_f2(pack_f2(ex2_fast(u0), ex2_fast(u1)), pack_f2(1.0f, 1.0f)), d0, d1);
+    unpack_f2(mul_f2(x, pack_f2(rcp_fast(d0), rcp_fast(d1))), x0, x1);
 }
 
 // ---------------------------------------------------------------------------------------

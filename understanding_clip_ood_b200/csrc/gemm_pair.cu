@@ -31,6 +31,23 @@
 #include <cstdlib>
 #include <mutex>
 
+// 0 (default): GELU / QuickGELU are applied to the fp32 linear output (one rounding; 3 fewer instructions per output pair in the
+// epilogue that bounds the c_fc GEMM); 1: the linear output is first rounded to the storage type, the rounding point of the
+// reference's 16-bit eager path (F.linear returns a 16-bit tensor) -- two roundings, further from the fp32 result
+#ifndef B2C_ACT_ROUND
+#define B2C_ACT_ROUND 0
+#endif
+// 1 (default): ONE staging buffer per epilogue group for the epilogues without a loaded residual (32 KB of staging instead of
+// 64 KB; the group synchronises twice per chunk: buffer drained / buffer filled); 0: two buffers, one barrier per chunk
+#ifndef B2C_STG_SINGLE
+#define B2C_STG_SINGLE 1
+#endif
+// measurement-only builds (tools/build_variant.py): 1 = epilogue without the staging writes and the TMA store (results are
+// dropped), 2 = epilogue without the TMEM load (garbage results): which part of the epilogue slows the mainloop down?
+#ifndef B2C_EPI_DBG
+#define B2C_EPI_DBG 0
+#endif
+
 namespace b200clip {
 
 namespace {
@@ -88,6 +105,7 @@ struct PairParams {
     int group_m;
     int pf_dist;           // L2 prefetch distance of the A operand, in K-blocks (0 = off)
     int dbg;               // measurement-only switches (B200CLIP_GEMM_DBG): 1 = skip the epilogue, 2 = MMA without operand loads
+    int stages;            // operand-ring depth actually used (<= the compiled depth; B200CLIP_GEMM_STAGES, measurements only)
     // stream-K: tiles [0, sk_tiles) are cut into equal runs of K-blocks over the clusters, tiles [sk_tiles, ...) stay whole
     int sk_tiles;
     float4* sk_partial;    // [clusters][kSkSlotFloat4]
@@ -288,7 +306,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     constexpr bool kRes = epi_loads_residual(EPI);   // residual operand TMA-loaded into the staging ring
     constexpr bool kRelu = EPI == kEpiRelu || EPI == kEpiResidualRelu;
     constexpr bool kStats = EPI == kEpiResidualStats;
-    using Cfg = PairCfg<BLOCK_N, kRes ? 3 : 2>;
+    using Cfg = PairCfg<BLOCK_N, kRes ? 3 : (B2C_STG_SINGLE ? 1 : 2)>;
     using H = Half16<T>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kStgBufs = Cfg::kStgBufs;
@@ -324,6 +342,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int num_clusters = gridDim.x / kClusterCtas;
     const int num_tiles = p.m_tiles * p.n_tiles;
     const int num_kb = (p.K + kBK - 1) / kBK;
+    const int ring = p.stages > 0 && p.stages < kStages ? p.stages : kStages;
 
     // every CTA of the cluster must be resident before the pair-wide TMEM allocation / remote barrier traffic
     cluster_sync_all();
@@ -404,7 +423,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         tma_load_2d_pair_mcast(&tmap_w, &full_bar[stage], smem_b + stage * Cfg::kBBytes + pair * (kQRows * kBK * 2),
                                                kb * kBK, row_w + static_cast<int>(pair) * kQRows, mask, kCacheHintEvictLast);
                     }
-                    if (++stage == kStages) {
+                    if (++stage == ring) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -440,7 +459,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     // frees the slot in EVERY CTA of the cluster (each of them writes into some of the buffers just read)
                     if (!(p.dbg & 2)) umma_commit_pair(&empty_bar[stage], kAllCtas);
                     if (kb == pc.kb1 - 1) umma_commit_pair(&tmem_full_bar[acc], pair_mask);
-                    if (++stage == kStages) {
+                    if (++stage == ring) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -474,6 +493,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const T* bias = static_cast<const T*>(p.bias);
         const float* bias_f32 = static_cast<const float*>(p.bias);
         uint32_t bufc = 0;  // chunks processed by this group so far (buffer = bufc % kStgBufs)
+#if B2C_EPI_DBG == 1
+        uint32_t dbg_sink = 0;
+#endif
         // stream-K bookkeeping of this warp: its part of every cluster slot, its flag in every slot
         const int64_t sk_units = static_cast<int64_t>(p.sk_tiles) * num_kb;
         const int sk_lane_off = static_cast<int>(half) * (BLOCK_N / 4) * kBM + r;       // + col4 * kBM, in float4
@@ -620,7 +642,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t v[32];
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccStride + c * kChunkN + hf * 32;
+#if B2C_EPI_DBG == 2
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(ln_rstd * static_cast<float>(i + lane));
+#else
                     tmem_ld_32x32(taddr, v);
+#endif
                     uint4 bvec[4];
                     if constexpr (!kLn) {
 #pragma unroll
@@ -631,6 +658,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         }
                     }
                     tmem_ld_wait();
+                    if constexpr (!kRes && kStgBufs == 1) {
+                        if (hf == 0) {
+                            // single staging buffer: the previous chunk's store must have finished reading it
+                            if (grp_leader) tma_store_wait_read<0>();
+                            __syncwarp();
+                            named_bar_sync(bar_id, 128);
+                        }
+                    }
                     if (last_of_tile && hf == 1) {
                         // last TMEM read of this tile: hand the accumulator stage back to the MMA issuer early
                         tc_fence_before();
@@ -687,7 +722,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 unpack_f2(add_f2(pack_f2(__uint_as_float(v[g * 8 + 2 * j]), __uint_as_float(v[g * 8 + 2 * j + 1])),
                                                  pack_f2(b2.x, b2.y)), x0, x1);
                             }
-                            if constexpr (kAct != 0 || kRes || EPI == kEpiResidualInPlace) {
+                            if constexpr ((kAct != 0 && B2C_ACT_ROUND) || kRes || EPI == kEpiResidualInPlace) {
                                 const float2 xr = H::unpack(H::pack(x0, x1));  // linear output rounded to the storage type
                                 x0 = xr.x;
                                 x1 = xr.y;
@@ -713,11 +748,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 st_q = fmaf(rr.x, rr.x, fmaf(rr.y, rr.y, st_q));
                             }
                         }
+#if B2C_EPI_DBG == 1
+                        dbg_sink ^= ow[0] ^ ow[1] ^ ow[2] ^ ow[3];
+#else
                         sts128(saddr, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+#endif
                     }
                 }
+#if B2C_EPI_DBG == 1
+                if (dbg_sink == 0x7fc12345u && p.dbg == 77) p.sk_flags[threadIdx.x] = dbg_sink;   // keeps the arithmetic alive
+                ++bufc;
+                continue;
+#endif
                 fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
-                if constexpr (!kRes) {
+                if constexpr (!kRes && kStgBufs > 1) {
                     // every store but (at most) the previous chunk's has long completed; waiting for that one too BEFORE the
                     // barrier tells the whole group that the other staging buffer is free for the next chunk
                     if (grp_leader) tma_store_wait_read<0>();
@@ -766,7 +810,7 @@ int sk_clusters_planned() { return num_sms() / 2; }
 template <typename T, int BLOCK_N, int EPI, int PAIRS, bool SK>
 int launch_pair_sk(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr, const PairParams& p,
                    cudaStream_t stream) {
-    using Cfg = PairCfg<BLOCK_N, epi_loads_residual(EPI) ? 3 : 2>;
+    using Cfg = PairCfg<BLOCK_N, epi_loads_residual(EPI) ? 3 : (B2C_STG_SINGLE ? 1 : 2)>;
     auto kern = gemm_pair_kernel<T, BLOCK_N, EPI, PAIRS, SK>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -884,6 +928,16 @@ bool no_reduce_store() {
 int gemm_debug_switches() {
     static const int v = [] {
         const char* e = getenv("B200CLIP_GEMM_DBG");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    return v;
+}
+
+// B200CLIP_GEMM_STAGES=<n> shortens the operand ring (ring-depth sensitivity measurements: 3 -> 4 stages is worth 3 %, 4 -> 5
+// and 5 -> 6 nothing, profiles/r2_gemm_epilogue_dissection.txt)
+int gemm_ring_override() {
+    static const int v = [] {
+        const char* e = getenv("B200CLIP_GEMM_STAGES");
         return e != nullptr ? atoi(e) : 0;
     }();
     return v;
@@ -1057,6 +1111,7 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     p.group_m = pairs == 2 ? 4 : 8;
     p.pf_dist = l2_prefetch_distance();
     p.dbg = gemm_debug_switches();
+    p.stages = gemm_ring_override();
     p.sk_tiles = 0;
     p.sk_partial = nullptr;
     p.sk_flags = nullptr;
