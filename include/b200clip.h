@@ -177,6 +177,14 @@ int b200clip_cliploss_backward(const float* img_loc, const float* txt_loc, const
                                float* d_img_loc, float* d_txt_loc, float* d_all_img, float* d_all_txt, float* d_scale,
                                float* workspace, void* stream);
 
+/* Single-device form (world_size == 1, loss.py:102-131 with all_* == *_loc): the backward of
+ * b200clip_cliploss_forward(img, txt, img, txt, logit_scale, 0, n, n, D, loss, workspace) that writes the TOTAL gradient of
+ * each feature matrix (its row-operand and its column-operand term summed inside one GEMM launch), so the caller's autograd
+ * has nothing to add up.  d_img, d_txt [n,D], d_scale may be NULL; grad_out = device scalar or NULL for 1. */
+int b200clip_cliploss_single_backward(const float* img, const float* txt, const float* logit_scale, int n, int D,
+                                      const float* grad_out, float* d_img, float* d_txt, float* d_scale, float* workspace,
+                                      void* stream);
+
 /* Distributed form (--local-loss --gather-with-grad, world_size > 1): `gathered` [N, 2D] fp32 is the payload of the ONE
  * all-gather the host issues (row r*n + i = img_i | txt_i of rank r; loss.py:49-50 gathers the two halves separately); the
  * local operands are its rows [rank*n, rank*n + n).  `backward` writes d_gathered [N, 2D], the gradient w.r.t. every
@@ -201,6 +209,8 @@ int b200clip_cliploss_packed_backward(const float* gathered, const float* logit_
  *   d_slots[world], d_slots[world + 1]: two LOCAL [n, 2D] slots for the two K halves of the local-row terms.
  * b200clip_p2p_reduce_finish: *peer_flag[p] = epoch for every p, wait my_flags[q] >= epoch for all q < world, then
  *   out[elems] = sum over s < slots of recv[s * elems ...] (recv = the local receive buffer; slots = world + 2 here).
+ *   split_cols = 2D > 0: the blocks are rows of 2D floats (img | txt gradient) and `out` receives them as two contiguous
+ *   [rows, D] halves (d_img, then d_txt) instead of [rows, 2D] — dense tensors for autograd; 0: same layout as the blocks.
  *
  * Ring-slot protection: `my_busy` (may be NULL) is this rank's busy word of the ring slot in use — the all-gather sets it to
  * `epoch` when `hold` != 0 (a backward will read the gathered rows) or to 0, reduce_finish clears it; `peer_busy` (DEVICE array
@@ -219,7 +229,8 @@ int b200clip_cliploss_packed_backward_p2p(const float* gathered, const float* lo
                                           const float* grad_out, float* const* d_slots, float* d_scale, float* workspace,
                                           void* stream);
 int b200clip_p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag,
-                               const uint32_t* my_flags, int world, int slots, uint32_t epoch, uint32_t* my_busy, void* stream);
+                               const uint32_t* my_flags, int world, int slots, uint32_t epoch, uint32_t* my_busy,
+                               int split_cols, void* stream);
 
 /* ----- whole-tower drivers: one call per encode_image / encode_text ------------------------------ */
 

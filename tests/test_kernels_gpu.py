@@ -46,11 +46,12 @@ def test_gemm_tc(dtype, M, N, K, epi, bn):
     bias = (torch.randn(N, device=DEV, generator=g) * 0.1).to(dtype)
     res = torch.randn(M, N, device=DEV, generator=g).to(dtype) if epi == L.EPI_RESIDUAL else None
     out = ops.gemm(a, w, bias, epilogue=epi, residual=res, block_n=bn)
-    lin = (a.float() @ w.float().t() + bias.float()).to(dtype).float()   # the reference rounds the linear output
-    if epi == L.EPI_GELU:
-        ref = F.gelu(lin)
+    lin32 = a.float() @ w.float().t() + bias.float()
+    lin = lin32.to(dtype).float()   # the reference rounds the linear output before the residual add ...
+    if epi == L.EPI_GELU:           # ... the activations are applied to the fp32 value here (one rounding, gemm_pair.cu B2C_ACT_ROUND)
+        ref = F.gelu(lin32)
     elif epi == L.EPI_QUICKGELU:
-        ref = lin * torch.sigmoid(1.702 * lin)
+        ref = lin32 * torch.sigmoid(1.702 * lin32)
     elif epi == L.EPI_RESIDUAL:
         ref = lin + res.float()
     else:
@@ -96,8 +97,9 @@ def test_gemm_stream_k(dtype, M, N, K, epi, inplace):
     w = (torch.randn(N, K, device=DEV, generator=g) * 0.05).to(dtype)
     bias = (torch.randn(N, device=DEV, generator=g) * 0.1).to(dtype)
     res = torch.randn(M, N, device=DEV, generator=g).to(dtype) if epi == L.EPI_RESIDUAL else None
-    lin = (a.float() @ w.float().t() + bias.float()).to(dtype).float()
-    ref = {L.EPI_GELU: lambda: F.gelu(lin), L.EPI_RESIDUAL: lambda: lin + res.float(), L.EPI_BIAS: lambda: lin}[epi]().to(dtype).float()
+    lin32 = a.float() @ w.float().t() + bias.float()
+    lin = lin32.to(dtype).float()
+    ref = {L.EPI_GELU: lambda: F.gelu(lin32), L.EPI_RESIDUAL: lambda: lin + res.float(), L.EPI_BIAS: lambda: lin}[epi]().to(dtype).float()
     ws = torch.zeros(int(L.load().b200clip_gemm_workspace_bytes()), dtype=torch.uint8, device=DEV)
     outs = []
     for _ in range(2):
@@ -454,6 +456,35 @@ def test_cliploss_fwd_bwd(n, world, rank, D):
     assert _rel(grads3[0], 0.25 * il.grad) < 1e-4
 
 
+@pytest.mark.parametrize("n,D,dtype", [(256, 512, torch.float32), (6, 64, torch.float32), (7, 30, torch.float32), (130, 512, torch.bfloat16)])
+def test_cliploss_single_device_node(n, D, dtype):
+    """world_size == 1 through the public ClipLoss: one autograd node whose backward writes the TOTAL feature gradients with one
+    two-segment GEMM launch (b200clip_cliploss_single_backward) — against float64 autograd of loss.py:102-131, with an upstream
+    gradient other than 1 and with only some inputs requiring a gradient."""
+    from understanding_clip_ood_b200 import open_clip
+    g = _gen(13)
+    img0 = F.normalize(torch.randn(n, D, device=DEV, generator=g), dim=-1).to(dtype)
+    txt0 = F.normalize(torch.randn(n, D, device=DEV, generator=g) + 0.5 * img0.float(), dim=-1).to(dtype)
+    i64, t64 = img0.double().requires_grad_(True), txt0.double().requires_grad_(True)
+    s64 = torch.tensor(1 / 0.07, device=DEV, dtype=torch.float64, requires_grad=True)
+    labels = torch.arange(n, device=DEV)
+    ref = (F.cross_entropy(s64 * i64 @ t64.t(), labels) + F.cross_entropy(s64 * t64 @ i64.t(), labels)) / 2
+    (0.25 * ref).backward()
+    img, txt = img0.clone().requires_grad_(True), txt0.clone().requires_grad_(True)
+    scale = torch.tensor(1 / 0.07, device=DEV, requires_grad=True)
+    loss = open_clip.ClipLoss()(img, txt, scale)
+    assert type(loss.grad_fn).__name__ == "_SingleClipLossBackward"
+    (0.25 * loss).backward()
+    assert abs(loss.item() - ref.item()) / abs(ref.item()) < 1e-5
+    tol = 1e-4 if dtype == torch.float32 else 1e-2          # bf16 features: the gradients are returned in bf16
+    assert img.grad.dtype == dtype and _rel(img.grad, i64.grad) < tol and _rel(txt.grad, t64.grad) < tol
+    assert float(scale.grad) == pytest.approx(float(s64.grad), rel=1e-4)
+    # only the logit scale requires a gradient (frozen towers): the feature gradients are not computed
+    scale2 = torch.tensor(1 / 0.07, device=DEV, requires_grad=True)
+    open_clip.ClipLoss()(img0, txt0, scale2).backward()
+    assert float(scale2.grad) == pytest.approx(4 * float(s64.grad), rel=1e-4)
+
+
 # ------------------------------------------------------------------ uint8 preprocessing fused into the im2col --------
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
 @pytest.mark.parametrize("S,P,kpad", [(224, 32, 3072), (224, 16, 768), (224, 14, 640), (64, 8, 192)])
@@ -585,12 +616,19 @@ def test_slot_addressed_backward_and_reduce_finish(n, D, world, rank):
     out = torch.empty(n, 2 * D, device=DEV)
     pad[48] = 11                         # this rank's ring slot was held for the backward that ends here
     rc = L.load().b200clip_p2p_reduce_finish(recv[rank].data_ptr(), out.data_ptr(), S, flag.data_ptr(), pad.data_ptr() + 64, world,
-                                             world + 2, epoch, pad.data_ptr() + 4 * 48, L.stream_ptr())
+                                             world + 2, epoch, pad.data_ptr() + 4 * 48, 0, L.stream_ptr())
     L.check(rc, "b200clip_p2p_reduce_finish")
     torch.cuda.synchronize()
     assert int(pad[48]) == 0             # ... and is released
     assert torch.allclose(out, recv[rank].view(world + 2, n, 2 * D).sum(0), rtol=1e-6, atol=1e-7)
     assert all(int(others[p][16 + rank]) == epoch for p in range(world))
+    # split form: the same sums as two dense [n, D] halves (d_img, d_txt), what _PeerLocalClipLoss hands to autograd
+    out2 = torch.empty(2, n, D, device=DEV)
+    rc = L.load().b200clip_p2p_reduce_finish(recv[rank].data_ptr(), out2.data_ptr(), S, flag.data_ptr(), pad.data_ptr() + 64, world,
+                                             world + 2, epoch, pad.data_ptr() + 4 * 48, 2 * D, L.stream_ptr())
+    L.check(rc, "b200clip_p2p_reduce_finish")
+    torch.cuda.synchronize()
+    assert torch.equal(out2[0], out[:, :D]) and torch.equal(out2[1], out[:, D:])
 
 
 # ------------------------------------------------------------------ bicubic resize + centre crop (csrc/preprocess.cu) -------

@@ -15,13 +15,14 @@ def reference(a, w, bias, res, epi, dtype):
     ref = a.float() @ w.float().t()
     if bias is not None:
         ref = ref + bias.float()
-    ref = ref.to(dtype).float()
-    if epi == L.EPI_GELU:
+    if epi == L.EPI_GELU:          # activations on the fp32 linear output (gemm_pair.cu B2C_ACT_ROUND = 0)
         ref = torch.nn.functional.gelu(ref)
     elif epi == L.EPI_QUICKGELU:
         ref = ref * torch.sigmoid(1.702 * ref)
     elif epi == L.EPI_RESIDUAL:
-        ref = ref + res.float()
+        ref = ref.to(dtype).float() + res.float()
+    else:
+        ref = ref.to(dtype).float()
     return ref
 
 

@@ -111,12 +111,13 @@ SIGNATURES = {
     "b200clip_cliploss": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200clip_cliploss_forward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "b200clip_cliploss_backward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200clip_cliploss_single_backward": (C.c_int, [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "b200clip_cliploss_packed_forward": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "b200clip_cliploss_packed_backward": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "b200clip_p2p_configure": (C.c_int, [C.c_double, _P]),
     "b200clip_p2p_allgather": (C.c_int, [_I, _P, _P, _I, _I, _P, _P, _P, _P, _I, C.c_uint32, _P, _P, _I, _P]),
     "b200clip_cliploss_packed_backward_p2p": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "b200clip_p2p_reduce_finish": (C.c_int, [_P, _P, _L, _P, _P, _I, _I, C.c_uint32, _P, _P]),
+    "b200clip_p2p_reduce_finish": (C.c_int, [_P, _P, _L, _P, _P, _I, _I, C.c_uint32, _P, _I, _P]),
     "b200clip_workspace_bytes": (C.c_int64, [C.POINTER(TowerCfg), _I, _I]),
     "b200clip_vit_forward": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(VitWeights), _P, _P, _I, _I, _P, _L, _P]),
     "b200clip_vit_forward_u8": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(VitWeights), _P, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, _I,

@@ -285,6 +285,12 @@ int b200clip_cliploss_backward(const float* img_loc, const float* txt_loc, const
                              d_all_txt, d_scale, workspace, S(stream));
 }
 
+int b200clip_cliploss_single_backward(const float* img, const float* txt, const float* logit_scale, int n, int D,
+                                      const float* grad_out, float* d_img, float* d_txt, float* d_scale, float* workspace,
+                                      void* stream) {
+    return cliploss_single_backward(img, txt, logit_scale, n, D, grad_out, d_img, d_txt, d_scale, workspace, S(stream));
+}
+
 int b200clip_cliploss_packed_forward(const float* gathered, const float* logit_scale, int rank, int n, int N, int D, float* loss,
                                      float* workspace, void* stream) {
     return cliploss_packed_forward(gathered, logit_scale, rank, n, N, D, loss, workspace, S(stream));
@@ -311,8 +317,8 @@ int b200clip_cliploss_packed_backward_p2p(const float* gathered, const float* lo
 }
 
 int b200clip_p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag, const uint32_t* my_flags,
-                               int world, int slots, uint32_t epoch, uint32_t* my_busy, void* stream) {
-    return p2p_reduce_finish(recv, out, elems, peer_flag, my_flags, world, slots, epoch, my_busy, S(stream));
+                               int world, int slots, uint32_t epoch, uint32_t* my_busy, int split_cols, void* stream) {
+    return p2p_reduce_finish(recv, out, elems, peer_flag, my_flags, world, slots, epoch, my_busy, split_cols, S(stream));
 }
 
 // not part of the public header: timeline capture of the tcgen05 attention kernel (tools/attn_timeline.py)

@@ -30,6 +30,13 @@ struct GemmProb {
     int64_t lda, ldb, ldc;
     int M, N, K, ta, tb;
     int accumulate;   // C += A B instead of C = A B
+    // optional second contraction segment, summed into the same output tile before it is stored: C = A B + A2 B2 with A2 stored
+    // [K2, M] and B2 stored [K2, N] (both "transposed" forms).  The single-device backward uses it to write the TOTAL gradient of
+    // a feature matrix that is both the row and the column operand of the logit blocks (K2 == 0: none).
+    const float* A2;
+    const float* B2;
+    int64_t lda2, ldb2;
+    int K2;
     int tiles_n, tile_begin;
     // slot-addressed output (peer-memory scatter of the distributed backward, p2p.cu): row r of C lives at
     // slots[(slot_row0 + r) / slot_rows] + ((slot_row0 + r) % slot_rows) * ldc + slot_col0; C itself is unused then
@@ -40,6 +47,7 @@ constexpr int kMaxProbs = 6;
 struct GemmBatch {
     GemmProb prob[kMaxProbs];
     int count;
+    unsigned int* zero4;   // optional: four words cleared by the first CTA (the last-CTA-done counter of the kernel that follows)
 };
 
 // One k-step of an operand tile: [kTK x 64] in shared memory, k-major.  The global read and the shared-memory write are
@@ -91,25 +99,22 @@ __device__ __forceinline__ void store_mc(float (*S)[kT + 4], float4 a, int tid) 
     *reinterpret_cast<float4*>(&S[k][r]) = a;
 }
 
+// acc += op(A)[m0.., :K] op(B)[n0.., :K]^T for one 64 x 64 output tile (thread (ty, tx) owns a 4 x 4 block)
 template <bool TA, bool TB>
-__device__ __forceinline__ void tile_gemm(const GemmProb& p, int m0, int n0, float (*As)[kT + 4], float (*Bs)[kT + 4]) {
+__device__ __forceinline__ void tile_accumulate(const float* A, int64_t lda, int M, const float* B, int64_t ldb, int N, int K, int m0, int n0,
+                                                float (*As)[kT + 4], float (*Bs)[kT + 4], float (&acc)[4][4]) {
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    auto load_a = [&](int k0) { return TA ? load_mc(p.A, p.lda, m0, p.M, k0, p.K, tid) : load_kc(p.A, p.lda, m0, p.M, k0, p.K, tid); };
-    auto load_b = [&](int k0) { return TB ? load_mc(p.B, p.ldb, n0, p.N, k0, p.K, tid) : load_kc(p.B, p.ldb, n0, p.N, k0, p.K, tid); };
+    auto load_a = [&](int k0) { return TA ? load_mc(A, lda, m0, M, k0, K, tid) : load_kc(A, lda, m0, M, k0, K, tid); };
+    auto load_b = [&](int k0) { return TB ? load_mc(B, ldb, n0, N, k0, K, tid) : load_kc(B, ldb, n0, N, k0, K, tid); };
     float4 ra = load_a(0), rb = load_b(0);
-    for (int k0 = 0; k0 < p.K; k0 += kTK) {
+    for (int k0 = 0; k0 < K; k0 += kTK) {
         if constexpr (TA) store_mc(As, ra, tid);
         else store_kc(As, ra, tid);
         if constexpr (TB) store_mc(Bs, rb, tid);
         else store_kc(Bs, rb, tid);
         __syncthreads();
-        if (k0 + kTK < p.K) {   // next k-step's operands: in flight under the FMAs below
+        if (k0 + kTK < K) {   // next k-step's operands: in flight under the FMAs below
             ra = load_a(k0 + kTK);
             rb = load_b(k0 + kTK);
         }
@@ -126,6 +131,19 @@ __device__ __forceinline__ void tile_gemm(const GemmProb& p, int m0, int n0, flo
         }
         __syncthreads();
     }
+}
+
+template <bool TA, bool TB>
+__device__ __forceinline__ void tile_gemm(const GemmProb& p, int m0, int n0, float (*As)[kT + 4], float (*Bs)[kT + 4]) {
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    tile_accumulate<TA, TB>(p.A, p.lda, p.M, p.B, p.ldb, p.N, p.K, m0, n0, As, Bs, acc);
+    if (p.K2 > 0) tile_accumulate<true, true>(p.A2, p.lda2, p.M, p.B2, p.ldb2, p.N, p.K2, m0, n0, As, Bs, acc);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int row = m0 + ty * 4 + i;
@@ -159,6 +177,7 @@ __device__ __forceinline__ void tile_gemm(const GemmProb& p, int m0, int n0, flo
 __global__ void __launch_bounds__(256) batched_gemm_kernel(const GemmBatch batch) {
     __shared__ __align__(16) float As[kTK][kT + 4];
     __shared__ __align__(16) float Bs[kTK][kT + 4];
+    if (batch.zero4 != nullptr && blockIdx.x == 0 && threadIdx.x < 4) batch.zero4[threadIdx.x] = 0u;
     int pi = 0;
 #pragma unroll
     for (int i = 1; i < kMaxProbs; ++i)
@@ -193,8 +212,14 @@ GemmProb make_prob(const float* A, int64_t lda, bool ta, const float* B, int64_t
     p.M = M; p.N = N; p.K = K;
     p.ta = ta ? 1 : 0; p.tb = tb ? 1 : 0;
     p.accumulate = accumulate ? 1 : 0;
+    p.A2 = nullptr; p.B2 = nullptr; p.lda2 = 0; p.ldb2 = 0; p.K2 = 0;
     p.tiles_n = 0; p.tile_begin = 0;
     p.slots = nullptr; p.slot_rows = 1; p.slot_row0 = 0; p.slot_col0 = 0;
+    return p;
+}
+// + A2 B2 with A2 stored [K2, M], B2 stored [K2, N]
+GemmProb with_second_segment(GemmProb p, const float* A2, int64_t lda2, const float* B2, int64_t ldb2, int K2) {
+    p.A2 = A2; p.B2 = B2; p.lda2 = lda2; p.ldb2 = ldb2; p.K2 = K2;
     return p;
 }
 GemmProb to_slots(GemmProb p, float* const* slots, int slot_rows, int row0, int col0) {
@@ -211,6 +236,7 @@ int gemm_f32_general(const float* A, int64_t lda, bool ta, const float* B, int64
                      bool accumulate, cudaStream_t stream) {
     B2C_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "gemm_f32_general: bad arguments");
     GemmBatch b;
+    b.zero4 = nullptr;
     b.count = 1;
     b.prob[0] = make_prob(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, accumulate);
     return launch_batch(b, stream);
@@ -336,8 +362,9 @@ int forward_impl(const LossOperands& o, const float* logit_scale, int rank, int 
     if ((rc = check_shapes(rank, n, N, D)) != 0) return rc;
     B2C_CHECK_ARG(o.img_loc && o.txt_loc && o.all_img && o.all_txt && logit_scale && loss && workspace, "cliploss: null pointer");
     const Ws ws = carve(workspace, n, N);
-    B2C_CUDA(cudaMemsetAsync(ws.counter, 0, 16, stream));  // last-CTA-done counter (each kernel leaves it at zero again)
     GemmBatch b;
+    b.zero4 = ws.counter;   // last-CTA-done counter of the two cross-entropy kernels (each leaves it at zero again): cleared by the
+                            // GEMM launch that precedes them instead of a separate memset
     b.count = 2;
     b.prob[0] = make_prob(o.img_loc, o.ld_loc, false, o.all_txt, o.ld_all, false, ws.logits, N, n, N, D);
     b.prob[1] = make_prob(o.txt_loc, o.ld_loc, false, o.all_img, o.ld_all, false, ws.logits + static_cast<int64_t>(n) * N, N, n, N, D);
@@ -362,6 +389,7 @@ int backward_impl(const LossOperands& o, const float* logit_scale, int rank, int
     float* Li = ws.logits;
     float* Lt = ws.logits + static_cast<int64_t>(n) * N;
     GemmBatch b;
+    b.zero4 = nullptr;
     b.count = 0;
     if (!fold_local) {
         if (d_img_loc) b.prob[b.count++] = make_prob(Li, N, false, o.all_txt, o.ld_all, true, d_img_loc, ld_dloc, n, D, N);
@@ -393,6 +421,7 @@ int backward_impl(const LossOperands& o, const float* logit_scale, int rank, int
     if (fold_local) {
         B2C_CHECK_ARG(d_all_img && d_all_txt, "cliploss: folding the local gradients needs d_all_img and d_all_txt");
         GemmBatch f;
+        f.zero4 = nullptr;
         f.count = 2;
         f.prob[0] = make_prob(Li, N, false, o.all_txt, o.ld_all, true, d_all_img + static_cast<int64_t>(rank) * n * ld_dall, ld_dall, n, D, N, true);
         f.prob[1] = make_prob(Lt, N, false, o.all_img, o.ld_all, true, d_all_txt + static_cast<int64_t>(rank) * n * ld_dall, ld_dall, n, D, N, true);
@@ -447,6 +476,28 @@ int cliploss_packed_backward_p2p(const float* gathered, const float* logit_scale
     const LossOperands o{loc, loc + D, gathered, gathered + D, 2 * static_cast<int64_t>(D), 2 * static_cast<int64_t>(D)};
     return backward_impl(o, logit_scale, rank, n, N, D, grad_out, nullptr, nullptr, 0, nullptr, nullptr, 2 * static_cast<int64_t>(D), true,
                          d_scale, workspace, stream, d_slots);
+}
+
+// Single-device step (world_size == 1: the feature matrices are both the row and the column operands of the two logit blocks,
+// loss.py:102-131 with all_* == *_loc): backward of `cliploss_forward(img, txt, img, txt, ..., rank 0, n, n, D, ...)` that writes
+// the TOTAL gradients  d_img = Li txt + Lt^T txt,  d_txt = Lt img + Li^T img  (Li, Lt = s dL/dlogits of the two blocks) with one
+// two-segment GEMM launch: no separate row / column gradients for autograd to add up afterwards.
+int cliploss_single_backward(const float* img, const float* txt, const float* logit_scale, int n, int D, const float* grad_out,
+                             float* d_img, float* d_txt, float* d_scale, float* workspace, cudaStream_t stream) {
+    int rc;
+    if ((rc = check_shapes(0, n, n, D)) != 0) return rc;
+    B2C_CHECK_ARG(img && txt && logit_scale && workspace, "cliploss: null pointer");
+    const Ws ws = carve(workspace, n, n);
+    ce_backward_kernel<<<2 * n, 256, 0, stream>>>(ws.logits, logit_scale, grad_out, n, n, 0, ws.row_lse, ws.row_ds, ws.counter, d_scale);
+    B2C_LAUNCH_CHECK("ce_backward_kernel");
+    const float* Li = ws.logits;
+    const float* Lt = ws.logits + static_cast<int64_t>(n) * n;
+    GemmBatch b;
+    b.zero4 = nullptr;
+    b.count = 0;
+    if (d_img) b.prob[b.count++] = with_second_segment(make_prob(Li, n, false, txt, D, true, d_img, D, n, D, n), Lt, n, txt, D, n);
+    if (d_txt) b.prob[b.count++] = with_second_segment(make_prob(Lt, n, false, img, D, true, d_txt, D, n, D, n), Li, n, img, D, n);
+    return b.count > 0 ? launch_batch(b, stream) : 0;
 }
 
 // fused forward + backward (one call; used when the upstream gradient is already known or 1)

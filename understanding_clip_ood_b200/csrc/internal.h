@@ -79,6 +79,11 @@ int cliploss_backward(const float* img_loc, const float* txt_loc, const float* a
                       int rank, int n, int N, int D, const float* grad_out, float* d_img_loc, float* d_txt_loc, float* d_all_img,
                       float* d_all_txt, float* d_scale, float* workspace, cudaStream_t stream);
 
+// world_size == 1: total gradients of the two feature matrices in one two-segment GEMM launch (after cliploss_forward with
+// all_* == *_loc, rank 0, N == n)
+int cliploss_single_backward(const float* img, const float* txt, const float* logit_scale, int n, int D, const float* grad_out,
+                             float* d_img, float* d_txt, float* d_scale, float* workspace, cudaStream_t stream);
+
 int cliploss_packed_forward(const float* gathered, const float* logit_scale, int rank, int n, int N, int D, float* loss,
                             float* workspace, cudaStream_t stream);
 int cliploss_packed_backward(const float* gathered, const float* logit_scale, int rank, int n, int N, int D, const float* grad_out,
@@ -93,7 +98,7 @@ int p2p_allgather(int dtype, const void* img, const void* txt, int n, int D, flo
                   const uint32_t* my_flags, uint32_t* counters, int world, uint32_t epoch, uint32_t* const* peer_busy, uint32_t* my_busy,
                   int hold, cudaStream_t stream);
 int p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag, const uint32_t* my_flags, int world,
-                      int slots, uint32_t epoch, uint32_t* my_busy, cudaStream_t stream);
+                      int slots, uint32_t epoch, uint32_t* my_busy, int split_cols, cudaStream_t stream);
 
 // bicubic resize + centre crop of a decoded uint8 HWC image (preprocess.cu); tables from the host (Pillow's fixed-point coefficients)
 int resize_crop_u8(const uint8_t* src_hwc, int H, int W, int64_t row_stride, const int32_t* h_bounds, const int32_t* h_coeffs, int h_ksize,

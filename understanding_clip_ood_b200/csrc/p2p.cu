@@ -161,7 +161,8 @@ p2p_allgather_kernel(const T* __restrict__ img, const T* __restrict__ txt, int n
 // recv [slots][elems] (slot q < world written by rank q's backward GEMM, slots >= world by the local one) -> out[elems] = sum
 __global__ void __launch_bounds__(256)
 p2p_reduce_finish_kernel(const float* __restrict__ recv, float* __restrict__ out, int64_t elems, uint32_t* const* __restrict__ peer_flag,
-                         const uint32_t* __restrict__ my_flags, int world, int slots, uint32_t epoch, uint32_t* my_busy, WaitCfg wc) {
+                         const uint32_t* __restrict__ my_flags, int world, int slots, uint32_t epoch, uint32_t* my_busy, int split_cols,
+                         WaitCfg wc) {
     // the stores of the preceding kernel on this stream (the slot-addressed GEMM epilogue) are complete; publish them
     if (blockIdx.x == 0 && threadIdx.x < world) {
         __threadfence_system();
@@ -178,7 +179,18 @@ p2p_reduce_finish_kernel(const float* __restrict__ recv, float* __restrict__ out
             const float4 b = __ldcv(reinterpret_cast<const float4*>(recv + static_cast<int64_t>(q) * elems) + i);
             a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         }
-        reinterpret_cast<float4*>(out)[i] = a;
+        if (split_cols > 0) {
+            // rows of split_cols = 2D floats (img | txt gradient) -> two contiguous [rows, D] halves, so that the caller can hand
+            // each half to autograd as a dense tensor (a column slice of [n, 2D] would be copied by AccumulateGrad)
+            const int64_t e = i * 4;
+            const int64_t row = e / split_cols;
+            const int col = static_cast<int>(e - row * split_cols);
+            const int half_cols = split_cols / 2;
+            const int64_t dst = (col >= half_cols ? elems / 2 : 0) + row * half_cols + (col >= half_cols ? col - half_cols : col);
+            *reinterpret_cast<float4*>(out + dst) = a;
+        } else {
+            reinterpret_cast<float4*>(out)[i] = a;
+        }
     }
 }
 
@@ -220,15 +232,17 @@ int p2p_allgather(int dtype, const void* img, const void* txt, int n, int D, flo
 }
 
 int p2p_reduce_finish(const float* recv, float* out, int64_t elems, uint32_t* const* peer_flag, const uint32_t* my_flags, int world,
-                      int slots, uint32_t epoch, uint32_t* my_busy, cudaStream_t stream) {
+                      int slots, uint32_t epoch, uint32_t* my_busy, int split_cols, cudaStream_t stream) {
     const WaitCfg wc{wait_timeout_ns(), g_error_word.load(std::memory_order_relaxed)};
     B2C_CHECK_ARG(recv && out && peer_flag && my_flags, "p2p_reduce_finish: null pointer");
     B2C_CHECK_ARG(elems > 0 && elems % 4 == 0 && world >= 1 && world <= 16 && slots >= world,
                   "p2p_reduce_finish: bad shape elems=%lld world=%d slots=%d", static_cast<long long>(elems), world, slots);
+    B2C_CHECK_ARG(split_cols == 0 || (split_cols > 0 && split_cols % 8 == 0 && elems % split_cols == 0),
+                  "p2p_reduce_finish: split_cols=%d must be 0 or a multiple of 8 that divides elems", split_cols);
     int blocks = static_cast<int>((elems / 4 + 1023) / 1024);
     if (blocks > num_sms()) blocks = num_sms();
     if (blocks < 1) blocks = 1;
-    p2p_reduce_finish_kernel<<<blocks, 256, 0, stream>>>(recv, out, elems, peer_flag, my_flags, world, slots, epoch, my_busy, wc);
+    p2p_reduce_finish_kernel<<<blocks, 256, 0, stream>>>(recv, out, elems, peer_flag, my_flags, world, slots, epoch, my_busy, split_cols, wc);
     B2C_LAUNCH_CHECK("p2p_reduce_finish_kernel");
     return 0;
 }

@@ -96,6 +96,8 @@ def _consume(ctx) -> None:
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype is torch.float32 and t.is_contiguous():   # the usual case; only called inside Function.forward / backward (no graph)
+        return t
     t = t.detach()
     if t.dtype != torch.float32:
         t = t.float()
@@ -134,6 +136,38 @@ class _FusedClipLoss(torch.autograd.Function):
                 gr = gr.to(dt)
             out.append(gr.reshape(ctx.scale_shape) if i == 4 else gr)
         return (*out, None)
+
+
+class _SingleClipLoss(torch.autograd.Function):
+    """world_size == 1 as one node over (image_features, text_features, logit_scale): the features are both the row and the
+    column operands of the two logit blocks, and the backward writes their TOTAL gradients with one two-segment GEMM launch
+    (`b200clip_cliploss_single_backward`) instead of handing autograd a row and a column gradient per tensor to add up."""
+
+    @staticmethod
+    def forward(ctx, image_features, text_features, logit_scale):
+        img, txt = _f32c(image_features), _f32c(text_features)
+        scale = _f32c(logit_scale).reshape(())
+        loss, ws = ops.cliploss_forward(img, txt, img, txt, scale, 0)
+        ctx.meta = (image_features.dtype, text_features.dtype, logit_scale.dtype, logit_scale.shape)
+        ctx.save_for_backward(img, txt, scale, ws)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        needs = ctx.needs_input_grad
+        if not (needs[0] or needs[1] or needs[2]):
+            return None, None, None
+        _consume(ctx)
+        img, txt, scale, ws = ctx.saved_tensors
+        dt_i, dt_t, dt_s, s_shape = ctx.meta
+        d_i, d_t, d_s = ops.cliploss_single_backward(img, txt, scale, ws, _f32c(g).reshape(()), needs)
+        if d_i is not None and dt_i is not torch.float32:
+            d_i = d_i.to(dt_i)
+        if d_t is not None and dt_t is not torch.float32:
+            d_t = d_t.to(dt_t)
+        if d_s is not None:
+            d_s = (d_s if dt_s is torch.float32 else d_s.to(dt_s)).reshape(s_shape)
+        return d_i, d_t, d_s
 
 
 class _DistLocalClipLoss(torch.autograd.Function):
@@ -203,10 +237,10 @@ class _PeerLocalClipLoss(torch.autograd.Function):
         ws = ex.ws[slot]
         d_s = ops.cliploss_packed_backward_p2p(ex.gathered_view(slot), scale, rank, n, ws, _f32c(g).reshape(()), ex.rs_dst[slot],
                                                ctx.needs_input_grad[2])
-        d_both = ex.reduce_scatter_finish(slot)
+        d_both = ex.reduce_scatter_finish(slot)   # [2, n, D]: dense halves
         ctx.token = None                       # the ring slot may be reused by a later forward
-        d_i = d_both[:, :D].to(dt_i) if ctx.needs_input_grad[0] else None
-        d_t = d_both[:, D:].to(dt_t) if ctx.needs_input_grad[1] else None
+        d_i = d_both[0].to(dt_i) if ctx.needs_input_grad[0] else None
+        d_t = d_both[1].to(dt_t) if ctx.needs_input_grad[1] else None
         d_sc = d_s.to(dt_s).reshape(s_shape) if d_s is not None else None
         return d_i, d_t, d_sc, None, None, None
 
@@ -269,6 +303,8 @@ class ClipLoss(nn.Module):
                 total_loss = _PeerLocalClipLoss.apply(image_features, text_features, logit_scale, self.rank, self.world_size, ex)
             else:
                 total_loss = _DistLocalClipLoss.apply(image_features, text_features, logit_scale, self.rank, self.world_size, None)
+        elif self.world_size == 1:
+            total_loss = _SingleClipLoss.apply(image_features, text_features, logit_scale)
         else:
             rows_i, rows_t, all_img, all_txt, rank = self._operands(image_features, text_features)
             total_loss = _FusedClipLoss.apply(rows_i, rows_t, all_img, all_txt, logit_scale, rank)

@@ -144,13 +144,14 @@ class PeerExchange:
         return self.gathered_view(slot), slot
 
     def reduce_scatter_finish(self, slot: int) -> torch.Tensor:
-        """After the slot-addressed backward GEMM of every rank: -> d(img | txt) [n, 2D] of the local rows."""
+        """After the slot-addressed backward GEMM of every rank: -> [2, n, D] = (d_img, d_txt) of the local rows, each a dense
+        tensor (autograd's AccumulateGrad takes a dense gradient as is; a column slice of [n, 2D] would be copied)."""
         self.check_error()
         self.rs_epoch += 1
-        out = torch.empty((self.n, 2 * self.D), dtype=torch.float32, device=self.device)
+        out = torch.empty((2, self.n, self.D), dtype=torch.float32, device=self.device)
         rc = L.load().b200clip_p2p_reduce_finish(self.recv_view(slot).data_ptr(), out.data_ptr(), self.S, self.rs_flag.data_ptr(),
                                                  self.my_rs_flags, self.world, self.world + 2, self.rs_epoch & 0xFFFFFFFF, self.my_busy[slot],
-                                                 L.stream_ptr())
+                                                 2 * self.D, L.stream_ptr())
         L.check(rc, "b200clip_p2p_reduce_finish")
         return out
 

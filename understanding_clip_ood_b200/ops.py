@@ -330,6 +330,20 @@ def cliploss_backward(img_loc, txt_loc, all_img, all_txt, logit_scale, rank: int
     return grads
 
 
+def cliploss_single_backward(img, txt, logit_scale, ws, grad_out, needs):
+    """world_size == 1 (after cliploss_forward(img, txt, img, txt, scale, 0)): -> [d_img, d_txt, d_scale], the TOTAL gradients
+    (None where `needs[i]` is False); see b200clip_cliploss_single_backward."""
+    n, D = img.shape
+    dev = img.device
+    d_img = torch.empty((n, D), dtype=torch.float32, device=dev) if needs[0] else None
+    d_txt = torch.empty((n, D), dtype=torch.float32, device=dev) if needs[1] else None
+    d_s = torch.empty((), dtype=torch.float32, device=dev) if needs[2] else None
+    rc = L.load().b200clip_cliploss_single_backward(img.data_ptr(), txt.data_ptr(), logit_scale.data_ptr(), n, D, L.ptr(grad_out),
+                                                    L.ptr(d_img), L.ptr(d_txt), L.ptr(d_s), ws.data_ptr(), L.stream_ptr())
+    L.check(rc, "b200clip_cliploss_single_backward")
+    return [d_img, d_txt, d_s]
+
+
 def cliploss_packed_forward(gathered: torch.Tensor, logit_scale: torch.Tensor, rank: int, n: int, ws: torch.Tensor | None = None):
     """gathered [N, 2D] fp32 (img | txt of every rank).  -> (loss 0-dim, workspace); see b200clip_cliploss_packed_forward."""
     N, D2 = gathered.shape
