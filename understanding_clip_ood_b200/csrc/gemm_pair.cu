@@ -110,6 +110,9 @@ struct PairParams {
     int sk_tiles;
     float4* sk_partial;    // [clusters][kSkSlotFloat4]
     uint32_t* sk_flags;    // [clusters][kSkFlagsPerSlot], zero between launches (owners reset what they consume)
+    // N-split tail (MODE 2): tiles [ns_begin, ...) -- the ragged last round -- are cut along N into ns_split pieces of
+    // BLOCK_N / ns_split columns, one piece per cluster; no partial sums, no workspace (tmap_r = the W map with the piece-sized box)
+    int ns_begin, ns_split;
 };
 
 // STG_BUFS = staging buffers per epilogue group (3 with a loaded residual: landing / in-place update / store draining)
@@ -144,14 +147,15 @@ __device__ __forceinline__ void pair_tile_coords(int t, const PairParams& p, int
 // region (units = K-blocks of tiles [0, sk_tiles), run c = [c U / C, (c + 1) U / C)), then whole tiles round-robin.
 struct Piece {
     int tile, kb0, kb1;
+    int c0, nc;   // MODE 2 only: first 64-column chunk of the tile this piece covers, number of chunks
 };
 __device__ __forceinline__ int64_t sk_begin(int c, int64_t units, int clusters) { return static_cast<int64_t>(c) * units / clusters; }
-// SK == false: the plain persistent tile walk t = cluster, cluster + stride, ... (what the kernel ran before stream-K existed;
+// MODE 0: the plain persistent tile walk t = cluster, cluster + stride, ... (what the kernel ran before stream-K existed;
 // instantiated separately so that whole-tile GEMMs carry none of the stream-K code)
-template <bool SK> struct PieceIter;
-template <> struct PieceIter<false> {
+template <int MODE> struct PieceIter;   // 0 = whole tiles, 1 = stream-K, 2 = whole tiles + N-split tail
+template <> struct PieceIter<0> {
     int t_dp, num_tiles, num_kb, stride;
-    __device__ __forceinline__ PieceIter(const PairParams& p, int num_kb_, int cluster_id, int num_clusters)
+    __device__ __forceinline__ PieceIter(const PairParams& p, int num_kb_, int cluster_id, int num_clusters, int)
         : t_dp(cluster_id), num_tiles(p.m_tiles * p.n_tiles), num_kb(num_kb_), stride(num_clusters) {}
     __device__ __forceinline__ bool next(Piece& pc) {
         if (t_dp >= num_tiles) return false;
@@ -162,10 +166,10 @@ template <> struct PieceIter<false> {
         return true;
     }
 };
-template <> struct PieceIter<true> {
+template <> struct PieceIter<1> {
     int64_t u, end;
     int t_dp, num_tiles, num_kb, stride;
-    __device__ __forceinline__ PieceIter(const PairParams& p, int num_kb_, int cluster_id, int num_clusters) {
+    __device__ __forceinline__ PieceIter(const PairParams& p, int num_kb_, int cluster_id, int num_clusters, int) {
         const int64_t units = static_cast<int64_t>(p.sk_tiles) * num_kb_;
         u = sk_begin(cluster_id, units, num_clusters);
         end = sk_begin(cluster_id + 1, units, num_clusters);
@@ -188,6 +192,37 @@ template <> struct PieceIter<true> {
             pc.kb0 = 0;
             pc.kb1 = num_kb;
             t_dp += stride;
+            return true;
+        }
+        return false;
+    }
+};
+
+// MODE 2: whole tiles up to ns_begin (= the full rounds), then ONE piece of the N-split tail per cluster: tile ns_begin + j / s,
+// chunks [(j % s) * chunks / s, ...) for cluster j < (tiles - ns_begin) * s.  Instantiated separately so that neither the whole-tile
+// kernel nor the stream-K kernel carries the run-time tile width.
+template <> struct PieceIter<2> {
+    int t_dp, num_tiles, num_kb, stride, chunks, ns_begin, ns_split, ns_piece;
+    __device__ __forceinline__ PieceIter(const PairParams& p, int num_kb_, int cluster_id, int num_clusters, int chunks_)
+        : t_dp(cluster_id), num_tiles(p.ns_begin), num_kb(num_kb_), stride(num_clusters), chunks(chunks_), ns_begin(p.ns_begin),
+          ns_split(p.ns_split) {
+        ns_piece = cluster_id < (p.m_tiles * p.n_tiles - p.ns_begin) * p.ns_split ? cluster_id : -1;
+    }
+    __device__ __forceinline__ bool next(Piece& pc) {
+        pc.kb0 = 0;
+        pc.kb1 = num_kb;
+        if (t_dp < num_tiles) {
+            pc.tile = t_dp;
+            pc.c0 = 0;
+            pc.nc = chunks;
+            t_dp += stride;
+            return true;
+        }
+        if (ns_piece >= 0) {
+            pc.tile = ns_begin + ns_piece / ns_split;
+            pc.nc = chunks / ns_split;
+            pc.c0 = (ns_piece % ns_split) * pc.nc;
+            ns_piece = -1;
             return true;
         }
         return false;
@@ -299,10 +334,12 @@ __device__ __noinline__ void sk_add_partials(uint32_t tmem_row, const float4* sl
 // tiles of the same BLOCK_N columns; every CTA fetches one QUARTER of the W tile and TMA-multicasts it to the CTA of the
 // other pair that needs the same half, so the cluster reads each W byte from L2 once instead of twice (the single-pair
 // kernel is bound by the ~10 TB/s L2 -> SM read bandwidth, not by the tensor pipe: profiles/r1_gemm_pair_v1_ncu.md).
-template <typename T, int BLOCK_N, int EPI, int PAIRS, bool SK>
+template <typename T, int BLOCK_N, int EPI, int PAIRS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, const PairParams p) {
+    constexpr bool SK = MODE == 1;                   // stream-K pieces (partial accumulators through the workspace)
+    constexpr bool NS = MODE == 2;                   // N-split tail pieces (narrower UMMA on the ragged last round)
     constexpr bool kRes = epi_loads_residual(EPI);   // residual operand TMA-loaded into the staging ring
     constexpr bool kRelu = EPI == kEpiRelu || EPI == kEpiResidualRelu;
     constexpr bool kStats = EPI == kEpiResidualStats;
@@ -385,7 +422,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int row_in_cluster = static_cast<int>(pair) * kPairM + static_cast<int>(half) * kBM;
             // L2 prefetch cursor (whole-tile schedules only): runs p.pf_dist K-blocks ahead of the shared-memory ring (across tile
             // boundaries), so the ring only has to cover L2 latency, not the DRAM latency of the streamed activations
-            const int pf_dist = SK ? 0 : p.pf_dist;
+            const int pf_dist = MODE != 0 ? 0 : p.pf_dist;
             int pf_t = cluster_id, pf_kb = 0, pf_row = 0;
             auto prefetch_next = [&]() {
                 if (pf_t >= num_tiles) return;
@@ -401,21 +438,28 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             };
             for (int i = 0; i < pf_dist; ++i) prefetch_next();
-            PieceIter<SK> pieces(p, num_kb, cluster_id, num_clusters);
+            PieceIter<MODE> pieces(p, num_kb, cluster_id, num_clusters, Cfg::kChunks);
             Piece pc;
             while (pieces.next(pc)) {
                 int mt, nt;
                 pair_tile_coords(pc.tile, p, mt, nt);
                 const int row_a = mt * kClusterM + row_in_cluster;
-                const int row_w = nt * BLOCK_N + static_cast<int>(half) * (BLOCK_N / 2);
+                // a piece of the N-split tail covers pc.nc of the tile's 64-column chunks: this CTA holds half of those W rows
+                const bool narrow = NS && pc.nc != Cfg::kChunks;
+                const int piece_w_rows = NS ? pc.nc * (kChunkN / 2) : BLOCK_N / 2;
+                const int row_w = nt * BLOCK_N + (NS ? pc.c0 * kChunkN : 0) + static_cast<int>(half) * piece_w_rows;
+                const uint32_t stage_tx = NS ? 2u * static_cast<uint32_t>(Cfg::kABytes + piece_w_rows * kBK * 2) : 2u * Cfg::kStageBytes;
                 for (int kb = pc.kb0; kb < pc.kb1; ++kb) {
                     if (pf_dist > 0) prefetch_next();
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                    if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
                     else mbar_arrive_remote(&full_bar[stage], leader_rank);
                     tma_load_2d_pair(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBK, row_a, kCacheHintEvictNormal);
                     if constexpr (PAIRS == 1) {
-                        tma_load_2d_pair(&tmap_w, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBK, row_w, kCacheHintEvictLast);
+                        if (narrow)   // tmap_r = the W map with the piece-sized box (MODE 2 never loads a residual)
+                            tma_load_2d_pair(&tmap_r, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBK, row_w, kCacheHintEvictLast);
+                        else
+                            tma_load_2d_pair(&tmap_w, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBK, row_w, kCacheHintEvictLast);
                     } else {
                         // my quarter of the W tile -> the CTAs holding W half `half` in both pairs
                         constexpr int kQRows = BLOCK_N / 4;
@@ -440,7 +484,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            PieceIter<SK> pieces(p, num_kb, cluster_id, num_clusters);
+            PieceIter<MODE> pieces(p, num_kb, cluster_id, num_clusters, Cfg::kChunks);
             Piece pc;
             for (; pieces.next(pc); ++it) {
                 const int acc = it & 1;
@@ -448,6 +492,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * kAccStride;
+                // N-split tail pieces run a narrower UMMA (N = 64 x the piece's chunks) on the same A rows
+                const uint32_t idesc_pc = NS ? make_idesc_f16(H::kUmmaFormat, kPairM, static_cast<uint32_t>(pc.nc * kChunkN)) : idesc;
                 for (int kb = pc.kb0; kb < pc.kb1; ++kb) {
                     if (!(p.dbg & 2)) mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -455,7 +501,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k)
-                        umma_f16_pair(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc, ((kb - pc.kb0) | k) != 0);
+                        umma_f16_pair(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc_pc, ((kb - pc.kb0) | k) != 0);
                     // frees the slot in EVERY CTA of the cluster (each of them writes into some of the buffers just read)
                     if (!(p.dbg & 2)) umma_commit_pair(&empty_bar[stage], kAllCtas);
                     if (kb == pc.kb1 - 1) umma_commit_pair(&tmem_full_bar[acc], pair_mask);
@@ -529,7 +575,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
 
         int it = 0;
-        PieceIter<SK> pieces(p, num_kb, cluster_id, num_clusters);
+        PieceIter<MODE> pieces(p, num_kb, cluster_id, num_clusters, Cfg::kChunks);
         Piece pc;
         for (; pieces.next(pc); ++it) {
             const int t = pc.tile;
@@ -538,6 +584,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int row0 = mt * kClusterM + row_in_cluster;
+            const int pc_nc = NS ? pc.nc : Cfg::kChunks;   // 64-column chunks of this piece (N-split tail: fewer than the tile's)
+            const int pc_c0 = NS ? pc.c0 : 0;
             const bool dump = SK && pc.kb0 != 0;                          // run starts inside the tile: accumulator -> fp32 partial
             const bool fixup = SK && pc.kb0 == 0 && pc.kb1 < num_kb;     // tile's first K-block, but not its last: add the others' partials
 
@@ -629,15 +677,23 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 __syncwarp();
             }
 
+            if (NS && grp >= pc_nc) {
+                // a one-chunk piece of the N-split tail leaves the second epilogue group without work: free the accumulator
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[acc], leader_rank);
+                __syncwarp();
+                continue;
+            }
 #pragma unroll 1
-            for (int c = grp; c < Cfg::kChunks; c += 2) {
-                const bool last_of_tile = c + 2 >= Cfg::kChunks;
+            for (int c = grp; c < pc_nc; c += 2) {
+                const bool last_of_tile = c + 2 >= pc_nc;
                 const uint32_t buf = bufc % kStgBufs;
                 const uint32_t stg = stg_base + buf * kChunkBytes;
                 // Staging buffer `buf` is free here: the group leader drains its outstanding TMA store before it joins the
                 // barrier that ends each chunk (below), so the store issued kStgBufs chunks ago finished reading long ago.
                 if constexpr (kRes) mbar_wait(&my_res_bar[buf], (bufc / kStgBufs) & 1);
-                const int col0 = nt * BLOCK_N + c * kChunkN;
+                const int col0 = nt * BLOCK_N + (pc_c0 + c) * kChunkN;
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
                     uint32_t v[32];
@@ -807,11 +863,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // clusters the stream-K schedule is planned for = one per SM pair of the device (the persistent grid of a busy GEMM)
 int sk_clusters_planned() { return num_sms() / 2; }
 
-template <typename T, int BLOCK_N, int EPI, int PAIRS, bool SK>
+template <typename T, int BLOCK_N, int EPI, int PAIRS, int MODE>
 int launch_pair_sk(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr, const PairParams& p,
                    cudaStream_t stream) {
     using Cfg = PairCfg<BLOCK_N, epi_loads_residual(EPI) ? 3 : (B2C_STG_SINGLE ? 1 : 2)>;
-    auto kern = gemm_pair_kernel<T, BLOCK_N, EPI, PAIRS, SK>;
+    auto kern = gemm_pair_kernel<T, BLOCK_N, EPI, PAIRS, MODE>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     static int max_clusters = 0;
@@ -841,8 +897,8 @@ int launch_pair_sk(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorM
     B2C_CHECK_ARG(max_clusters > 0, "gemm_pair: the device cannot co-schedule a cluster of %d CTAs", 2 * PAIRS);
     const int tiles = p.m_tiles * p.n_tiles;
     int clusters = tiles < max_clusters ? tiles : max_clusters;
-    if constexpr (SK) {
-        // the stream-K split was planned for `sk_clusters` clusters: all of them must be co-resident (flag waits)
+    if constexpr (MODE != 0) {
+        // the stream-K split / the N-split tail were planned for `sk_clusters` clusters (stream-K: all co-resident, flag waits)
         B2C_CHECK_ARG(sk_clusters_planned() <= max_clusters, "gemm_pair: stream-K needs %d co-resident clusters, device holds %d",
                       sk_clusters_planned(), max_clusters);
         clusters = sk_clusters_planned();
@@ -860,10 +916,11 @@ template <typename T, int BLOCK_N, int EPI, int PAIRS>
 int launch_pair(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr, const PairParams& p,
                 cudaStream_t stream) {
     if constexpr (PAIRS == 1 && !epi_loads_residual(EPI)) {
-        if (p.sk_tiles > 0) return launch_pair_sk<T, BLOCK_N, EPI, PAIRS, true>(ta, tw, tc, tr, p, stream);
+        if (p.sk_tiles > 0) return launch_pair_sk<T, BLOCK_N, EPI, PAIRS, 1>(ta, tw, tc, tr, p, stream);
+        if (p.ns_split > 0) return launch_pair_sk<T, BLOCK_N, EPI, PAIRS, 2>(ta, tw, tc, tr, p, stream);
     }
-    B2C_CHECK_ARG(p.sk_tiles == 0, "gemm_pair: stream-K is not available for this kernel variant");
-    return launch_pair_sk<T, BLOCK_N, EPI, PAIRS, false>(ta, tw, tc, tr, p, stream);
+    B2C_CHECK_ARG(p.sk_tiles == 0 && p.ns_split == 0, "gemm_pair: stream-K / N-split is not available for this kernel variant");
+    return launch_pair_sk<T, BLOCK_N, EPI, PAIRS, 0>(ta, tw, tc, tr, p, stream);
 }
 
 template <typename T, int BLOCK_N, int PAIRS>
@@ -955,25 +1012,53 @@ int l2_prefetch_distance() {
 
 }  // namespace
 
+// N-split of the ragged last round: `rem` tiles of `bn` columns left over after `full` whole rounds are cut along N into `s` pieces
+// each (piece width bn / s, a multiple of the 64-column epilogue chunk), one piece per cluster, when all pieces fit into one round.
+// Measured (profiles/r2_gemm_epilogue_dissection.txt (6)): worth 2-3 % on the short grids of a 128-image shard (c_fc 33.3 -> 32.4 us,
+// ViT-B/32 forward 1.61 -> 1.57 ms) and a LOSS on long grids / long K (the few clusters of a ragged last round have the whole L2
+// bandwidth to themselves, so that round is much shorter than a full one, while narrow pieces re-read A once per piece): only for
+// grids of at most 6 whole rounds and K < 32 K-blocks.  Returns s (0 = leave the tail as whole tiles).
+// B200CLIP_NSPLIT=0 disables it, =1 applies it whenever the pieces fit.
+static int plan_n_split(int full, int rem, int bn, int clusters, int num_kb = 0) {
+    static const int mode = [] {
+        const char* e = getenv("B200CLIP_NSPLIT");
+        return e != nullptr ? atoi(e) : -1;
+    }();
+    if (mode == 0 || rem <= 0) return 0;
+    const double eff = static_cast<double>(full * clusters + rem) / (static_cast<double>(full + 1) * clusters);
+    if (mode != 1 && (eff >= 0.93 || full > 6 || num_kb >= 32)) return 0;
+    const int chunks = bn / kChunkN;
+    for (int s = chunks; s >= 2; --s)
+        if (chunks % s == 0 && rem * s <= clusters) return s;
+    return 0;
+}
+// measured cost per MAC relative to the 256-wide tile (profiles/r1_gemm_variants_vs_cublas.txt; 64: the N-split tail pieces):
+// narrower tiles read more operand bytes per MAC through the L2 -> SM path that bounds the mainloop
+static double width_cost(int w) { return w >= 256 ? 1.0 : w >= 192 ? 1.18 : w >= 128 ? 1.45 : 2.2; }
+
 // Tile-shape choice: the persistent grid runs ceil(tiles / clusters) rounds; pick the N tile that minimises
 // rounds x tile cost (a 256-wide tile is the most efficient per MAC, narrower ones waste less of the last round).
-int pick_pair_block_n(int M, int N, int pairs, bool stream_k = false) {
+// stream_k: the ragged part will be evened out by stream-K (long K); n_split: the last round may be cut along N.
+int pick_pair_block_n(int M, int N, int pairs, bool stream_k = false, bool n_split = false) {
     const int clusters = pairs == 2 ? 33 : num_sms() / 2;
     const long mt = (M + pairs * kPairM - 1) / (pairs * kPairM);
     double best_cost = 1e30;
     int best = 256;
     const int cands[3] = {256, 192, 128};
-    // measured cost per MAC relative to the 256-wide tile (profiles/r1_gemm_variants_vs_cublas.txt): narrower tiles read
-    // more operand bytes per MAC through the shared-memory port that bounds the mainloop
-    const double eff[3] = {1.0, 1.18, 1.45};
     for (int i = 0; i < 3; ++i) {
         const int bn = cands[i];
         const long nt = (N + bn - 1) / bn;
         const long tiles = mt * nt;
-        // whole rounds, or — with stream-K evening out the ragged part — the exact share of work per cluster
-        double rounds = static_cast<double>((tiles + clusters - 1) / clusters);
-        if (stream_k && tiles > clusters) rounds = static_cast<double>(tiles) / clusters;
-        const double cost = rounds * bn * eff[i];
+        const int full = static_cast<int>(tiles / clusters);
+        const int rem = static_cast<int>(tiles % clusters);
+        // whole rounds, or -- with stream-K evening out the ragged part -- the exact share of work per cluster
+        double cost = static_cast<double>(full + (rem > 0 ? 1 : 0)) * bn * width_cost(bn);
+        if (stream_k && tiles > clusters) {
+            cost = static_cast<double>(tiles) / clusters * bn * width_cost(bn);
+        } else if (n_split && rem > 0) {
+            const int s = plan_n_split(full, rem, bn, clusters);
+            if (s > 0) cost = static_cast<double>(full) * bn * width_cost(bn) + (bn / s) * width_cost(bn / s);
+        }
         if (cost < best_cost) {
             best_cost = cost;
             best = bn;
@@ -1064,8 +1149,11 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     // ahead on the whole-tile order): the in-place residual form (TMA reduce-add store) qualifies, a separate residual does not
     const bool res_in_place = epilogue == 3 && !relu && residual == C && ldr == ldc && !no_reduce_store();
     if (relu) pairs = 1;
-    const bool sk_ok = sk_workspace != nullptr && pairs == 1 && stats_out == nullptr && (epilogue != 3 || res_in_place);
-    const int bn = force_block_n > 0 ? force_block_n : pick_pair_block_n(M, N, pairs, sk_ok);
+    const bool sk_variant = pairs == 1 && stats_out == nullptr && (epilogue != 3 || res_in_place);   // MODE 1 / 2 instantiations exist
+    const bool sk_ok = sk_workspace != nullptr && sk_variant;
+    // stream-K pays off for long K only (plan_stream_k); the K = W GEMMs get their ragged last round cut along N instead
+    const bool long_k = (K + kBK - 1) / kBK >= 32;
+    const int bn = force_block_n > 0 ? force_block_n : pick_pair_block_n(M, N, pairs, sk_ok && long_k, sk_variant);
 
     CUtensorMap ta, tw, tc, tr;
     if (make_tmap_2d(&ta, is_bf16, A, M, K, lda, kBM, kBK) != 0) return -1;
@@ -1115,11 +1203,24 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     p.sk_tiles = 0;
     p.sk_partial = nullptr;
     p.sk_flags = nullptr;
+    p.ns_begin = 0;
+    p.ns_split = 0;
     if (sk_ok && epilogue != 3 && epilogue != kEpiResidualStats) {
         B2C_CHECK_ARG(reinterpret_cast<uintptr_t>(sk_workspace) % 16 == 0, "gemm: stream-K workspace must be 16-byte aligned");
         p.sk_tiles = plan_stream_k(p.m_tiles * p.n_tiles, (K + kBK - 1) / kBK, sk_clusters_planned());
         p.sk_partial = static_cast<float4*>(sk_workspace);
         p.sk_flags = sk_flags_of(sk_workspace);
+    }
+    if (sk_variant && p.sk_tiles == 0 && epilogue != 3 && epilogue != kEpiResidualStats && epilogue != kEpiResidualRelu) {
+        // ragged last round: cut its tiles along N, one piece per cluster (no partial sums, no workspace)
+        const int tiles = p.m_tiles * p.n_tiles, clusters = sk_clusters_planned();
+        const int split = plan_n_split(tiles / clusters, tiles % clusters, bn, clusters, (K + kBK - 1) / kBK);
+        if (split > 0) {
+            p.ns_split = split;
+            p.ns_begin = tiles / clusters * clusters;
+            // MODE 2 never loads a residual: its fourth tensor map carries W with the piece-sized box
+            if (make_tmap_2d(&tr, is_bf16, W, N, K, ldw, bn / split / 2, kBK) != 0) return -1;
+        }
     }
     if (pairs == 2)
         return is_bf16 ? launch_pair_bn<__nv_bfloat16, 2>(bn, epilogue, ta, tw, tc, tr, p, stream)
