@@ -66,6 +66,15 @@ int b200clip_gemm_ws(int dtype, const void* A, int64_t lda, const void* W, int64
                      const void* residual, int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The GEMMs of the tower backward (16-bit dtypes), whose contraction index is NOT the contiguous one of the stored operands:
+ *   C[M,N] = A' W    W stored [K, N] (row pitch ldw; N contiguous): the weight [out, in] of an nn.Linear as it lies in memory;
+ *   a_mn == 0: A' = A stored [M, K]              -> dgrad  dX = G W            (autograd of F.linear, transformer.py:253-264)
+ *   a_mn != 0: A' = A^T with A stored [K, M]     -> wgrad  dW = G^T X  (K = all token rows)
+ * The tcgen05 instruction reads such operands as MN-major shared-memory tiles, so no transposed copy is made.  Plain stores
+ * (no bias / activation).  workspace: optional stream-K scratch as for b200clip_gemm_ws (NULL = whole tiles only). */
+int b200clip_gemm_mn(int dtype, const void* A, int64_t lda, int a_mn, const void* W, int64_t ldw, void* C, int64_t ldc,
+                     int M, int N, int K, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* LayerNorm folded into the following GEMM (16-bit dtypes): C = act(LN(x) W^T + b) computed WITHOUT materialising LN(x):
  *   C[m,n] = act( rstd_m * (x W'^T)[m,n] - rstd_m * mean_m * colsum[n] + bias_f32[n] )
  * with W' = W diag(gamma) in `dtype`, colsum[n] = sum_k W'[n,k] and bias_f32 = b + W beta (both fp32, prepared once by

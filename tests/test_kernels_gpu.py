@@ -134,6 +134,40 @@ def test_gemm_stream_k_with_folded_layernorm():
     assert torch.equal(got, ops.gemm_ln_ws(x, wf, colsum, bf, stats, epilogue=L.EPI_GELU))
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("kind,M,N,K,stream_k", [
+    ("dgrad", 6400, 768, 3072, True),      # d(act) = dY Wproj: G [M, 4W] x W [4W... ] -> contraction over the weight's OUT index
+    ("dgrad", 6400, 2304, 768, True),
+    ("dgrad", 6400, 768, 768, False),
+    ("dgrad", 1000, 264, 72, True),        # ragged everything
+    ("wgrad", 768, 3072, 6400, True),      # dWproj [W, 4W] = dY^T a: contraction over the 6400 token rows (100 K-blocks, 36 tiles: stream-K)
+    ("wgrad", 3072, 768, 6400, True),
+    ("wgrad", 2304, 768, 6400, False),     # whole tiles only
+    ("wgrad", 1536, 512, 9856, True),      # text tower, 128 prompts x 77
+    ("wgrad", 768, 512, 128, True),        # projection: contraction over the batch
+    ("wgrad", 264, 1000, 6300, True),      # ragged token count / tile edges
+])
+def test_gemm_mn_major_operands(dtype, kind, M, N, K, stream_k):
+    """b200clip_gemm_mn: the backward GEMMs read their operands as they lie in memory (MN-major tcgen05 operand tiles), no
+    transposed copies: dgrad = a @ w with w [K, N]; wgrad = a.t() @ w with a [K, M], w [K, N].  fp32 torch matmul of the same
+    16-bit operands is the reference; stream-K runs are bit-identical when repeated."""
+    g = _gen(51)
+    w = (torch.randn(K, N, device=DEV, generator=g) * 0.05).to(dtype)
+    if kind == "dgrad":
+        a = (torch.randn(M, K, device=DEV, generator=g) * 0.5).to(dtype)
+        ref = a.float() @ w.float()
+    else:
+        a = (torch.randn(K, M, device=DEV, generator=g) * 0.5).to(dtype)
+        ref = a.float().t() @ w.float()
+    out = ops.gemm_mn(a, w, a_transposed=kind == "wgrad", stream_k=stream_k)
+    ref16 = ref.to(dtype).float()
+    ulp = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref16).abs().max().item() <= 2 * ulp * ref16.abs().max().item() + 1e-3
+    assert _rel(out, ref16) < 3e-3
+    assert torch.equal(out, ops.gemm_mn(a, w, a_transposed=kind == "wgrad", stream_k=stream_k))
+
+
 def test_gemm_bad_args_raise():
     a = torch.zeros(8, 12, device=DEV, dtype=torch.bfloat16)   # K % 8 != 0
     w = torch.zeros(16, 12, device=DEV, dtype=torch.bfloat16)

@@ -150,6 +150,19 @@ int b200clip_gemm_ws(int dtype, const void* A, int64_t lda, const void* W, int64
     return gemm_any(dtype, A, lda, W, ldw, bias, residual, ldr, C, ldc, M, N, K, epilogue, nullptr, 0, 0, S(stream), workspace);
 }
 
+int b200clip_gemm_mn(int dtype, const void* A, int64_t lda, int a_mn, const void* W, int64_t ldw, void* C, int64_t ldc, int M, int N, int K,
+                     void* workspace, int64_t workspace_bytes, void* stream) {
+    B2C_CHECK_ARG(A != nullptr && W != nullptr && C != nullptr, "gemm_mn: null pointer");
+    B2C_CHECK_ARG(dtype == B200CLIP_BF16 || dtype == B200CLIP_F16, "gemm_mn: 16-bit dtypes only (fp32 runs b200clip's FFMA GEMM with transpose flags)");
+    if (workspace != nullptr) {
+        B2C_CHECK_ARG(workspace_bytes >= gemm_pair_sk_workspace_bytes(), "gemm_mn: workspace too small (%lld < %lld bytes)",
+                      (long long)workspace_bytes, (long long)gemm_pair_sk_workspace_bytes());
+        int rc;
+        if ((rc = gemm_pair_sk_workspace_reset(workspace, S(stream))) != 0) return rc;
+    }
+    return gemm_pair_mn(dtype == B200CLIP_BF16, A, lda, a_mn != 0, W, ldw, true, C, ldc, M, N, K, S(stream), workspace);
+}
+
 int b200clip_gemm_ln_ws(int dtype, const void* x, int64_t ldx, const void* Wf, int64_t ldw, const float* colsum, const float* bias_f32,
                         const float* rowstats, void* C, int64_t ldc, int M, int N, int K, int epilogue, void* workspace,
                         int64_t workspace_bytes, void* stream) {

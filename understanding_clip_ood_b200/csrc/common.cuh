@@ -452,6 +452,20 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     return d;
 }
 
+// Shared-memory descriptor of an MN-major operand tile written by TMA with SWIZZLE_128B as [K rows][64 MN elements] boxes (128 B
+// rows, 8-row / 1024 B swizzle atoms), the 64-element MN blocks `lbo_bytes` apart.  Canonical form
+// ((64,m),(8,k)):((1,LBO),(64,SBO)) in elements: SBO = 1024 B between 8-row K groups, LBO = distance between MN blocks.  One
+// UMMA K step (16 rows) advances the start address by 2048 B.
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc_lbo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>(1024u >> 4) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+
 // Instruction descriptor for kind::f16: fp32 accumulate, A/B both K-major, no negate/saturate/sparsity.
 //   [4,6) c_format = 1 (F32)  [7,10) a_format  [10,13) b_format  [15] a_major  [16] b_major
 //   [17,23) N >> 3            [24,29) M >> 4

@@ -334,7 +334,11 @@ __device__ __noinline__ void sk_add_partials(uint32_t tmem_row, const float4* sl
 // tiles of the same BLOCK_N columns; every CTA fetches one QUARTER of the W tile and TMA-multicasts it to the CTA of the
 // other pair that needs the same half, so the cluster reads each W byte from L2 once instead of twice (the single-pair
 // kernel is bound by the ~10 TB/s L2 -> SM read bandwidth, not by the tensor pipe: profiles/r1_gemm_pair_v1_ncu.md).
-template <typename T, int BLOCK_N, int EPI, int PAIRS, int MODE>
+// MAJ: operand storage.  0 = both operands K-major (A [M, K], W [N, K]: the forward GEMMs).  Bit 0: A is MN-major (stored [K, M],
+// M contiguous); bit 1: W is MN-major (stored [K, N]).  The backward GEMMs contract over an index that is NOT contiguous in
+// memory: dgrad dX = G W reads W [N_out, K_in] as the MN-major operand (MAJ 2), wgrad dW = G^T X reads both G [tokens, N_out] and
+// X [tokens, K_in] MN-major (MAJ 3) -- no transposed copies.  TMA brings MN-major tiles as [64 K rows][64 MN elements] boxes.
+template <typename T, int BLOCK_N, int EPI, int PAIRS, int MODE, int MAJ = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, const PairParams p) {
@@ -422,7 +426,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int row_in_cluster = static_cast<int>(pair) * kPairM + static_cast<int>(half) * kBM;
             // L2 prefetch cursor (whole-tile schedules only): runs p.pf_dist K-blocks ahead of the shared-memory ring (across tile
             // boundaries), so the ring only has to cover L2 latency, not the DRAM latency of the streamed activations
-            const int pf_dist = MODE != 0 ? 0 : p.pf_dist;
+            const int pf_dist = (MODE != 0 || MAJ != 0) ? 0 : p.pf_dist;
             int pf_t = cluster_id, pf_kb = 0, pf_row = 0;
             auto prefetch_next = [&]() {
                 if (pf_t >= num_tiles) return;
@@ -454,8 +458,22 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
                     else mbar_arrive_remote(&full_bar[stage], leader_rank);
-                    tma_load_2d_pair(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBK, row_a, kCacheHintEvictNormal);
-                    if constexpr (PAIRS == 1) {
+                    if constexpr ((MAJ & 1) != 0) {
+                        // MN-major A: my 128 rows of the tile = two [64 k][64 m] boxes
+#pragma unroll
+                        for (int blk = 0; blk < kBM / 64; ++blk)
+                            tma_load_2d_pair(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes + blk * 8192, row_a + blk * 64, kb * kBK,
+                                             kCacheHintEvictNormal);
+                    } else {
+                        tma_load_2d_pair(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBK, row_a, kCacheHintEvictNormal);
+                    }
+                    if constexpr ((MAJ & 2) != 0) {
+                        static_assert(MAJ == 0 || (PAIRS == 1 && MODE != 2 && (BLOCK_N / 2) % 64 == 0), "MN-major W: single pairs, whole 64-column blocks");
+#pragma unroll
+                        for (int blk = 0; blk < BLOCK_N / 128; ++blk)
+                            tma_load_2d_pair(&tmap_w, &full_bar[stage], smem_b + stage * Cfg::kBBytes + blk * 8192, row_w + blk * 64, kb * kBK,
+                                             kCacheHintEvictLast);
+                    } else if constexpr (PAIRS == 1) {
                         if (narrow)   // tmap_r = the W map with the piece-sized box (MODE 2 never loads a residual)
                             tma_load_2d_pair(&tmap_r, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBK, row_w, kCacheHintEvictLast);
                         else
@@ -478,7 +496,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (warp == 1) {
         // ===================== MMA issuer (pair leaders only) =====================
         if (is_leader && lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(H::kUmmaFormat, kPairM, BLOCK_N);
+            constexpr uint32_t idesc = make_idesc_f16(H::kUmmaFormat, kPairM, BLOCK_N) | ((MAJ & 1) ? (1u << 15) : 0u) | ((MAJ & 2) ? (1u << 16) : 0u);
+            constexpr uint32_t kStepA = (MAJ & 1) ? (kUmmaK * 128) >> 4 : (kUmmaK * 2) >> 4;   // descriptor advance per UMMA K step
+            constexpr uint32_t kStepB = (MAJ & 2) ? (kUmmaK * 128) >> 4 : (kUmmaK * 2) >> 4;
             constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << kClusterCtas) - 1);
             const uint16_t pair_mask = static_cast<uint16_t>(0x3u << leader_rank);
             int stage = 0;
@@ -497,11 +517,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int kb = pc.kb0; kb < pc.kb1; ++kb) {
                     if (!(p.dbg & 2)) mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t desc_a = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
-                    const uint64_t desc_b = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+                    const uint32_t addr_a = smem_u32(smem_a + stage * Cfg::kABytes), addr_b = smem_u32(smem_b + stage * Cfg::kBBytes);
+                    const uint64_t desc_a = (MAJ & 1) ? make_sw128_mnmajor_desc_lbo(addr_a, 8192) : make_sw128_kmajor_desc(addr_a);
+                    const uint64_t desc_b = (MAJ & 2) ? make_sw128_mnmajor_desc_lbo(addr_b, 8192) : make_sw128_kmajor_desc(addr_b);
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k)
-                        umma_f16_pair(tmem_d, desc_a + 2 * k, desc_b + 2 * k, idesc_pc, ((kb - pc.kb0) | k) != 0);
+                        umma_f16_pair(tmem_d, desc_a + kStepA * k, desc_b + kStepB * k, idesc_pc, ((kb - pc.kb0) | k) != 0);
                     // frees the slot in EVERY CTA of the cluster (each of them writes into some of the buffers just read)
                     if (!(p.dbg & 2)) umma_commit_pair(&empty_bar[stage], kAllCtas);
                     if (kb == pc.kb1 - 1) umma_commit_pair(&tmem_full_bar[acc], pair_mask);
@@ -863,11 +884,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // clusters the stream-K schedule is planned for = one per SM pair of the device (the persistent grid of a busy GEMM)
 int sk_clusters_planned() { return num_sms() / 2; }
 
-template <typename T, int BLOCK_N, int EPI, int PAIRS, int MODE>
+template <typename T, int BLOCK_N, int EPI, int PAIRS, int MODE, int MAJ = 0>
 int launch_pair_sk(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr, const PairParams& p,
                    cudaStream_t stream) {
     using Cfg = PairCfg<BLOCK_N, epi_loads_residual(EPI) ? 3 : (B2C_STG_SINGLE ? 1 : 2)>;
-    auto kern = gemm_pair_kernel<T, BLOCK_N, EPI, PAIRS, MODE>;
+    auto kern = gemm_pair_kernel<T, BLOCK_N, EPI, PAIRS, MODE, MAJ>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     static int max_clusters = 0;
@@ -1227,6 +1248,96 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
                        : launch_pair_bn<__half, 2>(bn, epilogue, ta, tw, tc, tr, p, stream);
     return is_bf16 ? launch_pair_bn<__nv_bfloat16, 1>(bn, epilogue, ta, tw, tc, tr, p, stream)
                    : launch_pair_bn<__half, 1>(bn, epilogue, ta, tw, tc, tr, p, stream);
+}
+
+// Backward-GEMM form: C[M, N] = op(A) op(W)^T with plain stores (no bias / activation), operands optionally MN-major (see the MAJ
+// template parameter): a_mn: A is stored [K, M] (row pitch lda), w_mn: W is stored [K, N] (row pitch ldw).  dgrad = (false, true),
+// wgrad = (true, true).  Stream-K through `sk_workspace` as in gemm_pair (the wgrad contraction runs over all token rows: a few
+// dozen output tiles with hundreds of K-blocks).
+template <typename T, int BLOCK_N, int MAJ>
+static int launch_pair_mn(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const PairParams& p, cudaStream_t s) {
+    if (p.sk_tiles > 0) return launch_pair_sk<T, BLOCK_N, 0, 1, 1, MAJ>(ta, tw, tc, tc, p, s);
+    return launch_pair_sk<T, BLOCK_N, 0, 1, 0, MAJ>(ta, tw, tc, tc, p, s);
+}
+template <typename T>
+static int launch_pair_mn_bn(int bn, int maj, const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const PairParams& p,
+                             cudaStream_t s) {
+    if (bn == 256 && maj == 2) return launch_pair_mn<T, 256, 2>(ta, tw, tc, p, s);
+    if (bn == 256 && maj == 3) return launch_pair_mn<T, 256, 3>(ta, tw, tc, p, s);
+    if (bn == 128 && maj == 2) return launch_pair_mn<T, 128, 2>(ta, tw, tc, p, s);
+    if (bn == 128 && maj == 3) return launch_pair_mn<T, 128, 3>(ta, tw, tc, p, s);
+    set_last_error("gemm_pair_mn: unsupported tile / operand layout (BLOCK_N %d, layout %d)", bn, maj);
+    return -1;
+}
+
+int gemm_pair_mn(bool is_bf16, const void* A, int64_t lda, bool a_mn, const void* W, int64_t ldw, bool w_mn, void* C, int64_t ldc, int M, int N,
+                 int K, cudaStream_t stream, void* sk_workspace) {
+    B2C_CHECK_ARG(M > 0 && N > 0 && K > 0 && A && W && C, "gemm_mn: bad problem M=%d N=%d K=%d", M, N, K);
+    B2C_CHECK_ARG(w_mn, "gemm_mn: W must be MN-major (the all-K-major form is gemm_pair)");
+    B2C_CHECK_ARG(N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 8 == 0 && (a_mn ? M % 8 == 0 : K % 8 == 0),
+                  "gemm_mn: N, the row pitches and the contiguous extent of A must be multiples of 8 (16 B rows)");
+    B2C_CHECK_ARG((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) % 16 == 0,
+                  "gemm_mn: A, W, C must be 16-byte aligned");
+    const int num_kb = (K + kBK - 1) / kBK;
+    const int clusters = sk_clusters_planned();
+    const bool sk_ok = sk_workspace != nullptr;
+    // N tile: 256 or 128 (an MN-major W tile is made of whole 64-column blocks per CTA), same cost model as gemm_pair
+    int bn = 256;
+    {
+        double best = 1e30;
+        const int cands[2] = {256, 128};
+        const long mt = (M + kPairM - 1) / kPairM;
+        for (int i = 0; i < 2; ++i) {
+            const long tiles = mt * ((N + cands[i] - 1) / cands[i]);
+            double rounds = static_cast<double>((tiles + clusters - 1) / clusters);
+            if (sk_ok && num_kb >= 32 && tiles > clusters) rounds = static_cast<double>(tiles) / clusters;
+            const double cost = rounds * cands[i] * width_cost(cands[i]);
+            if (cost < best) {
+                best = cost;
+                bn = cands[i];
+            }
+        }
+    }
+    CUtensorMap ta, tw, tc;
+    if (a_mn) {
+        if (make_tmap_2d(&ta, is_bf16, A, K, M, lda, 64, 64) != 0) return -1;     // [K rows][M contiguous], boxes of 64 k x 64 m
+    } else {
+        if (make_tmap_2d(&ta, is_bf16, A, M, K, lda, kBM, kBK) != 0) return -1;
+    }
+    if (make_tmap_2d(&tw, is_bf16, W, K, N, ldw, 64, 64) != 0) return -1;          // [K rows][N contiguous]
+    if (make_tmap_2d(&tc, is_bf16, C, M, N, ldc, kBM, kChunkN) != 0) return -1;
+    PairParams p;
+    p.bias = nullptr;
+    p.colsum = nullptr;
+    p.rowstats = nullptr;
+    p.stats_part = nullptr;
+    p.stats_out = nullptr;
+    p.stats_slots = 0;
+    p.ln_eps = 0.f;
+    p.pos = nullptr;
+    p.pos_period = 0;
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.m_tiles = (M + kPairM - 1) / kPairM;
+    p.n_tiles = (N + bn - 1) / bn;
+    p.group_m = 8;
+    p.pf_dist = 0;
+    p.dbg = gemm_debug_switches();
+    p.stages = gemm_ring_override();
+    p.sk_tiles = 0;
+    p.sk_partial = nullptr;
+    p.sk_flags = nullptr;
+    p.ns_begin = 0;
+    p.ns_split = 0;
+    if (sk_ok) {
+        B2C_CHECK_ARG(reinterpret_cast<uintptr_t>(sk_workspace) % 16 == 0, "gemm_mn: stream-K workspace must be 16-byte aligned");
+        p.sk_tiles = plan_stream_k(p.m_tiles * p.n_tiles, num_kb, clusters);
+        p.sk_partial = static_cast<float4*>(sk_workspace);
+        p.sk_flags = sk_flags_of(sk_workspace);
+    }
+    const int maj = (a_mn ? 1 : 0) | 2;
+    return is_bf16 ? launch_pair_mn_bn<__nv_bfloat16>(bn, maj, ta, tw, tc, p, stream) : launch_pair_mn_bn<__half>(bn, maj, ta, tw, tc, p, stream);
 }
 
 }  // namespace b200clip

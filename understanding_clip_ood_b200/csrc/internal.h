@@ -11,6 +11,11 @@ int gemm_tc(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw
             int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, const float* pos, int g_in, int g_out,
             int force_block_n, cudaStream_t stream);
 
+// Backward-GEMM form of the pair kernel: C[M, N] = op(A) op(W)^T, plain stores, operands optionally MN-major (a_mn: A stored
+// [K, M]; w_mn: W stored [K, N]) so that dgrad (G W) and wgrad (G^T X) need no transposed copies.  Stream-K as in gemm_pair.
+int gemm_pair_mn(bool is_bf16, const void* A, int64_t lda, bool a_mn, const void* W, int64_t ldw, bool w_mn, void* C, int64_t ldc, int M, int N,
+                 int K, cudaStream_t stream, void* sk_workspace);
+
 // CTA-pair (cta_group::2) variant with the TMA-store epilogue (gemm_pair.cu); epilogues 0..3
 int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
               int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs, cudaStream_t stream,

@@ -21,6 +21,8 @@
 #include "common.cuh"
 #include "internal.h"
 
+#include <cstdlib>
+
 namespace b200clip {
 
 int eot_argmax(const int64_t* text, int ctx, int32_t* eot, int T, cudaStream_t stream);
@@ -91,11 +93,22 @@ struct Ctx {
     const BwdWs* ws;
 };
 
+// B200CLIP_BWD_TRANSPOSE=1: the round-2a path (transposed operand copies + the all-K-major GEMM), kept for A/B measurements
+bool bwd_transposed_operands() {
+    static const bool v = [] {
+        const char* e = getenv("B200CLIP_BWD_TRANSPOSE");
+        return e != nullptr && e[0] == '1';
+    }();
+    return v;
+}
+
 // dX[M, K] = G[M, N] W[N, K]
 int dgrad(const Ctx& c, const void* G, int64_t ldg, const void* Wt, int64_t ldw, void* dX, int64_t ldx, int M, int N, int K) {
     if (c.dt == B200CLIP_F32)
         return gemm_f32_general(static_cast<const float*>(G), ldg, false, static_cast<const float*>(Wt), ldw, true, static_cast<float*>(dX), ldx, M, K, N,
                                 false, c.s);
+    if (!bwd_transposed_operands())   // W [N, K] as it lies in memory is the MN-major operand of dX = G W: no transposed copy
+        return gemm_pair_mn(c.dt == B200CLIP_BF16, G, ldg, false, Wt, ldw, true, dX, ldx, M, K, N, c.s, c.ws->sk);
     int rc;
     if ((rc = transpose16(c.dt, Wt, ldw, c.ws->wT, N, N, K, N, c.s)) != 0) return rc;          // [N, K] -> [K, N]
     return gemm_pair(c.dt == B200CLIP_BF16, G, ldg, c.ws->wT, N, nullptr, nullptr, 0, dX, ldx, M, K, N, B200CLIP_EPI_BIAS, 0, 0, c.s, nullptr, nullptr,
@@ -110,6 +123,17 @@ int wgrad(const Ctx& c, const void* G, int64_t ldg, const void* X, int64_t ldx, 
     if (c.dt == B200CLIP_F32)
         return gemm_f32_general(static_cast<const float*>(G), ldg, true, static_cast<const float*>(X), ldx, true, static_cast<float*>(dW), ldw, N, K, M,
                                 false, c.s);
+    if (!bwd_transposed_operands()) {
+        // G [tokens, N] and X [tokens, K] as they lie in memory are the MN-major operands of dW = G^T X (contraction over the token
+        // rows): no transposed copies.  An activation that used to ride on X's transpose becomes one element-wise pass.
+        const void* Xa = X;
+        if (x_act != 0) {
+            B2C_CHECK_ARG(ldx == K, "wgrad: the activated operand must be contiguous");
+            if ((rc = act_forward(c.dt, X, c.ws->tB, static_cast<int64_t>(M) * K, x_act == 2 ? 1 : 0, c.s)) != 0) return rc;
+            Xa = c.ws->tB;
+        }
+        return gemm_pair_mn(c.dt == B200CLIP_BF16, G, ldg, true, Xa, ldx, true, dW, ldw, N, K, M, c.s, c.ws->sk);
+    }
     const int64_t ldt = c.ws->ldt;
     if ((rc = transpose16(c.dt, G, ldg, c.ws->tA, ldt, M, N, static_cast<int>(ldt), c.s)) != 0) return rc;     // [M, N] -> [N, Mpad]
     if ((rc = transpose16(c.dt, X, ldx, c.ws->tB, ldt, M, K, static_cast<int>(ldt), c.s, x_act)) != 0) return rc;   // [M, K] -> [K, Mpad]

@@ -70,6 +70,25 @@ def gemm_ws(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, 
     return out
 
 
+def gemm_mn(a: torch.Tensor, w: torch.Tensor, *, a_transposed: bool = False, out: torch.Tensor | None = None,
+            workspace: torch.Tensor | None = None, stream_k: bool = True) -> torch.Tensor:
+    """Backward GEMMs without transposed copies: `a @ w` (dgrad: a [M, K], w [K, N]) or `a.t() @ w` (wgrad, a_transposed: a [K, M],
+    w [K, N]); see b200clip_gemm_mn."""
+    L.require_cuda(a, w, out)
+    a, w = _c(a), _c(w)
+    K, N = w.shape
+    M = a.shape[1] if a_transposed else a.shape[0]
+    if (a.shape[0] if a_transposed else a.shape[1]) != K:
+        raise L.B200ClipError(f"gemm_mn: contraction extents differ ({tuple(a.shape)} vs {tuple(w.shape)})")
+    if out is None:
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    ws = (workspace if workspace is not None else gemm_workspace(a.device)) if stream_k else None
+    rc = L.load().b200clip_gemm_mn(L.dtype_code(a.dtype), a.data_ptr(), a.stride(0), 1 if a_transposed else 0, w.data_ptr(), w.stride(0),
+                                   out.data_ptr(), out.stride(0), M, N, K, L.ptr(ws), ws.numel() if ws is not None else 0, L.stream_ptr())
+    L.check(rc, "b200clip_gemm_mn")
+    return out
+
+
 def gemm_ln_ws(x: torch.Tensor, wf: torch.Tensor, colsum: torch.Tensor, bias_f32: torch.Tensor, stats: torch.Tensor, *,
                epilogue: int = L.EPI_BIAS, out: torch.Tensor | None = None, workspace: torch.Tensor | None = None) -> torch.Tensor:
     """`gemm_ln` with the stream-K workspace; see b200clip_gemm_ln_ws."""
