@@ -92,12 +92,17 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in
 // column sums: partial[chunk][col] over row chunks, then a fixed-order sum over the chunks
 // ------------------------------------------------------------------------------------------------------------------------
 constexpr int kColChunkRows = 64;
+constexpr int kColSumCounters = 256;   // column blocks (64 columns each) the single-launch column sum has counters for
 
 // block = 32 column pairs x 8 row lanes: 64 columns x kColChunkRows rows per block, rows strided over the 8 lanes, then a
 // shared-memory reduction over the lanes (fixed order)
-template <typename T>
-__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ g, int64_t ld, int rows, int cols, float* __restrict__ part) {
+// `counters` != nullptr (one zero-initialised word per 64-column block, left at zero): the row chunk that finishes LAST for a
+// column block also sums that block's partials (fixed order: deterministic) and writes out[c] -- no second launch.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ g, int64_t ld, int rows, int cols, float* __restrict__ part,
+                                                             unsigned int* __restrict__ counters, TO* __restrict__ out, int accumulate) {
     __shared__ float red[8][65];
+    __shared__ bool is_last;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 64 + tx * 2;
     const int r0 = blockIdx.y * kColChunkRows;
@@ -123,6 +128,30 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict
             for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
             part[static_cast<int64_t>(blockIdx.y) * cols + cc] = s;
         }
+    }
+    if (counters == nullptr) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(counters + blockIdx.x, 1u);
+        is_last = prev == gridDim.y - 1;
+        if (is_last) counters[blockIdx.x] = 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // 64 columns x 4 chunk lanes
+    const int col = threadIdx.x & 63, lane4 = threadIdx.x >> 6;
+    const int cc = blockIdx.x * 64 + col;
+    float s = 0.f;
+    if (cc < cols)
+        for (int k = lane4; k < static_cast<int>(gridDim.y); k += 4) s += __ldcg(part + static_cast<int64_t>(k) * cols + cc);
+    red[lane4][col] = s;
+    __syncthreads();
+    if (threadIdx.x < 64 && cc < cols) {
+        float t = (red[0][col] + red[1][col]) + (red[2][col] + red[3][col]);
+        if (accumulate) t += to_f<TO>(out[cc]);
+        out[cc] = from_f<TO>(t);
     }
 }
 // out[c] (+)= sum over chunks of part[chunk][c]: 32 columns x 8 chunk lanes per block (fixed summation order)
@@ -755,11 +784,25 @@ int transpose16(int dtype, const void* in, int64_t ldi, void* out, int64_t ldo, 
 int64_t col_sum_scratch_floats(int rows, int cols) { return static_cast<int64_t>((rows + kColChunkRows - 1) / kColChunkRows) * cols; }
 
 // out[c] (+)= sum_r g[r][c]; out_dtype: 0 = fp32, otherwise the storage type `dtype`
-int col_sum(int dtype, const void* g, int64_t ld, int rows, int cols, void* out, int out_f32, int accumulate, float* scratch, cudaStream_t stream) {
+int col_sum(int dtype, const void* g, int64_t ld, int rows, int cols, void* out, int out_f32, int accumulate, float* scratch, cudaStream_t stream,
+            unsigned int* counters) {
     B2C_CHECK_ARG(g && out && scratch && rows > 0 && cols > 0, "col_sum: bad arguments");
     const int chunks = (rows + kColChunkRows - 1) / kColChunkRows;
     dim3 grid((cols + 63) / 64, chunks);
-    B2C_DISPATCH_T(dtype, (colsum_partial_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(g), ld, rows, cols, scratch)));
+    if (counters != nullptr && static_cast<int>(grid.x) <= kColSumCounters) {
+        // one launch: the last row chunk of every column block finishes the sum
+        if (out_f32 || dtype == 0) {
+            B2C_DISPATCH_T(dtype, (colsum_partial_kernel<T, float><<<grid, 256, 0, stream>>>(static_cast<const T*>(g), ld, rows, cols, scratch, counters,
+                                                                                               static_cast<float*>(out), accumulate)));
+        } else {
+            B2C_DISPATCH_T(dtype, (colsum_partial_kernel<T, T><<<grid, 256, 0, stream>>>(static_cast<const T*>(g), ld, rows, cols, scratch, counters,
+                                                                                           static_cast<T*>(out), accumulate)));
+        }
+        B2C_LAUNCH_CHECK("colsum_partial_kernel");
+        return 0;
+    }
+    B2C_DISPATCH_T(dtype, (colsum_partial_kernel<T, float><<<grid, 256, 0, stream>>>(static_cast<const T*>(g), ld, rows, cols, scratch, nullptr,
+                                                                                       static_cast<float*>(nullptr), 0)));
     B2C_LAUNCH_CHECK("colsum_partial_kernel");
     if (out_f32 || dtype == 0) {
         colsum_final_kernel<float><<<(cols + 31) / 32, 256, 0, stream>>>(scratch, chunks, cols, static_cast<float*>(out), accumulate);

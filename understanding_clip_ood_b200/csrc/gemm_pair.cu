@@ -1254,6 +1254,15 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
 // template parameter): a_mn: A is stored [K, M] (row pitch lda), w_mn: W is stored [K, N] (row pitch ldw).  dgrad = (false, true),
 // wgrad = (true, true).  Stream-K through `sk_workspace` as in gemm_pair (the wgrad contraction runs over all token rows: a few
 // dozen output tiles with hundreds of K-blocks).
+// B200CLIP_MN_WIDE=1: prefer the 256-wide tile for stream-K grids with fewer tiles than clusters (A/B measurements)
+static bool mn_wide_tiles() {
+    static const bool v = [] {
+        const char* e = getenv("B200CLIP_MN_WIDE");
+        return e != nullptr && e[0] == '1';
+    }();
+    return v;
+}
+
 template <typename T, int BLOCK_N, int MAJ>
 static int launch_pair_mn(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const PairParams& p, cudaStream_t s) {
     if (p.sk_tiles > 0) return launch_pair_sk<T, BLOCK_N, 0, 1, 1, MAJ>(ta, tw, tc, tc, p, s);
@@ -1290,7 +1299,9 @@ int gemm_pair_mn(bool is_bf16, const void* A, int64_t lda, bool a_mn, const void
         for (int i = 0; i < 2; ++i) {
             const long tiles = mt * ((N + cands[i] - 1) / cands[i]);
             double rounds = static_cast<double>((tiles + clusters - 1) / clusters);
-            if (sk_ok && num_kb >= 32 && tiles > clusters) rounds = static_cast<double>(tiles) / clusters;
+            // long K with the workspace: stream-K gives every cluster an equal share also when there are FEWER tiles than clusters
+            // (wgrad: 27-54 tiles of 100-154 K-blocks), so the wide tile's lower operand traffic per MAC decides
+            if (sk_ok && num_kb >= 32 && (tiles > clusters || mn_wide_tiles())) rounds = static_cast<double>(tiles) / clusters;
             const double cost = rounds * cands[i] * width_cost(cands[i]);
             if (cost < best) {
                 best = cost;

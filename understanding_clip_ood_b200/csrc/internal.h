@@ -115,7 +115,10 @@ int gemm_f32_general(const float* A, int64_t lda, bool ta, const float* B, int64
                      bool accumulate, cudaStream_t stream);
 int transpose16(int dtype, const void* in, int64_t ldi, void* out, int64_t ldo, int R, int C, int Rpad, cudaStream_t stream, int act = 0);
 int64_t col_sum_scratch_floats(int rows, int cols);
-int col_sum(int dtype, const void* g, int64_t ld, int rows, int cols, void* out, int out_f32, int accumulate, float* scratch, cudaStream_t stream);
+// counters: optional kColSumCounters (= 256) zero-initialised words (left at zero): single-launch form (the last row chunk of each
+// 64-column block finishes the sum); nullptr: partial sums + a second launch
+int col_sum(int dtype, const void* g, int64_t ld, int rows, int cols, void* out, int out_f32, int accumulate, float* scratch, cudaStream_t stream,
+            unsigned int* counters = nullptr);
 int64_t ln_backward_scratch_floats(int rows, int width);
 int ln_backward(int dtype, const void* g, int64_t ldg, const void* x, int64_t ldx, const float* gamma, const void* dres, int64_t ldr, void* dx,
                 int64_t ldd, float* d_gamma, float* d_beta, int rows, int width, float eps, int row_stride, const int32_t* row_idx, int accumulate,

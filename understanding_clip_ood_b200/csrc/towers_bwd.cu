@@ -38,6 +38,7 @@ struct BwdWs {
     char *pooled, *feat, *dfeat, *dpooled;        // [batch, W] / [batch, D]
     int32_t* eot;
     float* scratch;                               // column-sum / LayerNorm partials
+    unsigned int* counters;                       // 256 words, zero between kernels: last-chunk-done counters of the column sums
     void* sk;                                     // stream-K workspace of the CTA-pair GEMM
     int64_t ldt;                                  // leading dimension of the transposed activations (M rounded up to 8)
     int64_t total;
@@ -82,6 +83,7 @@ BwdWs carve_bwd(const b200clip_tower_cfg& c, int batch, int L, void* base) {
     const int64_t lf = ln_backward_scratch_floats(static_cast<int>(M), static_cast<int>(W));
     if (lf > sf) sf = lf;
     w.scratch = reinterpret_cast<float*>(take(sf * 4));
+    w.counters = reinterpret_cast<unsigned int*>(take(256 * 4));
     w.sk = lp ? take(gemm_pair_sk_workspace_bytes()) : nullptr;
     w.total = off;
     return w;
@@ -119,7 +121,7 @@ int dgrad(const Ctx& c, const void* G, int64_t ldg, const void* Wt, int64_t ldw,
 // as the pre-activation and the activation (1 = GELU, 2 = QuickGELU) is applied inside the operand transpose.
 int wgrad(const Ctx& c, const void* G, int64_t ldg, const void* X, int64_t ldx, void* dW, int64_t ldw, void* db, int M, int N, int K, int x_act = 0) {
     int rc;
-    if (db != nullptr && (rc = col_sum(c.dt, G, ldg, M, N, db, 0, 0, c.ws->scratch, c.s)) != 0) return rc;
+    if (db != nullptr && (rc = col_sum(c.dt, G, ldg, M, N, db, 0, 0, c.ws->scratch, c.s, c.ws->counters)) != 0) return rc;
     if (c.dt == B200CLIP_F32)
         return gemm_f32_general(static_cast<const float*>(G), ldg, true, static_cast<const float*>(X), ldx, true, static_cast<float*>(dW), ldw, N, K, M,
                                 false, c.s);
@@ -225,6 +227,7 @@ int vit_backward(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, c
     const BwdWs ws = carve_bwd(c, batch, L, workspace);
     B2C_CHECK_ARG(ws.total <= workspace_bytes_, "vit_backward: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes_, (long long)ws.total);
     if (ws.sk != nullptr && (rc = gemm_pair_sk_workspace_reset(ws.sk, s)) != 0) return rc;
+    B2C_CUDA(cudaMemsetAsync(ws.counters, 0, 256 * 4, s));
     const Ctx cx{dt, s, &ws};
     if ((rc = head_backward(c, ws, slot_ptr(saved, c.layers + 1, c, batch, L), w->ln_post_g, w->ln_post_b, w->proj_t, d_out, batch, L, normalize, nullptr,
                             g->ln_post_g, g->ln_post_b, g->proj, s)) != 0)
@@ -254,6 +257,7 @@ int text_backward(const b200clip_tower_cfg* cfg, const b200clip_text_weights* w,
     const BwdWs ws = carve_bwd(c, batch, L, workspace);
     B2C_CHECK_ARG(ws.total <= workspace_bytes_, "text_backward: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes_, (long long)ws.total);
     if (ws.sk != nullptr && (rc = gemm_pair_sk_workspace_reset(ws.sk, s)) != 0) return rc;
+    B2C_CUDA(cudaMemsetAsync(ws.counters, 0, 256 * 4, s));
     if ((rc = eot_argmax(text, c.seq_len, ws.eot, batch, s)) != 0) return rc;
     if ((rc = head_backward(c, ws, slot_ptr(saved, c.layers + 1, c, batch, L), w->ln_final_g, w->ln_final_b, w->proj_t, d_out, batch, L, normalize, ws.eot,
                             g->ln_final_g, g->ln_final_b, g->proj, s)) != 0)
