@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in
 // column sums: partial[chunk][col] over row chunks, then a fixed-order sum over the chunks
 // ------------------------------------------------------------------------------------------------------------------------
 constexpr int kColChunkRows = 64;
+constexpr int kColVecChunkRows = 128;   // rows per block of the vectorised column sum
 constexpr int kColSumCounters = 256;   // column blocks (64 columns each) the single-launch column sum has counters for
 
 // block = 32 column pairs x 8 row lanes: 64 columns x kColChunkRows rows per block, rows strided over the 8 lanes, then a
@@ -388,26 +389,137 @@ bool launch_ln_backward_vec(const T* g, int64_t ldg, const T* x, int64_t ldx, co
 // ------------------------------------------------------------------------------------------------------------------------
 // activation backward
 // ------------------------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) act_backward_kernel(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ dz, int64_t n, int quick) {
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const float x = to_f<T>(z[i]);
-        float d;
-        if (quick) {
-            const float s = 1.0f / (1.0f + __expf(-1.702f * x));
-            d = s * (1.0f + 1.702f * x * (1.0f - s));
-        } else {
-            const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-            const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-            d = cdf + x * pdf;
+// Column sums with 16-byte loads: a block covers 32 lanes x V columns (256 for 16-bit types) and kColVecChunkRows rows (its 8 warps
+// stride over the rows), writes one partial row, and the block that finishes LAST for its column block (counter per column block,
+// zero on entry, left at zero) sums the partials in a fixed order and writes out[c]: one launch, deterministic.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ g, int64_t ld, int rows, int cols, float* __restrict__ part,
+                                                         unsigned int* __restrict__ counters, TO* __restrict__ out, int accumulate) {
+    constexpr int V = VecOf<T>::n;
+    constexpr int CB = 32 * V;
+    __shared__ float red[8][CB];
+    __shared__ bool is_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * CB + lane * V;
+    const int r0 = blockIdx.y * kColVecChunkRows;
+    const int r1 = min(rows, r0 + kColVecChunkRows);
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    if (c < cols) {
+        for (int r = r0 + warp; r < r1; r += 8) {
+            float v[V];
+            load16<T>(g + static_cast<int64_t>(r) * ld + c, v);
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] += v[j];
         }
-        dz[i] = from_f<T>(to_f<T>(da[i]) * d);
     }
+#pragma unroll
+    for (int j = 0; j < V; ++j) red[warp][lane * V + j] = acc[j];
+    __syncthreads();
+    for (int t = threadIdx.x; t < CB; t += 256) {
+        const int cc = blockIdx.x * CB + t;
+        if (cc < cols) {
+            float s2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s2 += red[k][t];
+            part[static_cast<int64_t>(blockIdx.y) * cols + cc] = s2;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(counters + blockIdx.x, 1u);
+        is_last = prev == gridDim.y - 1;
+        if (is_last) counters[blockIdx.x] = 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // the partial rows of this column block: warp w takes chunks w, w + 8, ... (short dependent chains), then the warps are summed
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    if (c < cols) {
+        for (int k = warp; k < static_cast<int>(gridDim.y); k += 8) {
+            const float4* src = reinterpret_cast<const float4*>(part + static_cast<int64_t>(k) * cols + c);
+#pragma unroll
+            for (int q4 = 0; q4 < V / 4; ++q4) {
+                const float4 v4 = __ldcg(src + q4);
+                acc[q4 * 4 + 0] += v4.x; acc[q4 * 4 + 1] += v4.y; acc[q4 * 4 + 2] += v4.z; acc[q4 * 4 + 3] += v4.w;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < V; ++j) red[warp][lane * V + j] = acc[j];
+    __syncthreads();
+    for (int t = threadIdx.x; t < CB; t += 256) {
+        const int cc = blockIdx.x * CB + t;
+        if (cc < cols) {
+            float s2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s2 += red[k][t];
+            if (accumulate) s2 += to_f<TO>(out[cc]);
+            out[cc] = from_f<TO>(s2);
+        }
+    }
+}
+
+__device__ __forceinline__ float act_grad(float x, int quick) {
+    if (quick) {
+        const float sg = 1.0f / (1.0f + __expf(-1.702f * x));
+        return sg * (1.0f + 1.702f * x * (1.0f - sg));
+    }
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+    return cdf + x * pdf;
+}
+// 16-byte accesses (8 / 4 elements per thread per step) when `vec`; the scalar loop handles unaligned buffers and the tail
+template <typename T>
+__global__ void __launch_bounds__(256) act_backward_kernel(const T* __restrict__ da, const T* __restrict__ z, T* __restrict__ dz, int64_t n, int quick,
+                                                           int vec) {
+    constexpr int V = VecOf<T>::n;
+    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x, nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t nv = vec ? n / V : 0;
+    for (int64_t i = tid; i < nv; i += nthr) {
+        float zv[V], dv[V];
+        load16<T>(z + i * V, zv);
+        load16<T>(da + i * V, dv);
+        if (quick || sizeof(T) == 4) {   // fp32 (parity mode) keeps erff / expf
+#pragma unroll
+            for (int j = 0; j < V; ++j) dv[j] *= act_grad(zv[j], quick);
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; j += 2) {
+                float d0, d1;
+                gelu_grad_pair_fast(zv[j], zv[j + 1], d0, d1);
+                dv[j] *= d0;
+                dv[j + 1] *= d1;
+            }
+        }
+        store16<T>(dz + i * V, dv);
+    }
+    for (int64_t i = nv * V + tid; i < n; i += nthr) dz[i] = from_f<T>(to_f<T>(da[i]) * act_grad(to_f<T>(z[i]), quick));
 }
 // forward activation as a separate pass (the training recompute keeps the pre-activation z for the backward)
 template <typename T>
-__global__ void __launch_bounds__(256) act_forward_kernel(const T* __restrict__ z, T* __restrict__ a, int64_t n, int quick) {
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+__global__ void __launch_bounds__(256) act_forward_kernel(const T* __restrict__ z, T* __restrict__ a, int64_t n, int quick, int vec) {
+    constexpr int V = VecOf<T>::n;
+    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x, nthr = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t nv = vec ? n / V : 0;
+    for (int64_t i = tid; i < nv; i += nthr) {
+        float zv[V];
+        load16<T>(z + i * V, zv);
+        if (quick || sizeof(T) == 4) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) zv[j] = quick ? quick_gelu(zv[j]) : gelu_erf(zv[j]);
+        } else {   // the fitted form of the fused forward epilogue (gemm_pair.cu): the recompute reproduces the forward's values
+#pragma unroll
+            for (int j = 0; j < V; j += 2) gelu_pair_fast(zv[j], zv[j + 1]);
+        }
+        store16<T>(a + i * V, zv);
+    }
+    for (int64_t i = nv * V + tid; i < n; i += nthr) {
         const float x = to_f<T>(z[i]);
         a[i] = from_f<T>(quick ? quick_gelu(x) : gelu_erf(x));
     }
@@ -789,16 +901,18 @@ int col_sum(int dtype, const void* g, int64_t ld, int rows, int cols, void* out,
     B2C_CHECK_ARG(g && out && scratch && rows > 0 && cols > 0, "col_sum: bad arguments");
     const int chunks = (rows + kColChunkRows - 1) / kColChunkRows;
     dim3 grid((cols + 63) / 64, chunks);
-    if (counters != nullptr && static_cast<int>(grid.x) <= kColSumCounters) {
-        // one launch: the last row chunk of every column block finishes the sum
+    const int V = dtype == 0 ? 4 : 8;
+    if (counters != nullptr && cols % V == 0 && ld % V == 0 && reinterpret_cast<uintptr_t>(g) % 16 == 0 && (cols + 32 * V - 1) / (32 * V) <= kColSumCounters) {
+        // one launch, 16-byte loads: the last row chunk of every column block finishes the sum
+        const dim3 vgrid((cols + 32 * V - 1) / (32 * V), (rows + kColVecChunkRows - 1) / kColVecChunkRows);
         if (out_f32 || dtype == 0) {
-            B2C_DISPATCH_T(dtype, (colsum_partial_kernel<T, float><<<grid, 256, 0, stream>>>(static_cast<const T*>(g), ld, rows, cols, scratch, counters,
-                                                                                               static_cast<float*>(out), accumulate)));
+            B2C_DISPATCH_T(dtype, (colsum_vec_kernel<T, float><<<vgrid, 256, 0, stream>>>(static_cast<const T*>(g), ld, rows, cols, scratch, counters,
+                                                                                            static_cast<float*>(out), accumulate)));
         } else {
-            B2C_DISPATCH_T(dtype, (colsum_partial_kernel<T, T><<<grid, 256, 0, stream>>>(static_cast<const T*>(g), ld, rows, cols, scratch, counters,
-                                                                                           static_cast<T*>(out), accumulate)));
+            B2C_DISPATCH_T(dtype, (colsum_vec_kernel<T, T><<<vgrid, 256, 0, stream>>>(static_cast<const T*>(g), ld, rows, cols, scratch, counters,
+                                                                                        static_cast<T*>(out), accumulate)));
         }
-        B2C_LAUNCH_CHECK("colsum_partial_kernel");
+        B2C_LAUNCH_CHECK("colsum_vec_kernel");
         return 0;
     }
     B2C_DISPATCH_T(dtype, (colsum_partial_kernel<T, float><<<grid, 256, 0, stream>>>(static_cast<const T*>(g), ld, rows, cols, scratch, nullptr,
@@ -843,14 +957,16 @@ int ln_backward(int dtype, const void* g, int64_t ldg, const void* x, int64_t ld
 
 int act_backward(int dtype, const void* da, const void* z, void* dz, int64_t n, int quick, cudaStream_t stream) {
     B2C_CHECK_ARG(da && z && dz && n > 0, "act_backward: bad arguments");
-    B2C_DISPATCH_T(dtype, (act_backward_kernel<T><<<grid_for(n), 256, 0, stream>>>(static_cast<const T*>(da), static_cast<const T*>(z), static_cast<T*>(dz), n, quick)));
+    const int vec = ((reinterpret_cast<uintptr_t>(da) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(dz)) & 15) == 0;
+    B2C_DISPATCH_T(dtype, (act_backward_kernel<T><<<grid_for(n / 4), 256, 0, stream>>>(static_cast<const T*>(da), static_cast<const T*>(z), static_cast<T*>(dz), n, quick, vec)));
     B2C_LAUNCH_CHECK("act_backward_kernel");
     return 0;
 }
 
 int act_forward(int dtype, const void* z, void* a, int64_t n, int quick, cudaStream_t stream) {
     B2C_CHECK_ARG(z && a && n > 0, "act_forward: bad arguments");
-    B2C_DISPATCH_T(dtype, (act_forward_kernel<T><<<grid_for(n), 256, 0, stream>>>(static_cast<const T*>(z), static_cast<T*>(a), n, quick)));
+    const int vec = ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(a)) & 15) == 0;
+    B2C_DISPATCH_T(dtype, (act_forward_kernel<T><<<grid_for(n / 4), 256, 0, stream>>>(static_cast<const T*>(z), static_cast<T*>(a), n, quick, vec)));
     B2C_LAUNCH_CHECK("act_forward_kernel");
     return 0;
 }

@@ -162,6 +162,26 @@ __device__ __forceinline__ void gelu_pair_fast(float& x0, float& x1) {
     unpack_f2(mul_f2(x, pack_f2(rcp_fast(d0), rcp_fast(d1))), x0, x1);
 }
 
+// d/dx of the erf-GELU, two elements per call:  Phi(x) + x phi(x)  with the same fitted Phi as gelu_pair_fast and
+// phi(x) = 2^(-x^2 log2(e) / 2) / sqrt(2 pi).  |error| < 1e-5 (the gradients it scales are 16-bit).
+__device__ __forceinline__ void gelu_grad_pair_fast(float x0, float x1, float& d0, float& d1) {
+    constexpr float kL = -1.4426950408889634f;
+    const uint64_t x = pack_f2(x0, x1);
+    const uint64_t s = mul_f2(x, x);
+    uint64_t q = fma_f2(pack_f2(2.28182475e-06f * kL, 2.28182475e-06f * kL), s, pack_f2(-6.19073477e-05f * kL, -6.19073477e-05f * kL));
+    q = fma_f2(q, s, pack_f2(-2.45941020e-04f * kL, -2.45941020e-04f * kL));
+    q = fma_f2(q, s, pack_f2(7.29314157e-02f * kL, 7.29314157e-02f * kL));
+    q = fma_f2(q, s, pack_f2(1.59565838e+00f * kL, 1.59565838e+00f * kL));
+    float u0, u1, h0, h1;
+    unpack_f2(mul_f2(q, x), u0, u1);
+    unpack_f2(mul_f2(s, pack_f2(0.5f * kL, 0.5f * kL)), h0, h1);
+    float e0, e1;
+    unpack_f2(add_f2(pack_f2(ex2_fast(u0), ex2_fast(u1)), pack_f2(1.0f, 1.0f)), e0, e1);
+    const uint64_t cdf = pack_f2(rcp_fast(e0), rcp_fast(e1));
+    const uint64_t xpdf = mul_f2(x, pack_f2(0.3989422804014327f * ex2_fast(h0), 0.3989422804014327f * ex2_fast(h1)));
+    unpack_f2(add_f2(cdf, xpdf), d0, d1);
+}
+
 // ---------------------------------------------------------------------------------------
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while
 // its predecessor in the stream is still draining; everything before pdl_wait() (barrier init, TMEM allocation, descriptor
