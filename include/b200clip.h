@@ -470,6 +470,21 @@ int b200clip_adamw_step(const b200clip_adamw_tensor* items, const int32_t* chunk
                         float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                         void* stream);
 
+
+/* Multi-tensor conversion: dst[i] = (dst dtype) src[i] for every tensor of a device table, ONE launch (chunks of
+ * b200clip_adamw_chunk() elements, as for b200clip_adamw_step).  The towers' engines refresh their 16-bit operand copies from the
+ * fp32 master parameters with it after an optimizer step (precision amp / amp_bf16: convert_weights_to_lp semantics,
+ * open_clip/model.py:396-423, applied to the whole parameter list at once). */
+typedef struct b200clip_cast_tensor {
+    const void* src;
+    void* dst;
+    int64_t count;
+    int32_t src_dtype; /* B200CLIP_* */
+    int32_t dst_dtype;
+} b200clip_cast_tensor;
+int b200clip_multi_cast(const b200clip_cast_tensor* items, const int32_t* chunk_item, const int64_t* chunk_off, int chunks,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

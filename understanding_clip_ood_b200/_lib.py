@@ -83,6 +83,10 @@ class AdamWTensor(C.Structure):
                 ("param_dtype", C.c_int32), ("grad_dtype", C.c_int32)]
 
 
+class CastTensor(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("count", C.c_int64), ("src_dtype", C.c_int32), ("dst_dtype", C.c_int32)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); must list every symbol include/b200clip.h declares (tests check this)
@@ -142,6 +146,7 @@ SIGNATURES = {
     "b200clip_vit_backward": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(VitWeights), _P, _P, _I, _I, _P, C.POINTER(VitGrads), _P, _L, _P]),
     "b200clip_text_backward": (C.c_int, [C.POINTER(TowerCfg), C.POINTER(TextWeights), _P, _P, _I, _I, _I, _P, C.POINTER(TextGrads), _P, _L, _P]),
     "b200clip_adamw_chunk": (C.c_int, []),
+    "b200clip_multi_cast": (C.c_int, [_P, _P, _P, _I, _P]),
     "b200clip_adamw_step": (C.c_int, [_P, _P, _P, _I, _F, _F, _F, _F, _F, _I, _F, _P]),
 }
 # not part of the public header: test hook that forces the GEMM N-tile

@@ -420,6 +420,9 @@ int b200clip_text_backward(const b200clip_tower_cfg* cfg, const b200clip_text_we
     return text_backward(cfg, w, text, d_out, batch, seq_len, normalize, saved, grads, workspace, workspace_bytes, S(stream));
 }
 int b200clip_adamw_chunk(void) { return 4096; }
+int b200clip_multi_cast(const b200clip_cast_tensor* items, const int32_t* chunk_item, const int64_t* chunk_off, int chunks, void* stream) {
+    return multi_cast(items, chunk_item, chunk_off, chunks, S(stream));
+}
 int b200clip_adamw_step(const b200clip_adamw_tensor* items, const int32_t* chunk_item, const int64_t* chunk_off, int chunks, float lr,
                         float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
     return adamw_step(items, chunk_item, chunk_off, chunks, lr, beta1, beta2, eps, weight_decay, step, grad_scale, S(stream));

@@ -135,7 +135,9 @@ inline int dtype_size(int dtype) { return dtype == 0 ? 4 : 2; }
 
 }  // namespace b200clip
 struct b200clip_adamw_tensor;
+struct b200clip_cast_tensor;
 namespace b200clip {
+int multi_cast(const b200clip_cast_tensor* items, const int32_t* chunk_item, const int64_t* chunk_off, int chunks, cudaStream_t stream);
 int adamw_step(const b200clip_adamw_tensor* items, const int32_t* chunk_item, const int64_t* chunk_off, int chunks, float lr, float beta1,
                float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream);
 

@@ -99,7 +99,34 @@ adamw_kernel(const b200clip_adamw_tensor* __restrict__ items, const int32_t* __r
     }
 }
 
+// multi-tensor conversion: tensors of a list converted (fp32 <-> 16-bit, or copied) by ONE launch; chunks as in adamw_kernel
+__global__ void __launch_bounds__(256)
+multi_cast_kernel(const b200clip_cast_tensor* __restrict__ items, const int32_t* __restrict__ chunk_item, const int64_t* __restrict__ chunk_off) {
+    const b200clip_cast_tensor it = items[chunk_item[blockIdx.x]];
+    const int64_t begin = chunk_off[blockIdx.x];
+    const int64_t end = min(it.count, begin + kChunk);
+    const bool vec = ((reinterpret_cast<uintptr_t>(it.src) | reinterpret_cast<uintptr_t>(it.dst)) & 15) == 0;
+    int64_t i = begin;
+    if (vec) {
+        const int64_t end4 = begin + (end - begin) / 4 * 4;
+        for (i = begin + threadIdx.x * 4; i < end4; i += 256 * 4) {
+            float v[4];
+            ld4_any(it.src, it.src_dtype, i, v);
+            st4_any(it.dst, it.dst_dtype, i, v);
+        }
+        i = end4;
+    }
+    for (i += threadIdx.x; i < end; i += 256) st_any(it.dst, it.dst_dtype, i, ld_any(it.src, it.src_dtype, i));
+}
+
 }  // namespace
+
+int multi_cast(const b200clip_cast_tensor* items, const int32_t* chunk_item, const int64_t* chunk_off, int chunks, cudaStream_t stream) {
+    B2C_CHECK_ARG(items && chunk_item && chunk_off && chunks > 0, "multi_cast: bad arguments");
+    multi_cast_kernel<<<chunks, 256, 0, stream>>>(items, chunk_item, chunk_off);
+    B2C_LAUNCH_CHECK("multi_cast_kernel");
+    return 0;
+}
 
 int adamw_step(const b200clip_adamw_tensor* items, const int32_t* chunk_item, const int64_t* chunk_off, int chunks, float lr, float beta1,
                float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream) {

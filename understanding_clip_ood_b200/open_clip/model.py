@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional
 
 import numpy as np
@@ -190,7 +191,7 @@ class _Engine:
             return False
         with torch.no_grad():
             if keep.pairs:
-                torch._foreach_copy_([d for d, _ in keep.pairs], [s_.detach() for _, s_ in keep.pairs])
+                keep.cast_pairs()
             for fn in keep.refresh:
                 fn()
         self.sig = self.signature(params) + static_sig
@@ -250,6 +251,39 @@ class _Keep(list):
         super().__init__()
         self.pairs: list = []
         self.refresh: list = []
+        self._cast_table = None
+
+    def cast_pairs(self) -> None:
+        """copy <- source for every pair with ONE launch (`b200clip_multi_cast`; torch._foreach_copy_ issues one kernel per tensor
+        when the dtypes differ: 199 launches per optimizer step for ViT-B/32)."""
+        pairs = [(d, s) for d, s in self.pairs if d.numel() > 0]
+        if not pairs:
+            return
+        if os.environ.get("B200CLIP_FOREACH_REFRESH") == "1":     # A/B: the per-tensor copies of torch._foreach_copy_
+            torch._foreach_copy_([d for d, _ in pairs], [s_.detach() for _, s_ in pairs])
+            return
+        key = tuple((d.data_ptr(), s.data_ptr(), d.dtype, s.dtype, d.numel()) for d, s in pairs)
+        if self._cast_table is None or self._cast_table[0] != key:
+            if any(not d.is_contiguous() or not s.is_contiguous() or d.numel() != s.numel() or d.device != s.device for d, s in pairs):
+                torch._foreach_copy_([d for d, _ in pairs], [s_.detach() for _, s_ in pairs])
+                return
+            dev = pairs[0][0].device
+            chunk = int(L.load().b200clip_adamw_chunk())
+            items = (L.CastTensor * len(pairs))()
+            chunk_item, chunk_off = [], []
+            for i, (d, s) in enumerate(pairs):
+                it = items[i]
+                it.src, it.dst, it.count = s.data_ptr(), d.data_ptr(), d.numel()
+                it.src_dtype, it.dst_dtype = L.dtype_code(s.dtype), L.dtype_code(d.dtype)
+                for off in range(0, d.numel(), chunk):
+                    chunk_item.append(i)
+                    chunk_off.append(off)
+            raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(dev)
+            self._cast_table = (key, raw, torch.tensor(chunk_item, dtype=torch.int32, device=dev),
+                                torch.tensor(chunk_off, dtype=torch.int64, device=dev))
+        _, raw, ci, co = self._cast_table
+        with torch.cuda.device(raw.device):
+            L.check(L.load().b200clip_multi_cast(raw.data_ptr(), ci.data_ptr(), co.data_ptr(), ci.numel(), L.stream_ptr()), "b200clip_multi_cast")
 
 
 def _f32(t: torch.Tensor, keep: list) -> int:
