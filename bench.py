@@ -725,8 +725,16 @@ def run_ours(args) -> None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for _ in range(steps):
-            count_hits(step_device(img), lab)
+        # predictions of every step are kept on the device and scored once after the loop, still inside the timed region (the
+        # reference's evaluation loop also collects predictions and scores them at the end, scripts/evaluate_domainnet_lso_openai.py:82-130):
+        # one copy launch per step instead of eight small bookkeeping launches, which matters for the 128-image shards
+        kept = torch.empty((steps, img.shape[0], TOPK), dtype=torch.int64, device=dev)
+        for i in range(steps):
+            kept[i].copy_(step_device(img))
+        eq = kept == lab[None, :, None]
+        hits[0] += eq[:, :, 0].sum()
+        hits[1] += eq.any(dim=2).sum()
+        hits[2] += steps * img.shape[0]
         if dist is not None and final_reduce:
             dist.all_reduce(hits)                                   # the only collective: final accuracy reduction
         e1.record()

@@ -47,6 +47,12 @@
 #ifndef B2C_EPI_DBG
 #define B2C_EPI_DBG 0
 #endif
+// 1: the LN-fold epilogues stage the tile's colsum / bias vectors in shared memory once per tile (all epilogue threads load one
+// element each before they wait for the accumulator) and read them with broadcast ld.shared in the chunk loop; 0: per-thread
+// __ldg of the vectors inside the chunk loop (2.76 M global-load sectors per c_fc launch, profiles/r1_gemm_pair_cfc_ncu.md)
+#ifndef B2C_LN_VEC_SMEM
+#define B2C_LN_VEC_SMEM 1
+#endif
 
 namespace b200clip {
 
@@ -88,6 +94,8 @@ constexpr int kEpiResidualStats = 10;
 // bottlenecks (deps/open_clip/src/open_clip/modified_resnet.py:42-55), the convolutions being GEMMs over NHWC rows
 constexpr int kEpiRelu = 11;
 constexpr int kEpiResidualRelu = 12;
+constexpr bool epi_is_ln_fold(int epi) { return epi >= kEpiLnFold && epi < kEpiPosAdd; }
+constexpr int epi_vec_bytes(int epi, int block_n) { return (B2C_LN_VEC_SMEM && epi_is_ln_fold(epi)) ? kAccStages * 2 * block_n * 4 : 0; }
 constexpr bool epi_loads_residual(int epi) { return epi == 3 || epi == kEpiResidualStats || epi == kEpiResidualRelu; }
 
 struct PairParams {
@@ -116,7 +124,7 @@ struct PairParams {
 };
 
 // STG_BUFS = staging buffers per epilogue group (3 with a loaded residual: landing / in-place update / store draining)
-template <int BLOCK_N, int STG_BUFS> struct PairCfg {
+template <int BLOCK_N, int STG_BUFS, int VEC_BYTES = 0> struct PairCfg {
     static_assert(BLOCK_N % 64 == 0 && BLOCK_N >= 128 && BLOCK_N <= 256, "BLOCK_N must be 128, 192 or 256");
     static constexpr int kABytes = kBM * kBK * 2;
     static constexpr int kBBytes = (BLOCK_N / 2) * kBK * 2;
@@ -124,10 +132,11 @@ template <int BLOCK_N, int STG_BUFS> struct PairCfg {
     static constexpr int kStgBufs = STG_BUFS;
     static constexpr int kStagingBytes = 2 * kStgBufs * kChunkBytes;
     static constexpr int kBarBytes = 256;
-    static constexpr int kBudget = 227 * 1024 - 1024 - kStagingBytes - kBarBytes;
+    static constexpr int kVecBytes = VEC_BYTES;   // LN-fold: colsum | bias of the tile, one copy per accumulator stage
+    static constexpr int kBudget = 227 * 1024 - 1024 - kStagingBytes - kBarBytes - kVecBytes;
     static constexpr int kStagesFit = kBudget / kStageBytes;
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBarBytes + 1024;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kVecBytes + kBarBytes + 1024;
     static constexpr int kChunks = BLOCK_N / kChunkN;
     static_assert(kStages >= 3, "not enough shared memory for the operand ring");
     static_assert((2 * kStages + 2 * kAccStages + 2 * kStgBufs) * 8 + 8 <= kBarBytes, "barrier block too small");
@@ -347,7 +356,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     constexpr bool kRes = epi_loads_residual(EPI);   // residual operand TMA-loaded into the staging ring
     constexpr bool kRelu = EPI == kEpiRelu || EPI == kEpiResidualRelu;
     constexpr bool kStats = EPI == kEpiResidualStats;
-    using Cfg = PairCfg<BLOCK_N, kRes ? 3 : (B2C_STG_SINGLE ? 1 : 2)>;
+    using Cfg = PairCfg<BLOCK_N, kRes ? 3 : (B2C_STG_SINGLE ? 1 : 2), epi_vec_bytes(EPI, BLOCK_N)>;
     using H = Half16<T>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kStgBufs = Cfg::kStgBufs;
@@ -365,7 +374,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Cfg::kABytes;
     uint8_t* staging = smem + kStages * Cfg::kStageBytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+    float* vec_smem = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);   // [acc stage][colsum | bias][BLOCK_N] (LN-fold only)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes + Cfg::kVecBytes);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full_bar = empty_bar + kStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + kAccStages;
@@ -637,6 +647,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 __syncwarp();
             }
 
+            uint32_t vec_addr = 0;
+            if constexpr (kLn && Cfg::kVecBytes > 0) {
+                // the tile's colsum | bias -> shared memory, one element per epilogue thread, while the MMAs of this tile still run.
+                // Buffer `acc` was last read two tiles ago: every epilogue warp has passed the barrier of the tile in between.
+                float* vs = vec_smem + acc * 2 * BLOCK_N;
+                const int et = static_cast<int>(threadIdx.x) - kEpiWarp0 * 32;
+                if (et < BLOCK_N) {
+                    const int ecol = nt * BLOCK_N + et;
+                    const bool eok = ecol < p.N;
+                    vs[et] = eok ? __ldg(p.colsum + ecol) : 0.f;
+                    vs[BLOCK_N + et] = eok ? __ldg(bias_f32 + ecol) : 0.f;
+                }
+                named_bar_sync(3, kEpiWarps * 32);
+                vec_addr = smem_u32(vs);
+            }
             const float* pos_row = nullptr;
             if constexpr (kPos) pos_row = p.pos + static_cast<int64_t>((row0 + r) % p.pos_period) * p.N;
             float ln_rstd = 0.f, ln_nmr = 0.f;
@@ -769,7 +794,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 bf[q4 * 4 + 0] = b4.x; bf[q4 * 4 + 1] = b4.y; bf[q4 * 4 + 2] = b4.z; bf[q4 * 4 + 3] = b4.w;
                             }
                         }
-                        if constexpr (kLn) {
+                        if constexpr (kLn && Cfg::kVecBytes > 0) {
+                            // broadcast reads of the staged vectors (every lane the same address)
+                            const uint32_t va = vec_addr + static_cast<uint32_t>(((pc_c0 + c) * kChunkN + hf * 32 + g * 8) * 4);
+#pragma unroll
+                            for (int q4 = 0; q4 < 2; ++q4) {
+                                const uint4 c4 = lds128(va + q4 * 16);
+                                const uint4 b4 = lds128(va + BLOCK_N * 4 + q4 * 16);
+                                cf[q4 * 4 + 0] = __uint_as_float(c4.x); cf[q4 * 4 + 1] = __uint_as_float(c4.y);
+                                cf[q4 * 4 + 2] = __uint_as_float(c4.z); cf[q4 * 4 + 3] = __uint_as_float(c4.w);
+                                bf[q4 * 4 + 0] = __uint_as_float(b4.x); bf[q4 * 4 + 1] = __uint_as_float(b4.y);
+                                bf[q4 * 4 + 2] = __uint_as_float(b4.z); bf[q4 * 4 + 3] = __uint_as_float(b4.w);
+                            }
+                        } else if constexpr (kLn) {
                             const int col = col0 + hf * 32 + g * 8;
                             const bool ok = col < p.N;
 #pragma unroll
@@ -887,7 +924,7 @@ int sk_clusters_planned() { return num_sms() / 2; }
 template <typename T, int BLOCK_N, int EPI, int PAIRS, int MODE, int MAJ = 0>
 int launch_pair_sk(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const CUtensorMap& tr, const PairParams& p,
                    cudaStream_t stream) {
-    using Cfg = PairCfg<BLOCK_N, epi_loads_residual(EPI) ? 3 : (B2C_STG_SINGLE ? 1 : 2)>;
+    using Cfg = PairCfg<BLOCK_N, epi_loads_residual(EPI) ? 3 : (B2C_STG_SINGLE ? 1 : 2), epi_vec_bytes(EPI, BLOCK_N)>;
     auto kern = gemm_pair_kernel<T, BLOCK_N, EPI, PAIRS, MODE, MAJ>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;

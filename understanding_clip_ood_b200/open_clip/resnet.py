@@ -138,11 +138,10 @@ class ResNetTower(nn.Module):
         return _resolve_compute_dtype(self.compute_dtype, self.conv1.weight.dtype)
 
     def _build(self, device):
-        from .model import _Engine, _Keep
-        tensors = list(self.parameters()) + list(self.buffers())
+        from .model import _Engine, _Keep, _snapshot
+        tensors = _snapshot(self, buffers=True).tensors
         dt = self._compute_dtype()
-        static_sig = (tuple((p.data_ptr(), p.dtype) for p in tensors), dt)
-        sig = _Engine.signature(tensors) + static_sig
+        sig, static_sig = _Engine.signatures(tensors, dt)
         eng = self._engine
         if eng.sig == sig:
             return eng
@@ -210,13 +209,13 @@ class ResNetTower(nn.Module):
 
     def forward(self, image: torch.Tensor, normalize: bool = False) -> torch.Tensor:
         """[B,3,S,S] -> [B,D] (modified_resnet.py:171-181); `normalize` fuses CLIP.encode_image's F.normalize."""
-        from .model import _check_device, _wants_grad
+        from .model import _check_device, _snapshot, _wants_grad
         _check_device(image, "encode_image")
         _check_device(self.conv1.weight, "encode_image (model weights)")
         if any(m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d)):
             raise RuntimeError("ModifiedResNet: BatchNorm batch statistics (training mode) are not on this path — call model.eval() "
                                "or visual.lock(freeze_bn_stats=True); the tower runs on BatchNorm's running statistics")
-        if _wants_grad(self, list(self.parameters())):
+        if _wants_grad(self, _snapshot(self, buffers=True).params):
             raise RuntimeError("ModifiedResNet: the tower backward is not on this path (inference / zero-shot evaluation only)")
         dt = self._compute_dtype()
         if image.dtype == torch.float32 and dt != torch.float32 and self.conv1.weight.dtype == torch.float32:
