@@ -113,10 +113,13 @@ def test_fused_adamw_matches_torch_adamw():
         ref = [p.detach().float().clone().requires_grad_(True) for p in ours]
         o1 = open_clip.AdamW([{"params": ours[:2], "weight_decay": 0.0}, {"params": ours[2:], "weight_decay": 0.2}], lr=1e-2, betas=(0.9, 0.98), eps=1e-6)
         o2 = torch.optim.AdamW([{"params": ref[:2], "weight_decay": 0.0}, {"params": ref[2:], "weight_decay": 0.2}], lr=1e-2, betas=(0.9, 0.98), eps=1e-6)
+        hold = []
         for step in range(4):
             for p, r in zip(ours, ref):
                 gr = torch.randn(p.shape, device=DEV, generator=g)
-                p.grad = gr.to(dtype)
+                if step % 2 == 0:
+                    hold.append(p.grad)      # keeps the old buffer alive: the next gradient lands at a NEW address (the optimizer
+                p.grad = gr.to(dtype)        # re-points its device table), on odd steps the allocator may hand the old one back
                 r.grad = gr.to(dtype).float()
             v0 = ours[0]._version
             o1.step()
@@ -124,6 +127,28 @@ def test_fused_adamw_matches_torch_adamw():
             assert ours[0]._version > v0
         for p, r in zip(ours, ref):
             assert rel(p.float(), r) < tol, (dtype, p.shape, rel(p.float(), r))
+
+
+def test_multi_tensor_cast_refreshes_the_operand_copies():
+    """_Keep.cast_pairs (b200clip_multi_cast): every (copy, source) pair converted by ONE launch — what the engines run after an
+    optimizer step in the amp modes — equals torch's per-tensor copy_, for aligned and unaligned / odd-sized tensors, fp32 -> 16-bit
+    and 16-bit -> fp32, and again after the sources changed (cached device table)."""
+    from understanding_clip_ood_b200.open_clip.model import _Keep
+    g = torch.Generator(device=DEV).manual_seed(6)
+    keep = _Keep()
+    flat = torch.randn(10000, device=DEV, generator=g)
+    srcs = [torch.randn(768, 768, device=DEV, generator=g), torch.randn(4097, device=DEV, generator=g), torch.randn(3, device=DEV, generator=g),
+            flat[1:1 + 2049], torch.randn(512, 77, device=DEV, generator=g).bfloat16(), torch.randn(9, device=DEV, generator=g).half()]
+    dsts = [torch.empty(768, 768, device=DEV, dtype=torch.bfloat16), torch.empty(4097, device=DEV, dtype=torch.float16),
+            torch.empty(3, device=DEV, dtype=torch.bfloat16), torch.empty(2049, device=DEV, dtype=torch.bfloat16),
+            torch.empty(512, 77, device=DEV), torch.empty(9, device=DEV)]
+    keep.pairs = list(zip(dsts, srcs))
+    for _ in range(2):
+        keep.cast_pairs()
+        for d, s_ in keep.pairs:
+            assert torch.equal(d, s_.to(d.dtype))
+        for s_ in srcs:
+            s_.mul_(1.5)
 
 
 def test_training_loop_reduces_the_loss(tiny):
