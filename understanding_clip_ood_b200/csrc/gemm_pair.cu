@@ -1097,7 +1097,7 @@ static double width_cost(int w) { return w >= 256 ? 1.0 : w >= 192 ? 1.18 : w >=
 // Tile-shape choice: the persistent grid runs ceil(tiles / clusters) rounds; pick the N tile that minimises
 // rounds x tile cost (a 256-wide tile is the most efficient per MAC, narrower ones waste less of the last round).
 // stream_k: the ragged part will be evened out by stream-K (long K); n_split: the last round may be cut along N.
-int pick_pair_block_n(int M, int N, int pairs, bool stream_k = false, bool n_split = false) {
+int pick_pair_block_n(int M, int N, int pairs, bool stream_k = false, bool n_split = false, int num_kb = 0) {
     const int clusters = pairs == 2 ? 33 : num_sms() / 2;
     const long mt = (M + pairs * kPairM - 1) / (pairs * kPairM);
     double best_cost = 1e30;
@@ -1114,7 +1114,7 @@ int pick_pair_block_n(int M, int N, int pairs, bool stream_k = false, bool n_spl
         if (stream_k && tiles > clusters) {
             cost = static_cast<double>(tiles) / clusters * bn * width_cost(bn);
         } else if (n_split && rem > 0) {
-            const int s = plan_n_split(full, rem, bn, clusters);
+            const int s = plan_n_split(full, rem, bn, clusters, num_kb);
             if (s > 0) cost = static_cast<double>(full) * bn * width_cost(bn) + (bn / s) * width_cost(bn / s);
         }
         if (cost < best_cost) {
@@ -1211,7 +1211,7 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     const bool sk_ok = sk_workspace != nullptr && sk_variant;
     // stream-K pays off for long K only (plan_stream_k); the K = W GEMMs get their ragged last round cut along N instead
     const bool long_k = (K + kBK - 1) / kBK >= 32;
-    const int bn = force_block_n > 0 ? force_block_n : pick_pair_block_n(M, N, pairs, sk_ok && long_k, sk_variant);
+    const int bn = force_block_n > 0 ? force_block_n : pick_pair_block_n(M, N, pairs, sk_ok && long_k, sk_variant, (K + kBK - 1) / kBK);
 
     CUtensorMap ta, tw, tc, tr;
     if (make_tmap_2d(&ta, is_bf16, A, M, K, lda, kBM, kBK) != 0) return -1;
