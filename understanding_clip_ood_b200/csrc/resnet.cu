@@ -82,20 +82,37 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const T* __restrict__ 
 
 // ---- 3x3 / stride 1 / padding 1 im2col over NHWC rows ------------------------------------------------------------------------
 // in [B*H*W, C] -> out [B*H*W, 9*C], out[row, tap*C + c] = in[row shifted by (tap/3 - 1, tap%3 - 1), c] (0 outside the image).
-// One thread per 16-byte vector; pure data movement, so it is typed by vector only.
-__global__ void __launch_bounds__(256) im2col3x3_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t total_vec, int H,
-                                                         int W, int cv) {
-    for (int64_t idx = blockIdx.x * 256ll + threadIdx.x; idx < total_vec; idx += gridDim.x * 256ll) {
-        const int v = static_cast<int>(idx % cv);
-        const int64_t t = idx / cv;
-        const int tap = static_cast<int>(t % 9);
-        const int64_t row = t / 9;
-        const int x = static_cast<int>(row % W);
-        const int y = static_cast<int>((row / W) % H);
-        const int sy = y + tap / 3 - 1, sx = x + tap % 3 - 1;
-        uint4 val = make_uint4(0u, 0u, 0u, 0u);
-        if (sy >= 0 && sy < H && sx >= 0 && sx < W) val = __ldg(in + (row + (sy - y) * W + (sx - x)) * cv + v);
-        out[idx] = val;
+// One thread per (row, 16-byte vector of the C channels): it derives (x, y) once and moves all nine taps (nine independent loads in
+// flight).  Pure data movement, so it is typed by vector only.  (The first version did one thread per OUTPUT vector with four 64-bit
+// divisions each: issue-bound at 2.9 TB/s of traffic, 44 % of the RN50 forward.)
+__global__ void __launch_bounds__(256) im2col3x3_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t n_rowvec, int H, int W,
+                                                         int cv, int cv_shift) {
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n_rowvec; i += gridDim.x * 256ll) {
+        int64_t row;
+        int v;
+        if (cv_shift >= 0) {
+            row = i >> cv_shift;
+            v = static_cast<int>(i & (cv - 1));
+        } else {
+            row = i / cv;
+            v = static_cast<int>(i - row * cv);
+        }
+        const uint32_t r32 = static_cast<uint32_t>(row);      // rows = B * H * W < 2^32 (checked by the caller)
+        const uint32_t q = r32 / static_cast<uint32_t>(W);
+        const int x = static_cast<int>(r32 - q * static_cast<uint32_t>(W));
+        const int y = static_cast<int>(q % static_cast<uint32_t>(H));
+        const uint4* src = in + row * cv + v;
+        uint4* dst = out + row * 9 * cv + v;
+        uint4 val[9];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            val[tap] = make_uint4(0u, 0u, 0u, 0u);
+            if (static_cast<unsigned>(y + dy) < static_cast<unsigned>(H) && static_cast<unsigned>(x + dx) < static_cast<unsigned>(W))
+                val[tap] = __ldg(src + (dy * W + dx) * cv);
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) dst[tap * cv] = val[tap];
     }
 }
 
@@ -194,8 +211,13 @@ int im2col3x3(int dtype, const void* in, void* out, int batch, int H, int W, int
     B2C_CHECK_ARG(dtype >= 0 && dtype <= 2 && (C * es) % 16 == 0, "im2col3x3: C=%d must give whole 16-byte vectors", C);
     B2C_CHECK_ARG((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0, "im2col3x3: buffers must be 16-byte aligned");
     const int cv = C * es / 16;
-    const int64_t total = static_cast<int64_t>(batch) * H * W * 9 * cv;
-    im2col3x3_kernel<<<grid_for(total), 256, 0, s>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), total, H, W, cv);
+    const int64_t rows = static_cast<int64_t>(batch) * H * W;
+    B2C_CHECK_ARG(rows < (1ll << 32), "im2col3x3: %lld rows do not fit the 32-bit pixel arithmetic", static_cast<long long>(rows));
+    int cv_shift = -1;
+    for (int sh = 0; sh < 16; ++sh)
+        if ((1 << sh) == cv) cv_shift = sh;
+    const int64_t total = rows * cv;
+    im2col3x3_kernel<<<grid_for(total), 256, 0, s>>>(static_cast<const uint4*>(in), static_cast<uint4*>(out), total, H, W, cv, cv_shift);
     B2C_LAUNCH_CHECK("im2col3x3_kernel");
     return 0;
 }
