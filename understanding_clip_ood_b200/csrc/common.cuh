@@ -295,6 +295,12 @@ __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_
                  : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const void* desc, const void* smem_src, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 // same, but global[box] += shared[box] element-wise (performed by the L2 in the tensor map's element type)
 __device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* smem_src, int32_t c0, int32_t c1) {
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
@@ -415,6 +421,17 @@ __device__ __forceinline__ void tma_load_2d_pair(const void* desc, uint64_t* bar
         :
         : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
           "l"(hint)
+        : "memory");
+}
+// 4-D tile load (NHWC pixel block, see make_tmap_nhwc), same completion mechanism
+__device__ __forceinline__ void tma_load_4d_pair(const void* desc, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1, int32_t c2,
+                                                 int32_t c3, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2),
+          "r"(c3), "l"(hint)
         : "memory");
 }
 // Same, multicast: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and each destination's bytes are

@@ -121,6 +121,9 @@ struct PairParams {
     // N-split tail (MODE 2): tiles [ns_begin, ...) -- the ragged last round -- are cut along N into ns_split pieces of
     // BLOCK_N / ns_split columns, one piece per cluster; no partial sums, no workspace (tmap_r = the W map with the piece-sized box)
     int ns_begin, ns_split;
+    // implicit 3x3 convolution (MAJ bit 2): A is the NHWC activation tensor read through a 4-D tensor map, an M tile of 128 rows is
+    // a block of cv_bb images x cv_by rows x cv_bx pixels, K block kb = tap (kb / cv_cblocks) x 64-channel block (kb % cv_cblocks)
+    int cv_bx, cv_by, cv_bb, cv_tx, cv_ty, cv_cblocks;
 };
 
 // STG_BUFS = staging buffers per epilogue group (3 with a loaded residual: landing / in-place update / store draining)
@@ -150,6 +153,16 @@ __device__ __forceinline__ void pair_tile_coords(int t, const PairParams& p, int
     const int gm = min(p.group_m, p.m_tiles - m0);
     nt = r / gm;
     mt = m0 + (r - nt * gm);
+}
+
+// implicit convolution: pixel block `blk` (128 output rows) -> coordinates of its first pixel
+__device__ __forceinline__ void conv_block_coords(int blk, const PairParams& p, int& x0, int& y0, int& b0) {
+    const int tx = blk % p.cv_tx;
+    const int r = blk / p.cv_tx;
+    const int ty = r % p.cv_ty;
+    x0 = tx * p.cv_bx;
+    y0 = ty * p.cv_by;
+    b0 = (r / p.cv_ty) * p.cv_bb;
 }
 
 // Work list of one cluster, generated identically by its producer, MMA and epilogue warps: first its run of the stream-K
@@ -347,6 +360,9 @@ __device__ __noinline__ void sk_add_partials(uint32_t tmem_row, const float4* sl
 // M contiguous); bit 1: W is MN-major (stored [K, N]).  The backward GEMMs contract over an index that is NOT contiguous in
 // memory: dgrad dX = G W reads W [N_out, K_in] as the MN-major operand (MAJ 2), wgrad dW = G^T X reads both G [tokens, N_out] and
 // X [tokens, K_in] MN-major (MAJ 3) -- no transposed copies.  TMA brings MN-major tiles as [64 K rows][64 MN elements] boxes.
+// Bit 2 (MAJ 4): implicit 3x3 / stride 1 / padding 1 convolution over an NHWC tensor: the A tile of K block (tap, channel block) is
+// the activation tensor itself, read through a 4-D tensor map at the tap's pixel offset (out-of-image pixels arrive as zeros = the
+// padding), and C is stored through the same kind of map -- the im2col matrix never exists (modified_resnet.py:17,42-47).
 template <typename T, int BLOCK_N, int EPI, int PAIRS, int MODE, int MAJ = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -458,6 +474,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 int mt, nt;
                 pair_tile_coords(pc.tile, p, mt, nt);
                 const int row_a = mt * kClusterM + row_in_cluster;
+                int cv_x0 = 0, cv_y0 = 0, cv_b0 = 0;
+                if constexpr ((MAJ & 4) != 0) conv_block_coords(row_a / kBM, p, cv_x0, cv_y0, cv_b0);
                 // a piece of the N-split tail covers pc.nc of the tile's 64-column chunks: this CTA holds half of those W rows
                 const bool narrow = NS && pc.nc != Cfg::kChunks;
                 const int piece_w_rows = NS ? pc.nc * (kChunkN / 2) : BLOCK_N / 2;
@@ -468,7 +486,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
                     else mbar_arrive_remote(&full_bar[stage], leader_rank);
-                    if constexpr ((MAJ & 1) != 0) {
+                    if constexpr ((MAJ & 4) != 0) {
+                        // implicit 3x3 convolution: this K block is tap kb / cblocks, channels [64 (kb % cblocks), +64) of my pixel block
+                        const int tap = kb / p.cv_cblocks, cb = kb - tap * p.cv_cblocks;
+                        tma_load_4d_pair(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, cb * kBK, cv_x0 + tap % 3 - 1, cv_y0 + tap / 3 - 1,
+                                         cv_b0, kCacheHintEvictNormal);
+                    } else if constexpr ((MAJ & 1) != 0) {
                         // MN-major A: my 128 rows of the tile = two [64 k][64 m] boxes
 #pragma unroll
                         for (int blk = 0; blk < kBM / 64; ++blk)
@@ -615,6 +638,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int row0 = mt * kClusterM + row_in_cluster;
+            int cv_x0 = 0, cv_y0 = 0, cv_b0 = 0;
+            if constexpr ((MAJ & 4) != 0) conv_block_coords(row0 / kBM, p, cv_x0, cv_y0, cv_b0);
             const int pc_nc = NS ? pc.nc : Cfg::kChunks;   // 64-column chunks of this piece (N-split tail: fewer than the tile's)
             const int pc_c0 = NS ? pc.c0 : 0;
             const bool dump = SK && pc.kb0 != 0;                          // run starts inside the tile: accumulator -> fp32 partial
@@ -884,6 +909,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 named_bar_sync(bar_id, 128);
                 if (grp_leader) {
                     if constexpr (EPI == kEpiResidualInPlace) tma_reduce_add_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, row0);
+                    else if constexpr ((MAJ & 4) != 0) tma_store_4d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, cv_x0, cv_y0, cv_b0);
                     else tma_store_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, row0);
                     tma_store_commit();
                     if constexpr (kRes) {
@@ -1263,6 +1289,7 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     p.sk_flags = nullptr;
     p.ns_begin = 0;
     p.ns_split = 0;
+    p.cv_bx = p.cv_by = p.cv_bb = p.cv_tx = p.cv_ty = p.cv_cblocks = 0;
     if (sk_ok && epilogue != 3 && epilogue != kEpiResidualStats) {
         B2C_CHECK_ARG(reinterpret_cast<uintptr_t>(sk_workspace) % 16 == 0, "gemm: stream-K workspace must be 16-byte aligned");
         p.sk_tiles = plan_stream_k(p.m_tiles * p.n_tiles, (K + kBK - 1) / kBK, sk_clusters_planned());
@@ -1378,6 +1405,7 @@ int gemm_pair_mn(bool is_bf16, const void* A, int64_t lda, bool a_mn, const void
     p.sk_flags = nullptr;
     p.ns_begin = 0;
     p.ns_split = 0;
+    p.cv_bx = p.cv_by = p.cv_bb = p.cv_tx = p.cv_ty = p.cv_cblocks = 0;
     if (sk_ok) {
         B2C_CHECK_ARG(reinterpret_cast<uintptr_t>(sk_workspace) % 16 == 0, "gemm_mn: stream-K workspace must be 16-byte aligned");
         p.sk_tiles = plan_stream_k(p.m_tiles * p.n_tiles, num_kb, clusters);
@@ -1386,6 +1414,64 @@ int gemm_pair_mn(bool is_bf16, const void* A, int64_t lda, bool a_mn, const void
     }
     const int maj = (a_mn ? 1 : 0) | 2;
     return is_bf16 ? launch_pair_mn_bn<__nv_bfloat16>(bn, maj, ta, tw, tc, p, stream) : launch_pair_mn_bn<__half>(bn, maj, ta, tw, tc, p, stream);
+}
+
+// Implicit 3x3 / stride 1 / padding 1 convolution + bias + ReLU over NHWC activations (the conv2 of a ModifiedResNet bottleneck with
+// its folded BatchNorm, modified_resnet.py:17-18,45):  out[b, y, x, n] = relu(sum_{tap, c} in[b, y + dy, x + dx, c] w[n, tap * C + c] + bias[n]).
+// C must be a multiple of 64 (one K block = 64 channels of one tap); W and H must be divisible by the pixel-block edges chosen here
+// (powers of two, bx * by * bb = 128) -- returns 1 ("not applicable") otherwise so that the caller falls back to im2col + GEMM.
+int gemm_pair_conv3x3(bool is_bf16, const void* in, const void* Wt, const void* bias, void* out, int batch, int H, int W, int C, int N,
+                      cudaStream_t stream) {
+    B2C_CHECK_ARG(in && Wt && bias && out && batch > 0 && H > 0 && W > 0 && C > 0 && N > 0, "conv3x3: bad arguments");
+    if (C % kBK != 0 || N % 8 != 0) return 1;
+    int bx = 1, by = 1;
+    while (bx < 16 && W % (bx * 2) == 0) bx *= 2;
+    while (bx * by < kBM && by < 16 && H % (by * 2) == 0) by *= 2;
+    if (bx * by > kBM || bx < 2 || by < 2) return 1;
+    const int bb = kBM / (bx * by);
+    if (bb > 256) return 1;
+    const int bn = N > 128 ? 256 : 128;
+    CUtensorMap ta, tw, tc;
+    if (make_tmap_nhwc(&ta, is_bf16, in, batch, H, W, C, bb, by, bx) != 0) return -1;
+    if (make_tmap_2d(&tw, is_bf16, Wt, N, 9 * static_cast<uint64_t>(C), 9 * static_cast<uint64_t>(C), bn / 2, kBK) != 0) return -1;
+    if (make_tmap_nhwc(&tc, is_bf16, out, batch, H, W, N, bb, by, bx) != 0) return -1;
+    PairParams p;
+    p.bias = bias;
+    p.colsum = nullptr;
+    p.rowstats = nullptr;
+    p.stats_part = nullptr;
+    p.stats_out = nullptr;
+    p.stats_slots = 0;
+    p.ln_eps = 0.f;
+    p.pos = nullptr;
+    p.pos_period = 0;
+    p.cv_bx = bx;
+    p.cv_by = by;
+    p.cv_bb = bb;
+    p.cv_tx = W / bx;
+    p.cv_ty = H / by;
+    p.cv_cblocks = C / kBK;
+    const int64_t blocks = static_cast<int64_t>(p.cv_tx) * p.cv_ty * ((batch + bb - 1) / bb);
+    B2C_CHECK_ARG(blocks * kBM < (1ll << 31), "conv3x3: too many output rows");
+    p.M = static_cast<int>(blocks * kBM);          // padded row count (pixel blocks beyond the batch are clipped by the tensor maps)
+    p.N = N;
+    p.K = 9 * C;
+    p.m_tiles = static_cast<int>((blocks + 1) / 2);
+    p.n_tiles = (N + bn - 1) / bn;
+    p.group_m = 8;
+    p.pf_dist = 0;
+    p.dbg = gemm_debug_switches();
+    p.stages = gemm_ring_override();
+    p.sk_tiles = 0;
+    p.sk_partial = nullptr;
+    p.sk_flags = nullptr;
+    p.ns_begin = 0;
+    p.ns_split = 0;
+    if (is_bf16)
+        return bn == 256 ? launch_pair_sk<__nv_bfloat16, 256, kEpiRelu, 1, 0, 4>(ta, tw, tc, tc, p, stream)
+                         : launch_pair_sk<__nv_bfloat16, 128, kEpiRelu, 1, 0, 4>(ta, tw, tc, tc, p, stream);
+    return bn == 256 ? launch_pair_sk<__half, 256, kEpiRelu, 1, 0, 4>(ta, tw, tc, tc, p, stream)
+                     : launch_pair_sk<__half, 128, kEpiRelu, 1, 0, 4>(ta, tw, tc, tc, p, stream);
 }
 
 }  // namespace b200clip

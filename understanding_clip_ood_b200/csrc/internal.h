@@ -16,6 +16,11 @@ int gemm_tc(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw
 int gemm_pair_mn(bool is_bf16, const void* A, int64_t lda, bool a_mn, const void* W, int64_t ldw, bool w_mn, void* C, int64_t ldc, int M, int N,
                  int K, cudaStream_t stream, void* sk_workspace);
 
+// Implicit 3x3 / stride 1 / padding 1 convolution + bias + ReLU over NHWC activations on the pair kernel (no im2col matrix):
+// 0 = launched, 1 = geometry not covered (caller falls back to im2col + GEMM), < 0 / > 0 = error
+int gemm_pair_conv3x3(bool is_bf16, const void* in, const void* Wt, const void* bias, void* out, int batch, int H, int W, int C, int N,
+                      cudaStream_t stream);
+
 // CTA-pair (cta_group::2) variant with the TMA-store epilogue (gemm_pair.cu); epilogues 0..3
 int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
               int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs, cudaStream_t stream,

@@ -19,6 +19,7 @@
 #include "internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace b200clip {
 
@@ -177,6 +178,15 @@ __global__ void __launch_bounds__(128) attnpool_tokens_kernel(const T* __restric
         r.v[e] = from_float<T>(m + to_float(from_float<T>(__ldg(pos + v * kN + e))));
     }
     store16(tb, r);
+}
+
+// B200CLIP_CONV_IM2COL=1: every 3x3 convolution through im2col + GEMM (the first version of the tower; A/B measurements)
+bool conv_via_im2col() {
+    static const bool v = [] {
+        const char* e = getenv("B200CLIP_CONV_IM2COL");
+        return e != nullptr && e[0] == '1';
+    }();
+    return v;
 }
 
 inline int grid_for(int64_t total) {
@@ -418,8 +428,16 @@ int resnet_forward_stages(const b200clip_resnet_cfg* cfg, const b200clip_resnet_
             char* y = bf.x[cur ^ 1];
             // conv1 1x1 -> conv2 3x3 -> [avgpool] -> conv3 1x1 (+ identity, ReLU)     (modified_resnet.py:42-56)
             if ((rc = conv(x, cin, b.conv1_w, b.conv1_b, bf.t[0], rows, b.planes, B200CLIP_EPI_RELU, nullptr)) != 0) return rc;
-            if ((rc = im2col3x3(dt, bf.t[0], bf.col, batch, H, H, b.planes, s)) != 0) return rc;
-            if ((rc = conv(bf.col, 9 * b.planes, b.conv2_w, b.conv2_b, bf.t[1], rows, b.planes, B200CLIP_EPI_RELU, nullptr)) != 0) return rc;
+            // conv2: implicit GEMM where the geometry allows it (16-bit, planes % 64 == 0, power-of-two pixel blocks): the A tiles are
+            // read from the NHWC tensor itself, tap by tap; otherwise im2col + GEMM
+            rc = 1;
+            if (dt != B200CLIP_F32 && !conv_via_im2col())
+                rc = gemm_pair_conv3x3(dt == B200CLIP_BF16, bf.t[0], b.conv2_w, b.conv2_b, bf.t[1], batch, H, H, b.planes, b.planes, s);
+            if (rc == 1) {
+                if ((rc = im2col3x3(dt, bf.t[0], bf.col, batch, H, H, b.planes, s)) != 0) return rc;
+                rc = conv(bf.col, 9 * b.planes, b.conv2_w, b.conv2_b, bf.t[1], rows, b.planes, B200CLIP_EPI_RELU, nullptr);
+            }
+            if (rc != 0) return rc;
             const char* main_in = bf.t[1];
             if (b.stride > 1) {
                 if ((rc = avgpool2(dt, bf.t[1], bf.p[0], batch, H, H, b.planes, s)) != 0) return rc;

@@ -96,4 +96,26 @@ int make_tmap_2d(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t rows,
     return 0;
 }
 
+int make_tmap_nhwc(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t bb, uint32_t by,
+                   uint32_t bx) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) {
+        set_last_error("cuTensorMapEncodeTiled not available from the driver");
+        return -1;
+    }
+    const cuuint64_t dims[4] = {C, W, H, B};
+    const cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+    const cuuint32_t box[4] = {64, bx, by, bb};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled (NHWC) failed (CUresult %d) for ptr=%p B=%llu H=%llu W=%llu C=%llu box=%ux%ux%u", (int)r, ptr,
+                       (unsigned long long)B, (unsigned long long)H, (unsigned long long)W, (unsigned long long)C, bb, by, bx);
+        return -1;
+    }
+    return 0;
+}
+
 }  // namespace b200clip
