@@ -75,6 +75,16 @@ int b200clip_gemm_ws(int dtype, const void* A, int64_t lda, const void* W, int64
 int b200clip_gemm_mn(int dtype, const void* A, int64_t lda, int a_mn, const void* W, int64_t ldw, void* C, int64_t ldc,
                      int M, int N, int K, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Patch embedding of the ViT (conv1 with kernel = stride = patch, no bias; class token; positional embedding,
+ * transformer.py:602-609) as an IMPLICIT GEMM over a 16-bit NCHW batch: the patches are read from `image` [batch, 3, S, S]
+ * through a 5-D tensor map, no im2col matrix is written:
+ *   x[b, 1 + py*G + px, :] = round(patch(b, py, px) . conv1_w^T) + round(pos_cls[1 + py*G + px, :]),  x[b, 0, :] = round(pos_cls[0, :])
+ * conv1_w [width, 3*P*P] (K order c, dy, dx), pos_cls fp32 [G*G + 1, width] with row 0 = class_embedding + positional_embedding[0],
+ * x [batch, G*G + 1, width].  Patch 16 or 32.  Same values as b200clip_patchify + the token-layout GEMM; measured slower than
+ * that pair on ViT-B/32 (64-byte gathers, A re-gathered per N tile), so the towers use it only with B200CLIP_PATCH_IMPLICIT=1. */
+int b200clip_patch_embed_implicit(int dtype, const void* image, const void* conv1_w, const float* pos_cls, void* x, int batch,
+                                  int image_size, int patch, int width, void* stream);
+
 /* LayerNorm folded into the following GEMM (16-bit dtypes): C = act(LN(x) W^T + b) computed WITHOUT materialising LN(x):
  *   C[m,n] = act( rstd_m * (x W'^T)[m,n] - rstd_m * mean_m * colsum[n] + bias_f32[n] )
  * with W' = W diag(gamma) in `dtype`, colsum[n] = sum_k W'[n,k] and bias_f32 = b + W beta (both fp32, prepared once by
@@ -332,8 +342,10 @@ int b200clip_text_forward(const b200clip_tower_cfg* cfg, const b200clip_text_wei
 /* The same two forwards split at the points where caller-owned buffers are touched, so that a host can replay the long
  * middle part as ONE captured CUDA graph that depends on nothing but the workspace, whatever buffers the inputs arrive in and
  * the outputs go to (a DataLoader loop hands over a fresh tensor per batch, evaluate_domainnet_lso_openai.py:18-36):
- *   B200CLIP_STAGE_INPUT   the only kernel that reads `image` / `image_u8` / `text` (im2col resp. embedding gather),
- *   B200CLIP_STAGE_BODY    patch GEMM, ln_pre, all blocks, ln_post / ln_final on the pooled rows (workspace -> workspace),
+ *   B200CLIP_STAGE_INPUT   the only kernels that read `image` / `image_u8` / `text`: the patch embedding up to the token rows
+ *                          (16-bit NCHW batches, patch 16 / 32: an implicit GEMM that reads the patches from the image itself
+ *                          through a 5-D tensor map; otherwise im2col + GEMM) resp. the embedding gather,
+ *   B200CLIP_STAGE_BODY    ln_pre, all blocks, ln_post / ln_final on the pooled rows (workspace -> workspace),
  *   B200CLIP_STAGE_OUTPUT  projection (+ L2 normalisation): the only kernels that write `out`.
  * `stages` is a bit mask; pointers a selected stage does not use may be NULL.  All three stages in one call, or in three
  * calls on the same stream and workspace, give bit-identical results to b200clip_vit_forward(_u8) / b200clip_text_forward.

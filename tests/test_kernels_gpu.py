@@ -168,6 +168,28 @@ def test_gemm_mn_major_operands(dtype, kind, M, N, K, stream_k):
     assert torch.equal(out, ops.gemm_mn(a, w, a_transposed=kind == "wgrad", stream_k=stream_k))
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,S,P,width", [(5, 224, 32, 768), (3, 224, 16, 768), (130, 64, 32, 128), (2, 224, 16, 1024)])
+def test_patch_embedding_as_implicit_gemm(dtype, B, S, P, width):
+    """b200clip_patch_embed_implicit: the ViT's conv1 (kernel = stride = patch) + class token + positional embedding with the
+    patches read from the NCHW batch through a 5-D tensor map (narrow-swizzle K-major sub-tiles), against F.conv2d in fp32 on
+    the same 16-bit operands with the reference's rounding points (transformer.py:602-609)."""
+    g = _gen(61)
+    G = S // P
+    image = torch.randn(B, 3, S, S, device=DEV, generator=g).to(dtype)
+    w = (torch.randn(width, 3, P, P, device=DEV, generator=g) * 0.02).to(dtype)
+    pos_cls = torch.randn(G * G + 1, width, device=DEV, generator=g) * 0.1
+    x = ops.patch_embed_implicit(image, w.reshape(width, -1), pos_cls, P)
+    conv = F.conv2d(image.float(), w.float(), stride=P).to(dtype).float()               # [B, width, G, G], rounded like the 16-bit conv
+    want = torch.cat([torch.zeros(B, 1, width, device=DEV), conv.flatten(2).transpose(1, 2)], dim=1) + pos_cls.to(dtype).float()[None]
+    want = want.to(dtype)
+    assert x.shape == want.shape and torch.isfinite(x.float()).all()
+    assert torch.equal(x[:, 0], want[:, 0])
+    ulp = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    assert (x.float() - want.float()).abs().max().item() <= 2 * ulp * want.float().abs().max().item() + 1e-3
+    assert _rel(x, want) < 3e-3
+
+
 def test_gemm_bad_args_raise():
     a = torch.zeros(8, 12, device=DEV, dtype=torch.bfloat16)   # K % 8 != 0
     w = torch.zeros(16, 12, device=DEV, dtype=torch.bfloat16)

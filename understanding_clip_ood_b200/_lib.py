@@ -97,6 +97,7 @@ SIGNATURES = {
     "b200clip_gemm": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _P, _I, _I, _P]),
     "b200clip_gemm_workspace_bytes": (C.c_int64, []),
     "b200clip_gemm_mn": (C.c_int, [_I, _P, _L, _I, _P, _L, _P, _L, _I, _I, _I, _P, _L, _P]),
+    "b200clip_patch_embed_implicit": (C.c_int, [_I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200clip_gemm_ws": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _P]),
     "b200clip_gemm_ln_ws": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P, _L, _P]),
     "b200clip_gemm_ln": (C.c_int, [_I, _P, _L, _P, _L, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),

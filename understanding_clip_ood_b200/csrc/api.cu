@@ -163,6 +163,14 @@ int b200clip_gemm_mn(int dtype, const void* A, int64_t lda, int a_mn, const void
     return gemm_pair_mn(dtype == B200CLIP_BF16, A, lda, a_mn != 0, W, ldw, true, C, ldc, M, N, K, S(stream), workspace);
 }
 
+int b200clip_patch_embed_implicit(int dtype, const void* image, const void* conv1_w, const float* pos_cls, void* x, int batch,
+                                  int image_size, int patch, int width, void* stream) {
+    B2C_CHECK_ARG(dtype == B200CLIP_BF16 || dtype == B200CLIP_F16, "patch_embed_implicit: 16-bit dtypes only");
+    const int rc = gemm_pair_patch_embed(dtype == B200CLIP_BF16, image, conv1_w, pos_cls, x, batch, image_size, patch, width, S(stream));
+    B2C_CHECK_ARG(rc != 1, "patch_embed_implicit: patch size %d is not covered (16-byte pixel rows that divide 64 elements: 16, 32)", patch);
+    return rc;
+}
+
 int b200clip_gemm_ln_ws(int dtype, const void* x, int64_t ldx, const void* Wf, int64_t ldw, const float* colsum, const float* bias_f32,
                         const float* rowstats, void* C, int64_t ldc, int M, int N, int K, int epilogue, void* workspace,
                         int64_t workspace_bytes, void* stream) {

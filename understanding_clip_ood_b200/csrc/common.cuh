@@ -434,6 +434,16 @@ __device__ __forceinline__ void tma_load_4d_pair(const void* desc, uint64_t* bar
           "r"(c3), "l"(hint)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d_pair(const void* desc, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1, int32_t c2,
+                                                 int32_t c3, int32_t c4, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2),
+          "r"(c3), "r"(c4), "l"(hint)
+        : "memory");
+}
 // Same, multicast: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and each destination's bytes are
 // credited to the mbarrier at this offset in the leader (even) CTA of that destination's pair.
 __device__ __forceinline__ void tma_load_2d_pair_mcast(const void* desc, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1,
@@ -500,6 +510,17 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc_lbo(uint32_t smem_ad
     d |= static_cast<uint64_t>(1024u >> 4) << 32;
     d |= 1ull << 46;
     d |= 2ull << 61;
+    return d;
+}
+
+// K-major operand tile with a narrower swizzle (rows of 64 B: layout 4 = SWIZZLE_64B, 8-row groups 512 B apart; rows of 32 B:
+// layout 6 = SWIZZLE_32B, groups 256 B apart) -- the patch-embedding A tiles, whose rows are one pixel row of a patch
+__device__ __forceinline__ uint64_t make_narrow_kmajor_desc(uint32_t smem_addr, uint32_t row_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((8u * row_bytes) >> 4) << 32;
+    d |= 1ull << 46;
+    d |= static_cast<uint64_t>(row_bytes == 64 ? 4u : 6u) << 61;
     return d;
 }
 

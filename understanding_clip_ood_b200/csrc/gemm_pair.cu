@@ -124,6 +124,9 @@ struct PairParams {
     // implicit 3x3 convolution (MAJ bit 2): A is the NHWC activation tensor read through a 4-D tensor map, an M tile of 128 rows is
     // a block of cv_bb images x cv_by rows x cv_bx pixels, K block kb = tap (kb / cv_cblocks) x 64-channel block (kb % cv_cblocks)
     int cv_bx, cv_by, cv_bb, cv_tx, cv_ty, cv_cblocks;
+    // implicit patch embedding (MAJ bit 3): A is the NCHW image batch read through a 5-D tensor map; the pixel blocks above are blocks
+    // of PATCHES (cv_bx x cv_by patches of cv_bb images), K block kb = channel kb / pe_kbpc, patch rows [(kb % pe_kbpc) * pe_rows, +pe_rows)
+    int pe_kbpc, pe_rows, pe_grid, pe_patch;
 };
 
 // STG_BUFS = staging buffers per epilogue group (3 with a loaded residual: landing / in-place update / store draining)
@@ -363,6 +366,9 @@ __device__ __noinline__ void sk_add_partials(uint32_t tmem_row, const float4* sl
 // Bit 2 (MAJ 4): implicit 3x3 / stride 1 / padding 1 convolution over an NHWC tensor: the A tile of K block (tap, channel block) is
 // the activation tensor itself, read through a 4-D tensor map at the tap's pixel offset (out-of-image pixels arrive as zeros = the
 // padding), and C is stored through the same kind of map -- the im2col matrix never exists (modified_resnet.py:17,42-47).
+// Bit 3 (MAJ 8): implicit patch embedding (conv1 of the ViT, kernel = stride = patch, transformer.py:602-609): the A tile is a block
+// of patches of the NCHW image batch read through a 5-D tensor map, the token rows 1 .. G*G of every image are stored through a 4-D
+// map (column, patch column, patch row, image) and the positional table row of each token is added in the epilogue.
 template <typename T, int BLOCK_N, int EPI, int PAIRS, int MODE, int MAJ = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -475,7 +481,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 pair_tile_coords(pc.tile, p, mt, nt);
                 const int row_a = mt * kClusterM + row_in_cluster;
                 int cv_x0 = 0, cv_y0 = 0, cv_b0 = 0;
-                if constexpr ((MAJ & 4) != 0) conv_block_coords(row_a / kBM, p, cv_x0, cv_y0, cv_b0);
+                if constexpr ((MAJ & 12) != 0) conv_block_coords(row_a / kBM, p, cv_x0, cv_y0, cv_b0);
                 // a piece of the N-split tail covers pc.nc of the tile's 64-column chunks: this CTA holds half of those W rows
                 const bool narrow = NS && pc.nc != Cfg::kChunks;
                 const int piece_w_rows = NS ? pc.nc * (kChunkN / 2) : BLOCK_N / 2;
@@ -486,7 +492,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
                     else mbar_arrive_remote(&full_bar[stage], leader_rank);
-                    if constexpr ((MAJ & 4) != 0) {
+                    if constexpr ((MAJ & 8) != 0) {
+                        // implicit patch embedding: this K block is channel kb / kbpc, pe_rows pixel rows of every patch of my block
+                        // (one box per pixel row: 128 patches x P pixels, P * 2 bytes = one swizzle row of the narrow layout)
+                        const int ch = kb / p.pe_kbpc, dy0 = (kb - ch * p.pe_kbpc) * p.pe_rows;
+                        for (int rr = 0; rr < p.pe_rows; ++rr)
+                            tma_load_5d_pair(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes + rr * (kBM * p.pe_patch * 2), 0, dy0 + rr, cv_x0,
+                                             cv_y0, cv_b0 * 3 + ch, kCacheHintEvictNormal);
+                    } else if constexpr ((MAJ & 4) != 0) {
                         // implicit 3x3 convolution: this K block is tap kb / cblocks, channels [64 (kb % cblocks), +64) of my pixel block
                         const int tap = kb / p.cv_cblocks, cb = kb - tap * p.cv_cblocks;
                         tma_load_4d_pair(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, cb * kBK, cv_x0 + tap % 3 - 1, cv_y0 + tap / 3 - 1,
@@ -553,9 +566,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const uint32_t addr_a = smem_u32(smem_a + stage * Cfg::kABytes), addr_b = smem_u32(smem_b + stage * Cfg::kBBytes);
                     const uint64_t desc_a = (MAJ & 1) ? make_sw128_mnmajor_desc_lbo(addr_a, 8192) : make_sw128_kmajor_desc(addr_a);
                     const uint64_t desc_b = (MAJ & 2) ? make_sw128_mnmajor_desc_lbo(addr_b, 8192) : make_sw128_kmajor_desc(addr_b);
+                    if constexpr ((MAJ & 8) != 0) {
+                        // patch embedding: the A stage is 64 / P sub-tiles of [128 patches][P pixels] in the narrow swizzle
+                        const uint32_t row_bytes = static_cast<uint32_t>(p.pe_patch) * 2u;
 #pragma unroll
-                    for (int k = 0; k < kBK / kUmmaK; ++k)
-                        umma_f16_pair(tmem_d, desc_a + kStepA * k, desc_b + kStepB * k, idesc_pc, ((kb - pc.kb0) | k) != 0);
+                        for (int k = 0; k < kBK / kUmmaK; ++k) {
+                            const uint32_t e = static_cast<uint32_t>(k * kUmmaK);
+                            const uint32_t sub = e / static_cast<uint32_t>(p.pe_patch), off = (e - sub * p.pe_patch) * 2u;
+                            umma_f16_pair(tmem_d, make_narrow_kmajor_desc(addr_a + sub * (kBM * row_bytes) + off, row_bytes), desc_b + kStepB * k,
+                                          idesc_pc, ((kb - pc.kb0) | k) != 0);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < kBK / kUmmaK; ++k)
+                            umma_f16_pair(tmem_d, desc_a + kStepA * k, desc_b + kStepB * k, idesc_pc, ((kb - pc.kb0) | k) != 0);
+                    }
                     // frees the slot in EVERY CTA of the cluster (each of them writes into some of the buffers just read)
                     if (!(p.dbg & 2)) umma_commit_pair(&empty_bar[stage], kAllCtas);
                     if (kb == pc.kb1 - 1) umma_commit_pair(&tmem_full_bar[acc], pair_mask);
@@ -639,7 +664,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t acc_phase = (it >> 1) & 1;
             const int row0 = mt * kClusterM + row_in_cluster;
             int cv_x0 = 0, cv_y0 = 0, cv_b0 = 0;
-            if constexpr ((MAJ & 4) != 0) conv_block_coords(row0 / kBM, p, cv_x0, cv_y0, cv_b0);
+            if constexpr ((MAJ & 12) != 0) conv_block_coords(row0 / kBM, p, cv_x0, cv_y0, cv_b0);
             const int pc_nc = NS ? pc.nc : Cfg::kChunks;   // 64-column chunks of this piece (N-split tail: fewer than the tile's)
             const int pc_c0 = NS ? pc.c0 : 0;
             const bool dump = SK && pc.kb0 != 0;                          // run starts inside the tile: accumulator -> fp32 partial
@@ -688,7 +713,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 vec_addr = smem_u32(vs);
             }
             const float* pos_row = nullptr;
-            if constexpr (kPos) pos_row = p.pos + static_cast<int64_t>((row0 + r) % p.pos_period) * p.N;
+            if constexpr (kPos && (MAJ & 8) != 0) {
+                // row r of my block is patch (cv_y0 + yl, cv_x0 + xl) of image cv_b0 + bl: token 1 + py * G + px (patches beyond the
+                // grid are clipped by the store: any valid table row will do for them)
+                const int xl = r % p.cv_bx, yl = (r / p.cv_bx) % p.cv_by;
+                const int px = cv_x0 + xl, py = cv_y0 + yl;
+                const int token = (px < p.pe_grid && py < p.pe_grid) ? 1 + py * p.pe_grid + px : 0;
+                pos_row = p.pos + static_cast<int64_t>(token) * p.N;
+            } else if constexpr (kPos) pos_row = p.pos + static_cast<int64_t>((row0 + r) % p.pos_period) * p.N;
             float ln_rstd = 0.f, ln_nmr = 0.f;
             if constexpr (kLn) {
                 if (row0 + r < p.M) {
@@ -909,7 +941,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 named_bar_sync(bar_id, 128);
                 if (grp_leader) {
                     if constexpr (EPI == kEpiResidualInPlace) tma_reduce_add_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, row0);
-                    else if constexpr ((MAJ & 4) != 0) tma_store_4d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, cv_x0, cv_y0, cv_b0);
+                    else if constexpr ((MAJ & 12) != 0) tma_store_4d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, cv_x0, cv_y0, cv_b0);
                     else tma_store_2d(&tmap_c, stg_ptr + buf * kChunkBytes, col0, row0);
                     tma_store_commit();
                     if constexpr (kRes) {
@@ -1290,6 +1322,7 @@ int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t l
     p.ns_begin = 0;
     p.ns_split = 0;
     p.cv_bx = p.cv_by = p.cv_bb = p.cv_tx = p.cv_ty = p.cv_cblocks = 0;
+    p.pe_kbpc = p.pe_rows = p.pe_grid = p.pe_patch = 0;
     if (sk_ok && epilogue != 3 && epilogue != kEpiResidualStats) {
         B2C_CHECK_ARG(reinterpret_cast<uintptr_t>(sk_workspace) % 16 == 0, "gemm: stream-K workspace must be 16-byte aligned");
         p.sk_tiles = plan_stream_k(p.m_tiles * p.n_tiles, (K + kBK - 1) / kBK, sk_clusters_planned());
@@ -1406,6 +1439,7 @@ int gemm_pair_mn(bool is_bf16, const void* A, int64_t lda, bool a_mn, const void
     p.ns_begin = 0;
     p.ns_split = 0;
     p.cv_bx = p.cv_by = p.cv_bb = p.cv_tx = p.cv_ty = p.cv_cblocks = 0;
+    p.pe_kbpc = p.pe_rows = p.pe_grid = p.pe_patch = 0;
     if (sk_ok) {
         B2C_CHECK_ARG(reinterpret_cast<uintptr_t>(sk_workspace) % 16 == 0, "gemm_mn: stream-K workspace must be 16-byte aligned");
         p.sk_tiles = plan_stream_k(p.m_tiles * p.n_tiles, num_kb, clusters);
@@ -1451,6 +1485,7 @@ int gemm_pair_conv3x3(bool is_bf16, const void* in, const void* Wt, const void* 
     p.cv_tx = W / bx;
     p.cv_ty = H / by;
     p.cv_cblocks = C / kBK;
+    p.pe_kbpc = p.pe_rows = p.pe_grid = p.pe_patch = 0;
     const int64_t blocks = static_cast<int64_t>(p.cv_tx) * p.cv_ty * ((batch + bb - 1) / bb);
     B2C_CHECK_ARG(blocks * kBM < (1ll << 31), "conv3x3: too many output rows");
     p.M = static_cast<int>(blocks * kBM);          // padded row count (pixel blocks beyond the batch are clipped by the tensor maps)
@@ -1472,6 +1507,103 @@ int gemm_pair_conv3x3(bool is_bf16, const void* in, const void* Wt, const void* 
                          : launch_pair_sk<__nv_bfloat16, 128, kEpiRelu, 1, 0, 4>(ta, tw, tc, tc, p, stream);
     return bn == 256 ? launch_pair_sk<__half, 256, kEpiRelu, 1, 0, 4>(ta, tw, tc, tc, p, stream)
                      : launch_pair_sk<__half, 128, kEpiRelu, 1, 0, 4>(ta, tw, tc, tc, p, stream);
+}
+
+// Implicit patch embedding of the ViT (conv1, kernel = stride = patch, no bias, transformer.py:602-609) for 16-bit NCHW batches:
+//   x[b, 1 + py * G + px, :] = round(patch(b, py, px) . conv1_w^T) + round(pos_cls[1 + py * G + px, :]),   x[b, 0, :] = round(pos_cls[0, :])
+// (pos_cls row 0 already holds class_embedding + positional_embedding[0]).  The patches are read from the image batch itself through
+// a 5-D tensor map -- no im2col matrix.  Patch sizes with 64 % P == 0 and 16-byte pixel rows (16, 32); returns 1 otherwise.
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) class_rows_kernel(T* __restrict__ x, const float* __restrict__ pos0, int batch, int64_t image_pitch, int width) {
+    const int64_t total = static_cast<int64_t>(batch) * width;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+        const int64_t b = i / width;
+        const int j = static_cast<int>(i - b * width);
+        const float v = pos0[j];
+        x[b * image_pitch + j] = Half16<T>::from_f(v);
+    }
+}
+}  // namespace
+
+int gemm_pair_patch_embed(bool is_bf16, const void* image, const void* conv1_w, const float* pos_cls, void* x, int batch, int image_size,
+                          int patch, int width, cudaStream_t stream) {
+    B2C_CHECK_ARG(image && conv1_w && pos_cls && x && batch > 0 && image_size > 0 && patch > 0 && width > 0, "patch_embed: bad arguments");
+    if (kBK % patch != 0 || (patch * 2) % 16 != 0 || image_size % patch != 0 || width % 8 != 0) return 1;
+    const int G = image_size / patch, L = G * G + 1;
+    int bx = 1;
+    while (bx < G) bx *= 2;
+    if (bx > 16) return 1;
+    int by = 1;
+    while (by < G && bx * by * 2 <= kBM) by *= 2;
+    const int bb = kBM / (bx * by);
+    const int rows = kBK / patch;
+    const int K = 3 * patch * patch;
+    const int bn = width > 128 ? 256 : 128;
+    CUtensorMap ta, tw, tc;
+    if (make_tmap_patches(&ta, is_bf16, image, batch, image_size, patch, rows, bb, by, bx) != 0) return -1;
+    if (make_tmap_2d(&tw, is_bf16, conv1_w, width, K, K, bn / 2, kBK) != 0) return -1;
+    // token rows 1 .. L-1 of x [batch, L, width] as (column, patch column, patch row, image)
+    {
+        CUtensorMap* m = &tc;
+        // a 4-D map with the same box order as the NHWC maps: dims {width, G, G, batch}, strides {width, G * width, L * width}
+        // (make_tmap_nhwc assumes dense packing, so this one is spelled out through the generic helper below)
+        if (make_tmap_nhwc_strided(m, is_bf16, static_cast<char*>(x) + static_cast<int64_t>(width) * 2, batch, G, G, width,
+                                   static_cast<uint64_t>(width), static_cast<uint64_t>(G) * width, static_cast<uint64_t>(L) * width, bb, by, bx) != 0)
+            return -1;
+    }
+    PairParams p;
+    p.bias = nullptr;
+    p.colsum = nullptr;
+    p.rowstats = nullptr;
+    p.stats_part = nullptr;
+    p.stats_out = nullptr;
+    p.stats_slots = 0;
+    p.ln_eps = 0.f;
+    p.pos = pos_cls;
+    p.pos_period = L;
+    p.cv_bx = bx;
+    p.cv_by = by;
+    p.cv_bb = bb;
+    p.cv_tx = (G + bx - 1) / bx;
+    p.cv_ty = (G + by - 1) / by;
+    p.cv_cblocks = 0;
+    p.pe_kbpc = patch * patch / kBK;
+    p.pe_rows = rows;
+    p.pe_grid = G;
+    p.pe_patch = patch;
+    const int64_t blocks = static_cast<int64_t>(p.cv_tx) * p.cv_ty * ((batch + bb - 1) / bb);
+    B2C_CHECK_ARG(blocks * kBM < (1ll << 31), "patch_embed: too many rows");
+    p.M = static_cast<int>(blocks * kBM);
+    p.N = width;
+    p.K = K;
+    p.m_tiles = static_cast<int>((blocks + 1) / 2);
+    p.n_tiles = (width + bn - 1) / bn;
+    p.group_m = 8;
+    p.pf_dist = 0;
+    p.dbg = gemm_debug_switches();
+    p.stages = gemm_ring_override();
+    p.sk_tiles = 0;
+    p.sk_partial = nullptr;
+    p.sk_flags = nullptr;
+    p.ns_begin = 0;
+    p.ns_split = 0;
+    int rc;
+    if (is_bf16)
+        rc = bn == 256 ? launch_pair_sk<__nv_bfloat16, 256, kEpiPosAdd, 1, 0, 8>(ta, tw, tc, tc, p, stream)
+                       : launch_pair_sk<__nv_bfloat16, 128, kEpiPosAdd, 1, 0, 8>(ta, tw, tc, tc, p, stream);
+    else
+        rc = bn == 256 ? launch_pair_sk<__half, 256, kEpiPosAdd, 1, 0, 8>(ta, tw, tc, tc, p, stream)
+                       : launch_pair_sk<__half, 128, kEpiPosAdd, 1, 0, 8>(ta, tw, tc, tc, p, stream);
+    if (rc != 0) return rc;
+    const int64_t total = static_cast<int64_t>(batch) * width;
+    const int grid = static_cast<int>((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    if (is_bf16)
+        class_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<__nv_bfloat16*>(x), pos_cls, batch, static_cast<int64_t>(L) * width, width);
+    else
+        class_rows_kernel<__half><<<grid, 256, 0, stream>>>(static_cast<__half*>(x), pos_cls, batch, static_cast<int64_t>(L) * width, width);
+    B2C_LAUNCH_CHECK("class_rows_kernel");
+    return 0;
 }
 
 }  // namespace b200clip

@@ -21,6 +21,11 @@ int gemm_pair_mn(bool is_bf16, const void* A, int64_t lda, bool a_mn, const void
 int gemm_pair_conv3x3(bool is_bf16, const void* in, const void* Wt, const void* bias, void* out, int batch, int H, int W, int C, int N,
                       cudaStream_t stream);
 
+// Implicit patch embedding of the ViT for 16-bit NCHW batches (token-layout x [batch, G*G + 1, width], pos_cls = fp32 [G*G + 1, width]
+// table whose row 0 holds class_embedding + positional_embedding[0]): 0 = launched, 1 = patch size not covered, otherwise an error
+int gemm_pair_patch_embed(bool is_bf16, const void* image, const void* conv1_w, const float* pos_cls, void* x, int batch, int image_size,
+                          int patch, int width, cudaStream_t stream);
+
 // CTA-pair (cta_group::2) variant with the TMA-store epilogue (gemm_pair.cu); epilogues 0..3
 int gemm_pair(bool is_bf16, const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, const void* residual,
               int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int epilogue, int force_block_n, int pairs, cudaStream_t stream,

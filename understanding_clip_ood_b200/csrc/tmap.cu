@@ -96,15 +96,15 @@ int make_tmap_2d(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t rows,
     return 0;
 }
 
-int make_tmap_nhwc(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t bb, uint32_t by,
-                   uint32_t bx) {
+int make_tmap_nhwc_strided(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint64_t pitch_w,
+                           uint64_t pitch_h, uint64_t pitch_b, uint32_t bb, uint32_t by, uint32_t bx) {
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) {
         set_last_error("cuTensorMapEncodeTiled not available from the driver");
         return -1;
     }
     const cuuint64_t dims[4] = {C, W, H, B};
-    const cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+    const cuuint64_t strides[3] = {pitch_w * 2, pitch_h * 2, pitch_b * 2};
     const cuuint32_t box[4] = {64, bx, by, bb};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides,
@@ -113,6 +113,35 @@ int make_tmap_nhwc(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t B, 
     if (r != CUDA_SUCCESS) {
         set_last_error("cuTensorMapEncodeTiled (NHWC) failed (CUresult %d) for ptr=%p B=%llu H=%llu W=%llu C=%llu box=%ux%ux%u", (int)r, ptr,
                        (unsigned long long)B, (unsigned long long)H, (unsigned long long)W, (unsigned long long)C, bb, by, bx);
+        return -1;
+    }
+    return 0;
+}
+
+int make_tmap_nhwc(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t bb, uint32_t by,
+                   uint32_t bx) {
+    return make_tmap_nhwc_strided(map, is_bf16, ptr, B, H, W, C, C, W * C, H * W * C, bb, by, bx);
+}
+
+int make_tmap_patches(CUtensorMap* map, bool is_bf16, const void* image, uint64_t B, uint64_t S, uint32_t P, uint32_t rows, uint32_t bb,
+                      uint32_t by, uint32_t bx) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) {
+        set_last_error("cuTensorMapEncodeTiled not available from the driver");
+        return -1;
+    }
+    const uint64_t G = S / P;
+    (void)rows;   // one pixel row of every patch per box: the inner box extent (P pixels) is exactly one swizzle row
+    const cuuint64_t dims[5] = {P, P, G, G, 3 * B};
+    const cuuint64_t strides[4] = {S * 2, static_cast<cuuint64_t>(P) * 2, S * P * 2, S * S * 2};
+    const cuuint32_t box[5] = {P, 1, bx, by, bb * 3};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 3};
+    const CUtensorMapSwizzle swz = P * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(image), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled (patches) failed (CUresult %d) for image=%p B=%llu S=%llu P=%u box=%ux%ux%ux%u", (int)r, image,
+                       (unsigned long long)B, (unsigned long long)S, P, rows, bx, by, bb);
         return -1;
     }
     return 0;

@@ -17,4 +17,16 @@ int make_tmap_2d(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t rows,
 int make_tmap_nhwc(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t bb, uint32_t by,
                    uint32_t bx);
 
+// The same 4-D box over a tensor with explicit element pitches of the W, H and B dimensions (C contiguous): e.g. the token rows
+// 1 .. G*G of x [B, G*G + 1, width] seen as [B, G, G, width].
+int make_tmap_nhwc_strided(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint64_t pitch_w,
+                           uint64_t pitch_h, uint64_t pitch_b, uint32_t bb, uint32_t by, uint32_t bx);
+
+// 5D view of an NCHW image batch [B, 3, S, S] (16-bit) for the implicit patch-embedding GEMM: dimensions (dx within a patch, dy
+// within a patch, patch column, patch row, channel + 3 * image), box = (P, 1, bx, by, bb images at ONE channel through an element
+// stride of 3 on the last dimension): bx * by * bb = 128 patches x P elements = a K-major operand sub-tile whose rows are ONE pixel
+// row of each patch, P * 2 bytes = one swizzle row (SWIZZLE_64B for P = 32, SWIZZLE_32B for P = 16); 64 / P such boxes make a K block.
+int make_tmap_patches(CUtensorMap* map, bool is_bf16, const void* image, uint64_t B, uint64_t S, uint32_t P, uint32_t rows, uint32_t bb,
+                      uint32_t by, uint32_t bx);
+
 }  // namespace b200clip

@@ -20,6 +20,18 @@
 
 namespace b200clip {
 
+// B200CLIP_PATCH_IMPLICIT=1: the patch embedding of 16-bit NCHW batches as an implicit GEMM (patches read from the image through a
+// 5-D tensor map, b200clip_patch_embed_implicit).  Correct (bit-identical token rows) but measured SLOWER than im2col + GEMM on
+// ViT-B/32 at batch 1024: 351 us against 109 + 191 us -- the gather moves 64-byte pixel rows, and every A tile is gathered once per
+// N tile (three times at width 768).  Off by default.
+static bool patch_embed_via_im2col() {
+    static const bool v = [] {
+        const char* e = getenv("B200CLIP_PATCH_IMPLICIT");
+        return !(e != nullptr && e[0] == '1');
+    }();
+    return v;
+}
+
 int text_embed_v(int dtype, const int64_t* text, int ctx, const float* tok_emb, const float* pos_emb, void* x, int32_t* eot,
                  int T, int L, int width, int vocab, cudaStream_t stream);
 
@@ -171,7 +183,7 @@ int64_t workspace_bytes(const b200clip_tower_cfg* cfg, int batch, int seq_len) {
 }
 
 // image_u8 != nullptr: uint8 pixels, ToTensor + Normalize(mean, std) fused into the im2col (`image` is ignored)
-// `stages`: B200CLIP_STAGE_INPUT (im2col: the only kernel that reads `image`) | _BODY (patch GEMM ... ln_post on the pooled rows,
+// `stages`: B200CLIP_STAGE_INPUT (the patch embedding: the only kernels that read `image`) | _BODY (patch GEMM ... ln_post on the pooled rows,
 // workspace -> workspace) | _OUTPUT (projection + optional normalise: the only kernels that write `out`).
 static int vit_forward_impl(const b200clip_tower_cfg* cfg, const b200clip_vit_weights* w, const void* image, const uint8_t* image_u8,
                             const float* mean, const float* std, void* out, int batch, int normalize, void* workspace,
@@ -201,33 +213,40 @@ static int vit_forward_impl(const b200clip_tower_cfg* cfg, const b200clip_vit_we
 
     const bool token_layout = dt != B200CLIP_F32 && w->pos_cls != nullptr;
     if (stages & B200CLIP_STAGE_INPUT) {
-        // token layout: im2col with an all-zero row in every class-token slot; otherwise the im2col also writes the class-token
-        // rows of x (class_emb + pos[0])
-        if (token_layout)
-            rc = image_u8 != nullptr
-                     ? patchify_u8(dt, image_u8, mean, std, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, nullptr, nullptr, nullptr, W, s, 1)
-                     : patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, nullptr, nullptr, nullptr, W, s, 1);
-        else
-            rc = image_u8 != nullptr
-                     ? patchify_u8(dt, image_u8, mean, std, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s)
-                     : patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s);
+        // Everything that depends on the caller's batch: the patch embedding up to the token rows x [B*L, W] (+ class / positional rows).
+        // 16-bit NCHW batches with patch 16 / 32: implicit GEMM, the patches are read from the image itself through a 5-D tensor map
+        // (no im2col matrix); otherwise im2col (from uint8 pixels: ToTensor + Normalize fused) + GEMM.
+        rc = 1;
+        if (token_layout && image_u8 == nullptr && c.patch_kpad == 3 * c.patch_size * c.patch_size && !patch_embed_via_im2col())
+            rc = gemm_pair_patch_embed(dt == B200CLIP_BF16, image, w->conv1_w, w->pos_cls, ws.x, batch, c.image_size, c.patch_size, W, s);
+        if (rc == 1) {
+            // token layout: im2col with an all-zero row in every class-token slot; otherwise the im2col also writes the class-token
+            // rows of x (class_emb + pos[0])
+            if (token_layout)
+                rc = image_u8 != nullptr
+                         ? patchify_u8(dt, image_u8, mean, std, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, nullptr, nullptr, nullptr, W, s, 1)
+                         : patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, nullptr, nullptr, nullptr, W, s, 1);
+            else
+                rc = image_u8 != nullptr
+                         ? patchify_u8(dt, image_u8, mean, std, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s)
+                         : patchify(dt, image, ws.mlp, batch, c.image_size, c.patch_size, c.patch_kpad, w->class_emb, w->pos_emb, ws.x, W, s);
+            if (rc != 0) return rc;
+            if (token_layout) {
+                // ONE CTA-pair GEMM over all B*L rows whose epilogue adds the (class + positional) table row of each token
+                if (ws.sk != nullptr && (rc = gemm_pair_sk_workspace_reset(ws.sk, s)) != 0) return rc;
+                rc = gemm_pair(dt == B200CLIP_BF16, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, M, W,
+                               c.patch_kpad, B200CLIP_EPI_BIAS, 0, 0, s, nullptr, nullptr, w->pos_cls, L, nullptr, nullptr, 0, 1e-5f, ws.sk);
+            } else {
+                // GEMM whose epilogue scatters to token rows 1..L-1 and adds the positional embedding
+                rc = gemm_any(dt, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, batch * g * g, W, c.patch_kpad,
+                              B200CLIP_EPI_PATCH, w->pos_emb, g * g, L, s);
+            }
+        }
         if (rc != 0) return rc;
     }
     if (stages & B200CLIP_STAGE_BODY) {
         // stream-K flag words start at zero (the kernels leave them at zero; this also heals a workspace a failed launch left dirty)
         if (ws.sk != nullptr && (rc = gemm_pair_sk_workspace_reset(ws.sk, s)) != 0) return rc;
-        if (token_layout) {
-            // ONE CTA-pair GEMM over all B*L rows whose epilogue adds the (class + positional) table row of each token
-            if ((rc = gemm_pair(dt == B200CLIP_BF16, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, M, W,
-                                c.patch_kpad, B200CLIP_EPI_BIAS, 0, 0, s, nullptr, nullptr, w->pos_cls, L, nullptr, nullptr, 0, 1e-5f,
-                                ws.sk)) != 0)
-                return rc;
-        } else {
-            // GEMM whose epilogue scatters to token rows 1..L-1 and adds the positional embedding
-            if ((rc = gemm_any(dt, ws.mlp, c.patch_kpad, w->conv1_w, c.patch_kpad, nullptr, nullptr, 0, ws.x, W, batch * g * g, W,
-                               c.patch_kpad, B200CLIP_EPI_PATCH, w->pos_emb, g * g, L, s)) != 0)
-                return rc;
-        }
         if ((rc = save_slot(saved, 0, ws.x, c, batch, L, s)) != 0) return rc;
         if ((rc = layernorm(dt, ws.x, W, w->ln_pre_g, w->ln_pre_b, ws.x, W, M, W, 1e-5f, 1, nullptr, s)) != 0) return rc;
         if ((rc = run_blocks(c, w->blocks_host, ws, batch, L, 0, s, saved)) != 0) return rc;

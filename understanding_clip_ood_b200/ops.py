@@ -89,6 +89,21 @@ def gemm_mn(a: torch.Tensor, w: torch.Tensor, *, a_transposed: bool = False, out
     return out
 
 
+def patch_embed_implicit(image: torch.Tensor, conv1_w: torch.Tensor, pos_cls: torch.Tensor, patch: int) -> torch.Tensor:
+    """ViT patch embedding as an implicit GEMM over a 16-bit NCHW batch (no im2col matrix); see b200clip_patch_embed_implicit.
+    conv1_w [width, 3*P*P], pos_cls fp32 [G*G + 1, width] (row 0 = class + positional[0]) -> x [B, G*G + 1, width]."""
+    L.require_cuda(image, conv1_w, pos_cls)
+    image, conv1_w, pos_cls = _c(image), _c(conv1_w), _c(pos_cls)
+    B, _, S, _ = image.shape
+    width = conv1_w.shape[0]
+    G = S // patch
+    x = torch.empty((B, G * G + 1, width), dtype=image.dtype, device=image.device)
+    rc = L.load().b200clip_patch_embed_implicit(L.dtype_code(image.dtype), image.data_ptr(), conv1_w.data_ptr(), pos_cls.data_ptr(), x.data_ptr(),
+                                               B, S, patch, width, L.stream_ptr())
+    L.check(rc, "b200clip_patch_embed_implicit")
+    return x
+
+
 def gemm_ln_ws(x: torch.Tensor, wf: torch.Tensor, colsum: torch.Tensor, bias_f32: torch.Tensor, stats: torch.Tensor, *,
                epilogue: int = L.EPI_BIAS, out: torch.Tensor | None = None, workspace: torch.Tensor | None = None) -> torch.Tensor:
     """`gemm_ln` with the stream-K workspace; see b200clip_gemm_ln_ws."""
