@@ -662,17 +662,21 @@ __global__ void __launch_bounds__(256) attention_backward_tc_kernel(const T* __r
     namespace wmma = nvcuda::wmma;
     using WT = typename WmmaT<T>::type;
     constexpr int LDT = kHd + 8;        // 72: operand tiles [LP][64] in the storage type
-    constexpr int LDS = LP + 8;         // score matrices [LP][LP]
+    constexpr int LDS = LP + 8;         // score matrices [LP][LP], fp32
+    constexpr int LDP = 2 * LDS;        // the same rows seen as storage-type rows (P / dS overwrite the fp32 rows they were made from)
     constexpr int NT = LP / 16;
+    constexpr int NJ = (LP + 31) / 32;  // row elements per lane
+    constexpr int LDW = 20;             // per-warp output staging tile [16][LDW] fp32
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* Qs = reinterpret_cast<T*>(smem_raw);
     T* Ks = Qs + LP * LDT;
     T* Vs = Ks + LP * LDT;
     T* dOs = Vs + LP * LDT;
-    T* Pb = dOs + LP * LDT;             // [LP][LDS] probabilities, storage type
-    T* dSb = Pb + LP * LDS;             // [LP][LDS] scale * dS, storage type
-    float* Sf = reinterpret_cast<float*>(dSb + LP * LDS);   // [LP][LDS] fp32: S, then reused as output staging
-    float* dPf = Sf + LP * LDS;                              // [LP][LDS] fp32: dP, then output staging
+    float* Sf = reinterpret_cast<float*>(dOs + LP * LDT);   // [LP][LDS] fp32: S; after the softmax its rows hold P in the storage type
+    float* dPf = Sf + LP * LDS;                              // [LP][LDS] fp32: dP; afterwards scale * dS in the storage type
+    float* wstage = dPf + LP * LDS;                          // [8 warps][16][LDW]
+    T* Pb = reinterpret_cast<T*>(Sf);
+    T* dSb = reinterpret_cast<T*>(dPf);
     const int W = heads * kHd;
     const int b = blockIdx.x / heads, h = blockIdx.x % heads;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -714,45 +718,56 @@ __global__ void __launch_bounds__(256) attention_backward_tc_kernel(const T* __r
         wmma::store_matrix_sync((which == 0 ? Sf : dPf) + mi * 16 * LDS + ni * 16, acc, LDS, wmma::mem_row_major);
     }
     __syncthreads();
-    // ---- softmax rows, dS: one warp per row
+    // ---- softmax rows, dS: one warp per row.  The row is read into registers, then P and scale * dS (storage type) are written
+    // over the first half of the fp32 rows they were computed from -- no separate P / dS buffers (the 80-row text variant fits two
+    // CTAs per SM that way: 110 KB instead of 143 KB).
     const float scale = 0.125f;
     for (int r = warp; r < LP; r += 8) {
-        if (r >= L) {
-            for (int j = lane; j < LP; j += 32) {
-                Pb[r * LDS + j] = from_f<T>(0.f);
-                dSb[r * LDS + j] = from_f<T>(0.f);
-            }
-            continue;
-        }
-        const int jmax = causal ? r + 1 : L;        // keys [0, jmax) take part
-        float m = -INFINITY;
-        for (int j = lane; j < jmax; j += 32) m = fmaxf(m, Sf[r * LDS + j] * scale);
-        m = warp_max(m);
-        float sum = 0.f;
-        for (int j = lane; j < jmax; j += 32) {
-            const float e = __expf(Sf[r * LDS + j] * scale - m);
-            Sf[r * LDS + j] = e;
-            sum += e;
-        }
-        const float inv = 1.0f / warp_sum(sum);
+        float pv[NJ], dv[NJ];
         float dot = 0.f;
-        for (int j = lane; j < jmax; j += 32) {
-            const float pv = Sf[r * LDS + j] * inv;
-            Sf[r * LDS + j] = pv;
-            dot = fmaf(pv, dPf[r * LDS + j], dot);
+        const int jmax = r < L ? (causal ? r + 1 : L) : 0;        // keys [0, jmax) take part (none for the padding rows)
+        if (r < L) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int t = 0; t < NJ; ++t) {
+                const int j = lane + 32 * t;
+                pv[t] = j < jmax ? Sf[r * LDS + j] * scale : -INFINITY;
+                dv[t] = j < jmax ? dPf[r * LDS + j] : 0.f;
+                m = fmaxf(m, pv[t]);
+            }
+            m = warp_max(m);
+            float sum = 0.f;
+#pragma unroll
+            for (int t = 0; t < NJ; ++t) {
+                pv[t] = lane + 32 * t < jmax ? __expf(pv[t] - m) : 0.f;
+                sum += pv[t];
+            }
+            const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+            for (int t = 0; t < NJ; ++t) {
+                pv[t] *= inv;
+                dot = fmaf(pv[t], dv[t], dot);
+            }
+            dot = warp_sum(dot);
+        } else {
+#pragma unroll
+            for (int t = 0; t < NJ; ++t) pv[t] = dv[t] = 0.f;
         }
-        dot = warp_sum(dot);
-        for (int j = lane; j < LP; j += 32) {
-            const bool on = j < jmax;
-            const float pv = on ? Sf[r * LDS + j] : 0.f;
-            Pb[r * LDS + j] = from_f<T>(pv);
-            dSb[r * LDS + j] = from_f<T>(on ? scale * pv * (dPf[r * LDS + j] - dot) : 0.f);
+        __syncwarp();      // every lane has read its part of the two fp32 rows before they are overwritten
+#pragma unroll
+        for (int t = 0; t < NJ; ++t) {
+            const int j = lane + 32 * t;
+            if (j < LP) {
+                const bool on = j < jmax;
+                Pb[r * LDP + j] = from_f<T>(on ? pv[t] : 0.f);
+                dSb[r * LDP + j] = from_f<T>(on ? scale * pv[t] * (dv[t] - dot) : 0.f);
+            }
         }
     }
     __syncthreads();
-    // ---- dV = P^T dO, dK = dS^T Q, dQ = dS K: 3 * NT * 4 output tiles [16 x 16] of [LP x 64] matrices, staged in fp32
-    float* stage = Sf;                 // [3][LP][LDO] fp32 over the (now free) score buffers; the allocation covers the larger of the two
-    constexpr int LDO = kHd + 8;
+    // ---- dV = P^T dO, dK = dS^T Q, dQ = dS K: 3 * NT * 4 output tiles [16 x 16] of [LP x 64] matrices; every warp converts its tile
+    // through a private fp32 staging tile and writes the rows (< L) in the storage type: 32 bytes per row and tile
+    float* mine = wstage + warp * 16 * LDW;
     for (int t = warp; t < 3 * NT * 4; t += 8) {
         const int which = t / (NT * 4), tt = t % (NT * 4);
         const int mi = tt / 4, ni = tt % 4;
@@ -765,7 +780,7 @@ __global__ void __launch_bounds__(256) attention_backward_tc_kernel(const T* __r
             for (int k = 0; k < LP; k += 16) {
                 wmma::fragment<wmma::matrix_a, 16, 16, 16, WT, wmma::col_major> fa;
                 wmma::fragment<wmma::matrix_b, 16, 16, 16, WT, wmma::row_major> fb;
-                wmma::load_matrix_sync(fa, reinterpret_cast<const WT*>(A + k * LDS + mi * 16), LDS);
+                wmma::load_matrix_sync(fa, reinterpret_cast<const WT*>(A + k * LDP + mi * 16), LDP);
                 wmma::load_matrix_sync(fb, reinterpret_cast<const WT*>(Bm + k * LDT + ni * 16), LDT);
                 wmma::mma_sync(acc, fa, fb, acc);
             }
@@ -774,33 +789,31 @@ __global__ void __launch_bounds__(256) attention_backward_tc_kernel(const T* __r
             for (int k = 0; k < LP; k += 16) {
                 wmma::fragment<wmma::matrix_a, 16, 16, 16, WT, wmma::row_major> fa;
                 wmma::fragment<wmma::matrix_b, 16, 16, 16, WT, wmma::row_major> fb;
-                wmma::load_matrix_sync(fa, reinterpret_cast<const WT*>(dSb + mi * 16 * LDS + k), LDS);
+                wmma::load_matrix_sync(fa, reinterpret_cast<const WT*>(dSb + mi * 16 * LDP + k), LDP);
                 wmma::load_matrix_sync(fb, reinterpret_cast<const WT*>(Bm + k * LDT + ni * 16), LDT);
                 wmma::mma_sync(acc, fa, fb, acc);
             }
         }
-        // stage: [which][LP][LDO] fp32 in the (now free) fp32 score buffers + the tail of the allocation
-        wmma::store_matrix_sync(stage + (which * LP + mi * 16) * LDO + ni * 16, acc, LDO, wmma::mem_row_major);
-    }
-    __syncthreads();
-    // ---- write dq | dk | dv rows (< L) in the storage type
-    for (int i = tid; i < 3 * L * 8; i += 256) {
-        const int which = i / (L * 8), rem = i % (L * 8);
-        const int l = rem >> 3, c = (rem & 7) * 8;
-        const float* src = stage + ((which == 0 ? 2 : (which == 1 ? 1 : 0)) * LP + l) * LDO + c;   // output order q, k, v <- dQ(2), dK(1), dV(0)
-        alignas(16) T o[8];
+        wmma::store_matrix_sync(mine, acc, LDW, wmma::mem_row_major);
+        __syncwarp();
+        const int row = lane >> 1, half = lane & 1;
+        const int l = mi * 16 + row;
+        if (l < L) {
+            const float* src = mine + row * LDW + half * 8;
+            alignas(16) T o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = from_f<T>(src[j]);
-        *reinterpret_cast<uint4*>(d_qkv + (static_cast<int64_t>(b) * L + l) * 3 * W + which * W + h * kHd + c) = *reinterpret_cast<const uint4*>(o);
+            for (int j = 0; j < 8; ++j) o[j] = from_f<T>(src[j]);
+            const int slot = which == 0 ? 2 : (which == 1 ? 1 : 0);      // output order q, k, v <- dQ (2), dK (1), dV (0)
+            *reinterpret_cast<uint4*>(d_qkv + (static_cast<int64_t>(b) * L + l) * 3 * W + slot * W + h * kHd + ni * 16 + half * 8) =
+                *reinterpret_cast<const uint4*>(o);
+        }
+        __syncwarp();      // the staging tile is free for this warp's next output tile
     }
 }
 
 template <typename T, int LP> constexpr size_t attn_bwd_tc_smem() {
-    constexpr size_t LDT = kHd + 8, LDS = LP + 8, LDO = kHd + 8;
-    constexpr size_t ops = 4 * LP * LDT * sizeof(T) + 2 * LP * LDS * sizeof(T);
-    constexpr size_t scores = 2 * LP * LDS * sizeof(float);
-    constexpr size_t stage = 3 * LP * LDO * sizeof(float);
-    return ops + (scores > stage ? scores : stage);
+    constexpr size_t LDT = kHd + 8, LDS = LP + 8;
+    return 4 * LP * LDT * sizeof(T) + 2 * LP * LDS * sizeof(float) + 8 * 16 * 20 * sizeof(float);
 }
 
 template <typename T, int LP>
